@@ -1,0 +1,225 @@
+/* ia_b200.h -- C ABI of the B200-native (sm_100a) Instant-angelo training hot path.
+ *
+ * This is the drop-in boundary: plain pointers + sizes + a cudaStream_t (passed as void*), an int32
+ * status return (0 = OK, negative = ia_status), no exceptions and no torch types.  Every entry point
+ * names the reference interface it replaces (file:line under the hugoycj/Instant-angelo tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host or the parameter is a plan/desc
+ *     struct (plain POD, read on the host, passed to kernels by value);
+ *   - all tensors are contiguous, row-major, fp32 unless stated; the caller owns every allocation;
+ *   - kernels are enqueued on `stream`; no call synchronises the device except ia_march_total();
+ *   - functions are re-entrant; the only global state is the thread-local last-error string.
+ */
+#ifndef IA_B200_H
+#define IA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IA_MAX_LEVELS 32
+#define IA_ABI_VERSION 1
+
+typedef enum ia_status {
+    IA_OK = 0,
+    IA_ERR_INVALID_ARG = -1,
+    IA_ERR_UNSUPPORTED = -2,
+    IA_ERR_CUDA = -3,
+    IA_ERR_NO_DEVICE = -4
+} ia_status;
+
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char *ia_last_error_string(void);
+int32_t ia_abi_version(void);
+/* Compute capability of the current device (major*10+minor); IA_ERR_NO_DEVICE without a GPU. */
+int32_t ia_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multiresolution hash grid            replaces tcnn.Encoding(otype=HashGrid) as constructed at
+ *                                      models/network_utils.py:44-48 and called at :56-59
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ia_grid_plan {
+    int32_t n_levels;
+    int32_t n_features;                  /* must be 2 */
+    int32_t log2_hashmap_size;
+    int32_t base_resolution;
+    float per_level_scale;
+    float scale[IA_MAX_LEVELS];          /* exp2f(l*log2f(pls))*base - 1, float32 arithmetic */
+    uint32_t res[IA_MAX_LEVELS];         /* ceilf(scale)+1 */
+    uint32_t size[IA_MAX_LEVELS];        /* entries in the level */
+    uint32_t offset[IA_MAX_LEVELS + 1];  /* entry offset of each level; offset[L] = total entries */
+    uint32_t hashed[IA_MAX_LEVELS];      /* 1: coherent prime hash, 0: dense index */
+} ia_grid_plan;
+
+/* Host-only: fills `plan` with tcnn's per-level geometry (flat param layout: level-major, entry-major,
+ * feature-minor; config keys of configs/neuralangelo-colmap_sparse.yaml:45-51). */
+int32_t ia_hashgrid_plan(int32_t n_levels, int32_t n_features, int32_t log2_hashmap_size,
+                         int32_t base_resolution, float per_level_scale, ia_grid_plan *plan_host);
+
+/* out[n, L*F] = encode(x[n,3] in [0,1]); levels >= active_levels are written as exact zeros, which is
+ * the progressive mask of ProgressiveBandHashGrid.forward (models/network_utils.py:56-59) folded in.
+ * `table` is the flat fp32 parameter vector (tcnn Encoding.params). */
+int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table, const ia_grid_plan *plan_host,
+                        int32_t active_levels, float *out, void *stream);
+
+/* dtable[...] += scatter(w_corner * dy[n, L*F]) (accumulates; caller zeroes).  Autograd of the call at
+ * models/network_utils.py:57 w.r.t. Encoding.params. */
+int32_t ia_hashgrid_bwd_table(const float *x, int64_t n, const float *dy, const ia_grid_plan *plan_host,
+                              int32_t active_levels, float *dtable, void *stream);
+
+/* dx[n,3] = d enc / d x contracted with dy (overwrites).  Needed because curvature tap positions
+ * depend on parameters (models/geometry.py:238-246, no detach). */
+int32_t ia_hashgrid_bwd_input(const float *x, int64_t n, const float *table, const float *dy,
+                              const ia_grid_plan *plan_host, int32_t active_levels, float *dx, void *stream);
+
+/* Both of the above in one pass; dtable and/or dx may be NULL. */
+int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table, const float *dy,
+                        const ia_grid_plan *plan_host, int32_t active_levels, float *dtable, float *dx,
+                        void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spherical harmonics                  replaces tcnn.Encoding(otype=SphericalHarmonics) built at
+ *                                      models/network_utils.py:90-91, called at models/texture.py:25,52,129,134
+ * ------------------------------------------------------------------------------------------------ */
+int32_t ia_sh_fwd(const float *d01, int64_t n, int32_t degree, float *out /*[n,degree^2]*/, void *stream);
+int32_t ia_sh_bwd(const float *d01, int64_t n, int32_t degree, const float *dout, float *dd01, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Width-64 fused MLP                   replaces VanillaMLP.forward (models/network_utils.py:108-113) and
+ *                                      tcnn.Network (models/network_utils.py:181-184)
+ * ------------------------------------------------------------------------------------------------ */
+typedef enum ia_act { IA_ACT_NONE = 0, IA_ACT_RELU = 1, IA_ACT_SOFTPLUS100 = 2, IA_ACT_SIGMOID = 3 } ia_act;
+typedef enum ia_mlp_precision { IA_MLP_FP32 = 0, IA_MLP_TC_F16 = 1 } ia_mlp_precision;
+
+typedef struct ia_mlp_desc {
+    int32_t n_in0;            /* leading input columns taken from in0 as in0*in0_scale+in0_offset (0..8) */
+    float in0_scale, in0_offset;
+    int32_t n_in1;            /* remaining input columns taken from in1 (row stride n_in1) */
+    int32_t n_hidden_layers;  /* 1 or 2 hidden layers of `width` neurons */
+    int32_t width;            /* must be 64 */
+    int32_t n_out;            /* 1..128 */
+    int32_t hidden_act;       /* IA_ACT_RELU | IA_ACT_SOFTPLUS100 */
+    int32_t out_act;          /* IA_ACT_NONE | IA_ACT_SIGMOID */
+    int32_t precision;        /* ia_mlp_precision */
+} ia_mlp_desc;
+
+/* Flat parameter layout (effective weights, i.e. after weight-norm is folded on the host side):
+ *   W0[width, n_in0+n_in1], b0[width], (W1[width,width], b1[width]), Wl[n_out, width], bl[n_out]
+ * each W row-major [out, in] like nn.Linear.weight. */
+int64_t ia_mlp_param_count(const ia_mlp_desc *desc_host);
+
+/* out[n, n_out_used] (row stride ld_out) = first n_out_used outputs of the network.  n_out_used < n_out
+ * is the SDF-only evaluation of the finite-difference taps (models/geometry.py:233, 266). */
+int32_t ia_mlp_fwd(const ia_mlp_desc *desc_host, const float *in0, const float *in1, int64_t n,
+                   const float *params, int32_t n_out_used, float *out, int64_t ld_out, void *stream);
+
+/* Backward with in-kernel recomputation of the hidden activations.  dout[n, n_out_used] (row stride
+ * ld_dout).  din0/din1 may be NULL; dparams (same layout as params) is ACCUMULATED. */
+int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *in1, int64_t n,
+                   const float *params, const float *dout, int32_t n_out_used, int64_t ld_dout,
+                   float *din0, float *din1, float *dparams, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy grid + ray marching        replaces nerfacc.OccupancyGrid / ray_aabb_intersect /
+ *                                      ray_marching as called at models/neus.py:64-74, 108-111, 153,
+ *                                      159-169, 209-220
+ * ------------------------------------------------------------------------------------------------ */
+typedef enum ia_contraction { IA_AABB = 0, IA_UN_BOUNDED_TANH = 1, IA_UN_BOUNDED_SPHERE = 2 } ia_contraction;
+
+typedef struct ia_grid_desc {
+    float roi[6];             /* xmin ymin zmin xmax ymax zmax */
+    int32_t res[3];
+    int32_t contraction;      /* ia_contraction */
+} ia_grid_desc;
+
+/* occs[idx[i]] = max(occs[idx[i]]*decay, max over duplicates occ[i]); then
+ * binary = occs > min(mean(occs), thre) written both as bool bytes (nerfacc `_binary`, C order
+ * x*ry*rz + y*rz + z) and as a packed bitfield (bit c of word c/32).  `idx` int64, NULL = all cells in
+ * order.  workspace: >= ia_occ_workspace_bytes(num_cells) bytes. */
+int64_t ia_occ_workspace_bytes(int64_t num_cells);
+int32_t ia_occ_update(const int64_t *idx, const float *occ, int64_t n, float *occs, int64_t num_cells,
+                      float ema_decay, float occ_thre, uint8_t *binary, uint32_t *bitfield, void *workspace,
+                      void *stream);
+/* bool bytes -> bitfield (for grids loaded from a checkpoint or set by hand). */
+int32_t ia_occ_pack(const uint8_t *binary, int64_t num_cells, uint32_t *bitfield, void *stream);
+
+/* nerfacc ray_aabb_intersect: miss => (1e10,1e10); clamp_zero applies t_min = max(t_min, 0). */
+int32_t ia_aabb(const float *rays_o, const float *rays_d, int64_t n_rays, const float *aabb_host6,
+                int32_t clamp_zero, float *t_min, float *t_max, void *stream);
+
+/* Pass 1: num_steps[r] = number of marched samples of ray r.  bitfield may be NULL (all occupied). */
+int32_t ia_march_count(const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
+                       int64_t n_rays, const ia_grid_desc *grid_host, const uint32_t *bitfield,
+                       float step_size, float cone_angle, int32_t *num_steps, void *stream);
+/* Exclusive scan: packed_info[r] = (offset, count); *total_dev (int64) = sum.  workspace >=
+ * ia_march_scan_workspace_bytes(n_rays). */
+int64_t ia_march_scan_workspace_bytes(int64_t n_rays);
+int32_t ia_march_scan(const int32_t *num_steps, int64_t n_rays, int32_t *packed_info, int64_t *total_dev,
+                      void *workspace, void *stream);
+/* Synchronises `stream` and returns *total_dev on the host (the one D2H sync nerfacc also performs). */
+int32_t ia_march_total(const int64_t *total_dev, int64_t *total_host, void *stream);
+/* Pass 2: writes ray_indices[S] (int32), t_starts[S], t_ends[S]. */
+int32_t ia_march_write(const float *rays_o, const float *rays_d, const float *t_min, const float *t_max,
+                       int64_t n_rays, const ia_grid_desc *grid_host, const uint32_t *bitfield,
+                       float step_size, float cone_angle, const int32_t *packed_info, int32_t *ray_indices,
+                       float *t_starts, float *t_ends, void *stream);
+/* nerfacc render_visibility on packed samples (sequential per-ray transmittance). */
+int32_t ia_visibility(const float *alphas, const int32_t *packed_info, int64_t n_rays, float early_stop_eps,
+                      float alpha_thre, uint8_t *visible, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-ray segmented compositing        replaces NeuSModel.get_alpha (models/neus.py:117-139) +
+ *                                      nerfacc.render_weight_from_alpha/_density + accumulate_along_rays
+ *                                      (models/neus.py:181-184, 234-239)
+ * ------------------------------------------------------------------------------------------------ */
+typedef enum ia_alpha_mode { IA_ALPHA_GIVEN = 0, IA_ALPHA_NEUS = 1, IA_ALPHA_DENSITY = 2 } ia_alpha_mode;
+
+typedef struct ia_composite_args {
+    int32_t mode;               /* ia_alpha_mode */
+    int64_t n_rays, n_samples;
+    const int32_t *packed_info; /* [n_rays,2] (offset,count), samples sorted by ray */
+    /* IA_ALPHA_GIVEN */
+    const float *alpha_in;      /* [S] */
+    /* IA_ALPHA_NEUS */
+    const float *sdf;           /* [S] */
+    const float *normal;        /* [S,3] unit normals */
+    const float *dirs;          /* [S,3] */
+    const float *dists;         /* [S] */
+    const float *inv_s;         /* device scalar, already clipped to [1e-6,1e6] */
+    float cos_anneal_ratio;
+    /* IA_ALPHA_DENSITY */
+    const float *sigma;         /* [S] */
+    const float *t_starts, *t_ends; /* [S] */
+    /* values to accumulate (any may be NULL) */
+    const float *t_mid;         /* [S]   -> depth   */
+    const float *rgb;           /* [S,3] -> comp_rgb */
+    const float *nrm;           /* [S,3] -> comp_normal (un-normalised sum) */
+} ia_composite_args;
+
+/* Forward: alpha[S], trans[S] (T_i = prod_{j<i}(1-alpha_j), saved for backward), weights[S],
+ * opacity[R], depth[R], comp_rgb[R,3], comp_normal[R,3] (outputs for absent values may be NULL). */
+int32_t ia_composite_fwd(const ia_composite_args *args_host, float *alpha, float *trans, float *weights,
+                         float *opacity, float *depth, float *comp_rgb, float *comp_normal, void *stream);
+/* Backward: upstream grads (NULL = zero) -> grads of the per-sample inputs (NULL = not wanted).
+ * d_inv_s (device scalar) is ACCUMULATED. */
+int32_t ia_composite_bwd(const ia_composite_args *args_host, const float *alpha, const float *trans,
+                         const float *g_weights, const float *g_opacity, const float *g_depth,
+                         const float *g_comp_rgb, const float *g_comp_normal,
+                         float *d_alpha_in, float *d_sdf, float *d_normal, float *d_inv_s, float *d_sigma,
+                         float *d_rgb, float *d_nrm, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused AdamW over a flat arena        replaces torch.optim.AdamW as configured at
+ *                                      configs/neuralangelo-colmap_sparse.yaml:134-139 (systems/utils.py:314-325)
+ * ------------------------------------------------------------------------------------------------ */
+int32_t ia_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                      float grad_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IA_B200_H */

@@ -1,0 +1,318 @@
+// Multiresolution hash-grid encoding for sm_100a: forward, backward-to-table, backward-to-input.
+// Replaces tcnn.Encoding(otype=HashGrid) as used by ProgressiveBandHashGrid
+// (reference models/network_utils.py:40-66); semantics per SURVEY.md Appendix A.1.
+//
+// Mapping (see DESIGN.md "hash grid"): one CTA owns a tile of 128 points and walks the active levels;
+// two adjacent lanes own one (point, level) pair -- lane 0 the x-corner, lane 1 the x+1 corner -- so the
+// two corners of an x-pair, which sit in the same 128-byte line for dense levels always and for hashed
+// levels 15 times out of 16 (x ^ h and (x+1) ^ h differ in the low bits only), are fetched by ONE
+// load instruction and coalesce into one L1 wavefront.  Each lane issues 4 independent 8-byte
+// (F=2 fp32) gathers per level and the level loop is unrolled 4x => 16 gathers in flight per lane.
+// Outputs / incoming gradients are transposed through a padded shared-memory tile so that global
+// traffic on the [n, L*F] side is fully coalesced.
+#include <math.h>
+
+#include "ia_common.cuh"
+
+namespace {
+
+constexpr int HG_TILE = 128;     // points per CTA
+constexpr int HG_THREADS = 256;  // 2 lanes per point
+constexpr int HG_ROW = 34;       // padded floats per tile row (32 + 2): conflict-free float2 stores
+
+struct GridParams {
+    int32_t n_levels;
+    int32_t active;
+    float scale[IA_MAX_LEVELS];
+    uint32_t res[IA_MAX_LEVELS];
+    uint32_t size[IA_MAX_LEVELS];
+    uint32_t offset[IA_MAX_LEVELS];
+    uint32_t hashed[IA_MAX_LEVELS];
+};
+
+__device__ __forceinline__ uint32_t entry_index(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t res, uint32_t size,
+                                                bool hashed)
+{
+    // tcnn grid_index(): dense stride index, or coherent prime hash when the dense grid would overflow
+    // the level.  Hashed levels have a power-of-two size (2^log2_hashmap_size) => mask; dense levels can
+    // exceed `size` only on the upper boundary (corner == res), by less than one `size`.
+    if (hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);
+    uint32_t idx = cx + cy * res + cz * res * res;
+    return idx >= size ? idx % size : idx;
+}
+
+struct CellCoords {
+    uint32_t ix, iy, iz;
+    float wx, wy, wz;
+};
+
+__device__ __forceinline__ CellCoords locate(float px, float py, float pz, float scale)
+{
+    CellCoords c;
+    float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
+    float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    c.wx = fx - gx;
+    c.wy = fy - gy;
+    c.wz = fz - gz;
+    c.ix = (uint32_t)(int)gx;
+    c.iy = (uint32_t)(int)gy;
+    c.iz = (uint32_t)(int)gz;
+    return c;
+}
+
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const GridParams P,
+                    float *__restrict__ out)
+{
+    __shared__ float tile[HG_TILE * HG_ROW];
+    const int tid = threadIdx.x;
+    const int pl = tid >> 1;
+    const uint32_t xc = tid & 1;
+    const int64_t base = (int64_t)blockIdx.x * HG_TILE;
+    const int64_t p = base + pl;
+    const bool valid = p < n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (valid) {
+        px = __ldg(x + 3 * p);
+        py = __ldg(x + 3 * p + 1);
+        pz = __ldg(x + 3 * p + 2);
+    }
+    // masked (inactive) levels are exact zeros
+    for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
+    __syncthreads();
+
+#pragma unroll 4
+    for (int l = 0; l < P.active; ++l) {
+        const float scale = P.scale[l];
+        const uint32_t res = P.res[l], size = P.size[l];
+        const bool hashed = P.hashed[l] != 0;
+        const float2 *__restrict__ tl = table + P.offset[l];
+        const CellCoords c = locate(px, py, pz, scale);
+        const uint32_t cx = c.ix + xc;
+        const float wx = xc ? c.wx : 1.f - c.wx;
+        float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+        if (valid) {
+            v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));
+            v10 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed));
+            v01 = __ldg(tl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed));
+            v11 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed));
+        }
+        const float w00 = wx * (1.f - c.wy) * (1.f - c.wz), w10 = wx * c.wy * (1.f - c.wz);
+        const float w01 = wx * (1.f - c.wy) * c.wz, w11 = wx * c.wy * c.wz;
+        float a0 = w00 * v00.x + w10 * v10.x + w01 * v01.x + w11 * v11.x;
+        float a1 = w00 * v00.y + w10 * v10.y + w01 * v01.y + w11 * v11.y;
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        if (xc == 0) *reinterpret_cast<float2 *>(&tile[pl * HG_ROW + 2 * l]) = make_float2(a0, a1);
+    }
+    __syncthreads();
+
+    const int row2 = P.n_levels;  // float2 per output row (F = 2)
+    float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
+    for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
+        const int r = i / row2, c2 = i - r * row2;
+        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+    }
+}
+
+template <bool WITH_TABLE, bool WITH_INPUT>
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table,
+                    const float *__restrict__ dy, const GridParams P, float2 *__restrict__ dtable,
+                    float *__restrict__ dx)
+{
+    __shared__ float tile[HG_TILE * HG_ROW];
+    const int tid = threadIdx.x;
+    const int pl = tid >> 1;
+    const uint32_t xc = tid & 1;
+    const int64_t base = (int64_t)blockIdx.x * HG_TILE;
+    const int64_t p = base + pl;
+    const bool valid = p < n;
+    const int row2 = P.n_levels;
+    const float2 *__restrict__ dy2 = reinterpret_cast<const float2 *>(dy);
+    for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
+        const int r = i / row2, c2 = i - r * row2;
+        float2 g = make_float2(0.f, 0.f);
+        if (base + r < n) g = __ldg(dy2 + (base + r) * row2 + c2);
+        *reinterpret_cast<float2 *>(&tile[r * HG_ROW + 2 * c2]) = g;
+    }
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (valid) {
+        px = __ldg(x + 3 * p);
+        py = __ldg(x + 3 * p + 1);
+        pz = __ldg(x + 3 * p + 2);
+    }
+    __syncthreads();
+
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 2
+    for (int l = 0; l < P.active; ++l) {
+        const float scale = P.scale[l];
+        const uint32_t res = P.res[l], size = P.size[l];
+        const bool hashed = P.hashed[l] != 0;
+        const CellCoords c = locate(px, py, pz, scale);
+        const uint32_t cx = c.ix + xc;
+        const float wx = xc ? c.wx : 1.f - c.wx;
+        const float2 g = *reinterpret_cast<const float2 *>(&tile[pl * HG_ROW + 2 * l]);
+        const uint32_t i00 = entry_index(cx, c.iy, c.iz, res, size, hashed);
+        const uint32_t i10 = entry_index(cx, c.iy + 1, c.iz, res, size, hashed);
+        const uint32_t i01 = entry_index(cx, c.iy, c.iz + 1, res, size, hashed);
+        const uint32_t i11 = entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed);
+        const float uy = 1.f - c.wy, uz = 1.f - c.wz;
+        if (WITH_TABLE) {
+            if (valid && (g.x != 0.f || g.y != 0.f)) {
+                float2 *__restrict__ dl = dtable + P.offset[l];
+                const float w00 = wx * uy * uz, w10 = wx * c.wy * uz, w01 = wx * uy * c.wz, w11 = wx * c.wy * c.wz;
+                atomicAdd(dl + i00, make_float2(w00 * g.x, w00 * g.y));
+                atomicAdd(dl + i10, make_float2(w10 * g.x, w10 * g.y));
+                atomicAdd(dl + i01, make_float2(w01 * g.x, w01 * g.y));
+                atomicAdd(dl + i11, make_float2(w11 * g.x, w11 * g.y));
+            }
+        }
+        if (WITH_INPUT) {
+            float d00 = 0.f, d10 = 0.f, d01 = 0.f, d11 = 0.f;
+            if (valid) {
+                const float2 *__restrict__ tl = table + P.offset[l];
+                const float2 v00 = __ldg(tl + i00), v10 = __ldg(tl + i10), v01 = __ldg(tl + i01), v11 = __ldg(tl + i11);
+                d00 = v00.x * g.x + v00.y * g.y;
+                d10 = v10.x * g.x + v10.y * g.y;
+                d01 = v01.x * g.x + v01.y * g.y;
+                d11 = v11.x * g.x + v11.y * g.y;
+            }
+            // x: (value at x+1) - (value at x), bilinear in (y,z); this lane holds one side
+            const float sx = uy * uz * d00 + c.wy * uz * d10 + uy * c.wz * d01 + c.wy * c.wz * d11;
+            gx += scale * (xc ? sx : -sx);
+            gy += scale * wx * (uz * (d10 - d00) + c.wz * (d11 - d01));
+            gz += scale * wx * (uy * (d01 - d00) + c.wy * (d11 - d10));
+        }
+    }
+    if (WITH_INPUT) {
+        gx += __shfl_xor_sync(0xffffffffu, gx, 1);
+        gy += __shfl_xor_sync(0xffffffffu, gy, 1);
+        gz += __shfl_xor_sync(0xffffffffu, gz, 1);
+        if (valid && xc == 0) {
+            dx[3 * p] = gx;
+            dx[3 * p + 1] = gy;
+            dx[3 * p + 2] = gz;
+        }
+    }
+}
+
+int fill_params(const ia_grid_plan *plan, int32_t active_levels, GridParams *P)
+{
+    IA_REQUIRE(plan != nullptr, "hashgrid: plan is NULL");
+    IA_REQUIRE(plan->n_features == 2, "hashgrid: only n_features_per_level == 2 is supported (got %d)", plan->n_features);
+    IA_REQUIRE(plan->n_levels >= 1 && plan->n_levels <= 16, "hashgrid: n_levels must be in [1,16] (got %d)", plan->n_levels);
+    IA_REQUIRE(active_levels >= 0 && active_levels <= plan->n_levels, "hashgrid: active_levels %d out of range", active_levels);
+    P->n_levels = plan->n_levels;
+    P->active = active_levels;
+    for (int l = 0; l < plan->n_levels; ++l) {
+        P->scale[l] = plan->scale[l];
+        P->res[l] = plan->res[l];
+        P->size[l] = plan->size[l];
+        P->offset[l] = plan->offset[l];
+        P->hashed[l] = plan->hashed[l];
+        IA_REQUIRE(!plan->hashed[l] || (plan->size[l] & (plan->size[l] - 1)) == 0,
+                   "hashgrid: hashed level %d has a non power-of-two size %u", l, plan->size[l]);
+    }
+    return IA_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t ia_hashgrid_plan(int32_t n_levels, int32_t n_features, int32_t log2_hashmap_size,
+                                    int32_t base_resolution, float per_level_scale, ia_grid_plan *plan)
+{
+    IA_REQUIRE(plan != nullptr, "hashgrid_plan: plan is NULL");
+    IA_REQUIRE(n_levels >= 1 && n_levels <= IA_MAX_LEVELS, "hashgrid_plan: n_levels %d out of range", n_levels);
+    IA_REQUIRE(log2_hashmap_size >= 3 && log2_hashmap_size <= 30, "hashgrid_plan: log2_hashmap_size %d out of range", log2_hashmap_size);
+    IA_REQUIRE(base_resolution >= 1 && per_level_scale >= 1.0f, "hashgrid_plan: bad resolution parameters");
+    plan->n_levels = n_levels;
+    plan->n_features = n_features;
+    plan->log2_hashmap_size = log2_hashmap_size;
+    plan->base_resolution = base_resolution;
+    plan->per_level_scale = per_level_scale;
+    const float log2_pls = log2f(per_level_scale);
+    uint32_t offset = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        // volatile: keep every step rounded to binary32 (no excess precision / contraction on the host)
+        volatile float arg = (float)l * log2_pls;
+        volatile float e = exp2f(arg);
+        volatile float sb = e * (float)base_resolution;
+        const float scale = sb - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+        const uint32_t max_params = 0xFFFFFFFFu / 2u;
+        uint32_t n = powf((float)res, 3.0f) > (float)max_params ? max_params : res * res * res;
+        n = (n + 7u) / 8u * 8u;
+        const uint32_t cap = 1u << log2_hashmap_size;
+        if (n > cap) n = cap;
+        uint64_t stride = 1;
+        for (int d = 0; d < 3 && stride <= n; ++d) stride *= res;
+        plan->scale[l] = scale;
+        plan->res[l] = res;
+        plan->size[l] = n;
+        plan->offset[l] = offset;
+        plan->hashed[l] = n < stride ? 1u : 0u;
+        offset += n;
+    }
+    plan->offset[n_levels] = offset;
+    for (int l = n_levels; l < IA_MAX_LEVELS; ++l) {
+        plan->scale[l] = 0.f;
+        plan->res[l] = plan->size[l] = plan->hashed[l] = 0;
+        plan->offset[l + 1] = offset;
+    }
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table, const ia_grid_plan *plan,
+                                   int32_t active_levels, float *out, void *stream)
+{
+    GridParams P;
+    int rc = fill_params(plan, active_levels, &P);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && table && out)), "hashgrid_fwd: NULL pointer with n=%lld", (long long)n);
+    if (n == 0) return IA_OK;
+    const int64_t blocks = ia_ceil_div(n, HG_TILE);
+    hashgrid_fwd_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
+        x, n, reinterpret_cast<const float2 *>(table), P, out);
+    IA_LAUNCH_OK("hashgrid_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table, const float *dy,
+                                   const ia_grid_plan *plan, int32_t active_levels, float *dtable, float *dx,
+                                   void *stream)
+{
+    GridParams P;
+    int rc = fill_params(plan, active_levels, &P);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && dy)), "hashgrid_bwd: NULL pointer with n=%lld", (long long)n);
+    IA_REQUIRE(dx == nullptr || table != nullptr, "hashgrid_bwd: dx requested without the table");
+    if (n == 0 || (!dtable && !dx)) return IA_OK;
+    const unsigned blocks = (unsigned)ia_ceil_div(n, HG_TILE);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *t2 = reinterpret_cast<const float2 *>(table);
+    float2 *d2 = reinterpret_cast<float2 *>(dtable);
+    if (dtable && dx)
+        hashgrid_bwd_kernel<true, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+    else if (dtable)
+        hashgrid_bwd_kernel<true, false><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+    else
+        hashgrid_bwd_kernel<false, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+    IA_LAUNCH_OK("hashgrid_bwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_bwd_table(const float *x, int64_t n, const float *dy, const ia_grid_plan *plan,
+                                         int32_t active_levels, float *dtable, void *stream)
+{
+    IA_REQUIRE(n == 0 || dtable != nullptr, "hashgrid_bwd_table: dtable is NULL");
+    return ia_hashgrid_bwd(x, n, nullptr, dy, plan, active_levels, dtable, nullptr, stream);
+}
+
+extern "C" int32_t ia_hashgrid_bwd_input(const float *x, int64_t n, const float *table, const float *dy,
+                                         const ia_grid_plan *plan, int32_t active_levels, float *dx, void *stream)
+{
+    IA_REQUIRE(n == 0 || dx != nullptr, "hashgrid_bwd_input: dx is NULL");
+    return ia_hashgrid_bwd(x, n, table, dy, plan, active_levels, nullptr, dx, stream);
+}

@@ -1,0 +1,174 @@
+"""Geometry fields with the reference's surface (models/geometry.py): VolumeSDF and VolumeDensity.
+
+VolumeSDF.forward reproduces reference models/geometry.py:195-287 for grad_type='finite_difference'
+bug-for-bug: taps clamped in world space, curvature shift applied to the
+normalised coordinates and then re-normalised as if it were a world point, un-normalised tangent, no
+detach on the shifted tap positions.  The 1 + 6 + 6 network evaluations per sample run as three
+hash-grid launches + three fused-MLP launches; the 12 tap evaluations compute the SDF column only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import registry as models
+from .nerfacc_api import ContractionType
+from .network_utils import fused_encode_mlp, get_encoding, get_encoding_with_network, get_mlp, update_module_step
+from .utils import get_activation, scale_anything
+
+
+def contract_to_unisphere(x, radius, contraction_type):
+    """reference models/geometry.py:19-31."""
+    if contraction_type == ContractionType.AABB:
+        return scale_anything(x, (-radius, radius), (0, 1))
+    if contraction_type == ContractionType.UN_BOUNDED_SPHERE:
+        x = scale_anything(x, (-radius, radius), (0, 1))
+        x = x * 2 - 1
+        mag = x.norm(dim=-1, keepdim=True)
+        x = torch.where(mag > 1, (2 - 1 / mag) * (x / mag), x)
+        return x / 4 + 0.5
+    raise NotImplementedError
+
+
+class BaseImplicitGeometry(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.radius = config["radius"]
+        self.contraction_type = None  # assigned by the model, as in the reference
+        self.setup()
+
+    def regularizations(self, out):
+        return {}
+
+
+@models.register("volume-density")
+class VolumeDensity(BaseImplicitGeometry):
+    """reference models/geometry.py:152-177 (background NeRF++ density)."""
+
+    def setup(self):
+        self.n_input_dims = self.config.get("n_input_dims", 3)
+        self.n_output_dims = self.config["feature_dim"]
+        self.encoding_with_network = get_encoding_with_network(self.n_input_dims, self.n_output_dims,
+                                                               self.config["xyz_encoding_config"],
+                                                               self.config["mlp_network_config"])
+
+    def forward(self, points):
+        points = contract_to_unisphere(points, self.radius, self.contraction_type)
+        out = self.encoding_with_network(points.view(-1, self.n_input_dims)).view(*points.shape[:-1], self.n_output_dims).float()
+        density, feature = out[..., 0], out
+        if "density_activation" in self.config:
+            density = get_activation(self.config["density_activation"])(density + float(self.config["density_bias"]))
+        if "feature_activation" in self.config:
+            feature = get_activation(self.config["feature_activation"])(feature)
+        return density, feature
+
+    def forward_level(self, points):
+        points = contract_to_unisphere(points, self.radius, self.contraction_type)
+        density = self.encoding_with_network(points.reshape(-1, self.n_input_dims), n_out_used=1).reshape(*points.shape[:-1])
+        if "density_activation" in self.config:
+            density = get_activation(self.config["density_activation"])(density + float(self.config["density_bias"]))
+        return -density
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding_with_network, epoch, global_step)
+
+
+@models.register("volume-sdf")
+class VolumeSDF(BaseImplicitGeometry):
+    """reference models/geometry.py:180-314."""
+
+    def setup(self):
+        self.n_output_dims = self.config["feature_dim"]
+        self.encoding = get_encoding(3, self.config["xyz_encoding_config"])
+        self.network = get_mlp(self.encoding.n_output_dims, self.n_output_dims, self.config["mlp_network_config"])
+        self.grad_type = self.config["grad_type"]
+        self.finite_difference_eps = self.config.get("finite_difference_eps", 1e-3)
+        self._finite_difference_eps = None
+        self.register_buffer("_fd_signs", torch.tensor([[1.0, 0, 0], [-1.0, 0, 0], [0, 1.0, 0], [0, -1.0, 0],
+                                                        [0, 0, 1.0], [0, 0, -1.0]]), persistent=False)
+
+    def _net(self, pts01, n_out_used, flat):
+        return fused_encode_mlp(self.encoding, self.network, pts01.reshape(-1, 3), n_out_used, flat)
+
+    def _fd_gradient(self, world_pts, eps, flat):
+        """geometry.py:219-234: six taps clamped to the AABB in world space, central differences."""
+        taps = (world_pts[..., None, :] + self._fd_signs * eps).clamp(-self.radius, self.radius)
+        taps01 = scale_anything(taps, (-self.radius, self.radius), (0, 1))
+        s = self._net(taps01, 1, flat).view(*world_pts.shape[:-1], 6)
+        return 0.5 * (s[..., 0::2] - s[..., 1::2]) / eps
+
+    def forward(self, points, with_grad=True, with_feature=True, with_laplace=False, with_auxiliary_feature=False,
+                rand_directions: Optional[torch.Tensor] = None):
+        if with_auxiliary_feature:
+            raise NotImplementedError("with_auxiliary_feature is not used by any shipped config")
+        if with_grad and self.grad_type == "analytic":
+            raise NotImplementedError(
+                "grad_type='analytic' needs second-order hash-grid/MLP adjoints (SURVEY section 8f rank 1); run the "
+                "B200 path with model.geometry.grad_type=finite_difference")
+        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+            flat = self.network.flat_params()
+            points_ = points
+            pts01 = contract_to_unisphere(points, self.radius, self.contraction_type)
+            need_full = with_feature
+            out = self._net(pts01, self.n_output_dims if need_full else 1, flat)
+            out = out.view(*pts01.shape[:-1], out.shape[-1])
+            sdf = out[..., 0]
+            feature = None
+            if with_feature:
+                feature = torch.cat([out, pts01 * 2 - 1], dim=-1)
+            if "sdf_activation" in self.config:
+                sdf = get_activation(self.config["sdf_activation"])(sdf + float(self.config["sdf_bias"]))
+            if with_feature and "feature_activation" in self.config:
+                feature = get_activation(self.config["feature_activation"])(feature)
+            grad = None
+            if with_grad:
+                grad = self._fd_gradient(points_, self._finite_difference_eps, flat)
+            laplace = None
+            if with_laplace:
+                eps = self._finite_difference_eps
+                if rand_directions is None:
+                    rand_directions = torch.randn_like(pts01)
+                rnd = F.normalize(rand_directions, dim=-1)
+                normals = F.normalize(grad, dim=-1)
+                tangent = torch.cross(normals, rnd, dim=-1)
+                shifted = pts01 + tangent * eps            # Appendix C-1/C-2/C-3
+                g_shift = self._fd_gradient(shifted, eps, flat)
+                n_shift = F.normalize(g_shift, dim=-1)
+                dot = (normals * n_shift).sum(dim=-1, keepdim=True)
+                laplace = torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.pi
+        rv = [sdf]
+        if with_grad:
+            rv.append(grad)
+        if with_feature:
+            rv.append(feature)
+        if with_laplace:
+            rv.append(laplace)
+        rv = [v if self.training else v.detach() for v in rv]
+        return rv[0] if len(rv) == 1 else rv
+
+    def forward_level(self, points):
+        pts01 = contract_to_unisphere(points, self.radius, self.contraction_type)
+        sdf = self._net(pts01, 1, None).view(*pts01.shape[:-1])
+        if "sdf_activation" in self.config:
+            sdf = get_activation(self.config["sdf_activation"])(sdf + float(self.config["sdf_bias"]))
+        return sdf
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+        update_module_step(self.network, epoch, global_step)
+        if isinstance(self.finite_difference_eps, float):
+            self._finite_difference_eps = self.finite_difference_eps
+        elif self.finite_difference_eps == "progressive":
+            hg = self.config["xyz_encoding_config"]
+            assert hg["otype"] == "ProgressiveBandHashGrid", \
+                "finite_difference_eps='progressive' only works with ProgressiveBandHashGrid"
+            level = min(hg["start_level"] + max(global_step - hg["start_step"], 0) // hg["update_steps"], hg["n_levels"])
+            grid_res = hg["base_resolution"] * hg["per_level_scale"] ** (level - 1)
+            self._finite_difference_eps = 2 * self.config["radius"] / grid_res
+        else:
+            raise ValueError(f"Unknown finite_difference_eps={self.finite_difference_eps}")

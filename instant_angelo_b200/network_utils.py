@@ -1,0 +1,282 @@
+"""Encoding + network factories with the reference's module surface (models/network_utils.py), backed by
+the sm_100a kernels.
+
+Same names and attributes (`n_input_dims`, `n_output_dims`, `update_step(epoch, global_step)`), same
+state-dict keys (`encoding.encoding.params`, `layers.{0,2,4}.{weight_g,weight_v,bias}`), so a reference
+checkpoint loads unchanged.  What differs is the execution: the progressive mask is folded into the
+hash-grid kernel as a level count, the xyz pass-through of CompositeEncoding and the weight-norm of
+VanillaMLP are folded into the fused MLP operator (`EncodingWithNetwork.forward` never materialises the
+concatenated input).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .config import to_primitive
+
+
+def update_module_step(m, epoch, global_step):
+    """reference systems/utils.py:349-351."""
+    if hasattr(m, "update_step"):
+        m.update_step(epoch, global_step)
+
+
+class Encoding(nn.Module):
+    """tcnn.Encoding(n_input_dims, encoding_config) for otype HashGrid | SphericalHarmonics
+    (reference models/network_utils.py:47, 91).  `.params` is the flat fp32 tcnn parameter vector."""
+
+    def __init__(self, n_input_dims: int, encoding_config: dict, seed: int = 1337):
+        super().__init__()
+        cfg = to_primitive(encoding_config)
+        self.n_input_dims = n_input_dims
+        self.otype = cfg["otype"]
+        if self.otype == "HashGrid":
+            assert n_input_dims == 3, "HashGrid is implemented for 3-D inputs"
+            self.plan = ops.make_grid_plan(cfg["n_levels"], cfg["n_features_per_level"], cfg["log2_hashmap_size"],
+                                           cfg["base_resolution"], cfg["per_level_scale"])
+            g = torch.Generator().manual_seed(seed)
+            self.params = nn.Parameter((torch.rand(self.plan.n_params, generator=g) * 2 - 1) * 1e-4)
+            self.n_output_dims = self.plan.n_levels * self.plan.n_features
+        elif self.otype == "SphericalHarmonics":
+            assert n_input_dims == 3
+            self.degree = int(cfg["degree"])
+            self.params = nn.Parameter(torch.zeros(0))
+            self.n_output_dims = self.degree ** 2
+        else:
+            raise NotImplementedError(f"encoding otype {self.otype}")
+
+    def forward(self, x: torch.Tensor, active_levels: Optional[int] = None) -> torch.Tensor:
+        if not x.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        if self.otype == "HashGrid":
+            return ops.hashgrid_encode(x, self.params, self.plan, active_levels)
+        return ops.sh_encode(x, self.degree)
+
+
+class ProgressiveBandHashGrid(nn.Module):
+    """reference models/network_utils.py:40-66.  `mask` is kept (same attribute, same growth rule) but the
+    forward pass hands the kernel `current_level` instead of multiplying: masked levels come out as exact
+    zeros and receive exactly-zero gradients, which is what the multiply does."""
+
+    def __init__(self, in_channels: int, config: dict):
+        super().__init__()
+        config = to_primitive(config)
+        self.n_input_dims = in_channels
+        encoding_config = dict(config)
+        encoding_config["otype"] = "HashGrid"
+        self.encoding = Encoding(in_channels, encoding_config)
+        self.n_output_dims = self.encoding.n_output_dims
+        self.n_level = config["n_levels"]
+        self.n_features_per_level = config["n_features_per_level"]
+        self.start_level, self.start_step, self.update_steps = config["start_level"], config["start_step"], config["update_steps"]
+        self.current_level = self.start_level
+        self._mask_level = self.start_level  # the mask only ever grows (Appendix C-7)
+        self.mask = torch.zeros(self.n_level * self.n_features_per_level, dtype=torch.float32)
+        self.mask[: self.current_level * self.n_features_per_level] = 1.0
+
+    @property
+    def active_levels(self) -> int:
+        return self._mask_level
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.encoding(x, self._mask_level)
+
+    def update_step(self, epoch, global_step):
+        self.current_level = min(self.start_level + max(global_step - self.start_step, 0) // self.update_steps, self.n_level)
+        self._mask_level = max(self._mask_level, self.current_level)
+        self.mask[: self.current_level * self.n_features_per_level] = 1.0
+
+
+class CompositeEncoding(nn.Module):
+    """reference models/network_utils.py:69-80."""
+
+    def __init__(self, encoding, include_xyz=False, xyz_scale=1.0, xyz_offset=0.0):
+        super().__init__()
+        self.encoding = encoding
+        self.include_xyz, self.xyz_scale, self.xyz_offset = include_xyz, xyz_scale, xyz_offset
+        self.n_input_dims = encoding.n_input_dims
+        self.n_output_dims = int(self.include_xyz) * self.encoding.n_input_dims + self.encoding.n_output_dims
+
+    def forward(self, x, *args):
+        enc = self.encoding(x, *args)
+        return enc if not self.include_xyz else torch.cat([x * self.xyz_scale + self.xyz_offset, enc], dim=-1)
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+
+
+def get_encoding(n_input_dims: int, config) -> CompositeEncoding:
+    """reference models/network_utils.py:83-93 (input is supposed to be in [0, 1])."""
+    otype = config["otype"]
+    if otype == "ProgressiveBandHashGrid":
+        encoding = ProgressiveBandHashGrid(n_input_dims, config)
+    elif otype in ("HashGrid", "SphericalHarmonics"):
+        encoding = Encoding(n_input_dims, config)
+    else:
+        raise NotImplementedError(f"encoding otype {otype} is outside the B200 hot path")
+    return CompositeEncoding(encoding, include_xyz=config.get("include_xyz", False), xyz_scale=2.0, xyz_offset=-1.0)
+
+
+class _Linear(nn.Module):
+    """Parameter holder with nn.Linear / torch weight_norm key names (weight_g, weight_v, bias | weight, bias)."""
+
+    def __init__(self, dim_in: int, dim_out: int, weight_norm: bool):
+        super().__init__()
+        self.dim_in, self.dim_out, self.weight_norm = dim_in, dim_out, weight_norm
+        self.bias = nn.Parameter(torch.zeros(dim_out))
+        if weight_norm:
+            self.weight_g = nn.Parameter(torch.ones(dim_out, 1))
+            self.weight_v = nn.Parameter(torch.empty(dim_out, dim_in))
+        else:
+            self.weight = nn.Parameter(torch.empty(dim_out, dim_in))
+
+    def raw_weight(self) -> torch.Tensor:
+        return self.weight_v if self.weight_norm else self.weight
+
+    def effective_weight(self) -> torch.Tensor:
+        if not self.weight_norm:
+            return self.weight
+        return self.weight_v * (self.weight_g / self.weight_v.norm(dim=1, keepdim=True))
+
+
+class _ActMarker(nn.Module):
+    """Occupies the activation slots of the reference's nn.Sequential so layer indices (0, 2, 4) match."""
+
+    def __init__(self, name: str):
+        super().__init__()
+        self.name = name
+
+    def extra_repr(self):
+        return self.name
+
+
+class VanillaMLP(nn.Module):
+    """reference models/network_utils.py:96-140, executed by the fused width-64 MLP kernel.
+
+    precision: IA_MLP_FP32 (default; the reference runs this module in fp32 with autocast disabled) or
+    IA_MLP_TC_F16 (tensor cores, selected by get_mlp for otype FullyFusedMLP / CutlassMLP)."""
+
+    def __init__(self, dim_in: int, dim_out: int, config: dict, precision: int = L.IA_MLP_FP32):
+        super().__init__()
+        config = to_primitive(config)
+        self.n_input_dims, self.n_output_dims = dim_in, dim_out
+        self.n_neurons, self.n_hidden_layers = config["n_neurons"], config["n_hidden_layers"]
+        if self.n_neurons != 64 or self.n_hidden_layers not in (1, 2):
+            raise NotImplementedError("the fused MLP supports n_neurons=64 and 1-2 hidden layers")
+        self.sphere_init, self.weight_norm = config.get("sphere_init", False), config.get("weight_norm", False)
+        self.sphere_init_radius = config.get("sphere_init_radius", 0.5)
+        self.precision = precision
+        dims = [dim_in] + [self.n_neurons] * self.n_hidden_layers + [dim_out]
+        mods = []
+        for i in range(len(dims) - 1):
+            mods.append(self.make_linear(dims[i], dims[i + 1], is_first=(i == 0), is_last=(i == len(dims) - 2)))
+            if i < len(dims) - 2:
+                mods.append(_ActMarker("Softplus(beta=100)" if self.sphere_init else "ReLU"))
+        self.layers = nn.Sequential(*mods)
+        self.output_activation_name = config.get("output_activation", None)
+        self.hidden_act = L.IA_ACT_SOFTPLUS100 if self.sphere_init else L.IA_ACT_RELU
+
+    def make_linear(self, dim_in, dim_out, is_first, is_last) -> _Linear:
+        layer = _Linear(dim_in, dim_out, self.weight_norm)
+        w = layer.raw_weight()
+        with torch.no_grad():
+            if self.sphere_init:
+                if is_last:
+                    layer.bias.fill_(-self.sphere_init_radius)
+                    nn.init.normal_(w, mean=math.sqrt(math.pi) / math.sqrt(dim_in), std=0.0001)
+                elif is_first:
+                    w.zero_()
+                    nn.init.normal_(w[:, :3], 0.0, math.sqrt(2) / math.sqrt(dim_out))
+                else:
+                    nn.init.normal_(w, 0.0, math.sqrt(2) / math.sqrt(dim_out))
+            else:
+                nn.init.kaiming_uniform_(w, nonlinearity="relu")
+            if self.weight_norm:
+                layer.weight_g.copy_(w.norm(dim=1, keepdim=True))
+        return layer
+
+    def linears(self):
+        return [m for m in self.layers if isinstance(m, _Linear)]
+
+    def flat_params(self) -> torch.Tensor:
+        """Effective weights (weight-norm folded) in the ABI's flat layout; differentiable."""
+        parts = []
+        for lin in self.linears():
+            parts.append(lin.effective_weight().reshape(-1))
+            parts.append(lin.bias)
+        return torch.cat(parts)
+
+    def _post(self, y: torch.Tensor) -> torch.Tensor:
+        name = self.output_activation_name
+        if name is None or str(name).lower() == "none":
+            return y
+        from .utils import get_activation
+        return get_activation(name)(y)
+
+    def run(self, in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], in0_scale=1.0, in0_offset=0.0,
+            n_out_used: Optional[int] = None, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Network on cat[in0*scale+offset, in1] without materialising the concatenation."""
+        n0 = 0 if in0 is None else in0.shape[-1]
+        n1 = 0 if in1 is None else in1.shape[-1]
+        assert n0 + n1 == self.n_input_dims, f"MLP expects {self.n_input_dims} inputs, got {n0}+{n1}"
+        desc = ops.make_mlp_desc(n0, n1, self.n_hidden_layers, self.n_output_dims, self.hidden_act, in0_scale, in0_offset,
+                                 self.precision)
+        if flat is None:
+            flat = self.flat_params()
+        return self._post(ops.mlp_apply(in0, in1, flat, desc, n_out_used))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        return self.run(None, x.float())
+
+
+def get_mlp(n_input_dims: int, n_output_dims: int, config) -> VanillaMLP:
+    """reference models/network_utils.py:177-185.  otype VanillaMLP -> fp32 arithmetic; the tcnn otypes
+    (FullyFusedMLP, CutlassMLP) -> tensor-core arithmetic with fp32 accumulate."""
+    otype = config.get("otype", "VanillaMLP")
+    if otype == "VanillaMLP":
+        return VanillaMLP(n_input_dims, n_output_dims, config, L.IA_MLP_FP32)
+    if otype in ("FullyFusedMLP", "CutlassMLP"):
+        return VanillaMLP(n_input_dims, n_output_dims, config, L.IA_MLP_TC_F16)
+    raise NotImplementedError(f"network otype {otype}")
+
+
+class EncodingWithNetwork(nn.Module):
+    """reference models/network_utils.py:188-198, fused: hash grid -> MLP with the xyz pass-through handled
+    inside the MLP operator."""
+
+    def __init__(self, encoding: CompositeEncoding, network: VanillaMLP):
+        super().__init__()
+        self.encoding, self.network = encoding, network
+
+    def forward(self, x: torch.Tensor, n_out_used: Optional[int] = None, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return fused_encode_mlp(self.encoding, self.network, x, n_out_used, flat)
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+        update_module_step(self.network, epoch, global_step)
+
+
+def fused_encode_mlp(encoding: CompositeEncoding, network: VanillaMLP, x: torch.Tensor, n_out_used: Optional[int] = None,
+                     flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """network(encoding(x)) for a CompositeEncoding without the torch.cat of reference
+    models/network_utils.py:77: the include_xyz columns are produced inside the MLP kernel."""
+    x = x.reshape(-1, encoding.n_input_dims)
+    enc = encoding.encoding(x)
+    if encoding.include_xyz:
+        return network.run(x, enc, encoding.xyz_scale, encoding.xyz_offset, n_out_used, flat)
+    return network.run(None, enc, 1.0, 0.0, n_out_used, flat)
+
+
+def get_encoding_with_network(n_input_dims, n_output_dims, encoding_config, network_config) -> EncodingWithNetwork:
+    """reference models/network_utils.py:201-216."""
+    encoding = get_encoding(n_input_dims, encoding_config)
+    network = get_mlp(encoding.n_output_dims, n_output_dims, network_config)
+    return EncodingWithNetwork(encoding, network)

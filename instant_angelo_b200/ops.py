@@ -1,0 +1,314 @@
+"""torch.autograd wrappers over the C ABI (include/ia_b200.h).  PyTorch supplies device memory,
+streams and the autograd tape; every arithmetic step runs in libia_b200.so.
+
+Each function documents the reference call it stands in for.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+# ---------------------------------------------------------------------------------------------
+# hash grid  (tcnn.Encoding(HashGrid).forward, reference models/network_utils.py:57)
+# ---------------------------------------------------------------------------------------------
+
+def make_grid_plan(n_levels: int, n_features: int, log2_hashmap_size: int, base_resolution: int,
+                   per_level_scale: float) -> L.GridPlan:
+    plan = L.GridPlan()
+    L.check(L.load().ia_hashgrid_plan(n_levels, n_features, log2_hashmap_size, base_resolution,
+                                      C.c_float(per_level_scale), C.byref(plan)), "hashgrid_plan")
+    return plan
+
+
+class _HashGridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, plan, active_levels):
+        L.require_cuda(x, table)
+        x = L.f32c(x)
+        n = x.shape[0]
+        out = torch.empty(n, plan.n_levels * plan.n_features, device=x.device, dtype=torch.float32)
+        L.check(L.load().ia_hashgrid_fwd(L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, L.ptr(out), L.stream()),
+                "hashgrid_fwd")
+        ctx.save_for_backward(x, table)
+        ctx.plan, ctx.active = plan, active_levels
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, table = ctx.saved_tensors
+        need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dy = L.f32c(dy)
+        n = x.shape[0]
+        dtable = torch.zeros_like(table) if need_t else None
+        dx = torch.empty_like(x) if need_x else None
+        if n > 0 and (need_t or need_x):
+            L.check(L.load().ia_hashgrid_bwd(L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active,
+                                             L.ptr(dtable), L.ptr(dx), L.stream()), "hashgrid_bwd")
+        elif need_x:
+            dx.zero_()
+        return dx, dtable, None, None
+
+
+def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, plan: L.GridPlan, active_levels: Optional[int] = None) -> torch.Tensor:
+    """x [N,3] in [0,1] -> [N, L*F]; levels >= active_levels are exact zeros (the progressive mask)."""
+    if active_levels is None:
+        active_levels = plan.n_levels
+    return _HashGridFn.apply(x, table, plan, int(active_levels))
+
+
+# ---------------------------------------------------------------------------------------------
+# spherical harmonics  (tcnn.Encoding(SphericalHarmonics), reference models/texture.py:25)
+# ---------------------------------------------------------------------------------------------
+
+class _SHFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d01, degree):
+        L.require_cuda(d01)
+        d01 = L.f32c(d01)
+        n = d01.shape[0]
+        out = torch.empty(n, degree * degree, device=d01.device, dtype=torch.float32)
+        L.check(L.load().ia_sh_fwd(L.ptr(d01), n, degree, L.ptr(out), L.stream()), "sh_fwd")
+        ctx.save_for_backward(d01)
+        ctx.degree = degree
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (d01,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        dout = L.f32c(dout)
+        dd = torch.empty_like(d01)
+        L.check(L.load().ia_sh_bwd(L.ptr(d01), d01.shape[0], ctx.degree, L.ptr(dout), L.ptr(dd), L.stream()), "sh_bwd")
+        return dd, None
+
+
+def sh_encode(d01: torch.Tensor, degree: int) -> torch.Tensor:
+    return _SHFn.apply(d01, int(degree))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused MLP  (VanillaMLP.forward, reference models/network_utils.py:108-113)
+# ---------------------------------------------------------------------------------------------
+
+def make_mlp_desc(n_in0: int, n_in1: int, n_hidden_layers: int, n_out: int, hidden_act: int, in0_scale: float = 1.0,
+                  in0_offset: float = 0.0, precision: int = L.IA_MLP_FP32) -> L.MlpDesc:
+    return L.MlpDesc(n_in0, in0_scale, in0_offset, n_in1, n_hidden_layers, 64, n_out, hidden_act, L.IA_ACT_NONE, precision)
+
+
+class _MLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in0, in1, params, desc, n_out_used):
+        L.require_cuda(in1 if in1 is not None else in0, params)
+        in0 = L.f32c(in0) if in0 is not None else None
+        in1 = L.f32c(in1) if in1 is not None else None
+        params = L.f32c(params)
+        n = (in1 if in1 is not None else in0).shape[0]
+        out = torch.empty(n, n_out_used, device=params.device, dtype=torch.float32)
+        L.check(L.load().ia_mlp_fwd(C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), n_out_used, L.ptr(out),
+                                    n_out_used, L.stream()), "mlp_fwd")
+        ctx.save_for_backward(in0, in1, params)
+        ctx.desc, ctx.nou = desc, n_out_used
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        in0, in1, params = ctx.saved_tensors
+        dout = L.f32c(dout)
+        n = dout.shape[0]
+        need0 = in0 is not None and ctx.needs_input_grad[0]
+        need1 = in1 is not None and ctx.needs_input_grad[1]
+        needp = ctx.needs_input_grad[2]
+        d0 = torch.empty_like(in0) if need0 else None
+        d1 = torch.empty_like(in1) if need1 else None
+        dp = torch.zeros_like(params) if needp else None
+        if n > 0:
+            L.check(L.load().ia_mlp_bwd(C.byref(ctx.desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dout), ctx.nou,
+                                        ctx.nou, L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream()), "mlp_bwd")
+        return d0, d1, dp, None, None
+
+
+def mlp_apply(in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], params: torch.Tensor, desc: L.MlpDesc,
+              n_out_used: Optional[int] = None) -> torch.Tensor:
+    """Network on cat[in0*scale+offset, in1]; returns the first n_out_used outputs."""
+    return _MLPFn.apply(in0, in1, params, desc, int(n_out_used or desc.n_out))
+
+
+# ---------------------------------------------------------------------------------------------
+# marching  (nerfacc.ray_aabb_intersect / ray_marching kernels, reference models/neus.py:153,159-169,209-220)
+# ---------------------------------------------------------------------------------------------
+
+def make_grid_desc(roi, res, contraction: int) -> L.GridDesc:
+    g = L.GridDesc()
+    for i in range(6):
+        g.roi[i] = float(roi[i])
+    for i in range(3):
+        g.res[i] = int(res[i])
+    g.contraction = int(contraction)
+    return g
+
+
+@torch.no_grad()
+def aabb_intersect(rays_o: torch.Tensor, rays_d: torch.Tensor, aabb6, clamp_zero: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    L.require_cuda(rays_o, rays_d)
+    rays_o, rays_d = L.f32c(rays_o), L.f32c(rays_d)
+    n = rays_o.shape[0]
+    t_min = torch.empty(n, device=rays_o.device, dtype=torch.float32)
+    t_max = torch.empty_like(t_min)
+    bb = (C.c_float * 6)(*[float(v) for v in aabb6])
+    L.check(L.load().ia_aabb(L.ptr(rays_o), L.ptr(rays_d), n, C.byref(bb), int(clamp_zero), L.ptr(t_min), L.ptr(t_max),
+                             L.stream()), "aabb")
+    return t_min, t_max
+
+
+@torch.no_grad()
+def march(rays_o, rays_d, t_min, t_max, grid: L.GridDesc, bitfield: Optional[torch.Tensor], step_size: float,
+          cone_angle: float):
+    """Two-pass marching.  Returns (packed_info [R,2] i32, ray_indices [S] i32, t_starts [S], t_ends [S])."""
+    L.require_cuda(rays_o, rays_d, t_min, t_max)
+    lib = L.load()
+    rays_o, rays_d, t_min, t_max = L.f32c(rays_o), L.f32c(rays_d), L.f32c(t_min), L.f32c(t_max)
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    num = torch.empty(n, device=dev, dtype=torch.int32)
+    packed = torch.empty(n, 2, device=dev, dtype=torch.int32)
+    total_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+    s = L.stream()
+    L.check(lib.ia_march_count(L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), n, C.byref(grid), L.ptr(bitfield),
+                               C.c_float(step_size), C.c_float(cone_angle), L.ptr(num), s), "march_count")
+    L.check(lib.ia_march_scan(L.ptr(num), n, L.ptr(packed), L.ptr(total_dev), None, s), "march_scan")
+    total = C.c_int64(0)
+    L.check(lib.ia_march_total(L.ptr(total_dev), C.byref(total), s), "march_total")
+    S = int(total.value)
+    ray_indices = torch.empty(S, device=dev, dtype=torch.int32)
+    t_starts = torch.empty(S, device=dev, dtype=torch.float32)
+    t_ends = torch.empty(S, device=dev, dtype=torch.float32)
+    if S > 0:
+        L.check(lib.ia_march_write(L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), n, C.byref(grid),
+                                   L.ptr(bitfield), C.c_float(step_size), C.c_float(cone_angle), L.ptr(packed),
+                                   L.ptr(ray_indices), L.ptr(t_starts), L.ptr(t_ends), s), "march_write")
+    return packed, ray_indices, t_starts, t_ends
+
+
+@torch.no_grad()
+def visibility(alphas: torch.Tensor, packed_info: torch.Tensor, early_stop_eps: float, alpha_thre: float) -> torch.Tensor:
+    L.require_cuda(alphas, packed_info)
+    alphas = L.f32c(alphas.reshape(-1))
+    vis = torch.empty(alphas.shape[0], device=alphas.device, dtype=torch.uint8)
+    L.check(L.load().ia_visibility(L.ptr(alphas), L.ptr(packed_info), packed_info.shape[0], C.c_float(early_stop_eps),
+                                   C.c_float(alpha_thre), L.ptr(vis), L.stream()), "visibility")
+    return vis.bool()
+
+
+@torch.no_grad()
+def occ_update(idx: Optional[torch.Tensor], occ: torch.Tensor, occs: torch.Tensor, ema_decay: float, occ_thre: float,
+               binary_u8: torch.Tensor, bitfield: torch.Tensor, workspace: torch.Tensor) -> None:
+    L.require_cuda(occ, occs)
+    occ = L.f32c(occ.reshape(-1))
+    n = occ.shape[0]
+    L.check(L.load().ia_occ_update(L.ptr(idx), L.ptr(occ), n, L.ptr(occs), occs.numel(), C.c_float(ema_decay),
+                                   C.c_float(occ_thre), L.ptr(binary_u8), L.ptr(bitfield), L.ptr(workspace), L.stream()),
+            "occ_update")
+
+
+@torch.no_grad()
+def occ_pack(binary_u8: torch.Tensor, bitfield: torch.Tensor) -> None:
+    L.check(L.load().ia_occ_pack(L.ptr(binary_u8), binary_u8.numel(), L.ptr(bitfield), L.stream()), "occ_pack")
+
+
+# ---------------------------------------------------------------------------------------------
+# compositing  (get_alpha + render_weight_from_alpha/_density + accumulate_along_rays,
+#               reference models/neus.py:117-139, 181-184, 234-239)
+# ---------------------------------------------------------------------------------------------
+
+class _CompositeFn(torch.autograd.Function):
+    """inputs: mode, packed_info, n_rays, cos_anneal, then tensors
+       a (alpha | sdf | sigma), normal, dirs, dists | t_starts, t_ends, inv_s, t_mid, rgb, nrm
+       outputs: weights[S], opacity[R], depth[R], comp_rgb[R,3], comp_nrm[R,3], alpha[S]"""
+
+    @staticmethod
+    def forward(ctx, mode, packed_info, cos_anneal, a, normal, dirs, dists, t_starts, t_ends, inv_s, t_mid, rgb, nrm):
+        L.require_cuda(a, packed_info)
+        R, S = packed_info.shape[0], a.shape[0]
+        dev = a.device
+        cz = lambda t: L.f32c(t) if t is not None else None
+        a, normal, dirs, dists, t_starts, t_ends, inv_s, t_mid, rgb, nrm = map(
+            cz, (a, normal, dirs, dists, t_starts, t_ends, inv_s, t_mid, rgb, nrm))
+        args = L.CompositeArgs()
+        args.mode, args.n_rays, args.n_samples = mode, R, S
+        args.packed_info = L.ptr(packed_info)
+        if mode == L.IA_ALPHA_GIVEN:
+            args.alpha_in = L.ptr(a)
+        elif mode == L.IA_ALPHA_NEUS:
+            args.sdf, args.normal, args.dirs, args.dists, args.inv_s = L.ptr(a), L.ptr(normal), L.ptr(dirs), L.ptr(dists), L.ptr(inv_s)
+            args.cos_anneal_ratio = float(cos_anneal)
+        else:
+            args.sigma, args.t_starts, args.t_ends = L.ptr(a), L.ptr(t_starts), L.ptr(t_ends)
+        args.t_mid, args.rgb, args.nrm = L.ptr(t_mid), L.ptr(rgb), L.ptr(nrm)
+        alpha = torch.empty(S, device=dev)
+        trans = torch.empty(S, device=dev)
+        weights = torch.empty(S, device=dev)
+        opacity = torch.empty(R, device=dev)
+        depth = torch.empty(R, device=dev) if t_mid is not None else None
+        comp_rgb = torch.empty(R, 3, device=dev) if rgb is not None else None
+        comp_nrm = torch.empty(R, 3, device=dev) if nrm is not None else None
+        L.check(L.load().ia_composite_fwd(C.byref(args), L.ptr(alpha), L.ptr(trans), L.ptr(weights), L.ptr(opacity),
+                                          L.ptr(depth), L.ptr(comp_rgb), L.ptr(comp_nrm), L.stream()), "composite_fwd")
+        ctx.args = args
+        ctx.keep = (packed_info, a, normal, dirs, dists, t_starts, t_ends, inv_s, t_mid, rgb, nrm, alpha, trans)
+        ctx.mode = mode
+        ctx.mark_non_differentiable(alpha)
+        z = lambda t, *shape: t if t is not None else torch.zeros(*shape, device=dev)
+        return weights, opacity, z(depth, R), z(comp_rgb, R, 3), z(comp_nrm, R, 3), alpha
+
+    @staticmethod
+    def backward(ctx, g_w, g_o, g_d, g_c, g_n, _g_alpha):
+        (packed_info, a, normal, dirs, dists, t_starts, t_ends, inv_s, t_mid, rgb, nrm, alpha, trans) = ctx.keep
+        dev = a.device
+        S = a.shape[0]
+        cz = lambda t: L.f32c(t) if t is not None else None
+        g_w, g_o, g_d, g_c, g_n = map(cz, (g_w, g_o, g_d, g_c, g_n))
+        mode = ctx.mode
+        d_a = torch.empty(S, device=dev)
+        d_normal = torch.empty(S, 3, device=dev) if mode == L.IA_ALPHA_NEUS else None
+        d_inv_s = torch.zeros(1, device=dev) if mode == L.IA_ALPHA_NEUS else None
+        d_rgb = torch.empty(S, 3, device=dev) if rgb is not None else None
+        d_nrm = torch.empty(S, 3, device=dev) if nrm is not None else None
+        L.check(L.load().ia_composite_bwd(
+            C.byref(ctx.args), L.ptr(alpha), L.ptr(trans), L.ptr(g_w), L.ptr(g_o), L.ptr(g_d), L.ptr(g_c), L.ptr(g_n),
+            L.ptr(d_a) if mode == L.IA_ALPHA_GIVEN else None, L.ptr(d_a) if mode == L.IA_ALPHA_NEUS else None,
+            L.ptr(d_normal), L.ptr(d_inv_s), L.ptr(d_a) if mode == L.IA_ALPHA_DENSITY else None, L.ptr(d_rgb), L.ptr(d_nrm),
+            L.stream()), "composite_bwd")
+        if d_inv_s is not None and inv_s is not None:
+            d_inv_s = d_inv_s.reshape(inv_s.shape)
+        return (None, None, None, d_a, d_normal, None, None, None, None, d_inv_s, None, d_rgb, d_nrm)
+
+
+def composite_neus(sdf, normal, dirs, dists, inv_s, cos_anneal: float, packed_info, t_mid=None, rgb=None, nrm=None):
+    """NeuS alpha + per-ray compositing.  inv_s: 1-element CUDA tensor (already clipped).
+    Returns (weights[S], opacity[R], depth[R], comp_rgb[R,3], comp_normal_sum[R,3], alpha[S])."""
+    return _CompositeFn.apply(L.IA_ALPHA_NEUS, packed_info, cos_anneal, sdf, normal, dirs, dists, None, None, inv_s, t_mid, rgb, nrm)
+
+
+def composite_density(sigma, t_starts, t_ends, packed_info, t_mid=None, rgb=None):
+    return _CompositeFn.apply(L.IA_ALPHA_DENSITY, packed_info, 0.0, sigma, None, None, None, t_starts, t_ends, None, t_mid, rgb, None)
+
+
+def composite_alpha(alpha, packed_info, t_mid=None, rgb=None, nrm=None):
+    return _CompositeFn.apply(L.IA_ALPHA_GIVEN, packed_info, 0.0, alpha, None, None, None, None, None, None, t_mid, rgb, nrm)
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizer
+# ---------------------------------------------------------------------------------------------
+
+@torch.no_grad()
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    L.check(L.load().ia_adamw_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
+                                   C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                   C.c_float(weight_decay), int(step), C.c_float(grad_scale), L.stream()), "adamw_step")

@@ -1,0 +1,90 @@
+"""Colour heads with the reference's surface (models/texture.py:10-64, 113-149) on the fused kernels.
+
+The concatenations of the reference (`torch.cat([features, dirs_embd, normals])`) are kept -- they are one
+[S, <=87] tensor per step against 13 geometry evaluations -- but the SH encoding and the MLPs run in
+libia_b200.so."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import registry as models
+from .network_utils import get_encoding, get_mlp, update_module_step
+from .utils import get_activation
+
+
+@models.register("volume-radiance")
+class VolumeRadiance(nn.Module):
+    """reference models/texture.py:10-36."""
+    dual = False
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.n_dir_dims = self.config.get("n_dir_dims", 3)
+        self.n_output_dims = 3
+        self.encoding = get_encoding(self.n_dir_dims, self.config["dir_encoding_config"])
+        self.n_input_dims = self.config["input_feature_dim"] + self.encoding.n_output_dims
+        self.network = get_mlp(self.n_input_dims, self.n_output_dims, self.config["mlp_network_config"])
+
+    def forward(self, features, dirs, *args):
+        dirs = (dirs + 1.0) / 2.0
+        dirs_embd = self.encoding(dirs.view(-1, self.n_dir_dims))
+        network_inp = torch.cat([features.view(-1, features.shape[-1]), dirs_embd] +
+                                [arg.view(-1, arg.shape[-1]) for arg in args], dim=-1)
+        color = self.network(network_inp).view(*features.shape[:-1], self.n_output_dims).float()
+        if "color_activation" in self.config:
+            act = get_activation(self.config["color_activation"])
+            if self.dual:
+                color = act(color) + act(features[..., 1:4])     # Appendix C-10: may exceed 1
+            else:
+                color = act(color)
+        return color
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+
+    def regularizations(self, out):
+        return {}
+
+
+@models.register("volume-dual-color")
+class VolumeDualColor(VolumeRadiance):
+    """reference models/texture.py:38-64."""
+    dual = True
+
+
+@models.register("volume-dual-colorV3")
+class VolumeDualColorV3(nn.Module):
+    """reference models/texture.py:113-149 (UniSDF camera / reflected-direction blend)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.n_dir_dims = self.config.get("n_dir_dims", 3)
+        self.n_output_dims = 3
+        self.encoding = get_encoding(self.n_dir_dims, self.config["dir_encoding_config"])
+        self.n_input_dims = self.config["input_feature_dim"] + self.encoding.n_output_dims
+        self.cam_network = get_mlp(self.n_input_dims, self.n_output_dims, self.config["mlp_network_config"])
+        self.ref_network = get_mlp(self.n_input_dims, self.n_output_dims, self.config["mlp_network_config"])
+        self.weight_network = get_mlp(self.config["input_feature_dim"], 1, self.config["weitht_network_config"])
+
+    def forward(self, features, viewdirs, normals):
+        dirs = (viewdirs + 1.0) / 2.0
+        dirs_embd = self.encoding(dirs.view(-1, self.n_dir_dims))
+        VdotN = (-viewdirs * normals).sum(-1, keepdim=True)
+        refdirs = 2 * VdotN * normals + viewdirs
+        refdirs = (refdirs + 1.0) / 2.0
+        refdirs_embd = self.encoding(refdirs.view(-1, self.n_dir_dims))
+        network_inp = torch.cat([features.view(-1, features.shape[-1]), normals.view(-1, normals.shape[-1])], dim=-1)
+        ref_weight = self.weight_network(network_inp)
+        cam_color = self.cam_network(torch.cat([network_inp, dirs_embd], dim=-1)).view(*features.shape[:-1], 3).float()
+        ref_color = self.ref_network(torch.cat([network_inp, refdirs_embd], dim=-1)).view(*features.shape[:-1], 3).float()
+        act = get_activation(self.config["color_activation"])
+        return ref_weight * act(ref_color) + (1 - ref_weight) * act(cam_color)
+
+    def update_step(self, epoch, global_step):
+        pass
+
+    def regularizations(self, out):
+        return {}

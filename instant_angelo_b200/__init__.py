@@ -13,3 +13,5 @@ from . import registry as models  # noqa: F401
 from .registry import make, register  # noqa: F401
 
 __all__ = ["models", "make", "register"]
+
+from . import neus as _neus  # noqa: E402,F401  (registers 'neus', 'volume-sdf', 'volume-density' and the colour heads)

@@ -118,8 +118,11 @@ class OccupancyGrid:
         self.num_cells = self.res[0] * self.res[1] * self.res[2]
         self.occs = torch.zeros(self.num_cells, dtype=torch.float32)
         self.binary = torch.zeros(self.res, dtype=torch.bool)
-        gx, gy, gz = torch.meshgrid(*[torch.arange(r) for r in self.res], indexing="ij")
-        self.grid_coords = torch.stack([gx, gy, gz], dim=-1).reshape(-1, 3)      # x-major flat order
+
+    def grid_coords(self, indices: torch.Tensor) -> torch.Tensor:
+        """Integer cell coordinates of flat indices (meshgrid 'ij', x-major: idx = x*ry*rz + y*rz + z)."""
+        rx, ry, rz = self.res
+        return torch.stack([indices // (ry * rz), (indices // rz) % ry, indices % rz], dim=-1)
 
     def sample_indices(self, step: int, warmup_steps: int = 256, gen: Optional[torch.Generator] = None) -> torch.Tensor:
         if step < warmup_steps:
@@ -135,7 +138,7 @@ class OccupancyGrid:
     def cell_points(self, indices: torch.Tensor, jitter: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Returns (indices kept, world points).  jitter: U[0,1) of shape [len(indices),3]."""
         res = torch.tensor(self.res, dtype=torch.float32)
-        x = (self.grid_coords[indices].float() + jitter) / res
+        x = (self.grid_coords(indices).float() + jitter) / res
         if self.contraction_type == ContractionType.UN_BOUNDED_SPHERE:
             keep = (x - 0.5).norm(dim=1) < 0.5
             x, indices = x[keep], indices[keep]

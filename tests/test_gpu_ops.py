@@ -1,0 +1,549 @@
+"""GPU parity tests, operator level: every kernel of libia_b200.so (called through the C ABI via
+instant_angelo_b200.ops) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): occupancy bits, packed_info, ray_indices, t_starts/t_ends: BIT-EXACT;
+floating-point outputs and gradients: within 1e-3 relative (fp32-accumulate) -- the fp32 kernels are held to
+much tighter tolerances here so that regressions show."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as mr
+from oracle import nerfacc_ref as nf
+from oracle import tcnn_ref as tc
+from tests.helpers import assert_close, grad_tol
+
+pytestmark = pytest.mark.gpu
+
+PLS = 1.3195079107728942
+
+
+def _dev(t):
+    return t.cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# hash grid
+# ---------------------------------------------------------------------------------------------
+GRID_CFGS = {
+    "sparse_2p19": dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=PLS),
+    "small_mixed": dict(n_levels=8, n_features=2, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.5),
+    "tiny_hash": dict(n_levels=5, n_features=2, log2_hashmap_size=8, base_resolution=16, per_level_scale=2.0),
+}
+
+
+def _points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, generator=g)
+    # edge cases: corners of the unit cube, exact cell boundaries, tap-like clusters
+    x[0] = 0.0
+    x[1] = 1.0
+    x[2] = torch.tensor([0.5, 0.25, 0.75])
+    x[3] = torch.tensor([1.0, 0.0, 1.0])
+    if n > 64:
+        x[8:15] = x[7] + torch.tensor([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]]) * 1e-3
+    return x.clamp(0, 1)
+
+
+@pytest.mark.parametrize("cfg_name", list(GRID_CFGS))
+@pytest.mark.parametrize("active", [None, 4])
+def test_hashgrid_forward_backward(cuda_lib, cfg_name, active):
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS[cfg_name]
+    plan_ref = tc.grid_plan(**cfg)
+    plan = ops.make_grid_plan(**cfg)
+    assert plan.n_params == plan_ref.n_params
+    n = 1000 if cfg_name == "sparse_2p19" else 777
+    act = active if active is None else min(active, cfg["n_levels"])
+    g = torch.Generator().manual_seed(7)
+    x = _points(n, 11).requires_grad_(True)
+    table = (torch.randn(plan_ref.n_params, generator=g) * 0.1).requires_grad_(True)
+    dy = torch.randn(n, plan_ref.n_output_dims, generator=g)
+
+    y_ref = tc.hashgrid_forward(x, table, plan_ref, act)
+    y_ref.backward(dy)
+
+    xg = x.detach().cuda().requires_grad_(True)
+    tg = table.detach().cuda().requires_grad_(True)
+    y = ops.hashgrid_encode(xg, tg, plan, act)
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+
+    assert_close(y, y_ref, rtol=1e-5, atol=1e-6, name="enc")
+    if act is not None:
+        assert torch.count_nonzero(y[:, act * 2:]) == 0, "masked levels must be exact zeros"
+    assert_close(tg.grad, table.grad, rtol=1e-4, atol=1e-5, name="dtable")
+    # d enc / d x is discontinuous at cell faces; points 0..3 sit exactly on faces -> compare the rest
+    rt, at = grad_tol(x.grad[4:], 1e-4)
+    assert_close(xg.grad[4:], x.grad[4:], rtol=rt, atol=at, name="dx")
+
+
+def test_hashgrid_abi_entry_points_and_errors(cuda_lib):
+    """ia_hashgrid_bwd_table / ia_hashgrid_bwd_input agree with the fused ia_hashgrid_bwd; bad args fail loudly."""
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS["small_mixed"]
+    plan = ops.make_grid_plan(**cfg)
+    g = torch.Generator().manual_seed(3)
+    n = 300
+    x = torch.rand(n, 3, generator=g).cuda()
+    table = (torch.randn(plan.n_params, generator=g) * 0.1).cuda()
+    dy = torch.randn(n, 16, generator=g).cuda()
+    s = L.stream()
+    dt_a, dx_a = torch.zeros_like(table), torch.empty_like(x)
+    dt_b, dx_b = torch.zeros_like(table), torch.empty_like(x)
+    L.check(cuda_lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), C.byref(plan), 8, dt_a.data_ptr(), dx_a.data_ptr(), s))
+    L.check(cuda_lib.ia_hashgrid_bwd_table(x.data_ptr(), n, dy.data_ptr(), C.byref(plan), 8, dt_b.data_ptr(), s))
+    L.check(cuda_lib.ia_hashgrid_bwd_input(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), C.byref(plan), 8, dx_b.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert_close(dt_b, dt_a, rtol=1e-5, atol=1e-6, name="bwd_table")
+    assert_close(dx_b, dx_a, rtol=1e-6, atol=1e-7, name="bwd_input")
+    # errors: status code + message, no exception across the ABI
+    rc = cuda_lib.ia_hashgrid_fwd(x.data_ptr(), n, table.data_ptr(), C.byref(plan), 99, dx_a.data_ptr(), s)
+    assert rc == -1 and b"active_levels" in cuda_lib.ia_last_error_string()
+    with pytest.raises(NotImplementedError):
+        ops.hashgrid_encode(x.cpu(), table.cpu(), plan)
+    # empty input
+    out = ops.hashgrid_encode(x[:0], table, plan)
+    assert out.shape == (0, 16)
+
+
+def test_hashgrid_full_size_properties(cuda_lib):
+    """BASELINE size (2^22 points, 2^19-entry tables): size-independent properties.
+    (1) partition of unity: an all-ones table encodes to all ones; (2) linearity in the table;
+    (3) checksum: per level/feature, sum(dtable) == sum(dy) because the 8 weights sum to 1."""
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS["sparse_2p19"]
+    plan = ops.make_grid_plan(**cfg)
+    n = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(n, 3, device="cuda", generator=g)
+    ones = torch.ones(plan.n_params, device="cuda")
+    y1 = ops.hashgrid_encode(x, ones, plan)
+    assert float((y1 - 1).abs().max()) < 2e-6
+    t1 = torch.randn(plan.n_params, device="cuda", generator=g)
+    t2 = torch.randn(plan.n_params, device="cuda", generator=g)
+    ya, yb = ops.hashgrid_encode(x, t1, plan), ops.hashgrid_encode(x, t2, plan)
+    yc = ops.hashgrid_encode(x, 2.0 * t1 - 0.5 * t2, plan)
+    assert float((yc - (2.0 * ya - 0.5 * yb)).abs().max()) < 2e-5
+    n2 = 1 << 20
+    tg = t1.clone().requires_grad_(True)
+    dy = torch.rand(n2, 32, device="cuda", generator=g)
+    ops.hashgrid_encode(x[:n2], tg, plan).backward(dy)
+    got = []
+    for l in range(16):
+        lo, hi = plan.offset[l] * 2, plan.offset[l + 1] * 2
+        got.append(tg.grad[lo:hi].view(-1, 2).double().sum(0))
+    got = torch.stack(got).reshape(-1)
+    want = dy.double().sum(0)
+    assert_close(got, want, rtol=1e-4, atol=1e-2, name="dtable checksum")
+
+
+# ---------------------------------------------------------------------------------------------
+# spherical harmonics
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("degree", [1, 2, 3, 4])
+def test_sh(cuda_lib, degree):
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(degree)
+    d = torch.nn.functional.normalize(torch.randn(513, 3, generator=g), dim=-1)
+    d01 = ((d + 1) / 2).requires_grad_(True)
+    y_ref = tc.sh_forward(d01, degree)
+    go = torch.randn_like(y_ref)
+    y_ref.backward(go)
+    dg = d01.detach().cuda().requires_grad_(True)
+    y = ops.sh_encode(dg, degree)
+    y.backward(go.cuda())
+    assert_close(y, y_ref, rtol=1e-5, atol=1e-6, name="sh")
+    assert_close(dg.grad, d01.grad, rtol=1e-4, atol=1e-5, name="dsh")
+
+
+# ---------------------------------------------------------------------------------------------
+# fused MLP (fp32)
+# ---------------------------------------------------------------------------------------------
+MLP_CASES = {
+    #                 n_in0 n_in1 hidden out  softplus weight_norm n_out_used
+    "geometry_full": (3, 32, 2, 65, True, True, 65),
+    "geometry_sdf": (3, 32, 2, 65, True, True, 1),
+    "texture": (0, 87, 2, 3, False, False, 3),
+    "v3_weight": (0, 71, 2, 1, False, False, 1),
+    "bg_geometry": (3, 32, 1, 8, False, False, 8),
+    "bg_texture": (0, 24, 2, 3, False, False, 3),
+    "neus_colmap_geo": (3, 32, 1, 13, True, True, 13),
+}
+
+
+@pytest.mark.parametrize("case", list(MLP_CASES))
+@pytest.mark.parametrize("n", [1, 1000])
+def test_mlp_fp32(cuda_lib, case, n):
+    from instant_angelo_b200 import _lib as L
+    from instant_angelo_b200 import ops
+    n0, n1, nh, nout, softplus, wn, nou = MLP_CASES[case]
+    torch.manual_seed(sum(map(ord, case)))
+    cfg = {"n_neurons": 64, "n_hidden_layers": nh, "sphere_init": softplus, "weight_norm": wn, "output_activation": "none"}
+    ref = mr.RefVanillaMLP(n0 + n1, nout, cfg)
+    with torch.no_grad():  # make every weight matter (sphere init zeroes the non-xyz columns)
+        for p in ref.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    g = torch.Generator().manual_seed(n)
+    a = torch.rand(n, n0, generator=g).requires_grad_(True) if n0 else None
+    b = (torch.randn(n, n1, generator=g) * 0.3).requires_grad_(True)
+    inp = torch.cat([a * 2 - 1, b], dim=1) if n0 else b
+    y_ref = ref(inp)[:, :nou]
+    go = torch.randn(n, nou, generator=g)
+    y_ref.backward(go)
+
+    # product: same effective weights in the ABI's flat layout
+    lin = [m for m in ref.layers if isinstance(m, mr.RefWNLinear)]
+    flat = torch.cat([t for m in lin for t in (m.effective_weight().reshape(-1), m.bias)]).detach().cuda().requires_grad_(True)
+    desc = ops.make_mlp_desc(n0, n1, nh, nout, L.IA_ACT_SOFTPLUS100 if softplus else L.IA_ACT_RELU, 2.0, -1.0)
+    assert cuda_lib.ia_mlp_param_count(desc) == flat.numel()
+    ag = a.detach().cuda().requires_grad_(True) if n0 else None
+    bg = b.detach().cuda().requires_grad_(True)
+    y = ops.mlp_apply(ag, bg, flat, desc, nou)
+    y.backward(go.cuda())
+    torch.cuda.synchronize()
+    assert_close(y, y_ref, rtol=1e-4, atol=1e-5, name="mlp out")
+    rt, at = grad_tol(b.grad, 2e-4)
+    assert_close(bg.grad, b.grad, rtol=rt, atol=at, name="d in1")
+    if n0:
+        rt, at = grad_tol(a.grad, 2e-4)
+        assert_close(ag.grad, a.grad, rtol=rt, atol=at, name="d in0")
+    # parameter grads: reference grads w.r.t. effective weights via autograd on a functional copy
+    eff = [(m.effective_weight().detach().requires_grad_(True), m.bias.detach().clone().requires_grad_(True)) for m in lin]
+    h = inp.detach()
+    for i, (w, bias) in enumerate(eff):
+        h = torch.nn.functional.linear(h, w, bias)
+        if i < len(eff) - 1:
+            h = torch.nn.functional.softplus(h, beta=100) if softplus else torch.relu(h)
+    h[:, :nou].backward(go)
+    want = torch.cat([t.grad.reshape(-1) if t.grad is not None else torch.zeros_like(t).reshape(-1) for pair in eff for t in pair])
+    rt, at = grad_tol(want, 2e-4)
+    assert_close(flat.grad, want, rtol=rt, atol=at, name="d params")
+
+
+def test_mlp_rejects_unsupported(cuda_lib):
+    from instant_angelo_b200 import _lib as L
+    from instant_angelo_b200 import ops
+    desc = ops.make_mlp_desc(0, 16, 2, 3, L.IA_ACT_RELU)
+    desc.width = 32
+    x = torch.zeros(4, 16, device="cuda")
+    p = torch.zeros(10000, device="cuda")
+    with pytest.raises(RuntimeError, match="width"):
+        ops.mlp_apply(None, x, p, desc)
+
+
+# ---------------------------------------------------------------------------------------------
+# AABB + marching: BIT-EXACT
+# ---------------------------------------------------------------------------------------------
+def _rays(n, seed, outside_frac=0.3):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * (0.6 + 0.6 * torch.rand(n, 1, generator=g))
+    k = int(n * outside_frac)
+    o[:k] *= 4.0
+    tgt = (torch.rand(n, 3, generator=g) - 0.5) * 1.6
+    tgt[-n // 16:] += 5.0
+    d = torch.nn.functional.normalize(tgt - o, dim=-1)
+    # axis-aligned rays (zero direction components exercise the inf/NaN paths of the DDA)
+    d[k] = torch.tensor([1.0, 0.0, 0.0])
+    d[k + 1] = torch.tensor([0.0, -1.0, 0.0])
+    d[k + 2] = torch.tensor([0.0, 0.0, 1.0])
+    return o.contiguous(), d.contiguous(), g
+
+
+def test_aabb_bit_exact(cuda_lib):
+    from instant_angelo_b200 import nerfacc_api as na
+    o, d, _ = _rays(4096, 1)
+    aabb = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    for clamp in (True, False):
+        tmin_ref, tmax_ref = nf.ray_aabb_intersect(o, d, aabb, clamp)
+        tmin, tmax = na.ray_aabb_intersect(o.cuda(), d.cuda(), aabb, clamp)
+        assert np.array_equal(tmin.cpu().numpy().view(np.uint32), tmin_ref.numpy().view(np.uint32))
+        assert np.array_equal(tmax.cpu().numpy().view(np.uint32), tmax_ref.numpy().view(np.uint32))
+    assert (tmin_ref == 1e10).any() and (tmin_ref == 0).any() and ((tmin_ref > 0) & (tmin_ref < 1e9)).any()
+
+
+def _bit_equal(a, b, name):
+    a = a.cpu().numpy()
+    b = b.cpu().numpy() if isinstance(b, torch.Tensor) else b
+    assert a.shape == b.shape, f"{name}: shape {a.shape} vs {b.shape}"
+    if a.dtype == np.float32:
+        a, b = a.view(np.uint32), b.view(np.uint32)
+    assert np.array_equal(a, b), f"{name}: {np.count_nonzero(a != b)} of {a.size} differ"
+
+
+@pytest.mark.parametrize("grid_kind", ["shell", "random", "none", "empty"])
+def test_march_foreground_bit_exact(cuda_lib, grid_kind):
+    """nerfacc.ray_marching as called at models/neus.py:209-220 (AABB grid, fixed step, stratified)."""
+    from instant_angelo_b200 import nerfacc_api as na
+    from tests.golden.scenes import sphere_shell_binary
+    n = 2048
+    o, d, g = _rays(n, 2)
+    aabb = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    step = 1.732 * 2 * 1.5 / 512
+    u = torch.rand(n, generator=g)
+    grid_ref = grid_gpu = None
+    if grid_kind != "none":
+        grid_ref = nf.OccupancyGrid(aabb, 128, nf.ContractionType.AABB)
+        if grid_kind == "shell":
+            grid_ref.binary = sphere_shell_binary(128, 1.5)
+        elif grid_kind == "random":
+            grid_ref.binary = torch.rand(128, 128, 128, generator=g) < 0.3
+        grid_gpu = na.OccupancyGrid(aabb, 128, na.ContractionType.AABB).cuda()
+        grid_gpu.set_binary(grid_ref.binary)
+    ri_ref, ts_ref, te_ref, pk_ref = nf.ray_marching(o, d, scene_aabb=aabb, grid=grid_ref, render_step_size=step,
+                                                     stratified=True, stratified_u=u, return_packed=True)
+    ri, ts, te, pk = na.ray_marching(o.cuda(), d.cuda(), scene_aabb=aabb.cuda(), grid=grid_gpu, render_step_size=step,
+                                     stratified=True, stratified_u=u.cuda(), return_packed=True)
+    _bit_equal(pk, pk_ref, "packed_info")
+    _bit_equal(ri, ri_ref, "ray_indices")
+    _bit_equal(ts, ts_ref, "t_starts")
+    _bit_equal(te, te_ref, "t_ends")
+    if grid_kind == "empty":
+        assert ri.numel() == 0
+    else:
+        assert ri.numel() > 1000
+        # size-independent structure: sorted by ray, increasing along each ray
+        assert bool((ri[1:] >= ri[:-1]).all())
+        same = ri[1:] == ri[:-1]
+        assert bool((ts[1:, 0][same] >= te[:-1, 0][same] - 1e-6).all())
+
+
+def test_march_background_bit_exact(cuda_lib):
+    """nerfacc.ray_marching as called at models/neus.py:159-169 (UN_BOUNDED_SPHERE grid, cone stepping,
+    per-ray near plane) + render_visibility filtering on identical alphas."""
+    from instant_angelo_b200 import nerfacc_api as na
+    from instant_angelo_b200 import ops
+    n = 1024
+    o, d, g = _rays(n, 3, outside_frac=0.0)
+    aabb = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    _, t_max = nf.ray_aabb_intersect(o, d, aabb)
+    near = torch.where(t_max > 1e9, torch.tensor(0.1), t_max)
+    cone = 10 ** (math.log10(1e3) / 256) - 1.0
+    u = torch.rand(n, generator=g)
+    grid_ref = nf.OccupancyGrid(aabb, 256, nf.ContractionType.UN_BOUNDED_SPHERE)
+    grid_ref.binary = torch.rand(256, 256, 256, generator=g) < 0.5
+    grid_gpu = na.OccupancyGrid(aabb, 256, na.ContractionType.UN_BOUNDED_SPHERE).cuda()
+    grid_gpu.set_binary(grid_ref.binary)
+    kw = dict(scene_aabb=None, render_step_size=0.01, stratified=True, cone_angle=cone, far_plane=1e3, return_packed=True)
+    ri_ref, ts_ref, te_ref, pk_ref = nf.ray_marching(o, d, grid=grid_ref, near_plane=near, stratified_u=u, **kw)
+    ri, ts, te, pk = na.ray_marching(o.cuda(), d.cuda(), grid=grid_gpu, near_plane=near.cuda(), stratified_u=u.cuda(), **kw)
+    _bit_equal(pk, pk_ref, "packed_info")
+    _bit_equal(ri, ri_ref, "ray_indices")
+    _bit_equal(ts, ts_ref, "t_starts")
+    _bit_equal(te, te_ref, "t_ends")
+    assert ri.numel() > 10000
+    # visibility on identical alphas
+    alphas = torch.rand(ri.numel(), generator=g) * 0.2
+    vis_ref = nf.render_visibility(alphas, packed_info=pk_ref, early_stop_eps=1e-4, alpha_thre=0.0)
+    vis = ops.visibility(alphas.cuda(), pk, 1e-4, 0.0)
+    assert np.array_equal(vis.cpu().numpy(), vis_ref.numpy())
+    assert 0 < int(vis_ref.sum()) < vis_ref.numel()
+    vis_ref2 = nf.render_visibility(alphas, packed_info=pk_ref, early_stop_eps=1e-3, alpha_thre=0.05)
+    vis2 = ops.visibility(alphas.cuda(), pk, 1e-3, 0.05)
+    assert np.array_equal(vis2.cpu().numpy(), vis_ref2.numpy())
+
+
+def test_march_scan_large(cuda_lib):
+    """prefix sum over 300k rays (multi-chunk path of the single-CTA scan) against numpy."""
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    n = 300_001
+    num = torch.randint(0, 600, (n,), dtype=torch.int32)
+    num_g = num.cuda()
+    packed = torch.empty(n, 2, dtype=torch.int32, device="cuda")
+    total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.check(cuda_lib.ia_march_scan(num_g.data_ptr(), n, packed.data_ptr(), total.data_ptr(), None, L.stream()))
+    out = C.c_int64(0)
+    L.check(cuda_lib.ia_march_total(total.data_ptr(), C.byref(out), L.stream()))
+    cum = np.cumsum(num.numpy().astype(np.int64))
+    assert out.value == cum[-1]
+    assert np.array_equal(packed[:, 1].cpu().numpy(), num.numpy())
+    assert np.array_equal(packed[:, 0].cpu().numpy().astype(np.int64), cum - num.numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# occupancy grid update: BIT-EXACT on identical occupancy values
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("res", [32, 128])
+def test_occupancy_update_bit_exact(cuda_lib, res):
+    from instant_angelo_b200 import nerfacc_api as na
+    aabb = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    g = torch.Generator().manual_seed(res)
+    ref = nf.OccupancyGrid(aabb, res, nf.ContractionType.AABB)
+    gpu = na.OccupancyGrid(aabb, res, na.ContractionType.AABB).cuda()
+    gpu.train()
+    nc = ref.num_cells
+    for it in range(4):
+        if it < 2:       # warm-up: every cell
+            idx = torch.arange(nc)
+            occ = torch.rand(nc, generator=g) ** 8 * (0.05 if it == 0 else 0.002)
+            idx_gpu = None
+        else:            # later: random subset with duplicates
+            idx = torch.randint(nc, (nc // 2,), generator=g)
+            occ = torch.rand(nc // 2, generator=g) ** 4 * 0.01
+            idx_gpu = idx.cuda()
+        ref.apply_update(idx, occ, occ_thre=0.001, ema_decay=0.95)
+        gpu._update(step=0, occ_eval_fn=lambda pts: occ.cuda(), occ_thre=0.001, ema_decay=0.95,
+                    indices=idx_gpu, jitter=torch.zeros(idx.numel(), 3, device="cuda"))
+        _bit_equal(gpu.occs, ref.occs, f"occs it{it}")
+        assert np.array_equal(gpu.binary.cpu().numpy(), ref.binary.numpy()), f"binary it{it}"
+        # the packed bitfield is the same grid
+        bits = np.unpackbits(gpu.bitfield.cpu().numpy().view(np.uint8), bitorder="little")[:nc]
+        assert np.array_equal(bits.astype(bool), ref.binary.numpy().reshape(-1)), f"bitfield it{it}"
+        assert 0 < int(ref.binary.sum()) < nc
+
+
+def test_occupancy_cell_points(cuda_lib):
+    from instant_angelo_b200 import nerfacc_api as na
+    aabb = torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5])
+    g = torch.Generator().manual_seed(9)
+    for ctype_ref, ctype in [(nf.ContractionType.AABB, na.ContractionType.AABB),
+                             (nf.ContractionType.UN_BOUNDED_SPHERE, na.ContractionType.UN_BOUNDED_SPHERE)]:
+        ref = nf.OccupancyGrid(aabb, 16, ctype_ref)
+        gpu = na.OccupancyGrid(aabb, 16, ctype).cuda()
+        idx = torch.randint(ref.num_cells, (500,), generator=g)
+        jit = torch.rand(500, 3, generator=g)
+        idx_r, pts_r = ref.cell_points(idx, jit)
+        idx_g, pts_g = gpu.cell_points(idx.cuda(), jit.cuda())
+        assert np.array_equal(idx_g.cpu().numpy(), idx_r.numpy())
+        assert_close(pts_g, pts_r, rtol=1e-5, atol=1e-5, name="cell points")
+
+
+# ---------------------------------------------------------------------------------------------
+# compositing
+# ---------------------------------------------------------------------------------------------
+def _packed(n_rays, g, max_n=90):
+    num = torch.randint(0, max_n, (n_rays,), generator=g)
+    num[0] = 0
+    num[1] = 1
+    num[2] = 32
+    num[3] = 33
+    num[4] = 64
+    cum = torch.cumsum(num, 0)
+    return torch.stack([cum - num, num], 1).int(), int(cum[-1])
+
+
+def test_composite_neus(cuda_lib):
+    """get_alpha + render_weight_from_alpha + 4x accumulate_along_rays (models/neus.py:117-139, 234-239)."""
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    R = 300
+    packed, S = _packed(R, g)
+    ri = nf.unpack_info(packed)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    sdf = (mk(S) * 0.05).requires_grad_(True)
+    normal = torch.nn.functional.normalize(mk(S, 3), dim=-1).requires_grad_(True)
+    dirs = torch.nn.functional.normalize(mk(S, 3), dim=-1)
+    dists = torch.rand(S, generator=g) * 0.02 + 0.005
+    rgb = torch.rand(S, 3, generator=g).requires_grad_(True)
+    tmid = torch.rand(S, generator=g) * 3
+    var = torch.tensor(0.3, requires_grad=True)
+    go, gd, gc, gn, gw = mk(R), mk(R), mk(R, 3), mk(R, 3), mk(S)
+    for anneal in (0.0, 0.37, 1.0):
+        model = mr.RefNeuSModel.__new__(mr.RefNeuSModel)
+        torch.nn.Module.__init__(model)
+        model.variance = mr.RefVarianceNetwork({"init_val": 0.3})
+        model.variance.variance = torch.nn.Parameter(var.detach().clone())
+        model.cos_anneal_ratio = anneal
+        for t in (sdf, normal, rgb):
+            t.grad = None
+        alpha = model.get_alpha(sdf, normal, dirs, dists)[:, None]
+        w = nf.render_weight_from_alpha(alpha, ray_indices=ri, n_rays=R)
+        op = nf.accumulate_along_rays(w, ri, None, R)
+        dp = nf.accumulate_along_rays(w, ri, tmid[:, None], R)
+        cr = nf.accumulate_along_rays(w, ri, rgb, R)
+        cn = nf.accumulate_along_rays(w, ri, normal, R)
+        loss = (op[:, 0] * go).sum() + (dp[:, 0] * gd).sum() + (cr * gc).sum() + (cn * gn).sum() + (w[:, 0] * gw).sum()
+        loss.backward()
+
+        c = lambda t: t.detach().cuda()
+        sdf_g, nrm_g, rgb_g = c(sdf).requires_grad_(True), c(normal).requires_grad_(True), c(rgb).requires_grad_(True)
+        var_g = c(var).requires_grad_(True)
+        inv_s = torch.exp(var_g * 10.0).reshape(1).clip(1e-6, 1e6)
+        W, OP, DP, CR, CN, A = ops.composite_neus(sdf_g, nrm_g, c(dirs), c(dists), inv_s, anneal, packed.cuda(),
+                                                  t_mid=c(tmid), rgb=rgb_g, nrm=nrm_g)
+        lg = (OP * c(go)).sum() + (DP * c(gd)).sum() + (CR * c(gc)).sum() + (CN * c(gn)).sum() + (W * c(gw)).sum()
+        lg.backward()
+        torch.cuda.synchronize()
+        assert_close(A, alpha[:, 0], rtol=1e-3, atol=2e-6, name="alpha")
+        assert_close(W, w[:, 0], rtol=1e-3, atol=2e-6, name="weights")
+        assert_close(OP, op[:, 0], rtol=1e-4, atol=1e-5, name="opacity")
+        assert_close(DP, dp[:, 0], rtol=1e-4, atol=1e-5, name="depth")
+        assert_close(CR, cr, rtol=1e-4, atol=1e-5, name="comp_rgb")
+        assert_close(CN, cn, rtol=1e-4, atol=1e-5, name="comp_normal")
+        for got, want, nm in [(sdf_g.grad, sdf.grad, "d sdf"), (nrm_g.grad, normal.grad, "d normal"),
+                              (rgb_g.grad, rgb.grad, "d rgb"), (var_g.grad, model.variance.variance.grad, "d variance")]:
+            rt, at = grad_tol(want, 1e-3)
+            assert_close(got, want, rtol=rt, atol=at, name=f"{nm} (anneal={anneal})")
+
+
+def test_composite_density_and_alpha(cuda_lib):
+    """render_weight_from_density / render_weight_from_alpha / accumulate (models/neus.py:181-184)."""
+    from instant_angelo_b200 import nerfacc_api as na
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(22)
+    R = 257
+    packed, S = _packed(R, g, max_n=300)
+    ri = nf.unpack_info(packed)
+    sigma = (torch.rand(S, generator=g) * 3).requires_grad_(True)
+    ts = torch.rand(S, generator=g)
+    te = ts + torch.rand(S, generator=g) * 0.1
+    rgb = torch.rand(S, 3, generator=g).requires_grad_(True)
+    tmid = (ts + te) / 2
+    go, gd, gc = torch.randn(R, generator=g), torch.randn(R, generator=g), torch.randn(R, 3, generator=g)
+    w = nf.render_weight_from_density(ts[:, None], te[:, None], sigma[:, None], ray_indices=ri, n_rays=R)
+    op = nf.accumulate_along_rays(w, ri, None, R)
+    dp = nf.accumulate_along_rays(w, ri, tmid[:, None], R)
+    cr = nf.accumulate_along_rays(w, ri, rgb, R)
+    ((op[:, 0] * go).sum() + (dp[:, 0] * gd).sum() + (cr * gc).sum()).backward()
+    c = lambda t: t.detach().cuda()
+    sg, rg = c(sigma).requires_grad_(True), c(rgb).requires_grad_(True)
+    W, OP, DP, CR, _, _ = ops.composite_density(sg, c(ts), c(te), packed.cuda(), t_mid=c(tmid), rgb=rg)
+    ((OP * c(go)).sum() + (DP * c(gd)).sum() + (CR * c(gc)).sum()).backward()
+    assert_close(W, w[:, 0], rtol=1e-4, atol=1e-6, name="weights")
+    assert_close(OP, op[:, 0], rtol=1e-4, atol=1e-5, name="opacity")
+    assert_close(CR, cr, rtol=1e-4, atol=1e-5, name="comp_rgb")
+    rt, at = grad_tol(sigma.grad, 1e-3)
+    assert_close(sg.grad, sigma.grad, rtol=rt, atol=at, name="d sigma")
+    rt, at = grad_tol(rgb.grad, 1e-3)
+    assert_close(rg.grad, rgb.grad, rtol=rt, atol=at, name="d rgb")
+    # nerfacc-style free functions
+    al = torch.rand(S, 1, generator=g).requires_grad_(True)
+    w_ref = nf.render_weight_from_alpha(al, ray_indices=ri, n_rays=R)
+    gw = torch.randn(S, 1, generator=g)
+    w_ref.backward(gw)
+    alg = c(al).requires_grad_(True)
+    w2 = na.render_weight_from_alpha(alg, ray_indices=ri.cuda().int(), n_rays=R)
+    w2.backward(gw.cuda())
+    assert_close(w2, w_ref, rtol=1e-4, atol=1e-6, name="render_weight_from_alpha")
+    rt, at = grad_tol(al.grad, 1e-3)
+    assert_close(alg.grad, al.grad, rtol=rt, atol=at, name="d alpha")
+    acc = na.accumulate_along_rays(w2.detach(), ri.cuda(), c(rgb), R)
+    assert_close(acc, nf.accumulate_along_rays(w_ref.detach(), ri, rgb.detach(), R), rtol=1e-4, atol=1e-5, name="accumulate")
+    # known answer: constant alpha a over n samples => weights a(1-a)^i, opacity 1-(1-a)^n
+    a, n = 0.25, 40
+    pk = torch.tensor([[0, n]], dtype=torch.int32).cuda()
+    Wk, OPk, *_ = ops.composite_alpha(torch.full((n,), a, device="cuda"), pk)
+    assert_close(Wk, a * (1 - a) ** torch.arange(n, dtype=torch.float64), rtol=1e-5, atol=1e-7, name="geometric series")
+    assert abs(float(OPk[0]) - (1 - (1 - a) ** n)) < 1e-6
+
+
+def test_adamw_matches_torch(cuda_lib):
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n = 100_003
+    p0 = torch.randn(n, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=0.01, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.01)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * (0.0 if step == 2 else 1.0)   # step 2: all-zero grads still decay
+        p_ref.grad = grad.clone()
+        opt.step()
+        ops.adamw_step(p, grad.cuda(), m, v, 0.01, 0.9, 0.99, 1e-15, 0.01, step)
+    assert_close(p, p_ref, rtol=1e-5, atol=1e-6, name="adamw")

@@ -17,7 +17,7 @@ def build_product(cfg_dict, state_dict, global_step, background_color):
     from instant_angelo_b200.config import to_config
     model = make("neus", to_config(cfg_dict)).cuda()
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
-    assert not [k for k in missing if "occupancy" not in k], missing
+    assert not [k for k in missing if "occupancy" not in k and k != "scene_aabb"], missing
     assert not [k for k in unexpected if "occupancy" not in k], unexpected
     model.train()
     model.occupancy_grid.set_binary(sphere_shell_binary(128, cfg_dict["radius"]))

@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- train rays/s of the Instant-angelo hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the training hot path over one batch of synthetic rays: occupancy refresh when due
+(every 16th step), occupancy-grid ray marching, VolumeSDF (1 + 6 finite-difference + 6 curvature taps through
+the hash grid and the width-64 MLP), colour head, NeuS alpha compositing, background NeRF++ branch, the losses
+of systems/neus.py:130-194, backward, gradient all-reduce over NCCL when N > 1 and a fused AdamW step.
+
+Workload (config.workload): BASELINE.json configs[1] -- configs/neuralangelo-colmap_sparse.yaml with
+model.geometry.grad_type=finite_difference on synthetic 512x512 cameras around an analytic sphere, 8192 rays per
+GPU per step (max_train_num_rays), 512 (+256 background) samples/ray budget, all 16 hash levels active.
+
+Rank 0 prints ONE JSON line.  `value` is measured with the ray batches already resident in HBM; `e2e` repeats
+the measurement with every step's rays copied from pinned host memory and the loss read back.
+`--impl reference`: the reference has no CPU implementation and its CUDA dependencies (tinycudann, nerfacc) are
+not installable in this image, so the reference arm times the CPU oracle restatement (oracle/) of the same
+workload on all host cores, on a bounded sample of rays per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+GLOBAL_STEP0 = 19000          # all 16 levels active (start_level 4 + (19000-5000)//1000 >= 16), curvature weight 0.5
+RAYS_PER_GPU = 8192           # max_train_num_rays of the config
+OCC_WARMUP_UPDATES = 16
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)})
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def build_b200(args, rank, world, device):
+    from instant_angelo_b200 import make
+    from instant_angelo_b200.configs import neuralangelo_colmap_sparse
+    from instant_angelo_b200.dp import FusedAdamW, ParamArena
+
+    torch.manual_seed(42)
+    cfg = neuralangelo_colmap_sparse("finite_difference", mlp_otype="FullyFusedMLP" if args.mlp == "tc" else "VanillaMLP")
+    model = make("neus", cfg.model).to(device)
+    model.train()
+    for grid in (model.occupancy_grid, model.occupancy_grid_bg):
+        grid.generator = torch.Generator(device=device).manual_seed(4242)      # identical on every rank
+    with torch.no_grad():
+        for i in range(OCC_WARMUP_UPDATES):
+            model.update_step(0, 16 * i)
+    main_params = [p for n, p in model.named_parameters() if not n.startswith("variance.")]
+    arena = ParamArena(main_params)
+    var_arena = ParamArena(list(model.variance.parameters()))
+    if world > 1:
+        arena.broadcast_params(0)
+        var_arena.broadcast_params(0)
+    opt = FusedAdamW(arena, lr=0.01)
+    opt_var = FusedAdamW(var_arena, lr=0.001)
+    return cfg, model, arena, var_arena, opt, opt_var
+
+
+def make_batches(n_batches, n_rays, rank, pin):
+    from instant_angelo_b200.synthetic import SphereScene
+    scene = SphereScene(seed=42)
+    gen = torch.Generator().manual_seed(42 + 1000 * rank)     # per-rank ray stream (Appendix C-13 neutralised)
+    out = []
+    for _ in range(n_batches):
+        rays, rgb = scene.sample(n_rays, gen)
+        pts, nrm, conf = scene.surface_points(n_rays, gen)
+        bg = torch.rand(3, generator=gen)
+        # one pinned staging buffer per batch: rays(6) rgb(3) pts(3) nrm(3) conf(1) = 16 floats per ray, + bg colour
+        buf = torch.cat([rays, rgb, pts, nrm, conf[:, None]], dim=1).contiguous()
+        if pin:
+            buf, bg = buf.pin_memory(), bg.pin_memory()
+        out.append((buf, bg))
+    return out
+
+
+def unpack_batch(buf, bg):
+    return {"rays": buf[:, 0:6], "rgb": buf[:, 6:9], "pts": buf[:, 9:12].contiguous(), "pts_normal": buf[:, 12:15],
+            "pts_weights": buf[:, 15]}, bg
+
+
+def train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world):
+    from instant_angelo_b200.losses import training_loss
+    model.update_step(0, gs)                                   # levels/eps/cos-anneal + occupancy refresh when gs % 16 == 0
+    model.background_color = bg
+    arena.zero_grad()
+    var_arena.zero_grad()
+    out = model(batch["rays"])
+    terms = training_loss(model, out, batch, cfg.system.loss, gs)
+    terms["loss"].backward()
+    if world > 1:
+        arena.all_reduce()
+        var_arena.all_reduce()
+    opt.step(gs, grad_scale=1.0 / world)
+    opt_var.step(gs, grad_scale=1.0 / world)
+    return terms["loss"], out
+
+
+def hashgrid_microbench(device, peaks):
+    """Secondary BASELINE metric: hash-grid G point-evals/s (16 levels, F=2, 2^19 entries/level, 2^22 incoherent points)."""
+    from instant_angelo_b200 import ops
+    plan = ops.make_grid_plan(16, 2, 19, 32, 1.3195079107728942)
+    n = 1 << 22
+    g = torch.Generator(device=device).manual_seed(7)
+    x = torch.rand(n, 3, device=device, generator=g)
+    table = torch.randn(plan.n_params, device=device, generator=g) * 0.1
+    dy = torch.randn(n, 32, device=device, generator=g)
+    dtab = torch.zeros_like(table)
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    lib, s = L.load(), L.stream()
+    out = torch.empty(n, 32, device=device)
+    dx = torch.empty_like(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps + 2):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = sorted(ts[2:])
+        return ts[len(ts) // 2]
+
+    res = {}
+    ms = timed(lambda: lib.ia_hashgrid_fwd(x.data_ptr(), n, table.data_ptr(), C.byref(plan), 16, out.data_ptr(), s))
+    b = ops.hashgrid_bytes_per_point(plan, 16, "fwd")
+    res["fwd"] = {"ms": ms, "gevals_per_s": n / ms / 1e6, "algorithmic_GBps": n * b / ms / 1e6, "frac_of_hbm": n * b / ms / 1e6 / peaks["hbm_gbs"]}
+    ms = timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), C.byref(plan), 16, dtab.data_ptr(), None, s))
+    b = ops.hashgrid_bytes_per_point(plan, 16, "bwd_table")
+    res["bwd_table"] = {"ms": ms, "gevals_per_s": n / ms / 1e6, "algorithmic_GBps": n * b / ms / 1e6, "frac_of_hbm": n * b / ms / 1e6 / peaks["hbm_gbs"]}
+    ms = timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), C.byref(plan), 16, None, dx.data_ptr(), s))
+    b = ops.hashgrid_bytes_per_point(plan, 16, "bwd_input")
+    res["bwd_input"] = {"ms": ms, "gevals_per_s": n / ms / 1e6, "algorithmic_GBps": n * b / ms / 1e6, "frac_of_hbm": n * b / ms / 1e6 / peaks["hbm_gbs"]}
+    res["config"] = "N=2^22 uniform random points, L=16 F=2 T=2^19 fp32 tables, L2 flushed between launches; bytes/point fwd=%d" % ops.hashgrid_bytes_per_point(plan, 16, "fwd")
+    return res
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from instant_angelo_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run"
+    peaks = measured_peaks()
+    K, W = args.steps, args.warmup
+    n_rays = args.rays
+
+    cfg, model, arena, var_arena, opt, opt_var = build_b200(args, rank, world, device)
+    host_batches = make_batches(K + W, n_rays, rank, pin=True)
+    dev_batches = [(b.to(device), g.to(device)) for b, g in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def sum_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([float(v)], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return float(v)
+
+    # ---- kernel-resident measurement (`value`) --------------------------------------------------------
+    gs = GLOBAL_STEP0
+    for i in range(W):
+        batch, bg = unpack_batch(*dev_batches[i])
+        train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
+        gs += 1
+    prof = ops.PROFILER
+    prof.reset()
+    prof.enabled, prof.timing = True, True
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n_samples_fg = n_samples_full = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    counts = []
+    for i in range(W, W + K):
+        batch, bg = unpack_batch(*dev_batches[i])
+        loss, out = train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
+        counts.append((out["num_samples"], out["num_samples_full"]))
+        gs += 1
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    prof.enabled = False
+    launches = prof.launches
+    summary = prof.summary()
+    for a, b in counts:
+        n_samples_fg += int(a.item()); n_samples_full += int(b.item())
+    total_rays = n_rays * world * K
+    value = total_rays / (ms_total / 1e3)
+    fg_total = sum_over_ranks(n_samples_fg)
+    full_total = sum_over_ranks(n_samples_full)
+
+    # ---- end-to-end measurement (`e2e`): host pinned rays -> H2D -> step -> loss D2H, every step -------
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    h2d = d2h = 0
+    for i in range(W, W + K):
+        hb, hbg = host_batches[i]
+        db, dbg = hb.to(device, non_blocking=True), hbg.to(device, non_blocking=True)
+        h2d = hb.numel() * 4 + hbg.numel() * 4
+        batch, bg = unpack_batch(db, dbg)
+        loss, out = train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
+        _ = float(loss.item())                                   # D2H read of the step result
+        d2h = 4
+        gs += 1
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e2e_value = total_rays / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region) ------------
+    per_kernel = {k: {"calls": c, "ms": t, "share_of_step": t / (e0.elapsed_time(e1))} for k, (c, t, w) in summary.items()}
+    def group(prefix):
+        items = [(k, v) for k, v in summary.items() if k.startswith(prefix)]
+        return sum(v[0] for _, v in items), sum(v[1] for _, v in items), sum(v[2] for _, v in items)
+    groups = {"hashgrid_fwd": group("ia_hashgrid_fwd"), "hashgrid_bwd": group("ia_hashgrid_bwd"), "mlp_fwd": group("ia_mlp_fwd"),
+              "mlp_bwd": group("ia_mlp_bwd")}
+    dom = max(groups, key=lambda k: groups[k][1])
+    calls, ms, work = groups[dom]
+    if dom.startswith("mlp"):
+        achieved = work / (ms / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16; the fp32 FFMA path cannot reach it)" if args.mlp != "tc" else peaks["source"],
+                "launches": calls, "avg_launch_ms": ms / max(calls, 1), "algorithmic_flop_per_launch": work / max(calls, 1)}
+    else:
+        achieved = work / (ms / 1e3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peaks["source"], "launches": calls, "avg_launch_ms": ms / max(calls, 1),
+                "algorithmic_bytes_per_launch": work / max(calls, 1)}
+
+    cpu = cpu_baseline_leg(cfg, model, args) if world == 1 and not args.no_cpu_baseline else None
+    hg = hashgrid_microbench(device, peaks) if world == 1 else None
+
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.mlp != "tc" else "f16 operands / f32 accumulate (MLP), f32 elsewhere", "data": "synthetic",
+        "config": {"workload": "neuralangelo-colmap_sparse.yaml, grad_type=finite_difference, synthetic 512x512 cameras around an "
+                               "analytic sphere (BASELINE.json configs[1])",
+                   "rays_per_gpu_per_step": n_rays, "global_rays_per_step": n_rays * world, "num_samples_per_ray": 512,
+                   "num_samples_per_ray_bg": 256, "hash_levels_active": 16, "log2_hashmap_size": 19, "global_step": GLOBAL_STEP0,
+                   "mean_fg_samples_per_ray": fg_total / total_rays, "mean_samples_per_ray_full": full_total / total_rays,
+                   "samples_per_s": full_total / (ms_total / 1e3), "hash_point_evals_per_s": (13 * fg_total + (full_total - fg_total)) / (ms_total / 1e3),
+                   "mlp": args.mlp, "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
+                   "l2": "per-step working set (hash tables 112 MB + >1 GB of per-sample activations) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "kernels": per_kernel,
+        "hashgrid_microbench": hg,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU oracle legs (cpu_baseline of the B200 arm, and the whole `--impl reference` arm)
+# ---------------------------------------------------------------------------------------------------------
+def build_oracle(cfg, fg_binary=None):
+    """CPU oracle model of the same workload.  fg_binary: occupancy grid to reuse; None -> one warm-up refresh of the
+    foreground grid with the oracle's own SDF and an analytic background grid (cells inside the unit ball)."""
+    from instant_angelo_b200.config import to_primitive
+    from oracle import model_ref as mr
+    torch.manual_seed(42)
+    ref = mr.RefNeuSModel(to_primitive(cfg.model))
+    ref.train()
+    ref.update_step(0, GLOBAL_STEP0, update_occupancy=False)
+    if fg_binary is not None:
+        ref.occupancy_grid.binary = fg_binary
+    else:
+        g = torch.Generator().manual_seed(4242)
+        ref.occupancy_grid.every_n_step(0, ref.occ_eval_fn, occ_thre=cfg.model.grid_prune_occ_thre, gen=g)
+    c = (torch.arange(256, dtype=torch.float32) + 0.5) / 256 - 0.5
+    x, y, z = torch.meshgrid(c, c, c, indexing="ij")
+    ref.occupancy_grid_bg.binary = (x * x + y * y + z * z) < 0.25
+    return ref
+
+
+def oracle_step(ref, cfg, rays, rgb, pts, nrm, conf, bg, gs):
+    from oracle import model_ref as mr
+    ref.zero_grad(set_to_none=True)
+    ref.background_color = bg
+    out = ref.forward_(rays)
+    batch = {"rays": rays, "rgb": rgb, "pts": pts, "pts_normal": nrm, "pts_weights": conf}
+    from instant_angelo_b200.config import to_primitive
+    terms = mr.training_loss(ref, out, batch, to_primitive(cfg.system.loss), gs)
+    terms["loss"].backward()
+    return float(terms["loss"]), int(out["num_samples_full"])
+
+
+def cpu_baseline_leg(cfg, model, args):
+    """Oracle ("port") timed on this box's host cores on a bounded sample of the same workload."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = build_oracle(cfg, fg_binary=model.occupancy_grid.binary.cpu())
+    ref.occupancy_grid_bg.binary = model.occupancy_grid_bg.binary.cpu()
+    n = args.cpu_rays
+    buf, bg = make_batches(1, n, 0, pin=False)[0]
+    b, bgc = unpack_batch(buf, bg)
+    t0 = time.perf_counter()
+    oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bgc, GLOBAL_STEP0)   # warm-up
+    t1 = time.perf_counter()
+    _, ns = oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bgc, GLOBAL_STEP0)
+    t2 = time.perf_counter()
+    return {"value": n / (t2 - t1), "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n} rays of the same workload (same occupancy grids, {ns / n:.1f} samples/ray), forward + losses + backward "
+                      f"through the CPU oracle (oracle/model_ref.py, PyTorch fp32, {cores} threads); warm-up run {t1 - t0:.1f} s, timed run {t2 - t1:.1f} s"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's path cannot run here (tinycudann / nerfacc are CUDA-only third-party packages
+    that are not installable offline), so this times the CPU oracle restatement of the SAME workload on all host
+    cores.  Each step is a bounded sample of `--cpu-rays` rays."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from instant_angelo_b200.configs import neuralangelo_colmap_sparse
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = neuralangelo_colmap_sparse("finite_difference")
+    ref = build_oracle(cfg)
+    n = args.cpu_rays
+    K, W = args.steps, args.warmup
+    batches = make_batches(K + W, n, 0, pin=False)
+    gs = GLOBAL_STEP0
+    total_samples = 0
+    for i in range(W):
+        b, bg = unpack_batch(*batches[i])
+        oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bg, gs)
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        b, bg = unpack_batch(*batches[i])
+        _, ns = oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bg, gs)
+        total_samples += ns
+    dt = time.perf_counter() - t0
+    value = n * K / dt
+    sample = (f"{n} rays per step of neuralangelo-colmap_sparse (finite_difference), {total_samples / max(n * K, 1):.1f} samples/ray, "
+              f"CPU oracle forward + losses + backward, {cores} threads")
+    line = {"impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "neuralangelo-colmap_sparse.yaml, grad_type=finite_difference, synthetic 512x512 cameras around an "
+                                   "analytic sphere (BASELINE.json configs[1])", "rays_per_step_sample": n,
+                       "note": "reference GPU path (tinycudann + nerfacc) is not installable in this image; CPU oracle port timed instead"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--mlp", default="fp32", choices=["fp32", "tc"], help="MLP arithmetic: fp32 FFMA (VanillaMLP) or tcgen05 f16")
+    ap.add_argument("--cpu-rays", type=int, default=48, help="rays per step of the bounded CPU-oracle sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,7 @@ class OccupancyGrid(nn.Module):
         self.register_buffer("_binary", torch.zeros(res, dtype=torch.bool))
         self.register_buffer("bitfield", torch.zeros((self.num_cells + 31) // 32, dtype=torch.int32), persistent=False)
         self._workspace = None
+        self.generator = None   # optional torch.Generator for cell sampling/jitter (data-parallel replicas share its seed)
         self._grid_desc = ops.make_grid_desc(self._roi_host, res, int(self._contraction_type))
 
     # -- nerfacc properties
@@ -99,10 +100,10 @@ class OccupancyGrid(nn.Module):
             return None  # all cells, in order
         n = self.num_cells // 4
         dev = self.occs.device
-        uniform = torch.randint(self.num_cells, (n,), device=dev)
+        uniform = torch.randint(self.num_cells, (n,), device=dev, generator=self.generator)
         occupied = torch.nonzero(self._binary.flatten())[:, 0]
         if n < occupied.numel():
-            occupied = occupied[torch.randint(occupied.numel(), (n,), device=dev)]
+            occupied = occupied[torch.randint(occupied.numel(), (n,), device=dev, generator=self.generator)]
         return torch.cat([uniform, occupied], dim=0)
 
     @torch.no_grad()
@@ -115,7 +116,7 @@ class OccupancyGrid(nn.Module):
         gz = idx % rz
         coords = torch.stack([gx, gy, gz], dim=-1).float()
         if jitter is None:
-            jitter = torch.rand(idx.shape[0], 3, device=dev)
+            jitter = torch.rand(idx.shape[0], 3, device=dev, generator=self.generator)
         x = (coords + jitter) / self.resolution.float()
         if self._contraction_type == ContractionType.UN_BOUNDED_SPHERE:
             keep = (x - 0.5).norm(dim=1) < 0.5

@@ -12,6 +12,60 @@ import torch
 
 from . import _lib as L
 
+# kernels launched per ABI call (for bench.py's gpu_launches claim)
+_LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
+             "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
+             "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
+             "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0}
+
+
+class Profiler:
+    """Optional per-call CUDA-event timing + launch counting (bench.py turns it on inside its timed region to
+    get the dominant kernel's live launch durations on the launching stream)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.timing = False
+        self.reset()
+
+    def reset(self):
+        self.launches = 0
+        self.calls = {}
+        self._events = []
+
+    def summary(self):
+        """name -> (calls, total_ms, total algorithmic work: bytes for gather kernels, FLOP for the MLP);
+        call after torch.cuda.synchronize()."""
+        out = {}
+        for name, tag, a, b, work in self._events:
+            key = name if tag is None else f"{name}[{tag}]"
+            c, t, w = out.get(key, (0, 0.0, 0.0))
+            out[key] = (c + 1, t + a.elapsed_time(b), w + work)
+        return out
+
+
+PROFILER = Profiler()
+
+
+def _run(name: str, *args, tag=None, work: float = 0.0) -> None:
+    fn = getattr(L.load(), name)
+    prof = PROFILER
+    if prof.enabled:
+        prof.launches += _LAUNCHES.get(name, 1)
+        prof.calls[name] = prof.calls.get(name, 0) + 1
+        if prof.timing:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            prof._events.append((name, tag, a, b, work))
+        else:
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        raise RuntimeError(f"instant_angelo_b200 {name} failed (status {rc}): {L.last_error()}")
+
 
 # ---------------------------------------------------------------------------------------------
 # hash grid  (tcnn.Encoding(HashGrid).forward, reference models/network_utils.py:57)
@@ -20,8 +74,8 @@ from . import _lib as L
 def make_grid_plan(n_levels: int, n_features: int, log2_hashmap_size: int, base_resolution: int,
                    per_level_scale: float) -> L.GridPlan:
     plan = L.GridPlan()
-    L.check(L.load().ia_hashgrid_plan(n_levels, n_features, log2_hashmap_size, base_resolution,
-                                      C.c_float(per_level_scale), C.byref(plan)), "hashgrid_plan")
+    _run("ia_hashgrid_plan", n_levels, n_features, log2_hashmap_size, base_resolution,
+                                      C.c_float(per_level_scale), C.byref(plan))
     return plan
 
 
@@ -32,8 +86,8 @@ class _HashGridFn(torch.autograd.Function):
         x = L.f32c(x)
         n = x.shape[0]
         out = torch.empty(n, plan.n_levels * plan.n_features, device=x.device, dtype=torch.float32)
-        L.check(L.load().ia_hashgrid_fwd(L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, L.ptr(out), L.stream()),
-                "hashgrid_fwd")
+        _run("ia_hashgrid_fwd", L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, L.ptr(out), L.stream(),
+             work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
         ctx.save_for_backward(x, table)
         ctx.plan, ctx.active = plan, active_levels
         return out
@@ -47,11 +101,30 @@ class _HashGridFn(torch.autograd.Function):
         dtable = torch.zeros_like(table) if need_t else None
         dx = torch.empty_like(x) if need_x else None
         if n > 0 and (need_t or need_x):
-            L.check(L.load().ia_hashgrid_bwd(L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active,
-                                             L.ptr(dtable), L.ptr(dx), L.stream()), "hashgrid_bwd")
+            work = (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_table") if need_t else 0) + \
+                   (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_input") if need_x else 0)
+            _run("ia_hashgrid_bwd", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active,
+                 L.ptr(dtable), L.ptr(dx), L.stream(), tag=("table+input" if need_t and need_x else "table" if need_t else "input"),
+                 work=n * work)
         elif need_x:
             dx.zero_()
         return dx, dtable, None, None
+
+
+def hashgrid_bytes_per_point(plan: L.GridPlan, active_levels: int, which: str = "fwd", param_bytes: int = 4,
+                             out_bytes: int = 4) -> int:
+    """ALGORITHMIC bytes per point-evaluation (BASELINE.md section 3 / SURVEY.md section 8d):
+    fwd = 12 + La*8*F*P + L*F*O; bwd_table the same; bwd_input = fwd + 12."""
+    Lv, F = plan.n_levels, plan.n_features
+    base = 12 + active_levels * 8 * F * param_bytes + Lv * F * out_bytes
+    return base + (12 if which == "bwd_input" else 0)
+
+
+def mlp_flops_per_row(desc: L.MlpDesc, n_out_used: int) -> int:
+    """2*MAC of one forward evaluation (unpadded)."""
+    din = desc.n_in0 + desc.n_in1
+    macs = din * desc.width + (desc.width * desc.width if desc.n_hidden_layers == 2 else 0) + desc.width * n_out_used
+    return 2 * macs
 
 
 def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, plan: L.GridPlan, active_levels: Optional[int] = None) -> torch.Tensor:
@@ -72,7 +145,7 @@ class _SHFn(torch.autograd.Function):
         d01 = L.f32c(d01)
         n = d01.shape[0]
         out = torch.empty(n, degree * degree, device=d01.device, dtype=torch.float32)
-        L.check(L.load().ia_sh_fwd(L.ptr(d01), n, degree, L.ptr(out), L.stream()), "sh_fwd")
+        _run("ia_sh_fwd", L.ptr(d01), n, degree, L.ptr(out), L.stream())
         ctx.save_for_backward(d01)
         ctx.degree = degree
         return out
@@ -84,7 +157,7 @@ class _SHFn(torch.autograd.Function):
             return None, None
         dout = L.f32c(dout)
         dd = torch.empty_like(d01)
-        L.check(L.load().ia_sh_bwd(L.ptr(d01), d01.shape[0], ctx.degree, L.ptr(dout), L.ptr(dd), L.stream()), "sh_bwd")
+        _run("ia_sh_bwd", L.ptr(d01), d01.shape[0], ctx.degree, L.ptr(dout), L.ptr(dd), L.stream())
         return dd, None
 
 
@@ -110,8 +183,8 @@ class _MLPFn(torch.autograd.Function):
         params = L.f32c(params)
         n = (in1 if in1 is not None else in0).shape[0]
         out = torch.empty(n, n_out_used, device=params.device, dtype=torch.float32)
-        L.check(L.load().ia_mlp_fwd(C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), n_out_used, L.ptr(out),
-                                    n_out_used, L.stream()), "mlp_fwd")
+        _run("ia_mlp_fwd", C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), n_out_used, L.ptr(out),
+             n_out_used, L.stream(), work=n * mlp_flops_per_row(desc, n_out_used))
         ctx.save_for_backward(in0, in1, params)
         ctx.desc, ctx.nou = desc, n_out_used
         return out
@@ -128,8 +201,8 @@ class _MLPFn(torch.autograd.Function):
         d1 = torch.empty_like(in1) if need1 else None
         dp = torch.zeros_like(params) if needp else None
         if n > 0:
-            L.check(L.load().ia_mlp_bwd(C.byref(ctx.desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dout), ctx.nou,
-                                        ctx.nou, L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream()), "mlp_bwd")
+            _run("ia_mlp_bwd", C.byref(ctx.desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dout), ctx.nou,
+                 ctx.nou, L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou))
         return d0, d1, dp, None, None
 
 
@@ -161,8 +234,8 @@ def aabb_intersect(rays_o: torch.Tensor, rays_d: torch.Tensor, aabb6, clamp_zero
     t_min = torch.empty(n, device=rays_o.device, dtype=torch.float32)
     t_max = torch.empty_like(t_min)
     bb = (C.c_float * 6)(*[float(v) for v in aabb6])
-    L.check(L.load().ia_aabb(L.ptr(rays_o), L.ptr(rays_d), n, C.byref(bb), int(clamp_zero), L.ptr(t_min), L.ptr(t_max),
-                             L.stream()), "aabb")
+    _run("ia_aabb", L.ptr(rays_o), L.ptr(rays_d), n, C.byref(bb), int(clamp_zero), L.ptr(t_min), L.ptr(t_max),
+                             L.stream())
     return t_min, t_max
 
 
@@ -171,7 +244,6 @@ def march(rays_o, rays_d, t_min, t_max, grid: L.GridDesc, bitfield: Optional[tor
           cone_angle: float):
     """Two-pass marching.  Returns (packed_info [R,2] i32, ray_indices [S] i32, t_starts [S], t_ends [S])."""
     L.require_cuda(rays_o, rays_d, t_min, t_max)
-    lib = L.load()
     rays_o, rays_d, t_min, t_max = L.f32c(rays_o), L.f32c(rays_d), L.f32c(t_min), L.f32c(t_max)
     n = rays_o.shape[0]
     dev = rays_o.device
@@ -179,19 +251,19 @@ def march(rays_o, rays_d, t_min, t_max, grid: L.GridDesc, bitfield: Optional[tor
     packed = torch.empty(n, 2, device=dev, dtype=torch.int32)
     total_dev = torch.zeros(1, device=dev, dtype=torch.int64)
     s = L.stream()
-    L.check(lib.ia_march_count(L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), n, C.byref(grid), L.ptr(bitfield),
-                               C.c_float(step_size), C.c_float(cone_angle), L.ptr(num), s), "march_count")
-    L.check(lib.ia_march_scan(L.ptr(num), n, L.ptr(packed), L.ptr(total_dev), None, s), "march_scan")
+    _run("ia_march_count", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), n, C.byref(grid), L.ptr(bitfield),
+                               C.c_float(step_size), C.c_float(cone_angle), L.ptr(num), s)
+    _run("ia_march_scan", L.ptr(num), n, L.ptr(packed), L.ptr(total_dev), None, s)
     total = C.c_int64(0)
-    L.check(lib.ia_march_total(L.ptr(total_dev), C.byref(total), s), "march_total")
+    _run("ia_march_total", L.ptr(total_dev), C.byref(total), s)
     S = int(total.value)
     ray_indices = torch.empty(S, device=dev, dtype=torch.int32)
     t_starts = torch.empty(S, device=dev, dtype=torch.float32)
     t_ends = torch.empty(S, device=dev, dtype=torch.float32)
     if S > 0:
-        L.check(lib.ia_march_write(L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), n, C.byref(grid),
+        _run("ia_march_write", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), n, C.byref(grid),
                                    L.ptr(bitfield), C.c_float(step_size), C.c_float(cone_angle), L.ptr(packed),
-                                   L.ptr(ray_indices), L.ptr(t_starts), L.ptr(t_ends), s), "march_write")
+                                   L.ptr(ray_indices), L.ptr(t_starts), L.ptr(t_ends), s)
     return packed, ray_indices, t_starts, t_ends
 
 
@@ -200,8 +272,8 @@ def visibility(alphas: torch.Tensor, packed_info: torch.Tensor, early_stop_eps: 
     L.require_cuda(alphas, packed_info)
     alphas = L.f32c(alphas.reshape(-1))
     vis = torch.empty(alphas.shape[0], device=alphas.device, dtype=torch.uint8)
-    L.check(L.load().ia_visibility(L.ptr(alphas), L.ptr(packed_info), packed_info.shape[0], C.c_float(early_stop_eps),
-                                   C.c_float(alpha_thre), L.ptr(vis), L.stream()), "visibility")
+    _run("ia_visibility", L.ptr(alphas), L.ptr(packed_info), packed_info.shape[0], C.c_float(early_stop_eps),
+                                   C.c_float(alpha_thre), L.ptr(vis), L.stream())
     return vis.bool()
 
 
@@ -211,14 +283,13 @@ def occ_update(idx: Optional[torch.Tensor], occ: torch.Tensor, occs: torch.Tenso
     L.require_cuda(occ, occs)
     occ = L.f32c(occ.reshape(-1))
     n = occ.shape[0]
-    L.check(L.load().ia_occ_update(L.ptr(idx), L.ptr(occ), n, L.ptr(occs), occs.numel(), C.c_float(ema_decay),
-                                   C.c_float(occ_thre), L.ptr(binary_u8), L.ptr(bitfield), L.ptr(workspace), L.stream()),
-            "occ_update")
+    _run("ia_occ_update", L.ptr(idx), L.ptr(occ), n, L.ptr(occs), occs.numel(), C.c_float(ema_decay),
+                                   C.c_float(occ_thre), L.ptr(binary_u8), L.ptr(bitfield), L.ptr(workspace), L.stream())
 
 
 @torch.no_grad()
 def occ_pack(binary_u8: torch.Tensor, bitfield: torch.Tensor) -> None:
-    L.check(L.load().ia_occ_pack(L.ptr(binary_u8), binary_u8.numel(), L.ptr(bitfield), L.stream()), "occ_pack")
+    _run("ia_occ_pack", L.ptr(binary_u8), binary_u8.numel(), L.ptr(bitfield), L.stream())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -257,8 +328,8 @@ class _CompositeFn(torch.autograd.Function):
         depth = torch.empty(R, device=dev) if t_mid is not None else None
         comp_rgb = torch.empty(R, 3, device=dev) if rgb is not None else None
         comp_nrm = torch.empty(R, 3, device=dev) if nrm is not None else None
-        L.check(L.load().ia_composite_fwd(C.byref(args), L.ptr(alpha), L.ptr(trans), L.ptr(weights), L.ptr(opacity),
-                                          L.ptr(depth), L.ptr(comp_rgb), L.ptr(comp_nrm), L.stream()), "composite_fwd")
+        _run("ia_composite_fwd", C.byref(args), L.ptr(alpha), L.ptr(trans), L.ptr(weights), L.ptr(opacity),
+                                          L.ptr(depth), L.ptr(comp_rgb), L.ptr(comp_nrm), L.stream())
         ctx.args = args
         ctx.keep = (packed_info, a, normal, dirs, dists, t_starts, t_ends, inv_s, t_mid, rgb, nrm, alpha, trans)
         ctx.mode = mode
@@ -279,11 +350,11 @@ class _CompositeFn(torch.autograd.Function):
         d_inv_s = torch.zeros(1, device=dev) if mode == L.IA_ALPHA_NEUS else None
         d_rgb = torch.empty(S, 3, device=dev) if rgb is not None else None
         d_nrm = torch.empty(S, 3, device=dev) if nrm is not None else None
-        L.check(L.load().ia_composite_bwd(
+        _run("ia_composite_bwd", 
             C.byref(ctx.args), L.ptr(alpha), L.ptr(trans), L.ptr(g_w), L.ptr(g_o), L.ptr(g_d), L.ptr(g_c), L.ptr(g_n),
             L.ptr(d_a) if mode == L.IA_ALPHA_GIVEN else None, L.ptr(d_a) if mode == L.IA_ALPHA_NEUS else None,
             L.ptr(d_normal), L.ptr(d_inv_s), L.ptr(d_a) if mode == L.IA_ALPHA_DENSITY else None, L.ptr(d_rgb), L.ptr(d_nrm),
-            L.stream()), "composite_bwd")
+            L.stream())
         if d_inv_s is not None and inv_s is not None:
             d_inv_s = d_inv_s.reshape(inv_s.shape)
         return (None, None, None, d_a, d_normal, None, None, None, None, d_inv_s, None, d_rgb, d_nrm)
@@ -309,6 +380,6 @@ def composite_alpha(alpha, packed_info, t_mid=None, rgb=None, nrm=None):
 
 @torch.no_grad()
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
-    L.check(L.load().ia_adamw_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
+    _run("ia_adamw_step", L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
                                    C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
-                                   C.c_float(weight_decay), int(step), C.c_float(grad_scale), L.stream()), "adamw_step")
+                                   C.c_float(weight_decay), int(step), C.c_float(grad_scale), L.stream())

@@ -140,7 +140,10 @@ def hashgrid_forward(x: torch.Tensor, table: torch.Tensor, plan: GridPlan, activ
         g = torch.floor(pos.detach())
         w = pos - g                                   # d w / d x = scale_l
         gi = g.long()
-        acc = torch.zeros(x.shape[0], F, dtype=x.dtype)
+        # all 8 corners of a level are gathered at once from the level's own slice of the table, so that
+        # autograd builds one level-sized gradient per level (not one table-sized gradient per corner)
+        tl = tab[plan.offset[l]: plan.offset[l + 1]]
+        idx8, w8 = [], []
         for corner in range(8):
             wgt = torch.ones(x.shape[0], dtype=x.dtype)
             c = []
@@ -151,8 +154,11 @@ def hashgrid_forward(x: torch.Tensor, table: torch.Tensor, plan: GridPlan, activ
                 else:
                     wgt = wgt * (1.0 - w[:, d])
                     c.append(gi[:, d])
-            idx = _corner_index(plan, l, c[0], c[1], c[2]) + plan.offset[l]
-            acc = acc + wgt[:, None] * tab[idx]
+            idx8.append(_corner_index(plan, l, c[0], c[1], c[2]))
+            w8.append(wgt)
+        idx8 = torch.stack(idx8, dim=1)                  # [N,8]
+        w8 = torch.stack(w8, dim=1)                      # [N,8]
+        acc = (w8[:, :, None] * tl[idx8]).sum(dim=1)     # [N,F]
         outs.append(acc)
     return torch.cat(outs, dim=1)
 

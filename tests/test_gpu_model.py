@@ -12,9 +12,21 @@ from tests.helpers import GOLDEN_CASES, assert_close, golden_batch, golden_state
 pytestmark = pytest.mark.gpu
 
 
-def build_product(cfg_dict, state_dict, global_step, background_color):
+def _set_mlp_otype(cfg, otype):
+    for v in cfg.values():
+        if isinstance(v, dict):
+            if "n_neurons" in v and "otype" in v:
+                v["otype"] = otype
+            else:
+                _set_mlp_otype(v, otype)
+
+
+def build_product(cfg_dict, state_dict, global_step, background_color, mlp_otype="VanillaMLP"):
+    import copy
     from instant_angelo_b200 import make
     from instant_angelo_b200.config import to_config
+    cfg_dict = copy.deepcopy(cfg_dict)
+    _set_mlp_otype(cfg_dict, mlp_otype)
     model = make("neus", to_config(cfg_dict)).cuda()
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not [k for k in missing if "occupancy" not in k and k != "scene_aabb"], missing
@@ -57,12 +69,14 @@ def compare_step(model, out, terms, want_out, want_terms, want_grads, rtol=1e-3)
 
 
 @pytest.mark.parametrize("case", list(GOLDEN_CASES))
-def test_training_step_matches_reference_fixture(cuda_lib, golden_dir, case):
+@pytest.mark.parametrize("mlp_otype", ["VanillaMLP", "FullyFusedMLP"])
+def test_training_step_matches_reference_fixture(cuda_lib, golden_dir, case, mlp_otype):
+    """VanillaMLP -> fp32 FFMA kernels; FullyFusedMLP -> tcgen05 (3xF16 split) kernels.  Same 1e-3 bar for both."""
     from instant_angelo_b200.losses import training_loss
     fx = load_golden(golden_dir, case)
     cfg = golden_model_config(**GOLDEN_CASES[case])
     gs = int(fx["global_step"])
-    model = build_product(cfg, golden_state_dict(fx), gs, torch.from_numpy(fx["background_color"]))
+    model = build_product(cfg, golden_state_dict(fx), gs, torch.from_numpy(fx["background_color"]), mlp_otype)
     batch = golden_batch(fx, "cuda")
     c = lambda k: torch.from_numpy(fx[k]).cuda()
     out = model(batch["rays"], stratified_u=c("u_fg"), rand_directions=c("rand_directions"), stratified_u_bg=c("u_bg"))
@@ -79,7 +93,8 @@ def test_training_step_matches_reference_fixture(cuda_lib, golden_dir, case):
     compare_step(model, out, terms, want_out, want_terms, want_grads)
 
 
-def test_training_step_matches_oracle_fresh_problem(cuda_lib):
+@pytest.mark.parametrize("mlp_otype", ["VanillaMLP", "FullyFusedMLP"])
+def test_training_step_matches_oracle_fresh_problem(cuda_lib, mlp_otype):
     """Fresh seed, more rays, all 8 levels active, cos_anneal mid-way; oracle and product share weights."""
     from instant_angelo_b200.losses import training_loss
     torch.manual_seed(1234)
@@ -115,7 +130,7 @@ def test_training_step_matches_oracle_fresh_problem(cuda_lib):
     terms_ref = mr.training_loss(ref, out_ref, batch, golden_loss_config(), gs)
     terms_ref["loss"].backward()
 
-    model = build_product(cfg, {k: v.detach().clone() for k, v in ref.state_dict().items()}, gs, bgc)
+    model = build_product(cfg, {k: v.detach().clone() for k, v in ref.state_dict().items()}, gs, bgc, mlp_otype)
     cb = {k: v.cuda() for k, v in batch.items()}
     out = model(cb["rays"], stratified_u=u_fg.cuda(), rand_directions=rnd.cuda(), stratified_u_bg=u_bg.cuda())
     terms = training_loss(model, out, cb, golden_loss_config(), gs)

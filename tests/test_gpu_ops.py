@@ -181,10 +181,13 @@ MLP_CASES = {
 
 @pytest.mark.parametrize("case", list(MLP_CASES))
 @pytest.mark.parametrize("n", [1, 1000])
-def test_mlp_fp32(cuda_lib, case, n):
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_mlp(cuda_lib, case, n, precision):
+    """fp32: FFMA kernel; tc: tcgen05 3xF16-split kernel (wide output layers route to the fp32 kernel inside)."""
     from instant_angelo_b200 import _lib as L
     from instant_angelo_b200 import ops
     n0, n1, nh, nout, softplus, wn, nou = MLP_CASES[case]
+    prec = L.IA_MLP_FP32 if precision == "fp32" else L.IA_MLP_TC_F16
     torch.manual_seed(sum(map(ord, case)))
     cfg = {"n_neurons": 64, "n_hidden_layers": nh, "sphere_init": softplus, "weight_norm": wn, "output_activation": "none"}
     ref = mr.RefVanillaMLP(n0 + n1, nout, cfg)
@@ -202,7 +205,7 @@ def test_mlp_fp32(cuda_lib, case, n):
     # product: same effective weights in the ABI's flat layout
     lin = [m for m in ref.layers if isinstance(m, mr.RefWNLinear)]
     flat = torch.cat([t for m in lin for t in (m.effective_weight().reshape(-1), m.bias)]).detach().cuda().requires_grad_(True)
-    desc = ops.make_mlp_desc(n0, n1, nh, nout, L.IA_ACT_SOFTPLUS100 if softplus else L.IA_ACT_RELU, 2.0, -1.0)
+    desc = ops.make_mlp_desc(n0, n1, nh, nout, L.IA_ACT_SOFTPLUS100 if softplus else L.IA_ACT_RELU, 2.0, -1.0, prec)
     assert cuda_lib.ia_mlp_param_count(desc) == flat.numel()
     ag = a.detach().cuda().requires_grad_(True) if n0 else None
     bg = b.detach().cuda().requires_grad_(True)

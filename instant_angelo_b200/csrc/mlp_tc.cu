@@ -7,16 +7,17 @@
 // fp32 TMEM accumulator, i.e. ~22 mantissa bits per operand.  This is REQUIRED by the workload, not a luxury: the
 // finite-difference normals divide SDF differences by 2*eps ~ 3e-3, so a single fp16 pass (2^-11 relative) would put
 // ~10 % noise on the eikonal term.  The MMA pipe is far from the bottleneck (the per-row activation epilogue is), so
-// the 3x issue cost is hidden.  The last layer (<= 8 outputs: SDF taps, colours, densities) is evaluated by the
-// row's own thread in fp32 registers.
+// the 3x issue cost is hidden.  The last layer (<= 8 outputs: SDF taps, colours, densities) is evaluated in fp32
+// registers.
 //
-// Mapping: CTA = 128 threads = 128 rows of the tile = the 128 TMEM lanes; thread r owns row r end to end
-// (tcgen05.ld 32x32b gives it its accumulator row), writes the next layer's A operand straight into the UMMA
-// canonical K-major no-swizzle layout (core matrix = 8 rows x 16 B; address = chunk*2048 + row*16), and the same
-// buffers are re-read as MN-major operands for the dW = dZ^T * H products (M=64, K=128 rows) of the backward pass.
-// Bias gradients come for free from a constant-one column appended to X / H1.  Parameter gradients accumulate in
-// shared memory across all tiles of the persistent CTA and are flushed with one atomic pass at the end.
-// Gradient operands are rescaled per tile by a power of two so that they sit in fp16's normal range.
+// Mapping: one CTA = one 128-row tile = the 128 TMEM lanes; 512 threads = 4 "column groups" x 128 rows: thread
+// (r, cg) owns accumulator columns [16cg, 16cg+16) of row r (tcgen05.ld 32x32b.x16), applies bias + activation and
+// writes the next layer's A operand straight into the UMMA canonical K-major no-swizzle layout (core matrix = 8 rows
+// x 16 B; address = chunk*2048 + row*16).  The same buffers are re-read as MN-major operands for the
+// dW = dZ^T * H products (M=64, K=128 rows) of the backward pass.  Bias gradients come for free from a constant-one
+// column appended to X / H1.  Parameter gradients accumulate in shared memory / registers across all tiles of the
+// persistent CTA and are flushed with one atomic pass at the end.  Gradient operands are rescaled per tile by a
+// power of two so that they sit in fp16's normal range.
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -27,7 +28,8 @@
 namespace {
 
 constexpr int ROWS = 128;
-constexpr int THREADS = 128;
+constexpr int CG = 4;                 // column groups: 4 threads share a row, 16 accumulator columns each
+constexpr int THREADS = ROWS * CG;
 constexpr int W = 64;
 constexpr int MAX_OUT = 8;
 constexpr float BETA = 100.f;
@@ -44,7 +46,7 @@ struct TcDims {
 
 struct SmemPlan {  // byte offsets
     uint32_t ax_hi, ax_lo, ah_hi, ah_lo, dz_hi, dz_lo, w0_hi, w0_lo, w1_hi, w1_lo, wl, b0, b1, bl, dw0, dw1, dwl, dbl, red,
-        mbar, tmem, total;
+        part, mbar, tmem, total;
 };
 
 __host__ __device__ inline SmemPlan make_plan(const TcDims &D, bool bwd)
@@ -61,11 +63,12 @@ __host__ __device__ inline SmemPlan make_plan(const TcDims &D, bool bwd)
     p.w1_hi = take(8 * 1024); p.w1_lo = take(8 * 1024);
     p.wl = take(MAX_OUT * W * 4);
     p.b0 = take(W * 4); p.b1 = take(W * 4); p.bl = take(MAX_OUT * 4);
-    p.dw0 = take(bwd ? (uint32_t)(W * D.K0 * 4) : 0);
-    p.dw1 = take(bwd ? W * 72 * 4 : 0);
+    p.dw0 = take(bwd ? (uint32_t)(W * (D.K0 + 1) * 4) : 0);
+    p.dw1 = take(bwd ? W * 73 * 4 : 0);
     p.dwl = take(bwd ? MAX_OUT * W * 4 : 0);
     p.dbl = take(bwd ? MAX_OUT * 4 : 0);
     p.red = take(64 * 4);
+    p.part = take(bwd ? 0 : (uint32_t)(CG * ROWS * MAX_OUT * 4));
     p.mbar = take(16);
     p.tmem = take(16);
     p.total = o;
@@ -157,22 +160,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[16])
 }
 
 // ---- numerics ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float act_fwd(float z, int act)
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float z)
 {
-    if (act == IA_ACT_SOFTPLUS100) {
+    if (ACT == IA_ACT_SOFTPLUS100) {
         const float t = z * BETA;
         return t > 20.f ? z : __logf(1.0f + __expf(t)) * (1.0f / BETA);
     }
     return fmaxf(z, 0.f);
 }
 
-__device__ __forceinline__ float act_bwd_from_out(float h, int act)
+template <int ACT>
+__device__ __forceinline__ float act_bwd_from_out(float h)
 {
-    if (act == IA_ACT_SOFTPLUS100) return 1.0f - __expf(-BETA * h);
+    if (ACT == IA_ACT_SOFTPLUS100) return 1.0f - __expf(-BETA * h);  // sigmoid(beta z) = 1 - exp(-beta h)
     return h > 0.f ? 1.f : 0.f;
 }
 
-// store 8 consecutive K-values of this thread's row as the fp16 (hi, lo) pair of 16-byte core-matrix rows
+// store 8 consecutive K-values of a row as the fp16 (hi, lo) pair of 16-byte core-matrix rows
 __device__ __forceinline__ void store_split8(char *hi_base, char *lo_base, uint32_t off, const float (&a)[8])
 {
     __half2 h[4], l[4];
@@ -241,35 +246,14 @@ __device__ __forceinline__ void stage_weight(char *smem, uint32_t hi_off, uint32
     }
 }
 
-// this thread's input row -> A_X (K0 columns: inputs, then the constant one, then zeros)
-__device__ __forceinline__ void stage_input_row(char *smem, const SmemPlan &P, const TcDims &D, const float *__restrict__ in0,
-                                                const float *__restrict__ in1, int64_t row, bool valid)
-{
-    const int r = threadIdx.x;
-    for (int c8 = 0; c8 < D.K0 / 8; ++c8) {
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = 8 * c8 + j;
-            float v = 0.f;
-            if (valid) {
-                if (c < D.n_in0) v = fmaf(__ldg(in0 + row * D.n_in0 + c), D.s0, D.o0);
-                else if (c < D.din) v = __ldg(in1 + row * D.n_in1 + (c - D.n_in0));
-                else if (c == D.din) v = 1.0f;
-            }
-            a[j] = v;
-        }
-        store_split8(smem + P.ax_hi, smem + P.ax_lo, (uint32_t)c8 * 2048u + (uint32_t)r * 16u, a);
-    }
-}
-
 struct Ctx {
     char *smem;
     SmemPlan P;
     uint32_t sbase;      // shared address of smem[0]
     uint32_t tmem;       // TMEM base address (lane 0, column 0)
-    uint32_t lane_addr;  // this warp's lane offset in TMEM address format
+    uint32_t lane_addr;  // this warp's lane-quarter offset in TMEM address format
     uint32_t phase;
+    int r, cg;           // row of the tile / column group (16 accumulator columns) owned by this thread
 };
 
 // all threads: make operand writes visible to the async proxy, sync, thread 0 issues via `issue`, everyone waits
@@ -289,23 +273,26 @@ __device__ __forceinline__ void run_mma(Ctx &c, F issue)
     tc_fence_after();
 }
 
+template <int NOU>
 __device__ __forceinline__ void setup_common(Ctx &c, const TcDims &D, const float *__restrict__ params)
 {
     const int tid = threadIdx.x;
     char *smem = c.smem;
+    c.r = tid & (ROWS - 1);
+    c.cg = tid >> 7;
     stage_weight(smem, c.P.w0_hi, c.P.w0_lo, params + D.pW0, D.din, D.K0);
     if (D.nh == 2) stage_weight(smem, c.P.w1_hi, c.P.w1_lo, params + D.pW1, W, W);
     float *wl = reinterpret_cast<float *>(smem + c.P.wl);
-    for (int i = tid; i < D.nou * W; i += THREADS) wl[i] = __ldg(params + D.pWl + i);
+    for (int i = tid; i < NOU * W; i += THREADS) wl[i] = i < D.nou * W ? __ldg(params + D.pWl + i) : 0.f;
     float *b0 = reinterpret_cast<float *>(smem + c.P.b0), *b1 = reinterpret_cast<float *>(smem + c.P.b1);
     float *bl = reinterpret_cast<float *>(smem + c.P.bl);
     for (int i = tid; i < W; i += THREADS) {
         b0[i] = __ldg(params + D.pb0 + i);
         b1[i] = D.nh == 2 ? __ldg(params + D.pb1 + i) : 0.f;
     }
-    if (tid < D.nou) bl[tid] = __ldg(params + D.pbl + tid);
+    if (tid < MAX_OUT) bl[tid] = tid < D.nou ? __ldg(params + D.pbl + tid) : 0.f;
     // constant-one column of the H1 buffer (chunk 8): hi = (1, 0, ..., 0), lo = 0  -> bias gradient of layer 1
-    {
+    if (tid < ROWS) {
         float a[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         store_split8(smem + c.P.ah_hi, smem + c.P.ah_lo, 8u * 2048u + (uint32_t)tid * 16u, a);
     }
@@ -320,7 +307,7 @@ __device__ __forceinline__ void setup_common(Ctx &c, const TcDims &D, const floa
     __syncthreads();
     tc_fence_after();
     c.tmem = *reinterpret_cast<volatile uint32_t *>(smem + c.P.tmem);
-    c.lane_addr = ((uint32_t)(tid >> 5) * 32u) << 16;
+    c.lane_addr = ((uint32_t)((tid >> 5) & 3) * 32u) << 16;
     c.phase = 0;
 }
 
@@ -333,34 +320,51 @@ __device__ __forceinline__ void teardown(Ctx &c)
     }
 }
 
-// hidden layer epilogue: TMEM accumulator (64 columns) -> h = act(z + b); optionally write h to the H1 buffer and/or
-// accumulate the fp32 output layer on the fly.  `keep`: callback (k0, h[16]).
-template <typename F>
-__device__ __forceinline__ void hidden_epilogue(Ctx &c, const float *__restrict__ bias, int act, bool write_h1, F keep)
+// this thread's share of the input row -> A_X (K0 columns: inputs, then the constant one, then zeros)
+__device__ __forceinline__ void stage_input(Ctx &c, const TcDims &D, const float *__restrict__ in0, const float *__restrict__ in1,
+                                            int64_t row, bool valid)
 {
-    const int r = threadIdx.x;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tmem_ld16(c.tmem + c.lane_addr + D0_COL + 16u * q, v);
+    for (int c8 = c.cg; c8 < D.K0 / 8; c8 += CG) {
+        float a[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j] + bias[16 * q + j], act);
-        if (write_h1) {
-            float a[8];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j];
-                store_split8(c.smem + c.P.ah_hi, c.smem + c.P.ah_lo, (uint32_t)(2 * q + half) * 2048u + (uint32_t)r * 16u, a);
+        for (int j = 0; j < 8; ++j) {
+            const int col = 8 * c8 + j;
+            float v = 0.f;
+            if (valid) {
+                if (col < D.n_in0) v = fmaf(__ldg(in0 + row * D.n_in0 + col), D.s0, D.o0);
+                else if (col < D.din) v = __ldg(in1 + row * D.n_in1 + (col - D.n_in0));
+                else if (col == D.din) v = 1.0f;
             }
+            a[j] = v;
         }
-        keep(16 * q, v);
+        store_split8(c.smem + c.P.ax_hi, c.smem + c.P.ax_lo, (uint32_t)c8 * 2048u + (uint32_t)c.r * 16u, a);
+    }
+}
+
+// this thread's 16 accumulator columns of a hidden layer: h = act(z + b)
+template <int ACT>
+__device__ __forceinline__ void hidden_cols(Ctx &c, const float *__restrict__ bias, float (&h)[16])
+{
+    tmem_ld16(c.tmem + c.lane_addr + D0_COL + 16u * c.cg, h);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + bias[16 * c.cg + j]);
+}
+
+__device__ __forceinline__ void store_cols16(Ctx &c, uint32_t hi_off, uint32_t lo_off, const float (&v)[16])
+{
+    float a[8];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j];
+        store_split8(c.smem + hi_off, c.smem + lo_off, (uint32_t)(2 * c.cg + half) * 2048u + (uint32_t)c.r * 16u, a);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
+template <int ACT, int NOU>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                   const float *__restrict__ params, float *__restrict__ out, int64_t ld_out)
@@ -370,45 +374,49 @@ mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     c.smem = smem;
     c.P = make_plan(D, false);
     c.sbase = smem_u32(smem);
-    setup_common(c, D, params);
+    setup_common<NOU>(c, D, params);
     const float *b0 = reinterpret_cast<const float *>(smem + c.P.b0), *b1 = reinterpret_cast<const float *>(smem + c.P.b1);
     const float *bl = reinterpret_cast<const float *>(smem + c.P.bl), *wl = reinterpret_cast<const float *>(smem + c.P.wl);
+    float *part = reinterpret_cast<float *>(smem + c.P.part);      // [CG][ROWS][NOU] partial output sums
     const uint32_t idesc_fwd = make_idesc(128, W, 0, 0);
     const Operand AX = act_as_A_kmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
     const Operand AH = act_as_A_kmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
     const Operand BW0 = w_as_B_kmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
     const Operand BW1 = w_as_B_kmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
-    const int r = threadIdx.x;
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * ROWS + r;
+        const int64_t row = tile * ROWS + c.r;
         const bool valid = row < n;
-        stage_input_row(smem, c.P, D, in0, in1, row, valid);
+        stage_input(c, D, in0, in1, row, valid);
         run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AX, BW0, idesc_fwd, D.K0 / 16); });
-        float acc[MAX_OUT];
+        float h[16];
+        hidden_cols<ACT>(c, b0, h);
+        if (D.nh == 2) {
+            store_cols16(c, c.P.ah_hi, c.P.ah_lo, h);
+            run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AH, BW1, idesc_fwd, W / 16); });
+            hidden_cols<ACT>(c, b1, h);
+        }
+        // output layer in fp32: partial dot products over this thread's 16 hidden units, combined through smem
 #pragma unroll
-        for (int o = 0; o < MAX_OUT; ++o) acc[o] = o < D.nou ? bl[o] : 0.f;
-        auto out_layer = [&](int k0, const float(&h)[16]) {
+        for (int o = 0; o < NOU; ++o) {
+            float acc = 0.f;
 #pragma unroll
-            for (int o = 0; o < MAX_OUT; ++o) {
+            for (int j = 0; j < 16; ++j) acc = fmaf(h[j], wl[o * W + 16 * c.cg + j], acc);
+            part[(c.cg * ROWS + c.r) * NOU + o] = acc;
+        }
+        __syncthreads();
+        if (c.cg == 0 && valid) {
+#pragma unroll
+            for (int o = 0; o < NOU; ++o) {
                 if (o < D.nou) {
+                    float acc = bl[o];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[o] = fmaf(h[j], wl[o * W + k0 + j], acc[o]);
+                    for (int g = 0; g < CG; ++g) acc += part[(g * ROWS + c.r) * NOU + o];
+                    out[row * ld_out + o] = acc;
                 }
             }
-        };
-        if (D.nh == 2) {
-            hidden_epilogue(c, b0, D.act, true, [](int, const float(&)[16]) {});
-            run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AH, BW1, idesc_fwd, W / 16); });
-            hidden_epilogue(c, b1, D.act, false, out_layer);
-        } else {
-            hidden_epilogue(c, b0, D.act, false, out_layer);
         }
-        if (valid) {
-#pragma unroll
-            for (int o = 0; o < MAX_OUT; ++o)
-                if (o < D.nou) out[row * ld_out + o] = acc[o];
-        }
+        // `part` is written again only after the barriers of the next tile's run_mma
     }
     teardown(c);
 }
@@ -423,22 +431,27 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// read a dW accumulator (M = 64 layout: output row o = 16*warp + lane for lane < 16) and add it, unscaled, to smem
+// read this thread's share of a dW accumulator (M = 64 layout: output row o = 16*(lane quarter) + lane for lane < 16;
+// 16-column chunk ci is handled by column group ci % CG) and add it, unscaled, to the padded smem accumulator
 __device__ __forceinline__ void drain_dw(Ctx &c, float *__restrict__ acc_smem, int n_cols, int ld, float inv_scale)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int o = 16 * warp + lane;
-    for (int c0 = 0; c0 < n_cols; c0 += 16) {
+    const int lane = threadIdx.x & 31;
+    const int o = 16 * ((threadIdx.x >> 5) & 3) + lane;
+    for (int ci = c.cg; ci * 16 < n_cols; ci += CG) {
+        const int c0 = 16 * ci;
         float v[16];
         const int m = n_cols - c0 >= 16 ? 16 : 8;
         if (m == 16) tmem_ld16(c.tmem + c.lane_addr + D1_COL + (uint32_t)c0, v);
         else tmem_ld8(c.tmem + c.lane_addr + D1_COL + (uint32_t)c0, v);
         if (lane < 16) {
-            for (int j = 0; j < m; ++j) acc_smem[o * ld + c0 + j] += v[j] * inv_scale;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < m) acc_smem[o * ld + c0 + j] += v[j] * inv_scale;
         }
     }
 }
 
+template <int ACT, int NOU>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                   const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
@@ -449,26 +462,29 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     c.smem = smem;
     c.P = make_plan(D, true);
     c.sbase = smem_u32(smem);
-    const int tid = threadIdx.x, r = tid, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld0 = D.K0 + 1, ld1 = 73;   // odd leading dimensions: conflict-free row-per-lane accumulation
     float *dw0 = reinterpret_cast<float *>(smem + c.P.dw0), *dw1 = reinterpret_cast<float *>(smem + c.P.dw1);
     float *dwl = reinterpret_cast<float *>(smem + c.P.dwl), *dbl = reinterpret_cast<float *>(smem + c.P.dbl);
     float *red = reinterpret_cast<float *>(smem + c.P.red);
-    for (int i = tid; i < W * D.K0; i += THREADS) dw0[i] = 0.f;
-    for (int i = tid; i < W * 72; i += THREADS) dw1[i] = 0.f;
+    for (int i = tid; i < W * ld0; i += THREADS) dw0[i] = 0.f;
+    for (int i = tid; i < W * ld1; i += THREADS) dw1[i] = 0.f;
     for (int i = tid; i < MAX_OUT * W; i += THREADS) dwl[i] = 0.f;
     if (tid < MAX_OUT) dbl[tid] = 0.f;
-    setup_common(c, D, params);
+    setup_common<NOU>(c, D, params);
     const float *b0 = reinterpret_cast<const float *>(smem + c.P.b0), *b1 = reinterpret_cast<const float *>(smem + c.P.b1);
     const float *wl = reinterpret_cast<const float *>(smem + c.P.wl);
-    // bound of |W_last| for the per-tile gradient scale
+    // bound of sum_o |W_last[o][k]| for the per-tile gradient scale
     float wmax = 0.f;
-    for (int i = tid; i < D.nou * W; i += THREADS) wmax = fmaxf(wmax, fabsf(wl[i]));
+    for (int i = tid; i < NOU * W; i += THREADS) wmax = fmaxf(wmax, fabsf(wl[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) red[tid >> 5] = wmax;
+    if (lane == 0) red[warp] = wmax;
     __syncthreads();
-    wmax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    wmax = fmaxf(wmax * (float)D.nou, 1e-30f);
+    wmax = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) wmax = fmaxf(wmax, red[w]);
+    wmax = fmaxf(wmax * (float)NOU, 1e-30f);
     __syncthreads();
 
     const bool want_dx = din0 != nullptr || din1 != nullptr;
@@ -488,71 +504,80 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     const Operand BW0T = w_as_B_mnmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
     const Operand BW1T = w_as_B_mnmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
 
+    // persistent per-thread partial sums of dW_last[o][16*cg + j] and db_last[o] (reduced over rows at the very end)
+    constexpr bool REG_DWL = NOU <= 3;
+    constexpr int NREG = REG_DWL ? NOU : 1;
+    float gwl[NREG][16];
+    float gbl[NOU];
+#pragma unroll
+    for (int o = 0; o < NOU; ++o) gbl[o] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NREG; ++o)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gwl[o][j] = 0.f;
+
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * ROWS + r;
+        const int64_t row = tile * ROWS + c.r;
         const bool valid = row < n;
-        stage_input_row(smem, c.P, D, in0, in1, row, valid);
-        float dy[MAX_OUT];
+        stage_input(c, D, in0, in1, row, valid);
+        float dy[NOU];
         float dymax = 0.f;
 #pragma unroll
-        for (int o = 0; o < MAX_OUT; ++o) {
+        for (int o = 0; o < NOU; ++o) {
             dy[o] = (valid && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
             dymax = fmaxf(dymax, fabsf(dy[o]));
+            if (c.cg == 0) gbl[o] += dy[o];
         }
         // per-tile power-of-two scale that bounds |dZ| of the tile by 2^6 (fp16 normal range, 2^10 headroom for dH)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dymax = fmaxf(dymax, __shfl_xor_sync(0xffffffffu, dymax, o));
-        if (lane == 0) red[tid >> 5] = dymax;
+        if (lane == 0) red[warp] = dymax;
         // ---- recompute forward
-        run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AX, BW0, idesc_fwd, D.K0 / 16); });   // (contains the __syncthreads for `red`)
-        dymax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AX, BW0, idesc_fwd, D.K0 / 16); });   // (its barrier publishes `red`)
+        dymax = 0.f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) dymax = fmaxf(dymax, red[w]);
         int e = 0;
         frexpf(fmaxf(dymax * wmax, 1e-30f), &e);                 // dymax*wmax = m * 2^e, m in [0.5, 1)
         e = max(min(e, 60), -60);
         const float scale = ldexpf(1.0f, 6 - e), inv_scale = ldexpf(1.0f, e - 6);
+        float h[16];
         const float *bL = b0;
         if (D.nh == 2) {
-            hidden_epilogue(c, b0, D.act, true, [](int, const float(&)[16]) {});
+            hidden_cols<ACT>(c, b0, h);
+            store_cols16(c, c.P.ah_hi, c.P.ah_lo, h);
             run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AH, BW1, idesc_fwd, W / 16); });
             bL = b1;
         }
         // ---- last hidden layer: h (recomputed), output-layer gradients in fp32 registers, dZ_last -> smem (scaled)
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            float v[16];
-            tmem_ld16(c.tmem + c.lane_addr + D0_COL + 16u * q, v);
+        hidden_cols<ACT>(c, bL, h);
+        {
             float dz[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int k = 16 * q + j;
-                const float h = act_fwd(v[j] + bL[k], D.act);
+                const int k = 16 * c.cg + j;
                 float dh = 0.f;
 #pragma unroll
-                for (int o = 0; o < MAX_OUT; ++o)
-                    if (o < D.nou) dh = fmaf(dy[o], wl[o * W + k], dh);
-                dz[j] = dh * act_bwd_from_out(h, D.act) * scale;
-                v[j] = h;
+                for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
+                dz[j] = dh * act_bwd_from_out<ACT>(h[j]) * scale;
             }
-            // dW_last[o][k] += sum_rows dy[o] * h[k]
-            for (int o = 0; o < D.nou; ++o) {
+            if (REG_DWL) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float s = warp_sum(dy[o] * v[j]);
-                    if (lane == 0) atomicAdd(&dwl[o * W + 16 * q + j], s);
+                for (int o = 0; o < NREG; ++o)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) gwl[o][j] = fmaf(dy[o], h[j], gwl[o][j]);
+            } else {
+#pragma unroll 1
+                for (int o = 0; o < NOU; ++o) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float s = warp_sum(dy[o] * h[j]);
+                        if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
+                    }
                 }
             }
-            float a[8];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = dz[8 * half + j];
-                store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, (uint32_t)(2 * q + half) * 2048u + (uint32_t)r * 16u, a);
-            }
-        }
-        for (int o = 0; o < D.nou; ++o) {
-            const float s = warp_sum(dy[o]);
-            if (lane == 0) atomicAdd(&dbl[o], s);
+            store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
         }
         if (D.nh == 2) {
             // ---- dH1 = dZ2 W1 ; dW1 (+db1) = dZ2^T [H1 | 1]
@@ -560,21 +585,18 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
                 issue_gemm(c.tmem + D0_COL, ADZ, BW1T, idesc_dh, W / 16);
                 issue_gemm(c.tmem + D1_COL, DZT, HT, idesc_dw1, ROWS / 16);
             });
-            drain_dw(c, dw1, 72, 72, inv_scale);
+            drain_dw(c, dw1, 72, ld1, inv_scale);
             // dZ1 = dH1 (*) act'(H1), H1 re-read from its operand buffer; overwrites the dZ buffer (its MMAs are complete)
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                float v[16];
-                tmem_ld16(c.tmem + c.lane_addr + D0_COL + 16u * q, v);
+            float v[16];
+            tmem_ld16(c.tmem + c.lane_addr + D0_COL + 16u * c.cg, v);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float h[8], a[8];
-                    const uint32_t off = (uint32_t)(2 * q + half) * 2048u + (uint32_t)r * 16u;
-                    load_split8(smem + c.P.ah_hi, smem + c.P.ah_lo, off, h);
+            for (int half = 0; half < 2; ++half) {
+                float hh[8], a[8];
+                const uint32_t off = (uint32_t)(2 * c.cg + half) * 2048u + (uint32_t)c.r * 16u;
+                load_split8(smem + c.P.ah_hi, smem + c.P.ah_lo, off, hh);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * act_bwd_from_out(h[j], D.act);
-                    store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, off, a);
-                }
+                for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * act_bwd_from_out<ACT>(hh[j]);
+                store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, off, a);
             }
         }
         // ---- dX = dZ1 W0 ; dW0 (+db0) = dZ1^T [X | 1]
@@ -582,9 +604,10 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
             if (want_dx) issue_gemm(c.tmem + D0_COL, ADZ, BW0T, idesc_dx, W / 16);
             issue_gemm(c.tmem + D1_COL, DZT, XT, idesc_dw0, ROWS / 16);
         });
-        drain_dw(c, dw0, D.K0, D.K0, inv_scale);
+        drain_dw(c, dw0, D.K0, ld0, inv_scale);
         if (want_dx) {
-            for (int c0 = 0; c0 < D.din; c0 += 16) {
+            for (int ci = c.cg; ci * 16 < D.din; ci += CG) {
+                const int c0 = 16 * ci;
                 float v[16];
                 tmem_ld16(c.tmem + c.lane_addr + D0_COL + (uint32_t)c0, v);
                 if (valid) {
@@ -601,19 +624,37 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
             }
         }
     }
+    // ---- reduce the register-resident output-layer gradients over the rows of the CTA
+    if (REG_DWL) {
+#pragma unroll
+        for (int o = 0; o < NREG; ++o) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float s = warp_sum(gwl[o][j]);
+                if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NOU; ++o) {
+        const float sb = warp_sum(gbl[o]);
+        if (lane == 0 && c.cg == 0) atomicAdd(&dbl[o], sb);
+    }
     __syncthreads();
     // ---- flush parameter gradients
     if (dparams != nullptr) {
         for (int i = tid; i < W * D.K0; i += THREADS) {
             const int o = i / D.K0, col = i - o * D.K0;
-            if (col < D.din) atomicAdd(dparams + D.pW0 + o * D.din + col, dw0[i]);
-            else if (col == D.din) atomicAdd(dparams + D.pb0 + o, dw0[i]);
+            const float g = dw0[o * ld0 + col];
+            if (col < D.din) atomicAdd(dparams + D.pW0 + o * D.din + col, g);
+            else if (col == D.din) atomicAdd(dparams + D.pb0 + o, g);
         }
         if (D.nh == 2) {
             for (int i = tid; i < W * 72; i += THREADS) {
                 const int o = i / 72, col = i - o * 72;
-                if (col < W) atomicAdd(dparams + D.pW1 + o * W + col, dw1[i]);
-                else if (col == W) atomicAdd(dparams + D.pb1 + o, dw1[i]);
+                const float g = dw1[o * ld1 + col];
+                if (col < W) atomicAdd(dparams + D.pW1 + o * W + col, g);
+                else if (col == W) atomicAdd(dparams + D.pb1 + o, g);
             }
         }
         for (int i = tid; i < D.nou * W; i += THREADS) atomicAdd(dparams + D.pWl + i, dwl[i]);
@@ -669,11 +710,19 @@ int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
     if (n == 0) return IA_OK;
     const SmemPlan P = make_plan(D, false);
     IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_fwd: needs %u B of shared memory", P.total);
-    IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));
     const int64_t n_tiles = ia_ceil_div(n, ROWS);
     const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));   // TMEM: 2 x 256 columns
     const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
-    mlp_tc_fwd_kernel<<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, out, ld_out);
+#define IA_TC_FWD(ACT, NOU)                                                                                                       \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_fwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total)); \
+        mlp_tc_fwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, out, ld_out);    \
+    } while (0)
+    const bool sp = D.act == IA_ACT_SOFTPLUS100;
+    if (D.nou == 1) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_FWD(IA_ACT_RELU, 1); }
+    else if (D.nou <= 3) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_FWD(IA_ACT_RELU, 3); }
+    else { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_FWD(IA_ACT_RELU, 8); }
+#undef IA_TC_FWD
     IA_LAUNCH_OK("mlp_tc_fwd_kernel");
     return IA_OK;
 }
@@ -693,11 +742,20 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
     if (n == 0) return IA_OK;
     const SmemPlan P = make_plan(D, true);
     IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_bwd: needs %u B of shared memory", P.total);
-    IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));
     const int64_t n_tiles = ia_ceil_div(n, ROWS);
     const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));
     const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
-    mlp_tc_bwd_kernel<<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams);
+#define IA_TC_BWD(ACT, NOU)                                                                                                       \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total)); \
+        mlp_tc_bwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout, ld_dout,   \
+                                                                                        din0, din1, dparams);                    \
+    } while (0)
+    const bool sp = D.act == IA_ACT_SOFTPLUS100;
+    if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
+    else if (D.nou <= 3) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_BWD(IA_ACT_RELU, 3); }
+    else { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_BWD(IA_ACT_RELU, 8); }
+#undef IA_TC_BWD
     IA_LAUNCH_OK("mlp_tc_bwd_kernel");
     return IA_OK;
 }

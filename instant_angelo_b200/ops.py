@@ -184,7 +184,8 @@ class _MLPFn(torch.autograd.Function):
         n = (in1 if in1 is not None else in0).shape[0]
         out = torch.empty(n, n_out_used, device=params.device, dtype=torch.float32)
         _run("ia_mlp_fwd", C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), n_out_used, L.ptr(out),
-             n_out_used, L.stream(), work=n * mlp_flops_per_row(desc, n_out_used))
+             n_out_used, L.stream(), work=n * mlp_flops_per_row(desc, n_out_used),
+             tag=f"{desc.n_in0 + desc.n_in1}>{n_out_used}/{desc.n_out}")
         ctx.save_for_backward(in0, in1, params)
         ctx.desc, ctx.nou = desc, n_out_used
         return out
@@ -202,7 +203,8 @@ class _MLPFn(torch.autograd.Function):
         dp = torch.zeros_like(params) if needp else None
         if n > 0:
             _run("ia_mlp_bwd", C.byref(ctx.desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dout), ctx.nou,
-                 ctx.nou, L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou))
+                 ctx.nou, L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou),
+                 tag=f"{ctx.desc.n_in0 + ctx.desc.n_in1}>{ctx.nou}/{ctx.desc.n_out}")
         return d0, d1, dp, None, None
 
 

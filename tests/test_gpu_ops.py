@@ -252,6 +252,7 @@ def _rays(n, seed, outside_frac=0.3):
     o[:k] *= 4.0
     tgt = (torch.rand(n, 3, generator=g) - 0.5) * 1.6
     tgt[-n // 16:] += 5.0
+    tgt[: max(4, k // 8)] += 8.0          # origins outside the box looking away: misses (t = 1e10)
     d = torch.nn.functional.normalize(tgt - o, dim=-1)
     # axis-aligned rays (zero direction components exercise the inf/NaN paths of the DDA)
     d[k] = torch.tensor([1.0, 0.0, 0.0])

@@ -1,0 +1,28 @@
+"""Small driver for ncu: one forward + backward of the geometry tap network (35 -> 64 -> 64 -> 1 of 65)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from instant_angelo_b200 import _lib as L, ops
+
+prec = L.IA_MLP_TC_F16 if (len(sys.argv) < 2 or sys.argv[1] == "tc") else L.IA_MLP_FP32
+case = sys.argv[2] if len(sys.argv) > 2 else "geo"
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
+torch.manual_seed(0)
+if case == "geo":
+    n0, n1, nh, nout, act, nou = 3, 32, 2, 65, L.IA_ACT_SOFTPLUS100, 1
+else:
+    n0, n1, nh, nout, act, nou = 0, 87, 2, 3, L.IA_ACT_RELU, 3
+desc = ops.make_mlp_desc(n0, n1, nh, nout, act, 2.0, -1.0, prec)
+npar = L.load().ia_mlp_param_count(desc)
+flat = (torch.randn(npar, device="cuda") * 0.15).requires_grad_(True)
+a = torch.rand(n, n0, device="cuda").requires_grad_(True) if n0 else None
+b = (torch.randn(n, n1, device="cuda") * 0.3).requires_grad_(True)
+go = torch.randn(n, nou, device="cuda") * 1e-4
+for it in range(3):
+    y = ops.mlp_apply(a, b, flat, desc, nou)
+    y.backward(go)
+torch.cuda.synchronize()
+e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+e0.record(); y = ops.mlp_apply(a, b, flat, desc, nou); e1.record(); y.backward(go); e2.record()
+torch.cuda.synchronize()
+print(f"{case} prec={prec} n={n}: fwd {e0.elapsed_time(e1):.3f} ms, bwd {e1.elapsed_time(e2):.3f} ms")

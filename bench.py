@@ -336,14 +336,16 @@ def run_b200(args):
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.mlp != "tc" else "f16 operands / f32 accumulate (MLP), f32 elsewhere", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": "neuralangelo-colmap_sparse.yaml, grad_type=finite_difference, synthetic 512x512 cameras around an "
                                "analytic sphere (BASELINE.json configs[1])",
                    "rays_per_gpu_per_step": n_rays, "global_rays_per_step": n_rays * world, "num_samples_per_ray": 512,
                    "num_samples_per_ray_bg": 256, "hash_levels_active": 16, "log2_hashmap_size": 19, "global_step": GLOBAL_STEP0,
                    "mean_fg_samples_per_ray": fg_total / total_rays, "mean_samples_per_ray_full": full_total / total_rays,
                    "samples_per_s": full_total / (ms_total / 1e3), "hash_point_evals_per_s": (13 * fg_total + (full_total - fg_total)) / (ms_total / 1e3),
-                   "mlp": args.mlp, "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
+                   "mlp": ("tcgen05 tensor cores, 3xf16-split operands + fp32 accumulate (fp32-equivalent, parity-tested at 1e-3); 65-wide "
+                           "centre evaluation on the fp32 FFMA kernel") if args.mlp == "tc" else "fp32 FFMA kernels",
+                   "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
                    "l2": "per-step working set (hash tables 112 MB + >1 GB of per-sample activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)"},
         "clocks": clocks,
@@ -354,7 +356,7 @@ def run_b200(args):
         "kernels": per_kernel,
         "hashgrid_microbench": hg,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -400,14 +402,20 @@ def cpu_baseline_leg(cfg, model, args):
     torch.set_num_threads(cores)
     ref = build_oracle(cfg, fg_binary=model.occupancy_grid.binary.cpu())
     ref.occupancy_grid_bg.binary = model.occupancy_grid_bg.binary.cpu()
-    n = args.cpu_rays
-    buf, bg = make_batches(1, n, 0, pin=False)[0]
-    b, bgc = unpack_batch(buf, bg)
+    def run(n_rays):
+        buf, bg = make_batches(1, n_rays, 0, pin=False)[0]
+        b, bgc = unpack_batch(buf, bg)
+        t = time.perf_counter()
+        _, n_s = oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bgc, GLOBAL_STEP0)
+        return time.perf_counter() - t, n_s
+
     t0 = time.perf_counter()
-    oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bgc, GLOBAL_STEP0)   # warm-up
+    probe_s, _ = run(32)                                        # warm-up + calibration
+    probe_s, _ = run(32)
+    n = args.cpu_rays if args.cpu_rays > 0 else max(32, min(4096, int(32 * 12.0 / max(probe_s, 1e-3))))   # ~12 s of CPU work
     t1 = time.perf_counter()
-    _, ns = oracle_step(ref, cfg, b["rays"], b["rgb"], b["pts"], b["pts_normal"], b["pts_weights"], bgc, GLOBAL_STEP0)
-    t2 = time.perf_counter()
+    dt, ns = run(n)
+    t2 = t1 + dt
     return {"value": n / (t2 - t1), "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{n} rays of the same workload (same occupancy grids, {ns / n:.1f} samples/ray), forward + losses + backward "
                       f"through the CPU oracle (oracle/model_ref.py, PyTorch fp32, {cores} threads); warm-up run {t1 - t0:.1f} s, timed run {t2 - t1:.1f} s"}
@@ -425,7 +433,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     cfg = neuralangelo_colmap_sparse("finite_difference")
     ref = build_oracle(cfg)
-    n = args.cpu_rays
+    n = args.cpu_rays if args.cpu_rays > 0 else 192
     K, W = args.steps, args.warmup
     batches = make_batches(K + W, n, 0, pin=False)
     gs = GLOBAL_STEP0
@@ -450,18 +458,38 @@ def run_reference(args):
                        "note": "reference GPU path (tinycudann + nerfacc) is not installable in this image; CPU oracle port timed instead"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """Print THE JSON line on the real stdout (everything else a library prints -- e.g. NCCL's version banner --
+    has been routed to stderr by main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # stray prints of libraries go to stderr; stdout carries exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
-    ap.add_argument("--mlp", default="fp32", choices=["fp32", "tc"], help="MLP arithmetic: fp32 FFMA (VanillaMLP) or tcgen05 f16")
-    ap.add_argument("--cpu-rays", type=int, default=48, help="rays per step of the bounded CPU-oracle sample")
+    ap.add_argument("--mlp", default="tc", choices=["fp32", "tc"],
+                    help="MLP arithmetic: tc = tcgen05 tensor cores with 3xf16-split operands (fp32-equivalent, default); fp32 = FFMA kernels")
+    ap.add_argument("--cpu-rays", type=int, default=0,
+                    help="rays per step of the bounded CPU-oracle sample (0: ~12 s of CPU work for cpu_baseline, 192 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

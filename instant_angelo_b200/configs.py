@@ -67,6 +67,8 @@ def neuralangelo_colmap_dense(grad_type: str = "analytic", log2_hashmap_size: in
     longer-lived point losses.  BASELINE config 3 runs it with log2_hashmap_size=21 and 256 samples/ray."""
     cfg = neuralangelo_colmap_sparse(grad_type, log2_hashmap_size)
     cfg.model.texture_bg["name"] = "volume-dual-color"
+    cfg.model.geometry.isosurface["threshold"] = 0.0
+    cfg.model.texture.pop("diffuse_warmup_steps", None)
     cfg.system.loss["lambda_curvature"] = [0, 0, 0.05, 5000]
     cfg.system.loss["lambda_sdf_l1"] = [0, 1, 0.1, 20000]
     return cfg
@@ -80,7 +82,7 @@ def neuralangelo_colmap_sparse_wreflection(grad_type: str = "analytic") -> Confi
     m["num_samples_per_ray"] = 1024
     m["texture"] = to_config({"name": "volume-dual-colorV3", "input_feature_dim": 65 + 6, "diffuse_warmup_steps": 5000,
                               "dir_encoding_config": _sh(3), "mlp_network_config": _mlp(2),
-                              "weitht_network_config": _mlp(2, output_activation="sigmoid"), "color_activation": "sigmoid"})
+                              "weitht_network_config": _mlp(1, output_activation="sigmoid"), "color_activation": "sigmoid"})
     cfg.system.loss["lambda_rgb_mse"] = 5.0
     cfg.system.loss["lambda_curvature"] = [0, 0, 1.0e-3, 5000]
     cfg.system.loss["lambda_sdf_l1"] = 0.0

@@ -22,7 +22,7 @@ def golden_model_config(texture: str = "volume-dual-color", learned_background: 
     mlp1 = dict(mlp2, n_hidden_layers=1)
     if texture == "volume-dual-colorV3":
         tex = {"name": texture, "input_feature_dim": feature_dim + 6, "dir_encoding_config": {"otype": "SphericalHarmonics", "degree": 3},
-               "mlp_network_config": mlp2, "weitht_network_config": dict(mlp2, output_activation="sigmoid"),
+               "mlp_network_config": mlp2, "weitht_network_config": dict(mlp1, output_activation="sigmoid"),
                "color_activation": "sigmoid"}
     else:
         tex = {"name": texture, "input_feature_dim": feature_dim + 6, "dir_encoding_config": {"otype": "SphericalHarmonics", "degree": 4},

@@ -1,0 +1,190 @@
+"""CPU: known-answer tests for the third-party restatements in oracle/ (SURVEY.md section 8c "golden vectors to
+author"): hash-grid indexing, SH basis, AABB / marching (C build vs independent numpy restatement vs hand counts),
+compositing series, sphere-init analytic scene."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as mr
+from oracle import nerfacc_ref as nf
+from oracle import tcnn_ref as tc
+
+PLS = 1.3195079107728942
+
+
+def test_hashgrid_index_kat():
+    plan = tc.grid_plan(16, 2, 19, 32, PLS)
+    # dense level 0 (res 32, scale 31): x=(0,0,0) -> pos 0.5 -> cell 0, corners idx = dx + 32 dy + 1024 dz
+    idx = tc.corner_indices(torch.zeros(1, 3), plan, 0)[0].tolist()
+    assert idx == [0, 1, 32, 33, 1024, 1025, 1056, 1057]
+    # cell centre (i+0.5)/31 of cell (3,5,7)
+    x = torch.tensor([[3.0 / 31, 5.0 / 31, 7.0 / 31]])
+    assert tc.corner_indices(x, plan, 0)[0, 0].item() == 3 + 5 * 32 + 7 * 1024
+    # hashed level 4 (res 98 > 2^19 entries): coherent prime hash, uint32 wrap, modulo table size
+    s4 = plan.scale[4]
+    x = torch.tensor([[10.2 / s4, 20.2 / s4, 30.2 / s4]])
+    want = (10 ^ ((20 * 2654435761) & 0xFFFFFFFF) ^ ((30 * 805459861) & 0xFFFFFFFF)) % (1 << 19)
+    assert plan.hashed[4] and tc.corner_indices(x, plan, 4)[0, 0].item() == want
+    # index -> value ramp table: the encoding of a grid vertex returns that vertex's entry
+    tab = torch.arange(plan.n_params, dtype=torch.float32)
+    v = torch.tensor([[4.5 / 31, 9.5 / 31, 2.5 / 31]])          # pos = (5, 10, 3) exactly: weight 1 on corner 0
+    enc = tc.hashgrid_forward(v, tab, plan, 1)
+    e = 5 + 10 * 32 + 3 * 1024
+    assert enc[0, 0].item() == 2 * e and enc[0, 1].item() == 2 * e + 1 and enc[0, 2:].abs().sum() == 0
+
+
+def test_hashgrid_partition_of_unity_and_mask():
+    plan = tc.grid_plan(8, 2, 12, 4, 1.5)
+    x = torch.rand(200, 3)
+    ones = torch.ones(plan.n_params)
+    y = tc.hashgrid_forward(x, ones, plan)
+    assert torch.allclose(y, torch.ones_like(y), atol=1e-6)
+    t = torch.randn(plan.n_params)
+    full, part = tc.hashgrid_forward(x, t, plan), tc.hashgrid_forward(x, t, plan, 3)
+    assert torch.equal(part[:, :6], full[:, :6]) and part[:, 6:].abs().sum() == 0
+
+
+def test_hashgrid_input_gradient_matches_formula():
+    """d enc / d x = scale_l * sum over corner pairs (Appendix A.1) -- autograd vs finite differences in float64-ish."""
+    plan = tc.grid_plan(4, 2, 10, 4, 1.5)
+    t = torch.randn(plan.n_params, dtype=torch.float32)
+    x = (torch.rand(50, 3) * 0.9 + 0.05).requires_grad_(True)
+    y = tc.hashgrid_forward(x, t, plan)
+    g = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, g)
+    eps = 1e-4
+    for d in range(3):
+        dx = torch.zeros(3); dx[d] = eps
+        fd = ((tc.hashgrid_forward(x.detach() + dx, t, plan) - tc.hashgrid_forward(x.detach() - dx, t, plan)) * g).sum(1) / (2 * eps)
+        ok = (fd - gx[:, d]).abs() < 2e-2 * (1 + gx[:, d].abs())          # points next to a cell face are excluded by the tolerance
+        assert ok.float().mean() > 0.9
+
+
+def test_sh_basis_values():
+    d = torch.tensor([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    y = tc.sh_forward((d + 1) / 2, 4)
+    assert torch.allclose(y[:, 0], torch.full((3,), 0.28209479177387814))
+    assert abs(y[0, 2].item() - 0.48860251190291987) < 1e-6 and abs(y[1, 3].item() + 0.48860251190291987) < 1e-6
+    assert abs(y[0, 6].item() - (0.94617469575755997 - 0.31539156525251999)) < 1e-6
+    assert abs(y[2, 8].item() + 0.54627421529603959) < 1e-6
+    # orthonormality over the sphere (Monte-Carlo)
+    g = torch.Generator().manual_seed(0)
+    v = torch.nn.functional.normalize(torch.randn(200000, 3, generator=g), dim=-1)
+    Y = tc.sh_forward((v + 1) / 2, 4).double()
+    gram = Y.t() @ Y / v.shape[0] * 4 * math.pi
+    assert torch.allclose(gram, torch.eye(16, dtype=torch.float64), atol=0.03)
+
+
+def test_aabb_kat():
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    o = torch.tensor([[-3.0, 0, 0], [0.0, 0, 0], [-3.0, 5, 0], [0.5, 0.5, -4.0]])
+    d = torch.tensor([[1.0, 0, 0], [0.0, 1, 0], [1.0, 0, 0], [0.0, 0, 1.0]])
+    tmin, tmax = nf.ray_aabb_intersect(o, d, aabb)
+    assert tmin.tolist() == [2.0, 0.0, 1e10, 3.0] and tmax.tolist() == [4.0, 1.0, 1e10, 5.0]
+    tmin2, _ = nf.ray_aabb_intersect(o, d, aabb, clamp_zero=False)
+    assert tmin2[1].item() == -1.0
+
+
+def test_march_hand_counted_and_python_restatement():
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    grid = nf.OccupancyGrid(aabb, 4, nf.ContractionType.AABB)
+    # all-ones grid: an axis-aligned ray through the box, step 0.25 -> samples at t0 = 2, 2.25, ..., 3.75: 8 samples
+    grid.binary = torch.ones(4, 4, 4, dtype=torch.bool)
+    o = torch.tensor([[-3.0, 0.1, 0.1]]); d = torch.tensor([[1.0, 0, 0]])
+    ri, ts, te = nf.ray_marching(o, d, scene_aabb=aabb, grid=grid, render_step_size=0.25)
+    assert ri.tolist() == [0] * 8 and ts[:, 0].tolist() == [2 + 0.25 * i for i in range(8)] and te[-1, 0].item() == 4.0
+    # half-empty grid (x < 0 cleared): only the x >= 0 half is sampled -> 4 samples starting at t = 3
+    grid.binary[:2] = False
+    ri, ts, te = nf.ray_marching(o, d, scene_aabb=aabb, grid=grid, render_step_size=0.25)
+    assert ri.numel() == 4 and abs(ts[0, 0].item() - 3.0) < 0.26 and te[-1, 0].item() <= 4.0 + 1e-6
+    # C build against the independent numpy-float32 restatement, fg (AABB + DDA skipping) and bg (sphere + cone)
+    g = torch.Generator().manual_seed(1)
+    grid = nf.OccupancyGrid(aabb * 1.5, 16, nf.ContractionType.AABB)
+    grid.binary = torch.rand(16, 16, 16, generator=g) < 0.4
+    n = 24
+    o = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * torch.linspace(0.5, 3.0, n)[:, None]
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(n, 3, generator=g), dim=-1)
+    d[0] = torch.tensor([0.0, 0.0, 1.0])
+    tmin, tmax = nf.ray_aabb_intersect(o, d, grid.roi_aabb)
+    ri, ts, te, pk = nf.ray_marching(o, d, t_min=tmin, t_max=tmax, grid=grid, render_step_size=0.05, return_packed=True)
+    py = nf.march_python(o, d, tmin, tmax, grid.roi_aabb, grid.binary, grid.res, grid.contraction_type, 0.05, 0.0)
+    assert [len(s) for s in py] == pk[:, 1].tolist()
+    flat = [t for s in py for t in s]
+    assert np.array_equal(np.array([a for a, _ in flat], np.float32), ts[:, 0].numpy())
+    assert np.array_equal(np.array([b for _, b in flat], np.float32), te[:, 0].numpy())
+    gridb = nf.OccupancyGrid(aabb * 1.5, 16, nf.ContractionType.UN_BOUNDED_SPHERE)
+    gridb.binary = torch.rand(16, 16, 16, generator=g) < 0.6
+    near = torch.full((n,), 0.1); far = torch.full((n,), 50.0)
+    ri, ts, te, pk = nf.ray_marching(o, d, t_min=near, t_max=far, grid=gridb, render_step_size=0.01, cone_angle=0.05, return_packed=True)
+    py = nf.march_python(o, d, near, far, gridb.roi_aabb, gridb.binary, gridb.res, gridb.contraction_type, 0.01, 0.05)
+    assert [len(s) for s in py] == pk[:, 1].tolist() and ri.numel() > 100
+    flat = [t for s in py for t in s]
+    assert np.array_equal(np.array([a for a, _ in flat], np.float32), ts[:, 0].numpy())
+
+
+def test_compositing_kat_and_visibility():
+    a, n = 0.3, 25
+    alphas = torch.full((2 * n, 1), a)
+    ri = torch.cat([torch.zeros(n), torch.ones(n)]).long()
+    w = nf.render_weight_from_alpha(alphas, ray_indices=ri, n_rays=2)
+    want = a * (1 - a) ** torch.arange(n, dtype=torch.float32)
+    assert torch.allclose(w[:n, 0], want, atol=1e-7) and torch.allclose(w[n:, 0], want, atol=1e-7)
+    op = nf.accumulate_along_rays(w, ri, None, 2)
+    assert torch.allclose(op[:, 0], torch.full((2,), 1 - (1 - a) ** n), atol=1e-6)
+    # density form and its equivalence with alpha = 1 - exp(-sigma dt)
+    sig = torch.rand(2 * n, 1) * 5; t0 = torch.rand(2 * n, 1); t1 = t0 + 0.1
+    w2 = nf.render_weight_from_density(t0, t1, sig, ray_indices=ri, n_rays=2)
+    w3 = nf.render_weight_from_alpha(1 - torch.exp(-sig * 0.1), ray_indices=ri, n_rays=2)
+    assert torch.allclose(w2, w3, atol=1e-6)
+    # render_visibility: T >= eps, sequential product
+    pk = nf.pack_info(ri, 2)
+    vis = nf.render_visibility(alphas, packed_info=pk, early_stop_eps=1e-2)
+    k = int(math.floor(math.log(1e-2) / math.log(1 - a))) + 1       # first index with T < 1e-2
+    assert vis[:n].tolist() == [True] * k + [False] * (n - k)
+    # empty / ragged rays
+    pk = nf.pack_info(torch.tensor([0, 0, 3]), 5)
+    assert pk.tolist() == [[0, 2], [2, 0], [2, 0], [2, 1], [3, 0]]
+
+
+def test_occupancy_update_rules():
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    g = nf.OccupancyGrid(aabb, 4, nf.ContractionType.AABB)
+    occ = torch.zeros(64); occ[5] = 0.5; occ[9] = 0.0005
+    g.apply_update(torch.arange(64), occ, occ_thre=0.01)
+    # threshold = min(mean, 0.01) = mean = 0.5005/64 = 0.0078 -> only cell 5
+    assert g.binary.flatten().nonzero().flatten().tolist() == [5]
+    g.apply_update(torch.tensor([9, 9, 5]), torch.tensor([0.2, 0.4, 0.0]), occ_thre=0.01)      # duplicates -> max; EMA decay on cell 5
+    assert abs(g.occs[9].item() - 0.4) < 1e-7 and abs(g.occs[5].item() - 0.475) < 1e-7
+    assert g.binary.flatten().nonzero().flatten().tolist() == [5, 9]
+    idx, pts = g.cell_points(torch.tensor([0, 63]), torch.full((2, 3), 0.5))
+    assert torch.allclose(pts, torch.tensor([[-0.75, -0.75, -0.75], [0.75, 0.75, 0.75]]))
+    # contraction round trip for the background grid
+    x = torch.rand(100, 3) * 8 - 4
+    u = nf.contract(x, aabb, nf.ContractionType.UN_BOUNDED_SPHERE)
+    assert torch.allclose(nf.contract_inv(u, aabb, nf.ContractionType.UN_BOUNDED_SPHERE), x, atol=2e-3, rtol=2e-3)
+
+
+def test_sphere_init_scene():
+    """Sphere-initialised VanillaMLP + tiny hash features: the network sees y = x / radius in [-1, 1] and represents
+    |y| - 0.5 (network_utils.py:117-127), i.e. SDF(x) ~ |x| / 1.5 - 0.5 in world units, normals ~ x/|x|."""
+    from tests.golden.scenes import golden_model_config
+    torch.manual_seed(0)
+    geo = mr.RefVolumeSDF(golden_model_config()["geometry"])
+    geo.train()
+    geo.update_step(0, 0)
+    geo._finite_difference_eps = 1e-2
+    g = torch.Generator().manual_seed(0)
+    p = torch.nn.functional.normalize(torch.randn(400, 3, generator=g), dim=-1) * (0.2 + torch.rand(400, 1, generator=g))
+    sdf, grad = geo(p, with_grad=True, with_feature=False)
+    r = p.norm(dim=-1)
+    assert (sdf - (r / 1.5 - 0.5)).abs().max() < 0.1
+    cos = (torch.nn.functional.normalize(grad, dim=-1) * p / r[:, None]).sum(-1)
+    assert cos.min() > 0.95 and (grad.norm(dim=-1) - 1 / 1.5).abs().mean() < 0.1
+
+
+def test_schedules():
+    assert mr.schedule_value(0.1, 123) == 0.1
+    assert mr.schedule_value([0, 0, 0.5, 5000], 2500) == 0.25 and mr.schedule_value([0, 0, 0.5, 5000], 9999) == 0.5
+    assert mr.schedule_value([0, 1, 0, 20000], 20000) == 0.0 and mr.schedule_value([1.0, 0.0, 1000], 500) == 0.5

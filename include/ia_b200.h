@@ -112,7 +112,10 @@ typedef struct ia_mlp_desc {
 int64_t ia_mlp_param_count(const ia_mlp_desc *desc_host);
 
 /* out[n, n_out_used] (row stride ld_out) = first n_out_used outputs of the network.  n_out_used < n_out
- * is the SDF-only evaluation of the finite-difference taps (models/geometry.py:233, 266). */
+ * is the SDF-only evaluation of the finite-difference taps (models/geometry.py:233, 266).
+ * IA_MLP_TC_F16 only: n_out_used <= 8 are fused; n_out_used == 0 returns the last hidden layer's activations
+ * [n, width] instead (and ia_mlp_bwd then takes their gradient), so that a wide output layer -- the 65-feature centre
+ * evaluation -- can be applied by the caller as one plain GEMM. */
 int32_t ia_mlp_fwd(const ia_mlp_desc *desc_host, const float *in0, const float *in1, int64_t n,
                    const float *params, int32_t n_out_used, float *out, int64_t ld_out, void *stream);
 

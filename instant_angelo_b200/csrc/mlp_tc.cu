@@ -206,29 +206,38 @@ __device__ __forceinline__ void load_split8(const char *hi_base, const char *lo_
 }
 
 // One "split" GEMM: D (+)= A * B^T with both operands as (hi, lo) pairs; 3 MMAs per 16-deep K step.
+// Descriptors are built once per kernel; a K step only adds (byte advance >> 4) to the start-address field.
 struct Operand {
-    uint32_t hi, lo;      // shared-memory byte addresses of the two halves
-    uint32_t lbo, sbo;    // descriptor strides (bytes)
-    uint32_t kstep;       // byte advance per K=16 step
+    uint64_t dhi, dlo;    // descriptors of the hi / lo halves at K step 0
+    uint32_t kstep16;     // (byte advance per K=16 step) >> 4
 };
+
+__device__ __forceinline__ Operand make_operand(uint32_t hi, uint32_t lo, uint32_t lbo, uint32_t sbo, uint32_t kstep)
+{
+    return {make_desc(hi, lbo, sbo), make_desc(lo, lbo, sbo), kstep >> 4};
+}
 
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Operand &A, const Operand &B, uint32_t idesc, int n_ksteps)
 {
-    for (int ks = 0; ks < n_ksteps; ++ks) {
-        const uint64_t ah = make_desc(A.hi + ks * A.kstep, A.lbo, A.sbo), al = make_desc(A.lo + ks * A.kstep, A.lbo, A.sbo);
-        const uint64_t bh = make_desc(B.hi + ks * B.kstep, B.lbo, B.sbo), bl = make_desc(B.lo + ks * B.kstep, B.lbo, B.sbo);
-        umma(tmem_d, ah, bh, idesc, ks > 0 ? 1u : 0u);
+    uint64_t ah = A.dhi, al = A.dlo, bh = B.dhi, bl = B.dlo;
+    umma(tmem_d, ah, bh, idesc, 0u);
+    umma(tmem_d, ah, bl, idesc, 1u);
+    umma(tmem_d, al, bh, idesc, 1u);
+#pragma unroll 4
+    for (int ks = 1; ks < n_ksteps; ++ks) {
+        ah += A.kstep16; al += A.kstep16; bh += B.kstep16; bl += B.kstep16;
+        umma(tmem_d, ah, bh, idesc, 1u);
         umma(tmem_d, ah, bl, idesc, 1u);
         umma(tmem_d, al, bh, idesc, 1u);
     }
 }
 
 // activation buffer [128 rows, C cols] (chunk c at c*2048, row r at r*16)
-__device__ __forceinline__ Operand act_as_A_kmajor(uint32_t hi, uint32_t lo) { return {hi, lo, 2048u, 128u, 4096u}; }
-__device__ __forceinline__ Operand act_as_mnmajor(uint32_t hi, uint32_t lo) { return {hi, lo, 128u, 2048u, 256u}; }
+__device__ __forceinline__ Operand act_as_A_kmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 2048u, 128u, 4096u); }
+__device__ __forceinline__ Operand act_as_mnmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 128u, 2048u, 256u); }
 // weight buffer [64 out rows, Cin cols] (chunk c at c*1024, row o at o*16)
-__device__ __forceinline__ Operand w_as_B_kmajor(uint32_t hi, uint32_t lo) { return {hi, lo, 1024u, 128u, 2048u}; }
-__device__ __forceinline__ Operand w_as_B_mnmajor(uint32_t hi, uint32_t lo) { return {hi, lo, 128u, 1024u, 256u}; }
+__device__ __forceinline__ Operand w_as_B_kmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 1024u, 128u, 2048u); }
+__device__ __forceinline__ Operand w_as_B_mnmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 128u, 1024u, 256u); }
 
 // W[64][n_in] fp32 (global) -> split fp16 canonical K-major B operand with Kpad columns (zero padded)
 __device__ __forceinline__ void stage_weight(char *smem, uint32_t hi_off, uint32_t lo_off, const float *__restrict__ Wg, int n_in,
@@ -246,6 +255,11 @@ __device__ __forceinline__ void stage_weight(char *smem, uint32_t hi_off, uint32
     }
 }
 
+// optional cycle accounting (tools/prof_mlp.py --timing): [0] barrier wait, [1] MMA issue, [2] MMA completion wait,
+// [3] whole tile, [4] tiles; accumulated by thread 0 of every CTA when enabled through ia_debug_tc_timing()
+__device__ unsigned long long g_tc_cycles[8];
+__device__ int g_tc_timing_on = 0;
+
 struct Ctx {
     char *smem;
     SmemPlan P;
@@ -260,17 +274,29 @@ struct Ctx {
 template <typename F>
 __device__ __forceinline__ void run_mma(Ctx &c, F issue)
 {
+    const bool timing = threadIdx.x == 0 && g_tc_timing_on;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (timing) t0 = clock64();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (timing) t1 = clock64();
         tc_fence_after();
         issue();
         umma_commit(c.sbase + c.P.mbar);
+        if (timing) t2 = clock64();
     }
     mbar_wait(c.sbase + c.P.mbar, c.phase);
     c.phase ^= 1u;
     tc_fence_after();
+    if (timing) {
+        const long long t3 = clock64();
+        atomicAdd(&g_tc_cycles[0], (unsigned long long)(t1 - t0));
+        atomicAdd(&g_tc_cycles[1], (unsigned long long)(t2 - t1));
+        atomicAdd(&g_tc_cycles[2], (unsigned long long)(t3 - t2));
+        atomicAdd(&g_tc_cycles[5], 1ull);
+    }
 }
 
 template <int NOU>
@@ -387,6 +413,7 @@ mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row = tile * ROWS + c.r;
         const bool valid = row < n;
+        const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
         stage_input(c, D, in0, in1, row, valid);
         run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AX, BW0, idesc_fwd, D.K0 / 16); });
         float h[16];
@@ -396,27 +423,40 @@ mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
             run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AH, BW1, idesc_fwd, W / 16); });
             hidden_cols<ACT>(c, b1, h);
         }
-        // output layer in fp32: partial dot products over this thread's 16 hidden units, combined through smem
+        if constexpr (NOU == 0) {
+            // feature mode: hand the last hidden layer's activations to the caller (wide output layers are a plain GEMM)
+            if (valid) {
+                float4 *dst = reinterpret_cast<float4 *>(out + row * ld_out + 16 * c.cg);
 #pragma unroll
-        for (int o = 0; o < NOU; ++o) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc = fmaf(h[j], wl[o * W + 16 * c.cg + j], acc);
-            part[(c.cg * ROWS + c.r) * NOU + o] = acc;
-        }
-        __syncthreads();
-        if (c.cg == 0 && valid) {
+                for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+            }
+        } else {
+            // output layer in fp32: partial dot products over this thread's 16 hidden units, combined through smem
 #pragma unroll
             for (int o = 0; o < NOU; ++o) {
-                if (o < D.nou) {
-                    float acc = bl[o];
+                float acc = 0.f;
 #pragma unroll
-                    for (int g = 0; g < CG; ++g) acc += part[(g * ROWS + c.r) * NOU + o];
-                    out[row * ld_out + o] = acc;
+                for (int j = 0; j < 16; ++j) acc = fmaf(h[j], wl[o * W + 16 * c.cg + j], acc);
+                part[(c.cg * ROWS + c.r) * NOU + o] = acc;
+            }
+            __syncthreads();
+            if (c.cg == 0 && valid) {
+#pragma unroll
+                for (int o = 0; o < NOU; ++o) {
+                    if (o < D.nou) {
+                        float acc = bl[o];
+#pragma unroll
+                        for (int g = 0; g < CG; ++g) acc += part[(g * ROWS + c.r) * NOU + o];
+                        out[row * ld_out + o] = acc;
+                    }
                 }
             }
         }
         // `part` is written again only after the barriers of the next tile's run_mma
+        if (threadIdx.x == 0 && g_tc_timing_on) {
+            atomicAdd(&g_tc_cycles[3], (unsigned long long)(clock64() - tile_t0));
+            atomicAdd(&g_tc_cycles[4], 1ull);
+        }
     }
     teardown(c);
 }
@@ -475,7 +515,8 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     const float *b0 = reinterpret_cast<const float *>(smem + c.P.b0), *b1 = reinterpret_cast<const float *>(smem + c.P.b1);
     const float *wl = reinterpret_cast<const float *>(smem + c.P.wl);
     // bound of sum_o |W_last[o][k]| for the per-tile gradient scale
-    float wmax = 0.f;
+    constexpr int NO = NOU > 0 ? NOU : 1;      // NOU == 0: feature mode, the incoming gradient is d(last hidden) [n, 64]
+    float wmax = NOU == 0 ? 1.f : 0.f;
     for (int i = tid; i < NOU * W; i += THREADS) wmax = fmaxf(wmax, fabsf(wl[i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
@@ -484,7 +525,7 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     wmax = 0.f;
 #pragma unroll
     for (int w = 0; w < THREADS / 32; ++w) wmax = fmaxf(wmax, red[w]);
-    wmax = fmaxf(wmax * (float)NOU, 1e-30f);
+    wmax = fmaxf(wmax * (float)NO, 1e-30f);
     __syncthreads();
 
     const bool want_dx = din0 != nullptr || din1 != nullptr;
@@ -505,12 +546,12 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     const Operand BW1T = w_as_B_mnmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
 
     // persistent per-thread partial sums of dW_last[o][16*cg + j] and db_last[o] (reduced over rows at the very end)
-    constexpr bool REG_DWL = NOU <= 3;
+    constexpr bool REG_DWL = NOU >= 1 && NOU <= 3;
     constexpr int NREG = REG_DWL ? NOU : 1;
     float gwl[NREG][16];
-    float gbl[NOU];
+    float gbl[NO];
 #pragma unroll
-    for (int o = 0; o < NOU; ++o) gbl[o] = 0.f;
+    for (int o = 0; o < NO; ++o) gbl[o] = 0.f;
 #pragma unroll
     for (int o = 0; o < NREG; ++o)
 #pragma unroll
@@ -520,14 +561,27 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row = tile * ROWS + c.r;
         const bool valid = row < n;
+        const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
         stage_input(c, D, in0, in1, row, valid);
-        float dy[NOU];
+        float dy[NO];
+        float dhf[NOU == 0 ? 16 : 1];
         float dymax = 0.f;
+        if constexpr (NOU == 0) {
+            const float4 *src = reinterpret_cast<const float4 *>(dout + row * ld_dout + 16 * c.cg);
 #pragma unroll
-        for (int o = 0; o < NOU; ++o) {
-            dy[o] = (valid && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
-            dymax = fmaxf(dymax, fabsf(dy[o]));
-            if (c.cg == 0) gbl[o] += dy[o];
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dhf[4 * q] = t.x; dhf[4 * q + 1] = t.y; dhf[4 * q + 2] = t.z; dhf[4 * q + 3] = t.w;
+                dymax = fmaxf(dymax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+            }
+            dy[0] = 0.f;
+        } else {
+#pragma unroll
+            for (int o = 0; o < NOU; ++o) {
+                dy[o] = (valid && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
+                dymax = fmaxf(dymax, fabsf(dy[o]));
+                if (c.cg == 0) gbl[o] += dy[o];
+            }
         }
         // per-tile power-of-two scale that bounds |dZ| of the tile by 2^6 (fp16 normal range, 2^10 headroom for dH)
 #pragma unroll
@@ -558,11 +612,17 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
             for (int j = 0; j < 16; ++j) {
                 const int k = 16 * c.cg + j;
                 float dh = 0.f;
+                if constexpr (NOU == 0) {
+                    dh = dhf[j];
+                } else {
 #pragma unroll
-                for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
+                    for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
+                }
                 dz[j] = dh * act_bwd_from_out<ACT>(h[j]) * scale;
             }
-            if (REG_DWL) {
+            if (NOU == 0) {
+                // nothing: the output layer lives outside this kernel
+            } else if (REG_DWL) {
 #pragma unroll
                 for (int o = 0; o < NREG; ++o)
 #pragma unroll
@@ -623,6 +683,10 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
                 }
             }
         }
+        if (threadIdx.x == 0 && g_tc_timing_on) {
+            atomicAdd(&g_tc_cycles[3], (unsigned long long)(clock64() - tile_t0));
+            atomicAdd(&g_tc_cycles[4], 1ull);
+        }
     }
     // ---- reduce the register-resident output-layer gradients over the rows of the CTA
     if (REG_DWL) {
@@ -671,7 +735,7 @@ int make_dims(const ia_mlp_desc *d, int32_t n_out_used, TcDims *D)
     IA_REQUIRE(d->n_in0 >= 0 && d->n_in0 <= 8 && d->n_in1 >= 0, "mlp_tc: bad input split");
     const int din = d->n_in0 + d->n_in1;
     IA_REQUIRE(din >= 1 && din <= 95, "mlp_tc: input width %d not in [1,95]", din);
-    IA_REQUIRE(n_out_used >= 1 && n_out_used <= d->n_out, "mlp_tc: n_out_used out of range");
+    IA_REQUIRE(n_out_used >= 0 && n_out_used <= d->n_out, "mlp_tc: n_out_used out of range");
     IA_REQUIRE(d->hidden_act == IA_ACT_RELU || d->hidden_act == IA_ACT_SOFTPLUS100, "mlp_tc: unsupported hidden activation");
     if (d->out_act != IA_ACT_NONE) {
         ia_set_error("mlp_tc: fused output activation not supported (apply it on the caller side)");
@@ -692,6 +756,16 @@ int make_dims(const ia_mlp_desc *d, int32_t n_out_used, TcDims *D)
 
 }  // namespace
 
+// debug hook (not part of the public ABI header): enable/disable cycle accounting and read the counters back
+extern "C" int32_t ia_debug_tc_timing(int32_t enable, unsigned long long *out8_host)
+{
+    if (out8_host) cudaMemcpyFromSymbol(out8_host, g_tc_cycles, sizeof(unsigned long long) * 8);
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_tc_cycles, zero, sizeof(zero));
+    cudaMemcpyToSymbol(g_tc_timing_on, &enable, sizeof(int));
+    return 0;
+}
+
 int ia_mlp_fwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, const float *, int32_t, float *, int64_t, void *);
 int ia_mlp_bwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, const float *, const float *, int32_t, int64_t,
                     float *, float *, float *, void *);
@@ -699,14 +773,18 @@ int ia_mlp_bwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, 
 int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, int64_t n, const float *params,
                   int32_t n_out_used, float *out, int64_t ld_out, void *stream)
 {
-    // wide output layers (the 65-feature centre evaluation) stay on the fp32 path for now
-    if (desc && n_out_used > MAX_OUT) return ia_mlp_fwd_fp32(desc, in0, in1, n, params, n_out_used, out, ld_out, stream);
+    if (desc && n_out_used > MAX_OUT) {
+        ia_set_error("mlp_tc: more than %d fused outputs; request n_out_used = 0 (last hidden layer) and apply the output "
+                     "layer as a GEMM", MAX_OUT);
+        return IA_ERR_UNSUPPORTED;
+    }
     TcDims D;
     int rc = make_dims(desc, n_out_used, &D);
     if (rc) return rc;
     IA_REQUIRE(n >= 0 && (n == 0 || (params && out)), "mlp_tc_fwd: NULL pointer");
     IA_REQUIRE(n == 0 || ((D.n_in0 == 0 || in0) && (D.n_in1 == 0 || in1)), "mlp_tc_fwd: missing input pointer");
-    IA_REQUIRE(ld_out >= n_out_used, "mlp_tc_fwd: ld_out < n_out_used");
+    IA_REQUIRE(ld_out >= (n_out_used == 0 ? W : n_out_used), "mlp_tc_fwd: ld_out too small");
+    IA_REQUIRE(n_out_used != 0 || (ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0), "mlp_tc_fwd: feature output must be 16-byte aligned");
     if (n == 0) return IA_OK;
     const SmemPlan P = make_plan(D, false);
     IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_fwd: needs %u B of shared memory", P.total);
@@ -719,7 +797,8 @@ int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
         mlp_tc_fwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, out, ld_out);    \
     } while (0)
     const bool sp = D.act == IA_ACT_SOFTPLUS100;
-    if (D.nou == 1) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_FWD(IA_ACT_RELU, 1); }
+    if (D.nou == 0) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_FWD(IA_ACT_RELU, 0); }
+    else if (D.nou == 1) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_FWD(IA_ACT_RELU, 1); }
     else if (D.nou <= 3) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_FWD(IA_ACT_RELU, 3); }
     else { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_FWD(IA_ACT_RELU, 8); }
 #undef IA_TC_FWD
@@ -731,14 +810,17 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
                   const float *dout, int32_t n_out_used, int64_t ld_dout, float *din0, float *din1, float *dparams,
                   void *stream)
 {
-    if (desc && n_out_used > MAX_OUT)
-        return ia_mlp_bwd_fp32(desc, in0, in1, n, params, dout, n_out_used, ld_dout, din0, din1, dparams, stream);
+    if (desc && n_out_used > MAX_OUT) {
+        ia_set_error("mlp_tc: more than %d fused outputs; request n_out_used = 0 (last hidden layer)", MAX_OUT);
+        return IA_ERR_UNSUPPORTED;
+    }
     TcDims D;
     int rc = make_dims(desc, n_out_used, &D);
     if (rc) return rc;
     IA_REQUIRE(n >= 0 && (n == 0 || (params && dout)), "mlp_tc_bwd: NULL pointer");
     IA_REQUIRE(n == 0 || ((D.n_in0 == 0 || in0) && (D.n_in1 == 0 || in1)), "mlp_tc_bwd: missing input pointer");
-    IA_REQUIRE(ld_dout >= n_out_used, "mlp_tc_bwd: ld_dout < n_out_used");
+    IA_REQUIRE(ld_dout >= (n_out_used == 0 ? W : n_out_used), "mlp_tc_bwd: ld_dout too small");
+    IA_REQUIRE(n_out_used != 0 || (ld_dout % 4 == 0 && ((uintptr_t)dout & 15) == 0), "mlp_tc_bwd: feature gradient must be 16-byte aligned");
     if (n == 0) return IA_OK;
     const SmemPlan P = make_plan(D, true);
     IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_bwd: needs %u B of shared memory", P.total);
@@ -752,7 +834,8 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
                                                                                         din0, din1, dparams);                    \
     } while (0)
     const bool sp = D.act == IA_ACT_SOFTPLUS100;
-    if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
+    if (D.nou == 0) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_BWD(IA_ACT_RELU, 0); }
+    else if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
     else if (D.nou <= 3) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_BWD(IA_ACT_RELU, 3); }
     else { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_BWD(IA_ACT_RELU, 8); }
 #undef IA_TC_BWD

@@ -229,7 +229,8 @@ class VanillaMLP(nn.Module):
                                  self.precision)
         if flat is None:
             flat = self.flat_params()
-        return self._post(ops.mlp_apply(in0, in1, flat, desc, n_out_used))
+        nou = self.n_output_dims if n_out_used is None else n_out_used
+        return self._post(ops.mlp_apply(in0, in1, flat, desc, nou))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:

@@ -182,9 +182,10 @@ class _MLPFn(torch.autograd.Function):
         in1 = L.f32c(in1) if in1 is not None else None
         params = L.f32c(params)
         n = (in1 if in1 is not None else in0).shape[0]
-        out = torch.empty(n, n_out_used, device=params.device, dtype=torch.float32)
+        width_out = n_out_used if n_out_used > 0 else desc.width       # 0: last hidden layer ("feature mode")
+        out = torch.empty(n, width_out, device=params.device, dtype=torch.float32)
         _run("ia_mlp_fwd", C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), n_out_used, L.ptr(out),
-             n_out_used, L.stream(), work=n * mlp_flops_per_row(desc, n_out_used),
+             width_out, L.stream(), work=n * mlp_flops_per_row(desc, n_out_used),
              tag=f"{desc.n_in0 + desc.n_in1}>{n_out_used}/{desc.n_out}")
         ctx.save_for_backward(in0, in1, params)
         ctx.desc, ctx.nou = desc, n_out_used
@@ -203,15 +204,25 @@ class _MLPFn(torch.autograd.Function):
         dp = torch.zeros_like(params) if needp else None
         if n > 0:
             _run("ia_mlp_bwd", C.byref(ctx.desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dout), ctx.nou,
-                 ctx.nou, L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou),
+                 dout.shape[1], L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou),
                  tag=f"{ctx.desc.n_in0 + ctx.desc.n_in1}>{ctx.nou}/{ctx.desc.n_out}")
         return d0, d1, dp, None, None
 
 
 def mlp_apply(in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], params: torch.Tensor, desc: L.MlpDesc,
               n_out_used: Optional[int] = None) -> torch.Tensor:
-    """Network on cat[in0*scale+offset, in1]; returns the first n_out_used outputs."""
-    return _MLPFn.apply(in0, in1, params, desc, int(n_out_used or desc.n_out))
+    """Network on cat[in0*scale+offset, in1]; returns the first n_out_used outputs (n_out_used=None: all;
+    n_out_used=0, tensor-core precision only: the last hidden layer's activations [N, 64])."""
+    nou = int(desc.n_out if n_out_used is None else n_out_used)
+    if desc.precision == L.IA_MLP_TC_F16 and nou > 8:
+        # wide output layer (the 65-feature centre evaluation): hidden layers on the tensor-core kernel, the 64 -> nou
+        # projection as one plain fp32 GEMM (cuBLAS through torch.addmm)
+        h = _MLPFn.apply(in0, in1, params, desc, 0)
+        n_hidden = params.numel() - (desc.n_out * desc.width + desc.n_out)
+        w_last = params[n_hidden:n_hidden + desc.n_out * desc.width].view(desc.n_out, desc.width)
+        b_last = params[n_hidden + desc.n_out * desc.width:]
+        return torch.addmm(b_last[:nou], h, w_last[:nou].t())
+    return _MLPFn.apply(in0, in1, params, desc, nou)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -26,3 +26,15 @@ e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 e0.record(); y = ops.mlp_apply(a, b, flat, desc, nou); e1.record(); y.backward(go); e2.record()
 torch.cuda.synchronize()
 print(f"{case} prec={prec} n={n}: fwd {e0.elapsed_time(e1):.3f} ms, bwd {e1.elapsed_time(e2):.3f} ms")
+
+if "--timing" in sys.argv:
+    import ctypes as C
+    lib = L.load()
+    buf = (C.c_ulonglong * 8)()
+    for name, fn in (("fwd", lambda: ops.mlp_apply(a, b, flat, desc, nou)), ("fwd+bwd", lambda: ops.mlp_apply(a, b, flat, desc, nou).backward(go))):
+        lib.ia_debug_tc_timing(1, None)
+        fn(); torch.cuda.synchronize()
+        lib.ia_debug_tc_timing(0, buf)
+        v = list(buf)
+        tiles = max(v[4], 1)
+        print(f"{name}: tiles {v[4]} phases {v[5]} | per tile: total {v[3]/tiles:.0f} cyc, barrier-wait {v[0]/tiles:.0f}, mma-issue {v[1]/tiles:.0f}, mma-wait {v[2]/tiles:.0f}, other {(v[3]-v[0]-v[1]-v[2])/tiles:.0f}")

@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # sample counts change every step: no cudaMalloc stalls
 import torch  # noqa: E402
 
 GLOBAL_STEP0 = 19000          # all 16 levels active (start_level 4 + (19000-5000)//1000 >= 16), curvature weight 0.5
@@ -483,7 +484,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
     ap.add_argument("--mlp", default="tc", choices=["fp32", "tc"],

@@ -126,6 +126,27 @@ int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *
                    float *din0, float *din1, float *dparams, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Finite-difference / curvature stages  fused elementwise stages of VolumeSDF.forward
+ *                                       (models/geometry.py:219-234 FD taps + gradient, :236-275 curvature)
+ * ------------------------------------------------------------------------------------------------ */
+/* taps01[n,6,3] = ((clamp(base[n,3] + eps*e_k, -radius, radius)) + radius) / (2 radius), e_k = +x,-x,+y,-y,+z,-z */
+int32_t ia_fd_taps_fwd(const float *base, int64_t n, float eps, float radius, float *taps01, void *stream);
+int32_t ia_fd_taps_bwd(const float *base, int64_t n, float eps, float radius, const float *dtaps01, float *dbase,
+                       void *stream);
+/* grad[n,3] = 0.5 * (sdf6[n,2i] - sdf6[n,2i+1]) / eps */
+int32_t ia_fd_grad_fwd(const float *sdf6, int64_t n, float eps, float *grad, void *stream);
+int32_t ia_fd_grad_bwd(const float *dgrad, int64_t n, float eps, float *dsdf6, void *stream);
+/* normals = normalize(grad); shifted = pts01 + cross(normals, normalize(rnd)) * eps  (reference quirks kept) */
+int32_t ia_curv_shift_fwd(const float *grad, const float *rnd, const float *pts01, int64_t n, float eps, float *normals,
+                          float *shifted, void *stream);
+int32_t ia_curv_shift_bwd(const float *grad, const float *rnd, int64_t n, float eps, const float *dnormals,
+                          const float *dshifted, float *dgrad, void *stream);
+/* laplace[n] = acos(clamp(normals . normalize(gshift), -1+1e-6, 1-1e-6)) / pi */
+int32_t ia_curv_angle_fwd(const float *normals, const float *gshift, int64_t n, float *laplace, void *stream);
+int32_t ia_curv_angle_bwd(const float *normals, const float *gshift, int64_t n, const float *dlaplace, float *dnormals,
+                          float *dgshift, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Occupancy grid + ray marching        replaces nerfacc.OccupancyGrid / ray_aabb_intersect /
  *                                      ray_marching as called at models/neus.py:64-74, 108-111, 153,
  *                                      159-169, 209-220

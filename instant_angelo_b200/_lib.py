@@ -72,6 +72,14 @@ SIGNATURES = {
     "ia_mlp_param_count": (_I64, [C.POINTER(MlpDesc)]),
     "ia_mlp_fwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _I32, _P, _I64, _P]),
     "ia_mlp_bwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P]),
+    "ia_fd_taps_fwd": (_I32, [_P, _I64, _F, _F, _P, _P]),
+    "ia_fd_taps_bwd": (_I32, [_P, _I64, _F, _F, _P, _P, _P]),
+    "ia_fd_grad_fwd": (_I32, [_P, _I64, _F, _P, _P]),
+    "ia_fd_grad_bwd": (_I32, [_P, _I64, _F, _P, _P]),
+    "ia_curv_shift_fwd": (_I32, [_P, _P, _P, _I64, _F, _P, _P, _P]),
+    "ia_curv_shift_bwd": (_I32, [_P, _P, _I64, _F, _P, _P, _P, _P]),
+    "ia_curv_angle_fwd": (_I32, [_P, _P, _I64, _P, _P]),
+    "ia_curv_angle_bwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P]),
     "ia_occ_workspace_bytes": (_I64, [_I64]),
     "ia_occ_update": (_I32, [_P, _P, _I64, _P, _I64, _F, _F, _P, _P, _P, _P]),
     "ia_occ_pack": (_I32, [_P, _I64, _P, _P]),

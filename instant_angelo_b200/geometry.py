@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from . import registry as models
 from .nerfacc_api import ContractionType
 from .network_utils import fused_encode_mlp, get_encoding, get_encoding_with_network, get_mlp, update_module_step
@@ -97,10 +98,10 @@ class VolumeSDF(BaseImplicitGeometry):
 
     def _fd_gradient(self, world_pts, eps, flat):
         """geometry.py:219-234: six taps clamped to the AABB in world space, central differences."""
-        taps = (world_pts[..., None, :] + self._fd_signs * eps).clamp(-self.radius, self.radius)
-        taps01 = scale_anything(taps, (-self.radius, self.radius), (0, 1))
-        s = self._net(taps01, 1, flat).view(*world_pts.shape[:-1], 6)
-        return 0.5 * (s[..., 0::2] - s[..., 1::2]) / eps
+        lead = world_pts.shape[:-1]
+        taps01 = ops.fd_taps(world_pts.reshape(-1, 3), eps, self.radius)          # fused add / clamp / normalise
+        s = self._net(taps01, 1, flat).view(-1, 6)
+        return ops.fd_grad(s, eps).view(*lead, 3)                                 # fused central differences
 
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False, with_auxiliary_feature=False,
                 rand_directions: Optional[torch.Tensor] = None):
@@ -133,14 +134,11 @@ class VolumeSDF(BaseImplicitGeometry):
                 eps = self._finite_difference_eps
                 if rand_directions is None:
                     rand_directions = torch.randn_like(pts01)
-                rnd = F.normalize(rand_directions, dim=-1)
-                normals = F.normalize(grad, dim=-1)
-                tangent = torch.cross(normals, rnd, dim=-1)
-                shifted = pts01 + tangent * eps            # Appendix C-1/C-2/C-3
+                lead = pts01.shape[:-1]
+                # normals = normalize(grad); shifted = pts01 + cross(normals, normalize(rnd)) * eps   (Appendix C-1/2/3)
+                normals, shifted = ops.curv_shift(grad.reshape(-1, 3), rand_directions.reshape(-1, 3), pts01.reshape(-1, 3), eps)
                 g_shift = self._fd_gradient(shifted, eps, flat)
-                n_shift = F.normalize(g_shift, dim=-1)
-                dot = (normals * n_shift).sum(dim=-1, keepdim=True)
-                laplace = torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.pi
+                laplace = ops.curv_angle(normals, g_shift).view(*lead, 1)
         rv = [sdf]
         if with_grad:
             rv.append(grad)

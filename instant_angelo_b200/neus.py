@@ -168,7 +168,7 @@ class NeuSModel(nn.Module):
         opacity, depth = opacity[:, None], depth[:, None]
         comp_rgb = comp_rgb + self.background_color * (1.0 - opacity)
         out = {"comp_rgb": comp_rgb, "opacity": opacity, "depth": depth, "rays_valid": opacity > 0,
-               "num_samples": torch.as_tensor([len(t_starts)], dtype=torch.int32, device=rays.device)}
+               "num_samples": torch.full((1,), len(t_starts), dtype=torch.int32, device=rays.device)}
         if self.training:
             out.update({"weights": weights.view(-1), "points": midpoints.view(-1), "intervals": intervals.view(-1),
                         "ray_indices": ri.view(-1)})
@@ -205,7 +205,7 @@ class NeuSModel(nn.Module):
         comp_normal = comp_normal * rays_fg.float()      # Appendix C-9
         out = {"comp_rgb": comp_rgb, "comp_normal": comp_normal, "opacity": opacity, "depth": depth,
                "rays_valid": opacity > 0,
-               "num_samples": torch.as_tensor([len(t_starts)], dtype=torch.int32, device=rays.device)}
+               "num_samples": torch.full((1,), len(t_starts), dtype=torch.int32, device=rays.device)}
         if self.training:
             out.update({"sdf_samples": sdf, "sdf_grad_samples": sdf_grad, "weights": weights.view(-1),
                         "points": midpoints.view(-1), "intervals": dists.view(-1), "ray_indices": ri.view(-1),

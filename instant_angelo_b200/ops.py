@@ -226,6 +226,117 @@ def mlp_apply(in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], params: 
 
 
 # ---------------------------------------------------------------------------------------------
+# finite-difference / curvature stages of VolumeSDF.forward (reference models/geometry.py:219-275)
+# ---------------------------------------------------------------------------------------------
+
+class _FDTapsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base, eps, radius):
+        L.require_cuda(base)
+        base = L.f32c(base)
+        n = base.shape[0]
+        taps = torch.empty(n, 6, 3, device=base.device, dtype=torch.float32)
+        _run("ia_fd_taps_fwd", L.ptr(base), n, C.c_float(eps), C.c_float(radius), L.ptr(taps), L.stream())
+        ctx.save_for_backward(base)
+        ctx.eps, ctx.radius = eps, radius
+        return taps
+
+    @staticmethod
+    def backward(ctx, dtaps):
+        (base,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        dtaps = L.f32c(dtaps)
+        dbase = torch.empty_like(base)
+        _run("ia_fd_taps_bwd", L.ptr(base), base.shape[0], C.c_float(ctx.eps), C.c_float(ctx.radius), L.ptr(dtaps), L.ptr(dbase),
+             L.stream())
+        return dbase, None, None
+
+
+def fd_taps(base: torch.Tensor, eps: float, radius: float) -> torch.Tensor:
+    """[S,3] -> [S,6,3] normalised tap positions: ((base + eps*e_k).clamp(-r, r) + r) / (2r)."""
+    return _FDTapsFn.apply(base, float(eps), float(radius))
+
+
+class _FDGradFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdf6, eps):
+        L.require_cuda(sdf6)
+        sdf6 = L.f32c(sdf6)
+        n = sdf6.shape[0]
+        grad = torch.empty(n, 3, device=sdf6.device, dtype=torch.float32)
+        _run("ia_fd_grad_fwd", L.ptr(sdf6), n, C.c_float(eps), L.ptr(grad), L.stream())
+        ctx.eps = eps
+        return grad
+
+    @staticmethod
+    def backward(ctx, dgrad):
+        dgrad = L.f32c(dgrad)
+        n = dgrad.shape[0]
+        d6 = torch.empty(n, 6, device=dgrad.device, dtype=torch.float32)
+        _run("ia_fd_grad_bwd", L.ptr(dgrad), n, C.c_float(ctx.eps), L.ptr(d6), L.stream())
+        return d6, None
+
+
+def fd_grad(sdf6: torch.Tensor, eps: float) -> torch.Tensor:
+    """[S,6] tap SDFs -> [S,3] central differences 0.5*(s+ - s-)/eps."""
+    return _FDGradFn.apply(sdf6, float(eps))
+
+
+class _CurvShiftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grad, rnd, pts01, eps):
+        L.require_cuda(grad, rnd, pts01)
+        grad, rnd, pts01 = L.f32c(grad), L.f32c(rnd), L.f32c(pts01)
+        n = grad.shape[0]
+        normals = torch.empty_like(grad)
+        shifted = torch.empty_like(grad)
+        _run("ia_curv_shift_fwd", L.ptr(grad), L.ptr(rnd), L.ptr(pts01), n, C.c_float(eps), L.ptr(normals), L.ptr(shifted), L.stream())
+        ctx.save_for_backward(grad, rnd)
+        ctx.eps = eps
+        return normals, shifted
+
+    @staticmethod
+    def backward(ctx, dnormals, dshifted):
+        grad, rnd = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        dgrad = torch.empty_like(grad)
+        _run("ia_curv_shift_bwd", L.ptr(grad), L.ptr(rnd), grad.shape[0], C.c_float(ctx.eps), L.ptr(L.f32c(dnormals)),
+             L.ptr(L.f32c(dshifted)), L.ptr(dgrad), L.stream())
+        return dgrad, None, None, None
+
+
+def curv_shift(grad: torch.Tensor, rnd: torch.Tensor, pts01: torch.Tensor, eps: float):
+    """normals = normalize(grad); shifted = pts01 + cross(normals, normalize(rnd)) * eps."""
+    return _CurvShiftFn.apply(grad, rnd, pts01, float(eps))
+
+
+class _CurvAngleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, normals, gshift):
+        L.require_cuda(normals, gshift)
+        normals, gshift = L.f32c(normals), L.f32c(gshift)
+        n = normals.shape[0]
+        lap = torch.empty(n, 1, device=normals.device, dtype=torch.float32)
+        _run("ia_curv_angle_fwd", L.ptr(normals), L.ptr(gshift), n, L.ptr(lap), L.stream())
+        ctx.save_for_backward(normals, gshift)
+        return lap
+
+    @staticmethod
+    def backward(ctx, dlap):
+        normals, gshift = ctx.saved_tensors
+        dn, dg = torch.empty_like(normals), torch.empty_like(gshift)
+        _run("ia_curv_angle_bwd", L.ptr(normals), L.ptr(gshift), normals.shape[0], L.ptr(L.f32c(dlap)), L.ptr(dn), L.ptr(dg), L.stream())
+        return dn, dg
+
+
+def curv_angle(normals: torch.Tensor, gshift: torch.Tensor) -> torch.Tensor:
+    """laplace[S,1] = acos(clamp(normals . normalize(gshift), -1+1e-6, 1-1e-6)) / pi."""
+    return _CurvAngleFn.apply(normals, gshift)
+
+
+# ---------------------------------------------------------------------------------------------
 # marching  (nerfacc.ray_aabb_intersect / ray_marching kernels, reference models/neus.py:153,159-169,209-220)
 # ---------------------------------------------------------------------------------------------
 

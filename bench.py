@@ -53,50 +53,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), through NVML in a
+    background thread (the nvidia-smi CLI in loop mode re-enumerates every GPU on each tick and measurably stalls
+    kernel launches of the process being measured)."""
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.path = gpu_index, None, None
+    def __init__(self, gpu_index: int, period_s: float = 0.2):
+        self.idx, self.period = gpu_index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = None
+        self._thread = None
+
+    def _loop(self, nv, handle):
+        masks = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, m in masks.items():
+                    if r & m:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
+        import threading
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when mapping the CUDA ordinal to an NVML index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            nvml_idx = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].strip().isdigit() else self.idx
+            handle = nv.nvmlDeviceGetHandleByIndex(nvml_idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._stop = threading.Event()
+            self._thread = threading.Thread(target=self._loop, args=(nv, handle), daemon=True)
+            self._thread.start()
+        except Exception as e:       # NVML missing: report that no clock record exists rather than guessing
+            self._thread = None
+            self.error = str(e)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._thread is None:
+            out["error"] = getattr(self, "error", "sampler not started")
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                f = [t.strip() for t in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)})
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            sm = sorted(self.samples)
+            out.update({"sm_mhz": sm[len(sm) // 2], "reasons": sorted(self.reasons), "samples": len(sm)})
         return out
 
 

@@ -29,6 +29,7 @@ def _dev(t):
 # ---------------------------------------------------------------------------------------------
 GRID_CFGS = {
     "sparse_2p19": dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=PLS),
+    "dense_2p21": dict(n_levels=16, n_features=2, log2_hashmap_size=21, base_resolution=32, per_level_scale=PLS),   # BASELINE config 3
     "small_mixed": dict(n_levels=8, n_features=2, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.5),
     "tiny_hash": dict(n_levels=5, n_features=2, log2_hashmap_size=8, base_resolution=16, per_level_scale=2.0),
 }
@@ -55,7 +56,7 @@ def test_hashgrid_forward_backward(cuda_lib, cfg_name, active):
     plan_ref = tc.grid_plan(**cfg)
     plan = ops.make_grid_plan(**cfg)
     assert plan.n_params == plan_ref.n_params
-    n = 1000 if cfg_name == "sparse_2p19" else 777
+    n = 1000 if cfg_name in ("sparse_2p19", "dense_2p21") else 777
     act = active if active is None else min(active, cfg["n_levels"])
     g = torch.Generator().manual_seed(7)
     x = _points(n, 11).requires_grad_(True)

@@ -80,6 +80,14 @@ int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table, const flo
                         const ia_grid_plan *plan_host, int32_t active_levels, float *dtable, float *dx,
                         void *stream);
 
+/* As ia_hashgrid_bwd, for rows that arrive in groups of `group` consecutive, spatially close points (the six
+ * finite-difference taps of one sample, models/geometry.py:221-233): contributions of a group that fall into the same
+ * grid cell are summed in registers and scattered once.  group == 6 is specialised; other values use ia_hashgrid_bwd.
+ * Identical to ia_hashgrid_bwd up to fp32 summation order. */
+int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const float *table, const float *dy,
+                                const ia_grid_plan *plan_host, int32_t active_levels, int32_t group, float *dtable,
+                                float *dx, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Spherical harmonics                  replaces tcnn.Encoding(otype=SphericalHarmonics) built at
  *                                      models/network_utils.py:90-91, called at models/texture.py:25,52,129,134

@@ -198,6 +198,123 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     }
 }
 
+// Backward for points that arrive in GROUPS of G consecutive, spatially close rows (the 6 finite-difference taps of
+// one sample, reference models/geometry.py:221-233): at the coarse levels all taps of a group fall into the same
+// cell, so their corner contributions are summed in registers and scattered ONCE (4 REDs per x-corner instead of
+// 4*G).  One thread owns (group, x-corner, 4 levels); the taps of the group are walked sequentially and the pending
+// cell is flushed whenever the cell changes.  Same result as hashgrid_bwd_kernel up to fp32 summation order.
+constexpr int HGG_GROUPS = 32;   // groups per CTA (256 threads = 32 groups x 2 x-corners x 4 level slots)
+
+template <int G, bool WITH_TABLE, bool WITH_INPUT>
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table,
+                            const float *__restrict__ dy, const GridParams P, float2 *__restrict__ dtable,
+                            float *__restrict__ dx)
+{
+    constexpr int TP = HGG_GROUPS * G;   // points per CTA
+    __shared__ float tile[TP * HG_ROW];
+    __shared__ float xs[TP * 3];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * TP;
+    const int row2 = P.n_levels;
+    const float2 *__restrict__ dy2 = reinterpret_cast<const float2 *>(dy);
+    for (int i = tid; i < TP * row2; i += HG_THREADS) {
+        const int r = i / row2, c2 = i - r * row2;
+        float2 g = make_float2(0.f, 0.f);
+        if (base + r < n) g = __ldg(dy2 + (base + r) * row2 + c2);
+        *reinterpret_cast<float2 *>(&tile[r * HG_ROW + 2 * c2]) = g;
+    }
+    for (int i = tid; i < TP * 3; i += HG_THREADS) xs[i] = (base * 3 + i < n * 3) ? __ldg(x + base * 3 + i) : 0.f;
+    __syncthreads();
+
+    const int grp = tid >> 3, ls = (tid >> 1) & 3;
+    const uint32_t xc = tid & 1;
+    float gx[G], gy[G], gz[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) gx[k] = gy[k] = gz[k] = 0.f;
+
+    for (int l = ls; l < P.active; l += 4) {
+        const float scale = P.scale[l];
+        const uint32_t res = P.res[l], size = P.size[l];
+        const bool hashed = P.hashed[l] != 0;
+        float2 *__restrict__ dl = WITH_TABLE ? dtable + P.offset[l] : nullptr;
+        const float2 *__restrict__ tl = WITH_INPUT ? table + P.offset[l] : nullptr;
+        uint32_t px = 0xFFFFFFFFu, py = 0, pz = 0;     // pending cell
+        float2 a00 = make_float2(0.f, 0.f), a10 = a00, a01 = a00, a11 = a00;
+        float2 v00 = a00, v10 = a00, v01 = a00, v11 = a00;
+        auto flush = [&]() {
+            if (WITH_TABLE && px != 0xFFFFFFFFu) {
+                const uint32_t cx = px + xc;
+                if (a00.x != 0.f || a00.y != 0.f) atomicAdd(dl + entry_index(cx, py, pz, res, size, hashed), a00);
+                if (a10.x != 0.f || a10.y != 0.f) atomicAdd(dl + entry_index(cx, py + 1, pz, res, size, hashed), a10);
+                if (a01.x != 0.f || a01.y != 0.f) atomicAdd(dl + entry_index(cx, py, pz + 1, res, size, hashed), a01);
+                if (a11.x != 0.f || a11.y != 0.f) atomicAdd(dl + entry_index(cx, py + 1, pz + 1, res, size, hashed), a11);
+            }
+            a00 = a10 = a01 = a11 = make_float2(0.f, 0.f);
+        };
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const int p = grp * G + k;
+            if (base + p >= n) continue;
+            const CellCoords c = locate(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2], scale);
+            const bool same = c.ix == px && c.iy == py && c.iz == pz;
+            if (!same) {
+                flush();
+                px = c.ix; py = c.iy; pz = c.iz;
+                if (WITH_INPUT) {
+                    const uint32_t cx = c.ix + xc;
+                    v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));
+                    v10 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed));
+                    v01 = __ldg(tl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed));
+                    v11 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed));
+                }
+            }
+            const float2 g = *reinterpret_cast<const float2 *>(&tile[p * HG_ROW + 2 * l]);
+            const float wx = xc ? c.wx : 1.f - c.wx;
+            const float uy = 1.f - c.wy, uz = 1.f - c.wz;
+            if (WITH_TABLE) {
+                const float w00 = wx * uy * uz, w10 = wx * c.wy * uz, w01 = wx * uy * c.wz, w11 = wx * c.wy * c.wz;
+                a00.x += w00 * g.x; a00.y += w00 * g.y;
+                a10.x += w10 * g.x; a10.y += w10 * g.y;
+                a01.x += w01 * g.x; a01.y += w01 * g.y;
+                a11.x += w11 * g.x; a11.y += w11 * g.y;
+            }
+            if (WITH_INPUT) {
+                const float d00 = v00.x * g.x + v00.y * g.y, d10 = v10.x * g.x + v10.y * g.y;
+                const float d01 = v01.x * g.x + v01.y * g.y, d11 = v11.x * g.x + v11.y * g.y;
+                const float sx = uy * uz * d00 + c.wy * uz * d10 + uy * c.wz * d01 + c.wy * c.wz * d11;
+                gx[k] += scale * (xc ? sx : -sx);
+                gy[k] += scale * wx * (uz * (d10 - d00) + c.wz * (d11 - d01));
+                gz[k] += scale * wx * (uy * (d01 - d00) + c.wy * (d11 - d10));
+            }
+        }
+        flush();
+    }
+    if (WITH_INPUT) {
+        // the 8 lanes (4 level slots x 2 x-corners) of a group hold partial sums: butterfly over the low 3 lane bits
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                gx[k] += __shfl_xor_sync(0xffffffffu, gx[k], o);
+                gy[k] += __shfl_xor_sync(0xffffffffu, gy[k], o);
+                gz[k] += __shfl_xor_sync(0xffffffffu, gz[k], o);
+            }
+        }
+        if ((tid & 7) == 0) {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                const int64_t p = base + grp * G + k;
+                if (p < n) {
+                    dx[3 * p] = gx[k];
+                    dx[3 * p + 1] = gy[k];
+                    dx[3 * p + 2] = gz[k];
+                }
+            }
+        }
+    }
+}
+
 int fill_params(const ia_grid_plan *plan, int32_t active_levels, GridParams *P)
 {
     IA_REQUIRE(plan != nullptr, "hashgrid: plan is NULL");
@@ -300,6 +417,31 @@ extern "C" int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table
     else
         hashgrid_bwd_kernel<false, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
     IA_LAUNCH_OK("hashgrid_bwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const float *table, const float *dy,
+                                           const ia_grid_plan *plan, int32_t active_levels, int32_t group, float *dtable,
+                                           float *dx, void *stream)
+{
+    if (group != 6) return ia_hashgrid_bwd(x, n, table, dy, plan, active_levels, dtable, dx, stream);
+    GridParams P;
+    int rc = fill_params(plan, active_levels, &P);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && dy)), "hashgrid_bwd_grouped: NULL pointer with n=%lld", (long long)n);
+    IA_REQUIRE(dx == nullptr || table != nullptr, "hashgrid_bwd_grouped: dx requested without the table");
+    if (n == 0 || (!dtable && !dx)) return IA_OK;
+    const unsigned blocks = (unsigned)ia_ceil_div(n, HGG_GROUPS * 6);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *t2 = reinterpret_cast<const float2 *>(table);
+    float2 *d2 = reinterpret_cast<float2 *>(dtable);
+    if (dtable && dx)
+        hashgrid_bwd_grouped_kernel<6, true, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+    else if (dtable)
+        hashgrid_bwd_grouped_kernel<6, true, false><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+    else
+        hashgrid_bwd_grouped_kernel<6, false, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+    IA_LAUNCH_OK("hashgrid_bwd_grouped_kernel");
     return IA_OK;
 }
 

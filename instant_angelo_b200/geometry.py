@@ -93,14 +93,14 @@ class VolumeSDF(BaseImplicitGeometry):
         self.register_buffer("_fd_signs", torch.tensor([[1.0, 0, 0], [-1.0, 0, 0], [0, 1.0, 0], [0, -1.0, 0],
                                                         [0, 0, 1.0], [0, 0, -1.0]]), persistent=False)
 
-    def _net(self, pts01, n_out_used, flat):
-        return fused_encode_mlp(self.encoding, self.network, pts01.reshape(-1, 3), n_out_used, flat)
+    def _net(self, pts01, n_out_used, flat, group=1):
+        return fused_encode_mlp(self.encoding, self.network, pts01.reshape(-1, 3), n_out_used, flat, group)
 
     def _fd_gradient(self, world_pts, eps, flat):
         """geometry.py:219-234: six taps clamped to the AABB in world space, central differences."""
         lead = world_pts.shape[:-1]
         taps01 = ops.fd_taps(world_pts.reshape(-1, 3), eps, self.radius)          # fused add / clamp / normalise
-        s = self._net(taps01, 1, flat).view(-1, 6)
+        s = self._net(taps01, 1, flat, group=6).view(-1, 6)     # rows = 6 taps per sample: grouped scatter in backward
         return ops.fd_grad(s, eps).view(*lead, 3)                                 # fused central differences
 
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False, with_auxiliary_feature=False,

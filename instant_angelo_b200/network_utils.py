@@ -51,11 +51,11 @@ class Encoding(nn.Module):
         else:
             raise NotImplementedError(f"encoding otype {self.otype}")
 
-    def forward(self, x: torch.Tensor, active_levels: Optional[int] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, active_levels: Optional[int] = None, group: int = 1) -> torch.Tensor:
         if not x.is_cuda:
             raise NotImplementedError("Only support cuda inputs.")
         if self.otype == "HashGrid":
-            return ops.hashgrid_encode(x, self.params, self.plan, active_levels)
+            return ops.hashgrid_encode(x, self.params, self.plan, active_levels, group)
         return ops.sh_encode(x, self.degree)
 
 
@@ -84,8 +84,8 @@ class ProgressiveBandHashGrid(nn.Module):
     def active_levels(self) -> int:
         return self._mask_level
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.encoding(x, self._mask_level)
+    def forward(self, x: torch.Tensor, group: int = 1) -> torch.Tensor:
+        return self.encoding(x, self._mask_level, group)
 
     def update_step(self, epoch, global_step):
         self.current_level = min(self.start_level + max(global_step - self.start_step, 0) // self.update_steps, self.n_level)
@@ -266,11 +266,13 @@ class EncodingWithNetwork(nn.Module):
 
 
 def fused_encode_mlp(encoding: CompositeEncoding, network: VanillaMLP, x: torch.Tensor, n_out_used: Optional[int] = None,
-                     flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     flat: Optional[torch.Tensor] = None, group: int = 1) -> torch.Tensor:
     """network(encoding(x)) for a CompositeEncoding without the torch.cat of reference
     models/network_utils.py:77: the include_xyz columns are produced inside the MLP kernel."""
     x = x.reshape(-1, encoding.n_input_dims)
-    enc = encoding.encoding(x)
+    inner = encoding.encoding
+    enc = inner(x, group=group) if group > 1 and isinstance(inner, (ProgressiveBandHashGrid, Encoding)) and \
+        getattr(inner, "otype", "HashGrid") == "HashGrid" else inner(x)
     if encoding.include_xyz:
         return network.run(x, enc, encoding.xyz_scale, encoding.xyz_offset, n_out_used, flat)
     return network.run(None, enc, 1.0, 0.0, n_out_used, flat)

@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 
 # kernels launched per ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
+_LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_grouped": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
              "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
              "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
              "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0}
@@ -81,7 +81,7 @@ def make_grid_plan(n_levels: int, n_features: int, log2_hashmap_size: int, base_
 
 class _HashGridFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, table, plan, active_levels):
+    def forward(ctx, x, table, plan, active_levels, group=1):
         L.require_cuda(x, table)
         x = L.f32c(x)
         n = x.shape[0]
@@ -89,7 +89,7 @@ class _HashGridFn(torch.autograd.Function):
         _run("ia_hashgrid_fwd", L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, L.ptr(out), L.stream(),
              work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
         ctx.save_for_backward(x, table)
-        ctx.plan, ctx.active = plan, active_levels
+        ctx.plan, ctx.active, ctx.group = plan, active_levels, group
         return out
 
     @staticmethod
@@ -103,12 +103,16 @@ class _HashGridFn(torch.autograd.Function):
         if n > 0 and (need_t or need_x):
             work = (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_table") if need_t else 0) + \
                    (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_input") if need_x else 0)
-            _run("ia_hashgrid_bwd", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active,
-                 L.ptr(dtable), L.ptr(dx), L.stream(), tag=("table+input" if need_t and need_x else "table" if need_t else "input"),
-                 work=n * work)
+            tag = ("table+input" if need_t and need_x else "table" if need_t else "input") + (f",g{ctx.group}" if ctx.group > 1 else "")
+            if ctx.group > 1:
+                _run("ia_hashgrid_bwd_grouped", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active, ctx.group,
+                     L.ptr(dtable), L.ptr(dx), L.stream(), tag=tag, work=n * work)
+            else:
+                _run("ia_hashgrid_bwd", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active,
+                     L.ptr(dtable), L.ptr(dx), L.stream(), tag=tag, work=n * work)
         elif need_x:
             dx.zero_()
-        return dx, dtable, None, None
+        return dx, dtable, None, None, None
 
 
 def hashgrid_bytes_per_point(plan: L.GridPlan, active_levels: int, which: str = "fwd", param_bytes: int = 4,
@@ -127,11 +131,13 @@ def mlp_flops_per_row(desc: L.MlpDesc, n_out_used: int) -> int:
     return 2 * macs
 
 
-def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, plan: L.GridPlan, active_levels: Optional[int] = None) -> torch.Tensor:
-    """x [N,3] in [0,1] -> [N, L*F]; levels >= active_levels are exact zeros (the progressive mask)."""
+def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, plan: L.GridPlan, active_levels: Optional[int] = None,
+                    group: int = 1) -> torch.Tensor:
+    """x [N,3] in [0,1] -> [N, L*F]; levels >= active_levels are exact zeros (the progressive mask).
+    group=6: rows come in groups of 6 spatially close points (finite-difference taps) -- a hint for the backward scatter."""
     if active_levels is None:
         active_levels = plan.n_levels
-    return _HashGridFn.apply(x, table, plan, int(active_levels))
+    return _HashGridFn.apply(x, table, plan, int(active_levels), int(group))
 
 
 # ---------------------------------------------------------------------------------------------

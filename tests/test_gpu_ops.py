@@ -81,6 +81,40 @@ def test_hashgrid_forward_backward(cuda_lib, cfg_name, active):
     assert_close(xg.grad[4:], x.grad[4:], rtol=rt, atol=at, name="dx")
 
 
+@pytest.mark.parametrize("cfg_name", ["sparse_2p19", "small_mixed"])
+@pytest.mark.parametrize("active", [None, 5])
+def test_hashgrid_grouped_backward(cuda_lib, cfg_name, active):
+    """ia_hashgrid_bwd_grouped (6 finite-difference taps per group, same-cell contributions merged before the scatter)
+    against the oracle's autograd, for tap clusters at several scales (same cell at coarse levels, different cells at
+    fine ones) and a row count that is not a multiple of the CTA tile."""
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS[cfg_name]
+    plan_ref, plan = tc.grid_plan(**cfg), ops.make_grid_plan(**cfg)
+    g = torch.Generator().manual_seed(17)
+    S = 173
+    centre = torch.rand(S, 1, 3, generator=g) * 0.98 + 0.01
+    eps = torch.where(torch.arange(S) % 3 == 0, 5e-4, torch.where(torch.arange(S) % 3 == 1, 4e-3, 3e-2))[:, None, None]
+    signs = torch.tensor([[1.0, 0, 0], [-1.0, 0, 0], [0, 1.0, 0], [0, -1.0, 0], [0, 0, 1.0], [0, 0, -1.0]])
+    x = (centre + signs * eps).clamp(0, 1).reshape(-1, 3).contiguous().requires_grad_(True)
+    n = x.shape[0]
+    table = (torch.randn(plan_ref.n_params, generator=g) * 0.1).requires_grad_(True)
+    dy = torch.randn(n, plan_ref.n_output_dims, generator=g)
+    dy[5::7] = 0.0                                            # some rows with exactly-zero gradient
+    act = active if active is None else min(active, cfg["n_levels"])
+    tc.hashgrid_forward(x, table, plan_ref, act).backward(dy)
+    xg, tg = x.detach().cuda().requires_grad_(True), table.detach().cuda().requires_grad_(True)
+    y = ops.hashgrid_encode(xg, tg, plan, act, group=6)
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    assert_close(tg.grad, table.grad, rtol=1e-4, atol=1e-5, name="dtable (grouped)")
+    rt, at = grad_tol(x.grad, 1e-4)
+    assert_close(xg.grad, x.grad, rtol=rt, atol=at, name="dx (grouped)")
+    # table-only variant (taps that do not need d/dx)
+    tg2 = table.detach().cuda().requires_grad_(True)
+    ops.hashgrid_encode(x.detach().cuda(), tg2, plan, act, group=6).backward(dy.cuda())
+    assert_close(tg2.grad, table.grad, rtol=1e-4, atol=1e-5, name="dtable (grouped, table only)")
+
+
 def test_hashgrid_abi_entry_points_and_errors(cuda_lib):
     """ia_hashgrid_bwd_table / ia_hashgrid_bwd_input agree with the fused ia_hashgrid_bwd; bad args fail loudly."""
     import ctypes as C

@@ -97,6 +97,11 @@ class ClockSampler:
             self._thread = None
             self.error = str(e)
 
+    def mark(self):
+        """Start of the timed region: forget what was sampled during warm-up (NVML initialisation and its first
+        queries stall the driver for ~100 ms, so the sampler is started before the warm-up steps)."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         if self._thread is None:
@@ -260,6 +265,9 @@ def run_b200(args):
         return float(v)
 
     # ---- kernel-resident measurement (`value`) --------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     gs = GLOBAL_STEP0
     for i in range(W):
         batch, bg = unpack_batch(*dev_batches[i])
@@ -268,21 +276,27 @@ def run_b200(args):
     prof = ops.PROFILER
     prof.reset()
     prof.enabled, prof.timing = True, True
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     n_samples_fg = n_samples_full = 0
+    import gc
+    gc.collect()
+    gc.freeze()          # the training loop allocates thousands of short-lived Python objects per step: keep the cyclic
+    gc.disable()         # collector from pausing the launch thread inside the timed regions
     barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     counts = []
+    host_t = [time.perf_counter()]
     for i in range(W, W + K):
         batch, bg = unpack_batch(*dev_batches[i])
         loss, out = train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
         counts.append((out["num_samples"], out["num_samples_full"]))
         gs += 1
+        host_t.append(time.perf_counter())
     e1.record()
     barrier()
+    if rank == 0 and os.environ.get("IA_BENCH_VERBOSE"):
+        print("host ms per step:", [round(1e3 * (b - a), 1) for a, b in zip(host_t[:-1], host_t[1:])], file=sys.stderr)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     prof.enabled = False
@@ -309,10 +323,13 @@ def run_b200(args):
         _ = float(loss.item())                                   # D2H read of the step result
         d2h = 4
         gs += 1
+        if rank == 0 and os.environ.get("IA_BENCH_VERBOSE"):
+            print("e2e step done at", round(1e3 * time.perf_counter(), 1), file=sys.stderr)
     t1.record()
     barrier()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = total_rays / (e2e_ms / 1e3)
+    gc.enable()
 
     if rank != 0:
         if world > 1:
@@ -493,7 +510,7 @@ def main():
     os.dup2(2, 1)          # stray prints of libraries go to stderr; stdout carries exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")

@@ -391,7 +391,7 @@ __device__ __forceinline__ void store_cols16(Ctx &c, uint32_t hi_off, uint32_t l
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <int ACT, int NOU>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, (NOU <= 3 ? 2 : 1))
 mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                   const float *__restrict__ params, float *__restrict__ out, int64_t ld_out)
 {
@@ -405,10 +405,15 @@ mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     const float *bl = reinterpret_cast<const float *>(smem + c.P.bl), *wl = reinterpret_cast<const float *>(smem + c.P.wl);
     float *part = reinterpret_cast<float *>(smem + c.P.part);      // [CG][ROWS][NOU] partial output sums
     const uint32_t idesc_fwd = make_idesc(128, W, 0, 0);
-    const Operand AX = act_as_A_kmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
-    const Operand AH = act_as_A_kmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
-    const Operand BW0 = w_as_B_kmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
-    const Operand BW1 = w_as_B_kmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+    // operand descriptors live in shared memory: only the issuing thread needs them, keep them out of everyone's registers
+    __shared__ Operand s_op[4];
+    if (threadIdx.x == 0) {
+        s_op[0] = act_as_A_kmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
+        s_op[1] = act_as_A_kmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
+        s_op[2] = w_as_B_kmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
+        s_op[3] = w_as_B_kmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+    }
+    const Operand &AX = s_op[0], &AH = s_op[1], &BW0 = s_op[2], &BW1 = s_op[3];
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row = tile * ROWS + c.r;
@@ -534,16 +539,21 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
     const uint32_t idesc_dx = make_idesc(128, D.K0, 0, 1);        // dX  = dZ1 * W0      (B MN-major)
     const uint32_t idesc_dw1 = make_idesc(64, 72, 1, 1);          // dW1 = dZ2^T [H1|1]  (both MN-major)
     const uint32_t idesc_dw0 = make_idesc(64, D.K0, 1, 1);        // dW0 = dZ1^T [X|1]
-    const Operand AX = act_as_A_kmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
-    const Operand AH = act_as_A_kmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
-    const Operand ADZ = act_as_A_kmajor(c.sbase + c.P.dz_hi, c.sbase + c.P.dz_lo);
-    const Operand XT = act_as_mnmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
-    const Operand HT = act_as_mnmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
-    const Operand DZT = act_as_mnmajor(c.sbase + c.P.dz_hi, c.sbase + c.P.dz_lo);
-    const Operand BW0 = w_as_B_kmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
-    const Operand BW1 = w_as_B_kmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
-    const Operand BW0T = w_as_B_mnmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
-    const Operand BW1T = w_as_B_mnmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+    __shared__ Operand s_op[10];
+    if (threadIdx.x == 0) {
+        s_op[0] = act_as_A_kmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
+        s_op[1] = act_as_A_kmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
+        s_op[2] = act_as_A_kmajor(c.sbase + c.P.dz_hi, c.sbase + c.P.dz_lo);
+        s_op[3] = act_as_mnmajor(c.sbase + c.P.ax_hi, c.sbase + c.P.ax_lo);
+        s_op[4] = act_as_mnmajor(c.sbase + c.P.ah_hi, c.sbase + c.P.ah_lo);
+        s_op[5] = act_as_mnmajor(c.sbase + c.P.dz_hi, c.sbase + c.P.dz_lo);
+        s_op[6] = w_as_B_kmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
+        s_op[7] = w_as_B_kmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+        s_op[8] = w_as_B_mnmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
+        s_op[9] = w_as_B_mnmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+    }
+    const Operand &AX = s_op[0], &AH = s_op[1], &ADZ = s_op[2], &XT = s_op[3], &HT = s_op[4], &DZT = s_op[5];
+    const Operand &BW0 = s_op[6], &BW1 = s_op[7], &BW0T = s_op[8], &BW1T = s_op[9];
 
     // persistent per-thread partial sums of dW_last[o][16*cg + j] and db_last[o] (reduced over rows at the very end)
     constexpr bool REG_DWL = NOU >= 1 && NOU <= 3;

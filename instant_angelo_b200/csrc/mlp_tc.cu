@@ -20,6 +20,7 @@
 // power of two so that they sit in fp16's normal range.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -42,14 +43,15 @@ struct TcDims {
     float s0, o0;
     int nh, n_out, nou, act;
     int pW0, pb0, pW1, pb1, pWl, pbl;
+    int dbg;   // timing experiments only (IA_TC_DBG): 1 no global input loads, 2 identity activations, 4 no drains, 8 no dX stores
 };
 
 struct SmemPlan {  // byte offsets
     uint32_t ax_hi, ax_lo, ah_hi, ah_lo, dz_hi, dz_lo, w0_hi, w0_lo, w1_hi, w1_lo, wl, b0, b1, bl, dw0, dw1, dwl, dbl, red,
-        part, mbar, tmem, total;
+        part, mbar, tmem, ax2_hi, ax2_lo, ah2_hi, ah2_lo, total;
 };
 
-__host__ __device__ inline SmemPlan make_plan(const TcDims &D, bool bwd)
+__host__ __device__ inline SmemPlan make_plan(const TcDims &D, bool bwd, bool pipe = false)
 {
     SmemPlan p;
     uint32_t o = 0;
@@ -71,6 +73,9 @@ __host__ __device__ inline SmemPlan make_plan(const TcDims &D, bool bwd)
     p.part = take(bwd ? 0 : (uint32_t)(CG * ROWS * MAX_OUT * 4));
     p.mbar = take(16);
     p.tmem = take(16);
+    // software-pipelined backward: second set of X / H1 operand buffers (next tile's forward overlaps this tile's backward)
+    p.ax2_hi = take(pipe ? ax : 0); p.ax2_lo = take(pipe ? ax : 0);
+    p.ah2_hi = take(pipe ? 9 * 2048 : 0); p.ah2_lo = take(pipe ? 9 * 2048 : 0);
     p.total = o;
     return p;
 }
@@ -239,9 +244,14 @@ __device__ __forceinline__ Operand act_as_mnmajor(uint32_t hi, uint32_t lo) { re
 __device__ __forceinline__ Operand w_as_B_kmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 1024u, 128u, 2048u); }
 __device__ __forceinline__ Operand w_as_B_mnmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 128u, 1024u, 256u); }
 
+// Internal column order of the first layer's input: [in1 (n_in1) | in0 (n_in0) | constant one | zeros].  Putting the wide,
+// 16-byte aligned in1 block (the hash-grid features) first lets the input rows be read, and their gradients be written,
+// with float4 accesses.  `shift` = n_in1 for the first layer (global column = (c < n_in1) ? n_in0 + c : c - n_in1), 0 otherwise.
+__device__ __forceinline__ int global_col(int c, int n_in0, int n_in1) { return c < n_in1 ? n_in0 + c : c - n_in1; }
+
 // W[64][n_in] fp32 (global) -> split fp16 canonical K-major B operand with Kpad columns (zero padded)
 __device__ __forceinline__ void stage_weight(char *smem, uint32_t hi_off, uint32_t lo_off, const float *__restrict__ Wg, int n_in,
-                                             int Kpad)
+                                             int Kpad, int n_in0 = 0, int n_in1 = 0)
 {
     for (int i = threadIdx.x; i < W * (Kpad / 8); i += THREADS) {
         const int o = i % W, c8 = i / W;
@@ -249,7 +259,7 @@ __device__ __forceinline__ void stage_weight(char *smem, uint32_t hi_off, uint32
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = 8 * c8 + j;
-            a[j] = c < n_in ? __ldg(Wg + o * n_in + c) : 0.f;
+            a[j] = c < n_in ? __ldg(Wg + o * n_in + (n_in1 > 0 ? global_col(c, n_in0, n_in1) : c)) : 0.f;
         }
         store_split8(smem + hi_off, smem + lo_off, (uint32_t)c8 * 1024u + (uint32_t)o * 16u, a);
     }
@@ -306,7 +316,7 @@ __device__ __forceinline__ void setup_common(Ctx &c, const TcDims &D, const floa
     char *smem = c.smem;
     c.r = tid & (ROWS - 1);
     c.cg = tid >> 7;
-    stage_weight(smem, c.P.w0_hi, c.P.w0_lo, params + D.pW0, D.din, D.K0);
+    stage_weight(smem, c.P.w0_hi, c.P.w0_lo, params + D.pW0, D.din, D.K0, D.n_in0, D.n_in1);
     if (D.nh == 2) stage_weight(smem, c.P.w1_hi, c.P.w1_lo, params + D.pW1, W, W);
     float *wl = reinterpret_cast<float *>(smem + c.P.wl);
     for (int i = tid; i < NOU * W; i += THREADS) wl[i] = i < D.nou * W ? __ldg(params + D.pWl + i) : 0.f;
@@ -346,24 +356,77 @@ __device__ __forceinline__ void teardown(Ctx &c)
     }
 }
 
-// this thread's share of the input row -> A_X (K0 columns: inputs, then the constant one, then zeros)
+// ---- first-layer input rows.  Thread (r, cg) owns the 8-column chunks cg, cg+4, ... of row r.
+constexpr int MAX_IN_CHUNKS = 3;   // K0 <= 96 -> at most 3 chunks per thread
+
+struct InRegs { float v[MAX_IN_CHUNKS][8]; };
+
+__device__ __forceinline__ void load_input_regs(const Ctx &c, const TcDims &D, const float *__restrict__ in0,
+                                                const float *__restrict__ in1, int64_t row, bool valid, InRegs &R)
+{
+    const bool vec = (D.n_in1 & 3) == 0;
+#pragma unroll
+    for (int q = 0; q < MAX_IN_CHUNKS; ++q) {
+        const int c8 = c.cg + CG * q;
+        if (c8 * 8 >= D.K0) break;
+        if (valid && !(D.dbg & 1) && vec && c8 * 8 + 8 <= D.n_in1) {
+            const float4 *src = reinterpret_cast<const float4 *>(in1 + row * D.n_in1 + 8 * c8);
+            const float4 a = __ldg(src), b = __ldg(src + 1);
+            R.v[q][0] = a.x; R.v[q][1] = a.y; R.v[q][2] = a.z; R.v[q][3] = a.w;
+            R.v[q][4] = b.x; R.v[q][5] = b.y; R.v[q][6] = b.z; R.v[q][7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = 8 * c8 + j;
+                float v = 0.f;
+                if (valid && !(D.dbg & 1)) {
+                    if (col < D.n_in1) v = __ldg(in1 + row * D.n_in1 + col);
+                    else if (col < D.din) v = fmaf(__ldg(in0 + row * D.n_in0 + (col - D.n_in1)), D.s0, D.o0);
+                    else if (col == D.din) v = 1.0f;
+                }
+                R.v[q][j] = v;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void store_input_regs(Ctx &c, const TcDims &D, const InRegs &R, uint32_t hi_off, uint32_t lo_off)
+{
+#pragma unroll
+    for (int q = 0; q < MAX_IN_CHUNKS; ++q) {
+        const int c8 = c.cg + CG * q;
+        if (c8 * 8 >= D.K0) break;
+        store_split8(c.smem + hi_off, c.smem + lo_off, (uint32_t)c8 * 2048u + (uint32_t)c.r * 16u, R.v[q]);
+    }
+}
+
 __device__ __forceinline__ void stage_input(Ctx &c, const TcDims &D, const float *__restrict__ in0, const float *__restrict__ in1,
                                             int64_t row, bool valid)
 {
-    for (int c8 = c.cg; c8 < D.K0 / 8; c8 += CG) {
-        float a[8];
+    InRegs R;
+    load_input_regs(c, D, in0, in1, row, valid, R);
+    store_input_regs(c, D, R, c.P.ax_hi, c.P.ax_lo);
+}
+
+// this thread's 16-column share of d(input): internal columns [16ci, 16ci+16) of the dX accumulator -> din1 / din0
+__device__ __forceinline__ void write_dx16(const TcDims &D, int c0, const float (&v)[16], float inv_scale, int64_t row,
+                                           float *__restrict__ din0, float *__restrict__ din1)
+{
+    if (din1 && (D.n_in1 & 3) == 0 && c0 + 16 <= D.n_in1) {
+        float4 *dst = reinterpret_cast<float4 *>(din1 + row * D.n_in1 + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = 8 * c8 + j;
-            float v = 0.f;
-            if (valid) {
-                if (col < D.n_in0) v = fmaf(__ldg(in0 + row * D.n_in0 + col), D.s0, D.o0);
-                else if (col < D.din) v = __ldg(in1 + row * D.n_in1 + (col - D.n_in0));
-                else if (col == D.din) v = 1.0f;
-            }
-            a[j] = v;
+        for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        if (col < D.n_in1) {
+            if (din1) din1[row * D.n_in1 + col] = v[j] * inv_scale;
+        } else if (col < D.din) {
+            if (din0) din0[row * D.n_in0 + (col - D.n_in1)] = v[j] * inv_scale * D.s0;
         }
-        store_split8(c.smem + c.P.ax_hi, c.smem + c.P.ax_lo, (uint32_t)c8 * 2048u + (uint32_t)c.r * 16u, a);
     }
 }
 
@@ -680,17 +743,7 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
                 const int c0 = 16 * ci;
                 float v[16];
                 tmem_ld16(c.tmem + c.lane_addr + D0_COL + (uint32_t)c0, v);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int col = c0 + j;
-                        if (col < D.n_in0) {
-                            if (din0) din0[row * D.n_in0 + col] = v[j] * inv_scale * D.s0;
-                        } else if (col < D.din) {
-                            if (din1) din1[row * D.n_in1 + (col - D.n_in0)] = v[j] * inv_scale;
-                        }
-                    }
-                }
+                if (valid) write_dx16(D, c0, v, inv_scale, row, din0, din1);
             }
         }
         if (threadIdx.x == 0 && g_tc_timing_on) {
@@ -720,7 +773,7 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
         for (int i = tid; i < W * D.K0; i += THREADS) {
             const int o = i / D.K0, col = i - o * D.K0;
             const float g = dw0[o * ld0 + col];
-            if (col < D.din) atomicAdd(dparams + D.pW0 + o * D.din + col, g);
+            if (col < D.din) atomicAdd(dparams + D.pW0 + o * D.din + global_col(col, D.n_in0, D.n_in1), g);
             else if (col == D.din) atomicAdd(dparams + D.pb0 + o, g);
         }
         if (D.nh == 2) {
@@ -730,6 +783,321 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
                 if (col < W) atomicAdd(dparams + D.pW1 + o * W + col, g);
                 else if (col == W) atomicAdd(dparams + D.pb1 + o, g);
             }
+        }
+        for (int i = tid; i < D.nou * W; i += THREADS) atomicAdd(dparams + D.pWl + i, dwl[i]);
+        if (tid < D.nou) atomicAdd(dparams + D.pbl + tid, dbl[tid]);
+    }
+    teardown(c);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, software pipelined (two hidden layers, K0 <= 64): the forward recomputation of tile i+1 shares the two
+// MMA phases of tile i's backward, so a tile costs 2 barrier/MMA round trips instead of 4 and every phase carries more
+// independent epilogue work.
+//   phase 1 MMAs:  dH1(i) = dZ2 W1 -> D2 | dW1 += dZ2^T [H1(i)|1] -> D1 | L0(i+1) = X(i+1) W0^T -> D0
+//   phase 2 MMAs:  dX(i)  = dZ1 W0 -> D2 | dW0 += dZ1^T [X(i)|1]  -> D1 | L1(i+1) = H1(i+1) W1^T -> D0
+// X / H1 are double buffered (tile parity), dZ is single buffered (each MMA phase has completed before it is rewritten).
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t PD0 = 0, PD2 = 64, PD1 = 128;   // TMEM columns: forward acc | dH/dX acc | dW acc
+
+__device__ __forceinline__ void drain_dw_at(Ctx &c, uint32_t col0, float *__restrict__ acc_smem, int n_cols, int ld, float inv_scale)
+{
+    const int lane = threadIdx.x & 31;
+    const int o = 16 * ((threadIdx.x >> 5) & 3) + lane;
+    for (int ci = c.cg; ci * 16 < n_cols; ci += CG) {
+        const int c0 = 16 * ci;
+        float v[16];
+        const int m = n_cols - c0 >= 16 ? 16 : 8;
+        if (m == 16) tmem_ld16(c.tmem + c.lane_addr + col0 + (uint32_t)c0, v);
+        else tmem_ld8(c.tmem + c.lane_addr + col0 + (uint32_t)c0, v);
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < m) acc_smem[o * ld + c0 + j] += v[j] * inv_scale;
+        }
+    }
+}
+
+template <int ACT, int NOU>
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
+                       const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
+                       float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams)
+{
+    extern __shared__ __align__(1024) char smem[];
+    Ctx c;
+    c.smem = smem;
+    c.P = make_plan(D, true, true);
+    c.sbase = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld0 = D.K0 + 1, ld1 = 73;
+    float *dw0 = reinterpret_cast<float *>(smem + c.P.dw0), *dw1 = reinterpret_cast<float *>(smem + c.P.dw1);
+    float *dwl = reinterpret_cast<float *>(smem + c.P.dwl), *dbl = reinterpret_cast<float *>(smem + c.P.dbl);
+    float *red = reinterpret_cast<float *>(smem + c.P.red);      // [0,16): per-warp maxima of the current tile's |dy|
+    for (int i = tid; i < W * ld0; i += THREADS) dw0[i] = 0.f;
+    for (int i = tid; i < W * ld1; i += THREADS) dw1[i] = 0.f;
+    for (int i = tid; i < MAX_OUT * W; i += THREADS) dwl[i] = 0.f;
+    if (tid < MAX_OUT) dbl[tid] = 0.f;
+    setup_common<NOU>(c, D, params);
+    if (tid < ROWS) {   // constant-one column of the second H1 buffer
+        float a[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_split8(smem + c.P.ah2_hi, smem + c.P.ah2_lo, 8u * 2048u + (uint32_t)tid * 16u, a);
+    }
+    const float *b0 = reinterpret_cast<const float *>(smem + c.P.b0), *b1 = reinterpret_cast<const float *>(smem + c.P.b1);
+    const float *wl = reinterpret_cast<const float *>(smem + c.P.wl);
+    constexpr int NO = NOU > 0 ? NOU : 1;
+    float wmax = NOU == 0 ? 1.f : 0.f;
+    for (int i = tid; i < NOU * W; i += THREADS) wmax = fmaxf(wmax, fabsf(wl[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) red[warp] = wmax;
+    __syncthreads();
+    wmax = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) wmax = fmaxf(wmax, red[w]);
+    wmax = fmaxf(wmax * (float)NO, 1e-30f);
+    __syncthreads();
+
+    const bool want_dx = din0 != nullptr || din1 != nullptr;
+    const uint32_t idesc_fwd = make_idesc(128, W, 0, 0);
+    const uint32_t idesc_dh = make_idesc(128, W, 0, 1);
+    const uint32_t idesc_dx = make_idesc(128, D.K0, 0, 1);
+    const uint32_t idesc_dw1 = make_idesc(64, 72, 1, 1);
+    const uint32_t idesc_dw0 = make_idesc(64, D.K0, 1, 1);
+    // [parity][0: X as A (K-major), 1: H1 as A, 2: X^T (MN-major), 3: H1^T]; then dZ, dZ^T, W0, W1, W0^T, W1^T
+    __shared__ Operand s_buf[2][4];
+    __shared__ Operand s_op[6];
+    if (threadIdx.x == 0) {
+        const uint32_t axh[2] = {c.sbase + c.P.ax_hi, c.sbase + c.P.ax2_hi}, axl[2] = {c.sbase + c.P.ax_lo, c.sbase + c.P.ax2_lo};
+        const uint32_t ahh[2] = {c.sbase + c.P.ah_hi, c.sbase + c.P.ah2_hi}, ahl[2] = {c.sbase + c.P.ah_lo, c.sbase + c.P.ah2_lo};
+        for (int b = 0; b < 2; ++b) {
+            s_buf[b][0] = act_as_A_kmajor(axh[b], axl[b]);
+            s_buf[b][1] = act_as_A_kmajor(ahh[b], ahl[b]);
+            s_buf[b][2] = act_as_mnmajor(axh[b], axl[b]);
+            s_buf[b][3] = act_as_mnmajor(ahh[b], ahl[b]);
+        }
+        s_op[0] = act_as_A_kmajor(c.sbase + c.P.dz_hi, c.sbase + c.P.dz_lo);
+        s_op[1] = act_as_mnmajor(c.sbase + c.P.dz_hi, c.sbase + c.P.dz_lo);
+        s_op[2] = w_as_B_kmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
+        s_op[3] = w_as_B_kmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+        s_op[4] = w_as_B_mnmajor(c.sbase + c.P.w0_hi, c.sbase + c.P.w0_lo);
+        s_op[5] = w_as_B_mnmajor(c.sbase + c.P.w1_hi, c.sbase + c.P.w1_lo);
+    }
+    const Operand &ADZ = s_op[0], &DZT = s_op[1], &BW0 = s_op[2], &BW1 = s_op[3], &BW0T = s_op[4], &BW1T = s_op[5];
+    const uint32_t ax_hi[2] = {c.P.ax_hi, c.P.ax2_hi}, ax_lo[2] = {c.P.ax_lo, c.P.ax2_lo};
+    const uint32_t ah_hi[2] = {c.P.ah_hi, c.P.ah2_hi}, ah_lo[2] = {c.P.ah_lo, c.P.ah2_lo};
+
+    constexpr bool REG_DWL = NOU >= 1 && NOU <= 3;
+    constexpr int NREG = REG_DWL ? NOU : 1;
+    float gwl[NREG][16];
+    float gbl[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) gbl[o] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NREG; ++o)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gwl[o][j] = 0.f;
+
+    // loads this thread's share of the incoming gradient of a tile and returns the tile-local max |.| of this thread
+    float dy[NO];
+    float dhf[NOU == 0 ? 16 : 1];
+    auto load_dy = [&](int64_t row, bool valid) -> float {
+        float m = 0.f;
+        if constexpr (NOU == 0) {
+            const float4 *src = reinterpret_cast<const float4 *>(dout + row * ld_dout + 16 * c.cg);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dhf[4 * q] = t.x; dhf[4 * q + 1] = t.y; dhf[4 * q + 2] = t.z; dhf[4 * q + 3] = t.w;
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+            }
+            dy[0] = 0.f;
+        } else {
+#pragma unroll
+            for (int o = 0; o < NOU; ++o) {
+                dy[o] = (valid && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
+                m = fmaxf(m, fabsf(dy[o]));
+                if (c.cg == 0) gbl[o] += dy[o];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        return m;
+    };
+    auto tile_scale = [&](float &scale, float &inv_scale) {   // call after the barrier that published `red`
+        float m = 0.f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) m = fmaxf(m, red[w]);
+        int e = 0;
+        frexpf(fmaxf(m * wmax, 1e-30f), &e);
+        e = max(min(e, 60), -60);
+        scale = ldexpf(1.0f, 6 - e);
+        inv_scale = ldexpf(1.0f, e - 6);
+    };
+
+    const int64_t n_tiles = (n + ROWS - 1) / ROWS;
+    int64_t tile = blockIdx.x;
+    float scale = 1.f, inv_scale = 1.f;
+    if (tile < n_tiles) {
+        // ---- prologue: forward of the first tile, its incoming gradient and scale
+        const int64_t row = tile * ROWS + c.r;
+        const bool valid = row < n;
+        InRegs R0;
+        load_input_regs(c, D, in0, in1, row, valid, R0);
+        store_input_regs(c, D, R0, ax_hi[0], ax_lo[0]);
+        const float m = load_dy(row, valid);
+        if (lane == 0) red[warp] = m;
+        run_mma(c, [&]() { issue_gemm(c.tmem + PD0, s_buf[0][0], BW0, idesc_fwd, D.K0 / 16); });
+        tile_scale(scale, inv_scale);
+        float h[16];
+        tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
+        store_cols16(c, ah_hi[0], ah_lo[0], h);
+        run_mma(c, [&]() { issue_gemm(c.tmem + PD0, s_buf[0][1], BW1, idesc_fwd, W / 16); });
+    }
+    // input rows of the NEXT tile are fetched into registers one phase ahead of their use (global latency hidden)
+    InRegs Rn;
+    {
+        const int64_t ntile0 = tile + gridDim.x;
+        const int64_t nrow0 = ntile0 * ROWS + c.r;
+        if (ntile0 < n_tiles) load_input_regs(c, D, in0, in1, nrow0, nrow0 < n, Rn);
+    }
+    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        const int64_t row = tile * ROWS + c.r;
+        const bool valid = row < n;
+        const int64_t ntile = tile + gridDim.x;
+        const bool has_next = ntile < n_tiles;
+        const int64_t nrow = ntile * ROWS + c.r;
+        const bool nvalid = has_next && nrow < n;
+        const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
+        // ---- A: D0 = pre-activations of the last hidden layer of tile i; next tile's input goes to the other buffer
+        if (has_next) store_input_regs(c, D, Rn, ax_hi[nxt], ax_lo[nxt]);
+        {
+            float h[16], dz[16];
+            tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = 16 * c.cg + j;
+                h[j] = (D.dbg & 2) ? h[j] + b1[k] : act_fwd<ACT>(h[j] + b1[k]);
+                float dh = 0.f;
+                if constexpr (NOU == 0) {
+                    dh = dhf[j];
+                } else {
+#pragma unroll
+                    for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
+                }
+                dz[j] = dh * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(h[j])) * scale;
+            }
+            if (NOU == 0) {
+            } else if (REG_DWL) {
+#pragma unroll
+                for (int o = 0; o < NREG; ++o)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) gwl[o][j] = fmaf(dy[o], h[j], gwl[o][j]);
+            } else {
+#pragma unroll 1
+                for (int o = 0; o < NOU; ++o) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float s = warp_sum(dy[o] * h[j]);
+                        if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
+                    }
+                }
+            }
+            store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
+        }
+        // ---- phase 1
+        run_mma(c, [&]() {
+            issue_gemm(c.tmem + PD2, ADZ, BW1T, idesc_dh, W / 16);
+            issue_gemm(c.tmem + PD1, DZT, s_buf[cur][3], idesc_dw1, ROWS / 16);
+            if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][0], BW0, idesc_fwd, D.K0 / 16);
+        });
+        const float inv_cur = inv_scale;
+        if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
+        {
+            // dZ1(i) = dH1 (*) act'(H1(i)); H1(i+1) = act(L0(i+1) + b0)
+            float v[16];
+            tmem_ld16(c.tmem + c.lane_addr + PD2 + 16u * c.cg, v);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float hh[8], a[8];
+                const uint32_t off = (uint32_t)(2 * c.cg + half) * 2048u + (uint32_t)c.r * 16u;
+                load_split8(smem + ah_hi[cur], smem + ah_lo[cur], off, hh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(hh[j]));
+                store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, off, a);
+            }
+            if (has_next) {
+                float h[16];
+                tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h[j] = (D.dbg & 2) ? h[j] + b0[16 * c.cg + j] : act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
+                store_cols16(c, ah_hi[nxt], ah_lo[nxt], h);
+            }
+        }
+        // incoming gradient of the next tile: its per-warp maxima are published by the phase-2 barrier
+        // (dy / dhf of tile i are dead from here on: the output-layer work of tile i happened in stage A)
+        float mnext = 0.f;
+        if (has_next) mnext = load_dy(nrow, nvalid);
+        if (lane == 0) red[warp] = mnext;
+        // ---- phase 2
+        run_mma(c, [&]() {
+            if (want_dx) issue_gemm(c.tmem + PD2, ADZ, BW0T, idesc_dx, W / 16);
+            issue_gemm(c.tmem + PD1, DZT, s_buf[cur][2], idesc_dw0, ROWS / 16);
+            if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][1], BW1, idesc_fwd, W / 16);
+        });
+        tile_scale(scale, inv_scale);       // scale of tile i+1 (red was written before the barrier)
+        {
+            const int64_t n2tile = ntile + gridDim.x;          // prefetch the input rows of tile i+2
+            const int64_t n2row = n2tile * ROWS + c.r;
+            if (n2tile < n_tiles) load_input_regs(c, D, in0, in1, n2row, n2row < n, Rn);
+        }
+        if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw0, D.K0, ld0, inv_cur);
+        if (want_dx && !(D.dbg & 8)) {
+            for (int ci = c.cg; ci * 16 < D.din; ci += CG) {
+                const int c0 = 16 * ci;
+                float v[16];
+                tmem_ld16(c.tmem + c.lane_addr + PD2 + (uint32_t)c0, v);
+                if (valid) write_dx16(D, c0, v, inv_cur, row, din0, din1);
+            }
+        }
+        if (threadIdx.x == 0 && g_tc_timing_on) {
+            atomicAdd(&g_tc_cycles[3], (unsigned long long)(clock64() - tile_t0));
+            atomicAdd(&g_tc_cycles[4], 1ull);
+        }
+    }
+    // ---- reduce the register-resident output-layer gradients over the rows of the CTA
+    if (REG_DWL) {
+#pragma unroll
+        for (int o = 0; o < NREG; ++o) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float s = warp_sum(gwl[o][j]);
+                if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NOU; ++o) {
+        const float sb = warp_sum(gbl[o]);
+        if (lane == 0 && c.cg == 0) atomicAdd(&dbl[o], sb);
+    }
+    __syncthreads();
+    if (dparams != nullptr) {
+        for (int i = tid; i < W * D.K0; i += THREADS) {
+            const int o = i / D.K0, col = i - o * D.K0;
+            const float g = dw0[o * ld0 + col];
+            if (col < D.din) atomicAdd(dparams + D.pW0 + o * D.din + global_col(col, D.n_in0, D.n_in1), g);
+            else if (col == D.din) atomicAdd(dparams + D.pb0 + o, g);
+        }
+        for (int i = tid; i < W * 72; i += THREADS) {
+            const int o = i / 72, col = i - o * 72;
+            const float g = dw1[o * ld1 + col];
+            if (col < W) atomicAdd(dparams + D.pW1 + o * W + col, g);
+            else if (col == W) atomicAdd(dparams + D.pb1 + o, g);
         }
         for (int i = tid; i < D.nou * W; i += THREADS) atomicAdd(dparams + D.pWl + i, dwl[i]);
         if (tid < D.nou) atomicAdd(dparams + D.pbl + tid, dbl[tid]);
@@ -761,6 +1129,7 @@ int make_dims(const ia_mlp_desc *d, int32_t n_out_used, TcDims *D)
     if (D->nh == 2) { D->pW1 = p; p += W * W; D->pb1 = p; p += W; }
     D->pWl = p; p += d->n_out * W;
     D->pbl = p;
+    D->dbg = getenv("IA_TC_DBG") ? atoi(getenv("IA_TC_DBG")) : 0;
     return IA_OK;
 }
 
@@ -832,16 +1201,27 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
     IA_REQUIRE(ld_dout >= (n_out_used == 0 ? W : n_out_used), "mlp_tc_bwd: ld_dout too small");
     IA_REQUIRE(n_out_used != 0 || (ld_dout % 4 == 0 && ((uintptr_t)dout & 15) == 0), "mlp_tc_bwd: feature gradient must be 16-byte aligned");
     if (n == 0) return IA_OK;
-    const SmemPlan P = make_plan(D, true);
+    // software-pipelined variant when two hidden layers and the doubled X / H1 buffers fit in shared memory
+    const SmemPlan Ppipe = make_plan(D, true, true);
+    const bool pipe = D.nh == 2 && D.K0 <= 64 && Ppipe.total <= 227 * 1024 && getenv("IA_TC_NO_PIPE") == nullptr;
+    const SmemPlan P = pipe ? Ppipe : make_plan(D, true);
     IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_bwd: needs %u B of shared memory", P.total);
     const int64_t n_tiles = ia_ceil_div(n, ROWS);
     const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));
     const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
 #define IA_TC_BWD(ACT, NOU)                                                                                                       \
     do {                                                                                                                          \
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total)); \
-        mlp_tc_bwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout, ld_dout,   \
-                                                                                        din0, din1, dparams);                    \
+        if (pipe) {                                                                                                               \
+            IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                            (int)P.total));                                                                       \
+            mlp_tc_bwd_pipe_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,   \
+                                                                                                 ld_dout, din0, din1, dparams);  \
+        } else {                                                                                                                  \
+            IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                            (int)P.total));                                                                       \
+            mlp_tc_bwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,        \
+                                                                                            ld_dout, din0, din1, dparams);       \
+        }                                                                                                                         \
     } while (0)
     const bool sp = D.act == IA_ACT_SOFTPLUS100;
     if (D.nou == 0) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_BWD(IA_ACT_RELU, 0); }

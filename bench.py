@@ -343,24 +343,30 @@ def run_b200(args):
     prof_ms = (ms_total / K) * PROF_STEPS              # the per-kernel events cover the first PROF_STEPS timed steps
     per_kernel = {k: {"calls_per_step": c / PROF_STEPS, "ms_per_step": t / PROF_STEPS, "share_of_step": t / prof_ms}
                   for k, (c, t, w) in summary.items()}
-    def group(prefix):
-        items = [(k, v) for k, v in summary.items() if k.startswith(prefix)]
-        return sum(v[0] for _, v in items), sum(v[1] for _, v in items), sum(v[2] for _, v in items)
-    groups = {"hashgrid_fwd": group("ia_hashgrid_fwd"), "hashgrid_bwd": group("ia_hashgrid_bwd"), "mlp_fwd": group("ia_mlp_fwd"),
-              "mlp_bwd": group("ia_mlp_bwd")}
-    dom = max(groups, key=lambda k: groups[k][1])
-    calls, ms, work = groups[dom]
-    if dom.startswith("mlp"):
+    dom = max(summary, key=lambda k: summary[k][1])     # the (entry point, shape) with the largest total device time
+    calls, ms, work = summary[dom]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if dom in tj:       # DRAM bytes of the ncu capture, rescaled from its row count to this run's average launch
+            flop_per_row = 2.0 * 2 * (35 * 64 + 64 * 64 + 64 * 1)
+            traffic = tj[dom]["dram_bytes_per_row"] * (work / max(calls, 1)) / flop_per_row
+    if dom.startswith("ia_mlp"):
         achieved = work / (ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16; the fp32 FFMA path cannot reach it)" if args.mlp != "tc" else peaks["source"],
-                "launches": calls, "avg_launch_ms": ms / max(calls, 1), "algorithmic_flop_per_launch": work / max(calls, 1)}
+                "traffic": traffic, "peak_source": peaks["source"] + " (sustained bf16 GEMM)", "launches": calls,
+                "avg_launch_ms": ms / max(calls, 1), "algorithmic_flop_per_launch": work / max(calls, 1),
+                "note": "algorithmic FLOP = 2*MAC of the unpadded fp32 network (x2 for backward); the kernel issues 3 f16 MMAs per "
+                        "product (fp32-equivalent split) and is bound by its per-row activation epilogue (MUFU/FP32/smem), not by "
+                        "the tensor pipe: see DESIGN.md section 4.2 and profiles/r01_ncu_mlp_tc_bwd.md"}
     else:
         achieved = work / (ms / 1e3) / 1e9
         peak = peaks["hbm_gbs"]
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peaks["source"], "launches": calls, "avg_launch_ms": ms / max(calls, 1),
+                "traffic": traffic, "peak_source": peaks["source"], "launches": calls, "avg_launch_ms": ms / max(calls, 1),
                 "algorithmic_bytes_per_launch": work / max(calls, 1)}
 
     cpu = cpu_baseline_leg(cfg, model, args) if world == 1 and not args.no_cpu_baseline else None

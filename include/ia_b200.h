@@ -133,6 +133,13 @@ int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *
                    const float *params, const float *dout, int32_t n_out_used, int64_t ld_dout,
                    float *din0, float *din1, float *dparams, void *stream);
 
+/* Wide output layer for the feature mode above: out[n, n_out] = h[n, 64] W[n_out, 64]^T + b (n_out <= 128), fp32.
+ * Backward: dh[n,64] = dout W (may be NULL); dW[n_out,64] += dout^T h and db[n_out] += sum dout (ACCUMULATED; may be NULL). */
+int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out,
+                        int64_t ld_out, void *stream);
+int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
+                        float *dh, float *dW, float *db, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Finite-difference / curvature stages  fused elementwise stages of VolumeSDF.forward
  *                                       (models/geometry.py:219-234 FD taps + gradient, :236-275 curvature)

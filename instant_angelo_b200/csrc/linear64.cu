@@ -1,0 +1,215 @@
+// Wide output layer of the width-64 networks: out[n, n_out] = h[n, 64] * W[n_out, 64]^T + b   (n_out <= 128),
+// forward and backward, fp32 FFMA.  Used for the 65-feature centre evaluation of the SDF network
+// (reference models/geometry.py:206: the full `feature` output), whose hidden layers run on the tensor-core kernel
+// (mlp_tc.cu, feature mode).  Skinny-N / skinny-K GEMMs like these are where a general GEMM library does worst
+// (cuBLAS picks a large-K SIMT kernel for dW = dY^T h: 1.5 ms at 1.5 M rows); these kernels are memory-streaming:
+// each reads h / dY once.
+#include <algorithm>
+
+#include "ia_common.cuh"
+
+namespace {
+
+constexpr int LW = 64;          // input width
+constexpr int LROWS = 128;      // rows per tile
+constexpr int LTHREADS = 256;
+constexpr int LPAD = 65;        // padded row length of the activation tiles (conflict-free row-per-lane access)
+constexpr int WPAD = 68;        // padded row length of the weight tile (16-byte aligned rows for float4 broadcasts)
+constexpr int MAX_NOUT = 128;
+
+// out[r][o] = b[o] + sum_k h[r][k] W[o][k].  Thread (r = t & 127, half = t >> 7) produces outputs o = half, half+2, ...
+__global__ void __launch_bounds__(LTHREADS)
+linear64_fwd_kernel(const float *__restrict__ h, int64_t n, const float *__restrict__ Wg, const float *__restrict__ bg, int n_out,
+                    float *__restrict__ out, int64_t ld_out)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *Ws = sm;                       // [n_out][WPAD]
+    float *bs = Ws + n_out * WPAD;        // [n_out]
+    float *Hs = bs + ((n_out + 3) & ~3);  // [LROWS][LPAD]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_out * LW; i += LTHREADS) Ws[(i / LW) * WPAD + (i % LW)] = __ldg(Wg + i);
+    for (int i = tid; i < n_out; i += LTHREADS) bs[i] = __ldg(bg + i);
+    const int r = tid & (LROWS - 1), half = tid >> 7;
+    const int64_t n_tiles = (n + LROWS - 1) / LROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * LROWS;
+        __syncthreads();
+        for (int i = tid; i < LROWS * LW; i += LTHREADS) {
+            const int rr = i / LW, k = i - rr * LW;
+            Hs[rr * LPAD + k] = (row0 + rr < n) ? __ldg(h + (row0 + rr) * LW + k) : 0.f;
+        }
+        __syncthreads();
+        float hv[LW];
+#pragma unroll
+        for (int k = 0; k < LW; ++k) hv[k] = Hs[r * LPAD + k];
+        if (row0 + r < n) {
+            for (int o = half; o < n_out; o += 2) {
+                float acc = bs[o];
+                const float4 *w4 = reinterpret_cast<const float4 *>(Ws + o * WPAD);
+#pragma unroll
+                for (int q = 0; q < LW / 4; ++q) {
+                    const float4 w = w4[q];
+                    acc = fmaf(hv[4 * q], w.x, acc);
+                    acc = fmaf(hv[4 * q + 1], w.y, acc);
+                    acc = fmaf(hv[4 * q + 2], w.z, acc);
+                    acc = fmaf(hv[4 * q + 3], w.w, acc);
+                }
+                out[(row0 + r) * ld_out + o] = acc;
+            }
+        }
+    }
+}
+
+// dh[r][k] = sum_o dy[r][o] W[o][k]   (thread (r, half) produces k in [32*half, 32*half+32))
+__global__ void __launch_bounds__(LTHREADS)
+linear64_bwd_input_kernel(const float *__restrict__ dy, int64_t ld_dy, int64_t n, const float *__restrict__ Wg, int n_out,
+                          float *__restrict__ dh)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *Ws = sm;                         // [n_out][WPAD]
+    float *Ds = Ws + n_out * WPAD;          // [LROWS][n_out + 1]
+    const int ldd = n_out + 1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_out * LW; i += LTHREADS) Ws[(i / LW) * WPAD + (i % LW)] = __ldg(Wg + i);
+    const int r = tid & (LROWS - 1), half = tid >> 7;
+    const int64_t n_tiles = (n + LROWS - 1) / LROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * LROWS;
+        __syncthreads();
+        for (int i = tid; i < LROWS * n_out; i += LTHREADS) {
+            const int rr = i / n_out, o = i - rr * n_out;
+            Ds[rr * ldd + o] = (row0 + rr < n) ? __ldg(dy + (row0 + rr) * ld_dy + o) : 0.f;
+        }
+        __syncthreads();
+        float acc[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+        for (int o = 0; o < n_out; ++o) {
+            const float g = Ds[r * ldd + o];
+            const float4 *w4 = reinterpret_cast<const float4 *>(Ws + o * WPAD + 32 * half);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 w = w4[q];
+                acc[4 * q] = fmaf(g, w.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(g, w.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(g, w.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(g, w.w, acc[4 * q + 3]);
+            }
+        }
+        if (row0 + r < n) {
+            float4 *dst = reinterpret_cast<float4 *>(dh + (row0 + r) * LW + 32 * half);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+    }
+}
+
+// dW[o][k] += sum_r dy[r][o] h[r][k];  db[o] += sum_r dy[r][o].  Thread (ty = t >> 4, tx = t & 15) owns outputs
+// o in {ty, ty+16, ...} x k in [4tx, 4tx+4); accumulators persist over all tiles of the CTA, one atomic flush at the end.
+template <int NOBLK>     // ceil(n_out / 16): compile-time so that only the live output blocks cost instructions
+__global__ void __launch_bounds__(LTHREADS)
+linear64_bwd_weight_kernel(const float *__restrict__ h, const float *__restrict__ dy, int64_t ld_dy, int64_t n, int n_out,
+                           float *__restrict__ dW, float *__restrict__ db)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *Hs = sm;                         // [LROWS][WPAD]  (16-byte aligned rows)
+    float *Ds = Hs + LROWS * WPAD;          // [LROWS][16*NOBLK + 1], columns >= n_out are zero
+    const int ldd = 16 * NOBLK + 1;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[NOBLK][4], bsum[NOBLK];
+#pragma unroll
+    for (int a = 0; a < NOBLK; ++a) {
+        bsum[a] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+    }
+    // rows of dY beyond n_out read as zero: pad the tile's leading dimension so that o = ty + 16a is always in bounds
+    
+    const int64_t n_tiles = (n + LROWS - 1) / LROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * LROWS;
+        __syncthreads();
+        for (int i = tid; i < LROWS * LW; i += LTHREADS) {
+            const int rr = i / LW, k = i - rr * LW;
+            Hs[rr * WPAD + k] = (row0 + rr < n) ? __ldg(h + (row0 + rr) * LW + k) : 0.f;
+        }
+        for (int i = tid; i < LROWS * 16 * NOBLK; i += LTHREADS) {
+            const int rr = i / (16 * NOBLK), o = i - rr * (16 * NOBLK);
+            Ds[rr * ldd + o] = (row0 + rr < n && o < n_out) ? __ldg(dy + (row0 + rr) * ld_dy + o) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < LROWS; ++rr) {
+            const float4 hv = *reinterpret_cast<const float4 *>(Hs + rr * WPAD + 4 * tx);
+#pragma unroll
+            for (int a = 0; a < NOBLK; ++a) {
+                const float g = Ds[rr * ldd + ty + 16 * a];
+                acc[a][0] = fmaf(g, hv.x, acc[a][0]);
+                acc[a][1] = fmaf(g, hv.y, acc[a][1]);
+                acc[a][2] = fmaf(g, hv.z, acc[a][2]);
+                acc[a][3] = fmaf(g, hv.w, acc[a][3]);
+                if (tx == 0) bsum[a] += g;
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NOBLK; ++a) {
+        const int o = ty + 16 * a;
+        if (o < n_out) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(dW + o * LW + 4 * tx + j, acc[a][j]);
+            if (tx == 0 && db != nullptr) atomicAdd(db + o, bsum[a]);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out,
+                                   int64_t ld_out, void *stream)
+{
+    IA_REQUIRE(n_out >= 1 && n_out <= MAX_NOUT, "linear64_fwd: n_out %d not in [1,%d]", n_out, MAX_NOUT);
+    IA_REQUIRE(n >= 0 && (n == 0 || (h && W && b && out)), "linear64_fwd: NULL pointer");
+    IA_REQUIRE(ld_out >= n_out, "linear64_fwd: ld_out < n_out");
+    if (n == 0) return IA_OK;
+    const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + ((n_out + 3) & ~3) + (size_t)LROWS * LPAD);
+    IA_CUDA_OK(cudaFuncSetAttribute(linear64_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * 2);
+    linear64_fwd_kernel<<<blocks, LTHREADS, bytes, (cudaStream_t)stream>>>(h, n, W, b, n_out, out, ld_out);
+    IA_LAUNCH_OK("linear64_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
+                                   float *dh, float *dW, float *db, void *stream)
+{
+    IA_REQUIRE(n_out >= 1 && n_out <= MAX_NOUT, "linear64_bwd: n_out %d not in [1,%d]", n_out, MAX_NOUT);
+    IA_REQUIRE(n >= 0 && (n == 0 || (h && W && dout)), "linear64_bwd: NULL pointer");
+    IA_REQUIRE(ld_dout >= n_out, "linear64_bwd: ld_dout < n_out");
+    IA_REQUIRE(dh == nullptr || ((uintptr_t)dh & 15) == 0, "linear64_bwd: dh must be 16-byte aligned");
+    if (n == 0) return IA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * 2);
+    if (dh != nullptr) {
+        const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + (size_t)LROWS * (n_out + 1));
+        IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        linear64_bwd_input_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, n, W, n_out, dh);
+        IA_LAUNCH_OK("linear64_bwd_input_kernel");
+    }
+    if (dW != nullptr) {
+        const int noblk = (n_out + 15) / 16;
+        const size_t bytes = sizeof(float) * ((size_t)LROWS * WPAD + (size_t)LROWS * (16 * noblk + 1));
+        const unsigned wblocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * (bytes <= 72 * 1024 ? 3 : 2));
+#define IA_L64W(NB)                                                                                                              \
+    case NB:                                                                                                                     \
+        IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_weight_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
+        linear64_bwd_weight_kernel<NB><<<wblocks, LTHREADS, bytes, s>>>(h, dout, ld_dout, n, n_out, dW, db);                    \
+        break;
+        switch (noblk) {
+            IA_L64W(1) IA_L64W(2) IA_L64W(3) IA_L64W(4) IA_L64W(5) IA_L64W(6) IA_L64W(7) IA_L64W(8)
+        }
+#undef IA_L64W
+        IA_LAUNCH_OK("linear64_bwd_weight_kernel");
+    }
+    return IA_OK;
+}

@@ -14,7 +14,7 @@ from . import _lib as L
 
 # kernels launched per ABI call (for bench.py's gpu_launches claim)
 _LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_grouped": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
-             "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
+             "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_linear64_fwd": 1, "ia_linear64_bwd": 2, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
              "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
              "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0}
 
@@ -215,19 +215,52 @@ class _MLPFn(torch.autograd.Function):
         return d0, d1, dp, None, None
 
 
+class _Linear64Fn(torch.autograd.Function):
+    """out = h @ W.T + b for h [N,64], W [n_out,64] (the wide output layer behind the tensor-core feature mode)."""
+
+    @staticmethod
+    def forward(ctx, h, W, b):
+        L.require_cuda(h, W, b)
+        h, W, b = L.f32c(h), L.f32c(W), L.f32c(b)
+        n, n_out = h.shape[0], W.shape[0]
+        out = torch.empty(n, n_out, device=h.device, dtype=torch.float32)
+        _run("ia_linear64_fwd", L.ptr(h), n, L.ptr(W), L.ptr(b), n_out, L.ptr(out), n_out, L.stream(), work=2.0 * n * n_out * 64,
+             tag=f"64>{n_out}")
+        ctx.save_for_backward(h, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, W = ctx.saved_tensors
+        dout = L.f32c(dout)
+        n, n_out = h.shape[0], W.shape[0]
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        dW = torch.zeros_like(W) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(n_out, device=h.device) if ctx.needs_input_grad[2] else None
+        if dW is None and db is not None:
+            dW = torch.zeros_like(W)
+        _run("ia_linear64_bwd", L.ptr(h), n, L.ptr(W), L.ptr(dout), dout.shape[1], n_out, L.ptr(dh), L.ptr(dW), L.ptr(db), L.stream(),
+             work=4.0 * n * n_out * 64, tag=f"64>{n_out}")
+        return dh, (dW if ctx.needs_input_grad[1] else None), db
+
+
+def linear64(h: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return _Linear64Fn.apply(h, W, b)
+
+
 def mlp_apply(in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], params: torch.Tensor, desc: L.MlpDesc,
               n_out_used: Optional[int] = None) -> torch.Tensor:
     """Network on cat[in0*scale+offset, in1]; returns the first n_out_used outputs (n_out_used=None: all;
     n_out_used=0, tensor-core precision only: the last hidden layer's activations [N, 64])."""
     nou = int(desc.n_out if n_out_used is None else n_out_used)
     if desc.precision == L.IA_MLP_TC_F16 and nou > 8:
-        # wide output layer (the 65-feature centre evaluation): hidden layers on the tensor-core kernel, the 64 -> nou
-        # projection as one plain fp32 GEMM (cuBLAS through torch.addmm)
+        # wide output layer (the 65-feature centre evaluation): hidden layers on the tensor-core kernel (feature mode), the
+        # 64 -> nou projection by the streaming fp32 kernels of linear64.cu
         h = _MLPFn.apply(in0, in1, params, desc, 0)
         n_hidden = params.numel() - (desc.n_out * desc.width + desc.n_out)
         w_last = params[n_hidden:n_hidden + desc.n_out * desc.width].view(desc.n_out, desc.width)
         b_last = params[n_hidden + desc.n_out * desc.width:]
-        return torch.addmm(b_last[:nou], h, w_last[:nou].t())
+        return linear64(h, w_last[:nou], b_last[:nou])
     return _MLPFn.apply(in0, in1, params, desc, nou)
 
 

@@ -220,6 +220,27 @@ def hashgrid_microbench(device, peaks):
     ms = timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), C.byref(plan), 16, None, dx.data_ptr(), s))
     b = ops.hashgrid_bytes_per_point(plan, 16, "bwd_input")
     res["bwd_input"] = {"ms": ms, "gevals_per_s": n / ms / 1e6, "algorithmic_GBps": n * b / ms / 1e6, "frac_of_hbm": n * b / ms / 1e6 / peaks["hbm_gbs"]}
+    # L2 / HBM random 32-byte-sector gather peaks: table resident in the 126 MB L2 vs. larger than it
+    lib.ia_debug_sector_gather.restype = C.c_int32
+    lib.ia_debug_sector_gather.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    big = torch.randn((1 << 30) // 4, device=device, generator=g)            # 1 GiB
+    sink = torch.empty(1 << 22, device=device)
+    gather = {}
+    for label, nbytes in (("l2_resident_48MB", 48 << 20), ("hbm_1GiB", 1 << 30)):
+        nsec, nthr, iters = nbytes // 32, 1 << 22, 64
+
+        def run_gather():
+            assert lib.ia_debug_sector_gather(big.data_ptr(), nsec, nthr, iters, sink.data_ptr(), s) == 0
+        run_gather()                                                           # warm the L2 for the resident case
+        ts = []
+        for _ in range(5):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); run_gather(); b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        ms = sorted(ts)[2]
+        gather[label] = {"ms": ms, "gsectors_per_s": nthr * iters / ms / 1e6, "sector_GBps": nthr * iters * 32 / ms / 1e6}
+    res["sector_gather_peaks"] = gather
     res["config"] = "N=2^22 uniform random points, L=16 F=2 T=2^19 fp32 tables, L2 flushed between launches; bytes/point fwd=%d" % ops.hashgrid_bytes_per_point(plan, 16, "fwd")
     return res
 

@@ -458,3 +458,35 @@ extern "C" int32_t ia_hashgrid_bwd_input(const float *x, int64_t n, const float 
     IA_REQUIRE(n == 0 || dx != nullptr, "hashgrid_bwd_input: dx is NULL");
     return ia_hashgrid_bwd(x, n, table, dy, plan, active_levels, nullptr, dx, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Measurement aid ("L2 peak must be measured on the box by a resident-set random-sector read
+// micro-benchmark"): every thread issues `iters` independent 8-byte loads (one hash-grid entry with F=2) at
+// pseudo-random 32-byte-sector-aligned addresses inside [table, table + n_sectors*32).  bench.py times it on a table
+// that fits the L2 (hash-grid resident case) and on one that does not, and reports sectors/s * 32 B next to the HBM peak.
+namespace {
+__global__ void sector_gather_kernel(const float2 *__restrict__ table, uint32_t n_sectors, int iters, uint32_t seed,
+                                     float *__restrict__ out)
+{
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = (tid + 1u) * 2654435761u ^ seed;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        s = s * 1664525u + 1013904223u;
+        uint32_t sector = (uint32_t)(((uint64_t)(s ^ (s >> 15)) * n_sectors) >> 32);
+        float2 v = __ldg(table + (size_t)sector * 4);          // 4 float2 per 32-byte sector
+        acc += v.x + v.y;
+    }
+    if (acc == 123456.789f) out[tid] = acc;                     // keep the loads alive, practically never writes
+}
+}  // namespace
+
+extern "C" int32_t ia_debug_sector_gather(const float *table, int64_t n_sectors, int64_t n_threads, int32_t iters,
+                                          float *out, void *stream)
+{
+    if (n_sectors <= 0 || n_sectors > 0xffffffffll || n_threads <= 0 || (n_threads % 256) != 0) return 1;
+    sector_gather_kernel<<<(unsigned)(n_threads / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float2 *)table, (uint32_t)n_sectors, iters, 0x9e3779b9u, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}

@@ -30,10 +30,15 @@ def training_loss(model, out: Dict[str, torch.Tensor], batch: Dict[str, torch.Te
     """reference systems/neus.py:130-194.  Returns every term plus 'loss'."""
     c = lambda v: C(v, global_step)
     terms = {}
+    # mean over the valid rays' channels, as F.mse_loss / F.l1_loss on comp_rgb_full[valid] (systems/neus.py:134-138),
+    # written as a masked sum so that no boolean compaction (a host read-back per use) sits inside the step;
+    # with no valid ray both forms give 0/0 = nan
     valid = out["rays_valid_full"][..., 0]
-    terms["rgb_mse"] = F.mse_loss(out["comp_rgb_full"][valid], batch["rgb"][valid])
+    diff = torch.where(valid[:, None], out["comp_rgb_full"] - batch["rgb"], 0.0)
+    n_valid = valid.sum().to(diff.dtype) * diff.shape[-1]
+    terms["rgb_mse"] = (diff * diff).sum() / n_valid
     loss = terms["rgb_mse"] * c(loss_cfg["lambda_rgb_mse"])
-    terms["rgb_l1"] = F.l1_loss(out["comp_rgb_full"][valid], batch["rgb"][valid])
+    terms["rgb_l1"] = diff.abs().sum() / n_valid
     loss = loss + terms["rgb_l1"] * c(loss_cfg["lambda_rgb_l1"])
     terms["eikonal"] = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
     loss = loss + terms["eikonal"] * c(loss_cfg["lambda_eikonal"])

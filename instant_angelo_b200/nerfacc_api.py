@@ -223,7 +223,8 @@ def ray_marching(rays_o: torch.Tensor, rays_d: torch.Tensor, t_min: Optional[tor
         else:
             alphas = alpha_fn(t_starts, t_ends, ray_indices)
         masks = ops.visibility(alphas, packed_info, early_stop_eps, alpha_thre)
-        ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
+        keep = torch.nonzero(masks).squeeze(1)          # one compaction (one host read-back) shared by the three arrays
+        ray_indices, t_starts, t_ends = ray_indices[keep], t_starts[keep], t_ends[keep]
         if return_packed:
             packed_info = pack_info(ray_indices, n_rays)
     if return_packed:

@@ -138,9 +138,11 @@ class NeuSModel(nn.Module):
         return w
 
     # ---- reference models/neus.py:141-203 --------------------------------------------------------------
-    def forward_bg_(self, rays, stratified_u: Optional[torch.Tensor] = None):
-        n_rays = rays.shape[0]
-        rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
+    def march_bg_(self, rays_o, rays_d, stratified_u: Optional[torch.Tensor] = None):
+        """The marching half of reference forward_bg_ (models/neus.py:141-169), including the early-stop pruning
+        through sigma_fn (a no-grad background density evaluation).  It depends on the rays, the background grid and
+        the background networks only, which lets forward_ issue it next to the foreground march: all host read-backs
+        of sample counts then sit at the start of the step instead of draining the GPU queue in the middle of it."""
 
         def sigma_fn(t_starts, t_ends, ray_indices):
             ri = ray_indices.long()
@@ -151,11 +153,18 @@ class NeuSModel(nn.Module):
         _, t_max = ray_aabb_intersect(rays_o, rays_d, self._aabb_host)
         near_plane = torch.where(t_max > 1e9, self.near_plane_bg, t_max)
         with torch.no_grad():
-            ray_indices, t_starts, t_ends, packed_info = ray_marching(
+            return ray_marching(
                 rays_o, rays_d, scene_aabb=None, grid=self.occupancy_grid_bg if self.grid_prune else None,
                 sigma_fn=sigma_fn, near_plane=near_plane, far_plane=self.far_plane_bg,
                 render_step_size=self.render_step_size_bg, stratified=self.randomized, cone_angle=self.cone_angle_bg,
                 alpha_thre=0.0, stratified_u=stratified_u, return_packed=True)
+
+    def forward_bg_(self, rays, stratified_u: Optional[torch.Tensor] = None, marched=None):
+        n_rays = rays.shape[0]
+        rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
+        if marched is None:
+            marched = self.march_bg_(rays_o, rays_d, stratified_u)
+        ray_indices, t_starts, t_ends, packed_info = marched
         ri = ray_indices.long()
         t_dirs = rays_d[ri]
         midpoints = (t_starts + t_ends) / 2.0
@@ -185,6 +194,9 @@ class NeuSModel(nn.Module):
                 grid=self.occupancy_grid if self.grid_prune else None, alpha_fn=None, near_plane=None, far_plane=None,
                 render_step_size=self.render_step_size, stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0,
                 stratified_u=stratified_u, return_packed=True)
+        # background marching is independent of the foreground networks: issue it now so that its sample-count
+        # read-back does not drain the GPU queue in the middle of the step
+        marched_bg = self.march_bg_(rays_o, rays_d, stratified_u_bg) if self.learned_background else None
         ri = ray_indices.long()
         t_origins = rays_o[ri]
         t_dirs = rays_d[ri]
@@ -211,7 +223,7 @@ class NeuSModel(nn.Module):
                         "points": midpoints.view(-1), "intervals": dists.view(-1), "ray_indices": ri.view(-1),
                         "sdf_laplace_samples": sdf_laplace})
         if self.learned_background:
-            out_bg = self.forward_bg_(rays, stratified_u=stratified_u_bg)
+            out_bg = self.forward_bg_(rays, stratified_u=stratified_u_bg, marched=marched_bg)
         else:
             out_bg = {"comp_rgb": self.background_color[None, :].expand(*comp_rgb.shape),
                       "num_samples": torch.zeros_like(out["num_samples"]),

@@ -42,3 +42,15 @@ print(f"step wall (no profiler) {wall:.2f} ms | per step: libia kernels {mine:.2
       f"GPU idle ~{wall - mine - glue:.2f} ms")
 for t, c, n in rows[:a.rows]:
     print(f"{t:8.3f} ms {c:6.0f}x  {n}")
+
+if os.environ.get("IA_PROF_SHAPES"):
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+        step(10)
+        torch.cuda.synchronize()
+    ev = [e for e in prof2.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") or "Backward" in e.key]
+    print("\n== torch ops by device time (one step), with shapes ==")
+    for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:60]:
+        print(f"{e.self_device_time_total/1e3:8.3f} ms {e.count:4d}x cpu {e.self_cpu_time_total/1e3:7.3f} ms  {e.key:34s} {str(e.input_shapes)[:120]}")
+    print("\n== torch ops by call count ==")
+    for e in sorted(ev, key=lambda e: -e.count)[:40]:
+        print(f"{e.count:4d}x dev {e.self_device_time_total/1e3:8.3f} ms cpu {e.self_cpu_time_total/1e3:7.3f} ms  {e.key:34s} {str(e.input_shapes)[:120]}")

@@ -71,7 +71,7 @@ __host__ __device__ inline SmemPlan make_plan(const TcDims &D, bool bwd, bool pi
     p.dbl = take(bwd ? MAX_OUT * 4 : 0);
     p.red = take(64 * 4);
     p.part = take(bwd ? 0 : (uint32_t)(CG * ROWS * MAX_OUT * 4));
-    p.mbar = take(16);
+    p.mbar = take(32);      // three mbarriers (8 bytes each)
     p.tmem = take(16);
     // software-pipelined backward: second set of X / H1 operand buffers (next tile's forward overlaps this tile's backward)
     p.ax2_hi = take(pipe ? ax : 0); p.ax2_lo = take(pipe ? ax : 0);
@@ -165,12 +165,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[16])
 }
 
 // ---- numerics ----------------------------------------------------------------------------------------------
+// MUFU.EX2 / MUFU.LG2 without the denormal pre/post-scaling that __expf / __logf wrap around them (an FSETP and two
+// FMULs per call): exp arguments here never produce results that matter below 2^-126, and lg2 sees 1 + e >= 1.
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float z)
 {
     if (ACT == IA_ACT_SOFTPLUS100) {
-        const float t = z * BETA;
-        return t > 20.f ? z : __logf(1.0f + __expf(t)) * (1.0f / BETA);
+        // torch.nn.Softplus(beta=100, threshold=20): z when beta z > 20, else log(1 + exp(beta z)) / beta
+        constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+        const float t = z * (BETA * LOG2E);
+        const float sp = lg2_ftz(1.0f + ex2_ftz(t)) * (LN2 / BETA);
+        return t > 20.f * LOG2E ? z : sp;
     }
     return fmaxf(z, 0.f);
 }
@@ -178,7 +196,8 @@ __device__ __forceinline__ float act_fwd(float z)
 template <int ACT>
 __device__ __forceinline__ float act_bwd_from_out(float h)
 {
-    if (ACT == IA_ACT_SOFTPLUS100) return 1.0f - __expf(-BETA * h);  // sigmoid(beta z) = 1 - exp(-beta h)
+    // sigmoid(beta z) = 1 - exp(-beta h)
+    if (ACT == IA_ACT_SOFTPLUS100) return 1.0f - ex2_ftz(h * (-BETA * 1.4426950408889634f));
     return h > 0.f ? 1.f : 0.f;
 }
 
@@ -280,6 +299,16 @@ struct Ctx {
     int r, cg;           // row of the tile / column group (16 accumulator columns) owned by this thread
 };
 
+// One lane of a CONVERGED warp (all callers sit right behind a CTA-wide barrier).  With elect.sync the compiler knows that
+// exactly one lane issues the warp-uniform tcgen05 instructions; behind a plain `threadIdx.x == 0` test it wraps every
+// UTCHMMA in an ELECT / BRA.U.ANY loop over the "possibly several" active lanes (6 instructions and a branch per MMA).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // all threads: make operand writes visible to the async proxy, sync, thread 0 issues via `issue`, everyone waits
 template <typename F>
 __device__ __forceinline__ void run_mma(Ctx &c, F issue)
@@ -290,14 +319,17 @@ __device__ __forceinline__ void run_mma(Ctx &c, F issue)
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (timing) t1 = clock64();
-        tc_fence_after();
-        issue();
-        umma_commit(c.sbase + c.P.mbar);
-        if (timing) t2 = clock64();
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            if (timing) t1 = clock64();
+            tc_fence_after();
+            issue();
+            umma_commit(c.sbase + c.P.mbar);
+            if (timing) t2 = clock64();
+        }
+        __syncwarp();
     }
-    mbar_wait(c.sbase + c.P.mbar, c.phase);
+    mbar_wait(c.sbase + c.P.mbar, c.phase & 1u);
     c.phase ^= 1u;
     tc_fence_after();
     if (timing) {
@@ -305,8 +337,80 @@ __device__ __forceinline__ void run_mma(Ctx &c, F issue)
         atomicAdd(&g_tc_cycles[0], (unsigned long long)(t1 - t0));
         atomicAdd(&g_tc_cycles[1], (unsigned long long)(t2 - t1));
         atomicAdd(&g_tc_cycles[2], (unsigned long long)(t3 - t2));
-        atomicAdd(&g_tc_cycles[5], 1ull);
     }
+}
+
+// Split form used by the software-pipelined backward: one CTA barrier publishes the operands, thread 0 issues several
+// GEMM groups and commits each to its own mbarrier (mbar_commit(c, k)); the consumers wait per group (mma_wait(c, k)),
+// so the epilogue of the first group runs while the tensor pipe is still busy with the later ones.
+// Bit k of c.phase is the parity of mbarrier k.
+template <typename F>
+__device__ __forceinline__ void mma_issue(Ctx &c, F issue)
+{
+    const bool timing = threadIdx.x == 0 && g_tc_timing_on;
+    const long long t0 = timing ? clock64() : 0;
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long t1 = timing ? clock64() : 0;
+        tc_fence_after();
+        issue();
+        if (timing) {
+            atomicAdd(&g_tc_cycles[0], (unsigned long long)(t1 - t0));
+            atomicAdd(&g_tc_cycles[1], (unsigned long long)(clock64() - t1));
+        }
+    }
+}
+// Warp-specialised form (pipelined backward): THREADS epilogue threads + one issuer warp.  The epilogue threads publish
+// their operand writes and meet the issuer warp on named barrier 1; lane 0 of the issuer warp then issues the GEMMs while
+// every epilogue warp (including warp 0) is free to run ahead into its mbarrier waits.
+#ifndef IA_TC_WS
+#define IA_TC_WS 0     // measured on B200: the 17th warp caps ptxas at 96 registers (5 warps on one SM sub-partition) and the
+                       // spills cost more than the freed issue slots give back (0.654 vs 0.60 ms per 2^20 rows), so off
+#endif
+constexpr int THREADS_WS = THREADS + (IA_TC_WS ? 32 : 0);
+template <typename F>
+__device__ __forceinline__ void ws_publish(Ctx &c, F issue)
+{
+    const bool timing = threadIdx.x == 0 && g_tc_timing_on;
+    const long long t0 = timing ? clock64() : 0;
+    fence_async_smem();
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS_WS) : "memory");
+    if (timing) atomicAdd(&g_tc_cycles[0], (unsigned long long)(clock64() - t0));
+    if (!IA_TC_WS && threadIdx.x < 32) {      // no issuer warp: one lane of warp 0 issues, then warp 0 joins the epilogue
+        if (elect_one()) {
+            const long long t1 = timing ? clock64() : 0;
+            tc_fence_after();
+            issue();
+            if (timing) atomicAdd(&g_tc_cycles[1], (unsigned long long)(clock64() - t1));
+        }
+        __syncwarp();
+    }
+}
+template <typename F>
+__device__ __forceinline__ void ws_issue(Ctx &c, F issue)
+{
+    asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS_WS) : "memory");
+    if (elect_one()) {
+        const bool timing = g_tc_timing_on;
+        const long long t1 = timing ? clock64() : 0;
+        tc_fence_after();
+        issue();
+        if (timing) atomicAdd(&g_tc_cycles[1], (unsigned long long)(clock64() - t1));
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void mbar_commit(const Ctx &c, int k) { umma_commit(c.sbase + c.P.mbar + 8u * (uint32_t)k); }
+__device__ __forceinline__ void mma_wait(Ctx &c, int k)
+{
+    const bool timing = threadIdx.x == 0 && g_tc_timing_on;
+    const long long t0 = timing ? clock64() : 0;
+    mbar_wait(c.sbase + c.P.mbar + 8u * (uint32_t)k, (c.phase >> k) & 1u);
+    c.phase ^= 1u << k;
+    tc_fence_after();
+    if (timing) atomicAdd(&g_tc_cycles[5 + k], (unsigned long long)(clock64() - t0));   // [5..7]: wait per mbarrier
 }
 
 template <int NOU>
@@ -332,7 +436,11 @@ __device__ __forceinline__ void setup_common(Ctx &c, const TcDims &D, const floa
         float a[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         store_split8(smem + c.P.ah_hi, smem + c.P.ah_lo, 8u * 2048u + (uint32_t)tid * 16u, a);
     }
-    if (tid == 0) mbar_init(c.sbase + c.P.mbar, 1);
+    if (tid == 0) {
+        mbar_init(c.sbase + c.P.mbar, 1);
+        mbar_init(c.sbase + c.P.mbar + 8, 1);
+        mbar_init(c.sbase + c.P.mbar + 16, 1);
+    }
     if (tid < 32) {  // warp 0 owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(c.sbase + c.P.tmem), "r"(TMEM_COLS)
                      : "memory");
@@ -820,7 +928,7 @@ __device__ __forceinline__ void drain_dw_at(Ctx &c, uint32_t col0, float *__rest
 }
 
 template <int ACT, int NOU>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_WS, 1)
 mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                        const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
                        float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams)
@@ -939,138 +1047,178 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;
     int64_t tile = blockIdx.x;
     float scale = 1.f, inv_scale = 1.f;
-    if (tile < n_tiles) {
-        // ---- prologue: forward of the first tile, its incoming gradient and scale
-        const int64_t row = tile * ROWS + c.r;
-        const bool valid = row < n;
-        InRegs R0;
-        load_input_regs(c, D, in0, in1, row, valid, R0);
-        store_input_regs(c, D, R0, ax_hi[0], ax_lo[0]);
-        const float m = load_dy(row, valid);
-        if (lane == 0) red[warp] = m;
-        run_mma(c, [&]() { issue_gemm(c.tmem + PD0, s_buf[0][0], BW0, idesc_fwd, D.K0 / 16); });
-        tile_scale(scale, inv_scale);
-        float h[16];
-        tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
-        store_cols16(c, ah_hi[0], ah_lo[0], h);
-        run_mma(c, [&]() { issue_gemm(c.tmem + PD0, s_buf[0][1], BW1, idesc_fwd, W / 16); });
-    }
-    // input rows of the NEXT tile are fetched into registers one phase ahead of their use (global latency hidden)
-    InRegs Rn;
-    {
-        const int64_t ntile0 = tile + gridDim.x;
-        const int64_t nrow0 = ntile0 * ROWS + c.r;
-        if (ntile0 < n_tiles) load_input_regs(c, D, in0, in1, nrow0, nrow0 < n, Rn);
-    }
-    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
-        const int cur = it & 1, nxt = cur ^ 1;
-        const int64_t row = tile * ROWS + c.r;
-        const bool valid = row < n;
-        const int64_t ntile = tile + gridDim.x;
-        const bool has_next = ntile < n_tiles;
-        const int64_t nrow = ntile * ROWS + c.r;
-        const bool nvalid = has_next && nrow < n;
-        const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
-        // ---- A: D0 = pre-activations of the last hidden layer of tile i; next tile's input goes to the other buffer
-        if (has_next) store_input_regs(c, D, Rn, ax_hi[nxt], ax_lo[nxt]);
-        {
-            float h[16], dz[16];
+    // GEMM batches, in the order the tensor pipe executes them (issue order); each group commits to its own mbarrier
+    auto issue_first0 = [&]() {
+        issue_gemm(c.tmem + PD0, s_buf[0][0], BW0, idesc_fwd, D.K0 / 16);
+        mbar_commit(c, 0);
+    };
+    auto issue_first1 = [&]() {
+        issue_gemm(c.tmem + PD0, s_buf[0][1], BW1, idesc_fwd, W / 16);
+        mbar_commit(c, 2);
+    };
+    // phase 1: the next tile's first forward GEMM goes first so that its epilogue (H1(i+1)) runs while the pipe works
+    // through dH1 and the (longest) dW1 GEMM of tile i
+    auto issue_phase1 = [&](int cur, int nxt, bool has_next) {
+        if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][0], BW0, idesc_fwd, D.K0 / 16);
+        mbar_commit(c, 0);
+        issue_gemm(c.tmem + PD2, ADZ, BW1T, idesc_dh, W / 16);
+        issue_gemm(c.tmem + PD1, DZT, s_buf[cur][3], idesc_dw1, ROWS / 16);
+        mbar_commit(c, 1);
+    };
+    // phase 2: dX first (its store streams out while dW0 and the next tile's second forward GEMM execute)
+    auto issue_phase2 = [&](int cur, int nxt, bool has_next) {
+        if (want_dx) issue_gemm(c.tmem + PD2, ADZ, BW0T, idesc_dx, W / 16);
+        mbar_commit(c, 0);
+        issue_gemm(c.tmem + PD1, DZT, s_buf[cur][2], idesc_dw0, ROWS / 16);
+        mbar_commit(c, 1);
+        if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][1], BW1, idesc_fwd, W / 16);
+        mbar_commit(c, 2);
+    };
+    if (IA_TC_WS && warp == THREADS / 32) {
+        // ---- optional issuer warp: mirrors the tile loop of the epilogue threads, one named-barrier rendezvous per batch
+        if (tile < n_tiles) {
+            ws_issue(c, issue_first0);
+            ws_issue(c, issue_first1);
+        }
+        for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+            const int cur = it & 1, nxt = cur ^ 1;
+            const bool has_next = tile + gridDim.x < n_tiles;
+            ws_issue(c, [&]() { issue_phase1(cur, nxt, has_next); });
+            ws_issue(c, [&]() { issue_phase2(cur, nxt, has_next); });
+        }
+    } else {
+        if (tile < n_tiles) {
+            // ---- prologue: forward of the first tile, its incoming gradient and scale
+            const int64_t row = tile * ROWS + c.r;
+            const bool valid = row < n;
+            InRegs R0;
+            load_input_regs(c, D, in0, in1, row, valid, R0);
+            store_input_regs(c, D, R0, ax_hi[0], ax_lo[0]);
+            const float m = load_dy(row, valid);
+            if (lane == 0) red[warp] = m;
+            ws_publish(c, issue_first0);
+            mma_wait(c, 0);
+            tile_scale(scale, inv_scale);
+            float h[16];
             tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k = 16 * c.cg + j;
-                h[j] = (D.dbg & 2) ? h[j] + b1[k] : act_fwd<ACT>(h[j] + b1[k]);
-                float dh = 0.f;
-                if constexpr (NOU == 0) {
-                    dh = dhf[j];
-                } else {
-#pragma unroll
-                    for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
+    #pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
+            store_cols16(c, ah_hi[0], ah_lo[0], h);
+            ws_publish(c, issue_first1);
+        }
+        // input rows of the NEXT tile are fetched into registers one phase ahead of their use (global latency hidden)
+        InRegs Rn;
+        {
+            const int64_t ntile0 = tile + gridDim.x;
+            const int64_t nrow0 = ntile0 * ROWS + c.r;
+            if (ntile0 < n_tiles) load_input_regs(c, D, in0, in1, nrow0, nrow0 < n, Rn);
+        }
+        for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+            const int cur = it & 1, nxt = cur ^ 1;
+            const int64_t row = tile * ROWS + c.r;
+            const bool valid = row < n;
+            const int64_t ntile = tile + gridDim.x;
+            const bool has_next = ntile < n_tiles;
+            const int64_t nrow = ntile * ROWS + c.r;
+            const bool nvalid = has_next && nrow < n;
+            const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
+            // ---- A: D0 = pre-activations of the last hidden layer of tile i; next tile's input goes to the other buffer
+            if (has_next) store_input_regs(c, D, Rn, ax_hi[nxt], ax_lo[nxt]);
+            mma_wait(c, 2);      // second forward GEMM of tile i (issued by the prologue / the previous phase 2)
+            {
+                float h[16], dz[16];
+                tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
+    #pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = 16 * c.cg + j;
+                    h[j] = (D.dbg & 2) ? h[j] + b1[k] : act_fwd<ACT>(h[j] + b1[k]);
+                    float dh = 0.f;
+                    if constexpr (NOU == 0) {
+                        dh = dhf[j];
+                    } else {
+    #pragma unroll
+                        for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
+                    }
+                    dz[j] = dh * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(h[j])) * scale;
                 }
-                dz[j] = dh * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(h[j])) * scale;
-            }
-            if (NOU == 0) {
-            } else if (REG_DWL) {
-#pragma unroll
-                for (int o = 0; o < NREG; ++o)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) gwl[o][j] = fmaf(dy[o], h[j], gwl[o][j]);
-            } else {
-#pragma unroll 1
-                for (int o = 0; o < NOU; ++o) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float s = warp_sum(dy[o] * h[j]);
-                        if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
+                if (NOU == 0) {
+                } else if (REG_DWL) {
+    #pragma unroll
+                    for (int o = 0; o < NREG; ++o)
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) gwl[o][j] = fmaf(dy[o], h[j], gwl[o][j]);
+                } else {
+    #pragma unroll 1
+                    for (int o = 0; o < NOU; ++o) {
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float s = warp_sum(dy[o] * h[j]);
+                            if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
+                        }
                     }
                 }
+                store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
             }
-            store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
-        }
-        // ---- phase 1
-        run_mma(c, [&]() {
-            issue_gemm(c.tmem + PD2, ADZ, BW1T, idesc_dh, W / 16);
-            issue_gemm(c.tmem + PD1, DZT, s_buf[cur][3], idesc_dw1, ROWS / 16);
-            if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][0], BW0, idesc_fwd, D.K0 / 16);
-        });
-        const float inv_cur = inv_scale;
-        if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
-        {
-            // dZ1(i) = dH1 (*) act'(H1(i)); H1(i+1) = act(L0(i+1) + b0)
-            float v[16];
-            tmem_ld16(c.tmem + c.lane_addr + PD2 + 16u * c.cg, v);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float hh[8], a[8];
-                const uint32_t off = (uint32_t)(2 * c.cg + half) * 2048u + (uint32_t)c.r * 16u;
-                load_split8(smem + ah_hi[cur], smem + ah_lo[cur], off, hh);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(hh[j]));
-                store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, off, a);
-            }
+            // ---- phase 1
+                ws_publish(c, [&]() { issue_phase1(cur, nxt, has_next); });
+            const float inv_cur = inv_scale;
+            // incoming gradient of the next tile: its per-warp maxima are published by the phase-2 barrier
+            // (dy / dhf of tile i are dead from here on: the output-layer work of tile i happened in stage A)
+            float mnext = 0.f;
+            if (has_next) mnext = load_dy(nrow, nvalid);
+            if (lane == 0) red[warp] = mnext;
+            mma_wait(c, 0);
             if (has_next) {
+                // H1(i+1) = act(L0(i+1) + b0)
                 float h[16];
                 tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
-#pragma unroll
+    #pragma unroll
                 for (int j = 0; j < 16; ++j) h[j] = (D.dbg & 2) ? h[j] + b0[16 * c.cg + j] : act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
                 store_cols16(c, ah_hi[nxt], ah_lo[nxt], h);
             }
-        }
-        // incoming gradient of the next tile: its per-warp maxima are published by the phase-2 barrier
-        // (dy / dhf of tile i are dead from here on: the output-layer work of tile i happened in stage A)
-        float mnext = 0.f;
-        if (has_next) mnext = load_dy(nrow, nvalid);
-        if (lane == 0) red[warp] = mnext;
-        // ---- phase 2
-        run_mma(c, [&]() {
-            if (want_dx) issue_gemm(c.tmem + PD2, ADZ, BW0T, idesc_dx, W / 16);
-            issue_gemm(c.tmem + PD1, DZT, s_buf[cur][2], idesc_dw0, ROWS / 16);
-            if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][1], BW1, idesc_fwd, W / 16);
-        });
-        tile_scale(scale, inv_scale);       // scale of tile i+1 (red was written before the barrier)
-        {
-            const int64_t n2tile = ntile + gridDim.x;          // prefetch the input rows of tile i+2
-            const int64_t n2row = n2tile * ROWS + c.r;
-            if (n2tile < n_tiles) load_input_regs(c, D, in0, in1, n2row, n2row < n, Rn);
-        }
-        if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw0, D.K0, ld0, inv_cur);
-        if (want_dx && !(D.dbg & 8)) {
-            for (int ci = c.cg; ci * 16 < D.din; ci += CG) {
-                const int c0 = 16 * ci;
+            mma_wait(c, 1);      // dH1 in PD2, dW1 in PD1; the dZ buffer is free to be overwritten
+            {
+                // dZ1(i) = dH1 (*) act'(H1(i))
                 float v[16];
-                tmem_ld16(c.tmem + c.lane_addr + PD2 + (uint32_t)c0, v);
-                if (valid) write_dx16(D, c0, v, inv_cur, row, din0, din1);
+                tmem_ld16(c.tmem + c.lane_addr + PD2 + 16u * c.cg, v);
+    #pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float hh[8], a[8];
+                    const uint32_t off = (uint32_t)(2 * c.cg + half) * 2048u + (uint32_t)c.r * 16u;
+                    load_split8(smem + ah_hi[cur], smem + ah_lo[cur], off, hh);
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(hh[j]));
+                    store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, off, a);
+                }
             }
-        }
-        if (threadIdx.x == 0 && g_tc_timing_on) {
-            atomicAdd(&g_tc_cycles[3], (unsigned long long)(clock64() - tile_t0));
-            atomicAdd(&g_tc_cycles[4], 1ull);
+            if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
+            // ---- phase 2
+            ws_publish(c, [&]() { issue_phase2(cur, nxt, has_next); });
+            tile_scale(scale, inv_scale);       // scale of tile i+1 (red was written before the barrier)
+            {
+                const int64_t n2tile = ntile + gridDim.x;          // prefetch the input rows of tile i+2
+                const int64_t n2row = n2tile * ROWS + c.r;
+                if (n2tile < n_tiles) load_input_regs(c, D, in0, in1, n2row, n2row < n, Rn);
+            }
+            mma_wait(c, 0);
+            if (want_dx && !(D.dbg & 8)) {
+                for (int ci = c.cg; ci * 16 < D.din; ci += CG) {
+                    const int c0 = 16 * ci;
+                    float v[16];
+                    tmem_ld16(c.tmem + c.lane_addr + PD2 + (uint32_t)c0, v);
+                    if (valid) write_dx16(D, c0, v, inv_cur, row, din0, din1);
+                }
+            }
+            mma_wait(c, 1);
+            if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw0, D.K0, ld0, inv_cur);
+            if (threadIdx.x == 0 && g_tc_timing_on) {
+                atomicAdd(&g_tc_cycles[3], (unsigned long long)(clock64() - tile_t0));
+                atomicAdd(&g_tc_cycles[4], 1ull);
+            }
         }
     }
     // ---- reduce the register-resident output-layer gradients over the rows of the CTA
-    if (REG_DWL) {
+    if (REG_DWL && tid < THREADS) {
 #pragma unroll
         for (int o = 0; o < NREG; ++o) {
 #pragma unroll
@@ -1086,7 +1234,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
         if (lane == 0 && c.cg == 0) atomicAdd(&dbl[o], sb);
     }
     __syncthreads();
-    if (dparams != nullptr) {
+    if (dparams != nullptr && tid < THREADS) {
         for (int i = tid; i < W * D.K0; i += THREADS) {
             const int o = i / D.K0, col = i - o * D.K0;
             const float g = dw0[o * ld0 + col];
@@ -1214,7 +1362,7 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
         if (pipe) {                                                                                                               \
             IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                             (int)P.total));                                                                       \
-            mlp_tc_bwd_pipe_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,   \
+            mlp_tc_bwd_pipe_kernel<ACT, NOU><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,   \
                                                                                                  ld_dout, din0, din1, dparams);  \
         } else {                                                                                                                  \
             IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \

@@ -37,4 +37,5 @@ if "--timing" in sys.argv:
         lib.ia_debug_tc_timing(0, buf)
         v = list(buf)
         tiles = max(v[4], 1)
-        print(f"{name}: tiles {v[4]} phases {v[5]} | per tile: total {v[3]/tiles:.0f} cyc, barrier-wait {v[0]/tiles:.0f}, mma-issue {v[1]/tiles:.0f}, mma-wait {v[2]/tiles:.0f}, other {(v[3]-v[0]-v[1]-v[2])/tiles:.0f}")
+        print(f"{name}: tiles {v[4]} | per tile (thread 0): total {v[3]/tiles:.0f} cyc, barrier-wait {v[0]/tiles:.0f}, mma-issue {v[1]/tiles:.0f}, "
+              f"mma-wait(run_mma) {v[2]/tiles:.0f}, split waits m0 {v[5]/tiles:.0f} m1 {v[6]/tiles:.0f} m2 {v[7]/tiles:.0f}")

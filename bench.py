@@ -403,8 +403,9 @@ def run_b200(args):
                    "num_samples_per_ray_bg": 256, "hash_levels_active": 16, "log2_hashmap_size": 19, "global_step": GLOBAL_STEP0,
                    "mean_fg_samples_per_ray": fg_total / total_rays, "mean_samples_per_ray_full": full_total / total_rays,
                    "samples_per_s": full_total / (ms_total / 1e3), "hash_point_evals_per_s": (13 * fg_total + (full_total - fg_total)) / (ms_total / 1e3),
-                   "mlp": ("tcgen05 tensor cores, 3xf16-split operands + fp32 accumulate (fp32-equivalent, parity-tested at 1e-3); 65-wide "
-                           "centre evaluation on the fp32 FFMA kernel") if args.mlp == "tc" else "fp32 FFMA kernels",
+                   "mlp": ("tcgen05 tensor cores, 3xf16-split operands + fp32 accumulate (fp32-equivalent, parity-tested at 1e-3); the 65-wide "
+                           "centre evaluation returns the last hidden layer from the same kernel and applies the output layer with "
+                           "the streaming fp32 linear64 kernels") if args.mlp == "tc" else "fp32 FFMA kernels",
                    "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
                    "l2": "per-step working set (hash tables 112 MB + >1 GB of per-sample activations) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)"},
@@ -470,9 +471,9 @@ def cpu_baseline_leg(cfg, model, args):
         return time.perf_counter() - t, n_s
 
     t0 = time.perf_counter()
-    probe_s, _ = run(32)                                        # warm-up + calibration
-    probe_s, _ = run(32)
-    n = args.cpu_rays if args.cpu_rays > 0 else max(32, min(4096, int(32 * 12.0 / max(probe_s, 1e-3))))   # ~12 s of CPU work
+    run(32)                                                     # warm-up (thread pool, allocator)
+    probe_s, _ = run(256)                                       # calibration at a batch large enough to amortise fixed costs
+    n = args.cpu_rays if args.cpu_rays > 0 else max(256, min(8192, int(256 * 15.0 / max(probe_s, 1e-3))))   # ~15 s of CPU work
     t1 = time.perf_counter()
     dt, ns = run(n)
     t2 = t1 + dt
@@ -493,7 +494,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     cfg = neuralangelo_colmap_sparse("finite_difference")
     ref = build_oracle(cfg)
-    n = args.cpu_rays if args.cpu_rays > 0 else 192
+    n = args.cpu_rays if args.cpu_rays > 0 else 512
     K, W = args.steps, args.warmup
     batches = make_batches(K + W, n, 0, pin=False)
     gs = GLOBAL_STEP0
@@ -549,7 +550,7 @@ def main():
     ap.add_argument("--mlp", default="tc", choices=["fp32", "tc"],
                     help="MLP arithmetic: tc = tcgen05 tensor cores with 3xf16-split operands (fp32-equivalent, default); fp32 = FFMA kernels")
     ap.add_argument("--cpu-rays", type=int, default=0,
-                    help="rays per step of the bounded CPU-oracle sample (0: ~12 s of CPU work for cpu_baseline, 192 for --impl reference)")
+                    help="rays per step of the bounded CPU-oracle sample (0: ~15 s of CPU work for cpu_baseline, 512 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

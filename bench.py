@@ -220,6 +220,27 @@ def hashgrid_microbench(device, peaks):
     ms = timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), C.byref(plan), 16, None, dx.data_ptr(), s))
     b = ops.hashgrid_bytes_per_point(plan, 16, "bwd_input")
     res["bwd_input"] = {"ms": ms, "gevals_per_s": n / ms / 1e6, "algorithmic_GBps": n * b / ms / 1e6, "frac_of_hbm": n * b / ms / 1e6 / peaks["hbm_gbs"]}
+    # SURVEY 8d grid: T in {2^19, 2^21} x active levels in {4, 16} x {incoherent, ray-coherent} points, forward
+    grid = []
+    n_c = 8192 * 512
+    o = torch.nn.functional.normalize(torch.randn(8192, 3, device=device, generator=g), dim=-1) * 1.0
+    tgt = (torch.rand(8192, 3, device=device, generator=g) - 0.5) * 0.6
+    d = torch.nn.functional.normalize(tgt - o, dim=-1)
+    tt = torch.linspace(0.0, 2.0, 512, device=device)[None, :, None]
+    x_coh = (((o[:, None, :] + d[:, None, :] * tt) / 3.0 + 0.5).clamp(0.0, 1.0)).reshape(-1, 3).contiguous()   # 512 steps along 8192 rays
+    out_c = torch.empty(n_c, 32, device=device)
+    for log2_t in (19, 21):
+        plan_t = ops.make_grid_plan(16, 2, log2_t, 32, 1.3195079107728942)
+        table_t = torch.randn(plan_t.n_params, device=device, generator=g) * 0.1
+        for active in (4, 16):
+            for label, pts, dst in (("incoherent 2^22 uniform points", x, out), ("ray-coherent 8192 rays x 512 steps", x_coh, out_c)):
+                npts = pts.shape[0]
+                ms = timed(lambda: lib.ia_hashgrid_fwd(pts.data_ptr(), npts, table_t.data_ptr(), C.byref(plan_t), active, dst.data_ptr(), s))
+                bpp = ops.hashgrid_bytes_per_point(plan_t, active, "fwd")
+                grid.append({"log2_T": log2_t, "active_levels": active, "points": label, "ms": ms, "gevals_per_s": npts / ms / 1e6,
+                             "algorithmic_GBps": npts * bpp / ms / 1e6, "frac_of_hbm": npts * bpp / ms / 1e6 / peaks["hbm_gbs"]})
+        del table_t
+    res["fwd_grid"] = grid
     # L2 / HBM random 32-byte-sector gather peaks: table resident in the 126 MB L2 vs. larger than it
     lib.ia_debug_sector_gather.restype = C.c_int32
     lib.ia_debug_sector_gather.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
@@ -457,6 +478,17 @@ def oracle_step(ref, cfg, rays, rgb, pts, nrm, conf, bg, gs):
     return float(terms["loss"]), int(out["num_samples_full"])
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline_leg(cfg, model, args):
     """Oracle ("port") timed on this box's host cores on a bounded sample of the same workload."""
     cores = os.cpu_count() or 1
@@ -477,7 +509,7 @@ def cpu_baseline_leg(cfg, model, args):
     t1 = time.perf_counter()
     dt, ns = run(n)
     t2 = t1 + dt
-    return {"value": n / (t2 - t1), "unit": "rays/s", "cores": cores, "kind": "port",
+    return {"value": n / (t2 - t1), "unit": "rays/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
             "sample": f"{n} rays of the same workload (same occupancy grids, {ns / n:.1f} samples/ray), forward + losses + backward "
                       f"through the CPU oracle (oracle/model_ref.py, PyTorch fp32, {cores} threads); warm-up run {t1 - t0:.1f} s, timed run {t2 - t1:.1f} s"}
 
@@ -517,7 +549,7 @@ def run_reference(args):
             "config": {"workload": "neuralangelo-colmap_sparse.yaml, grad_type=finite_difference, synthetic 512x512 cameras around an "
                                    "analytic sphere (BASELINE.json configs[1])", "rays_per_step_sample": n,
                        "note": "reference GPU path (tinycudann + nerfacc) is not installable in this image; CPU oracle port timed instead"},
-            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(), "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 

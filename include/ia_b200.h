@@ -137,8 +137,21 @@ int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *
  * Backward: dh[n,64] = dout W (may be NULL); dW[n_out,64] += dout^T h and db[n_out] += sum dout (ACCUMULATED; may be NULL). */
 int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out,
                         int64_t ld_out, void *stream);
+/* dextra[n, n_extra] (may be NULL with n_extra = 0) is added to the first n_extra columns of dout on the fly: gradients that
+ * reach a few output columns through a second consumer (the SDF value and the diffuse albedo columns of the feature
+ * vector, models/geometry.py:206-207 + models/texture.py:58) need no separate accumulation pass. */
 int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
-                        float *dh, float *dW, float *db, void *stream);
+                        const float *dextra, int32_t n_extra, float *dh, float *dW, float *db, void *stream);
+
+/* Colour-head input assembly (models/geometry.py:207 `cat[feature, points*2-1]` + models/texture.py:26-27
+ * `cat[features, dirs_embd, normals]`).  The caller lets ia_linear64_fwd write the n_feat geometry outputs into columns
+ * [0, n_feat) of tin (row stride ld_tin); this call fills columns [n_feat, n_feat+3+n_enc+3) with (pts01*2-1 | enc | normal)
+ * and copies column 0 to sdf[n] and columns 1..3 to rgb_raw[n,3] (the dual-colour head's diffuse term).
+ * Backward: dpts01 = 2 dtin[:, n_feat:n_feat+3], denc, dnormal = the matching column blocks (each may be NULL). */
+int32_t ia_head_fill_fwd(const float *pts01, const float *enc, int32_t n_enc, const float *normal, int64_t n, int32_t n_feat,
+                         float *tin, int64_t ld_tin, float *sdf, float *rgb_raw, void *stream);
+int32_t ia_head_fill_bwd(const float *dtin, int64_t ld_tin, int64_t n, int32_t n_feat, int32_t n_enc, float *dpts01, float *denc,
+                         float *dnormal, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Finite-difference / curvature stages  fused elementwise stages of VolumeSDF.forward

@@ -62,8 +62,8 @@ linear64_fwd_kernel(const float *__restrict__ h, int64_t n, const float *__restr
 
 // dh[r][k] = sum_o dy[r][o] W[o][k]   (thread (r, half) produces k in [32*half, 32*half+32))
 __global__ void __launch_bounds__(LTHREADS)
-linear64_bwd_input_kernel(const float *__restrict__ dy, int64_t ld_dy, int64_t n, const float *__restrict__ Wg, int n_out,
-                          float *__restrict__ dh)
+linear64_bwd_input_kernel(const float *__restrict__ dy, int64_t ld_dy, const float *__restrict__ dex, int n_ex, int64_t n,
+                          const float *__restrict__ Wg, int n_out, float *__restrict__ dh)
 {
     extern __shared__ __align__(16) float sm[];
     float *Ws = sm;                         // [n_out][WPAD]
@@ -78,7 +78,12 @@ linear64_bwd_input_kernel(const float *__restrict__ dy, int64_t ld_dy, int64_t n
         __syncthreads();
         for (int i = tid; i < LROWS * n_out; i += LTHREADS) {
             const int rr = i / n_out, o = i - rr * n_out;
-            Ds[rr * ldd + o] = (row0 + rr < n) ? __ldg(dy + (row0 + rr) * ld_dy + o) : 0.f;
+            float g = 0.f;
+            if (row0 + rr < n) {
+                g = __ldg(dy + (row0 + rr) * ld_dy + o);
+                if (o < n_ex) g += __ldg(dex + (row0 + rr) * n_ex + o);
+            }
+            Ds[rr * ldd + o] = g;
         }
         __syncthreads();
         float acc[32];
@@ -108,8 +113,8 @@ linear64_bwd_input_kernel(const float *__restrict__ dy, int64_t ld_dy, int64_t n
 // o in {ty, ty+16, ...} x k in [4tx, 4tx+4); accumulators persist over all tiles of the CTA, one atomic flush at the end.
 template <int NOBLK>     // ceil(n_out / 16): compile-time so that only the live output blocks cost instructions
 __global__ void __launch_bounds__(LTHREADS)
-linear64_bwd_weight_kernel(const float *__restrict__ h, const float *__restrict__ dy, int64_t ld_dy, int64_t n, int n_out,
-                           float *__restrict__ dW, float *__restrict__ db)
+linear64_bwd_weight_kernel(const float *__restrict__ h, const float *__restrict__ dy, int64_t ld_dy, const float *__restrict__ dex,
+                           int n_ex, int64_t n, int n_out, float *__restrict__ dW, float *__restrict__ db)
 {
     extern __shared__ __align__(16) float sm[];
     float *Hs = sm;                         // [LROWS][WPAD]  (16-byte aligned rows)
@@ -135,7 +140,12 @@ linear64_bwd_weight_kernel(const float *__restrict__ h, const float *__restrict_
         }
         for (int i = tid; i < LROWS * 16 * NOBLK; i += LTHREADS) {
             const int rr = i / (16 * NOBLK), o = i - rr * (16 * NOBLK);
-            Ds[rr * ldd + o] = (row0 + rr < n && o < n_out) ? __ldg(dy + (row0 + rr) * ld_dy + o) : 0.f;
+            float g = 0.f;
+            if (row0 + rr < n && o < n_out) {
+                g = __ldg(dy + (row0 + rr) * ld_dy + o);
+                if (o < n_ex) g += __ldg(dex + (row0 + rr) * n_ex + o);
+            }
+            Ds[rr * ldd + o] = g;
         }
         __syncthreads();
 #pragma unroll 4
@@ -181,8 +191,9 @@ extern "C" int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, co
 }
 
 extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
-                                   float *dh, float *dW, float *db, void *stream)
+                                   const float *dextra, int32_t n_extra, float *dh, float *dW, float *db, void *stream)
 {
+    IA_REQUIRE(n_extra >= 0 && n_extra <= n_out && (n_extra == 0 || dextra != nullptr), "linear64_bwd: bad dextra / n_extra=%d", n_extra);
     IA_REQUIRE(n_out >= 1 && n_out <= MAX_NOUT, "linear64_bwd: n_out %d not in [1,%d]", n_out, MAX_NOUT);
     IA_REQUIRE(n >= 0 && (n == 0 || (h && W && dout)), "linear64_bwd: NULL pointer");
     IA_REQUIRE(ld_dout >= n_out, "linear64_bwd: ld_dout < n_out");
@@ -193,7 +204,7 @@ extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, co
     if (dh != nullptr) {
         const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + (size_t)LROWS * (n_out + 1));
         IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        linear64_bwd_input_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, n, W, n_out, dh);
+        linear64_bwd_input_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, dextra, n_extra, n, W, n_out, dh);
         IA_LAUNCH_OK("linear64_bwd_input_kernel");
     }
     if (dW != nullptr) {
@@ -203,7 +214,7 @@ extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, co
 #define IA_L64W(NB)                                                                                                              \
     case NB:                                                                                                                     \
         IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_weight_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
-        linear64_bwd_weight_kernel<NB><<<wblocks, LTHREADS, bytes, s>>>(h, dout, ld_dout, n, n_out, dW, db);                    \
+        linear64_bwd_weight_kernel<NB><<<wblocks, LTHREADS, bytes, s>>>(h, dout, ld_dout, dextra, n_extra, n, n_out, dW, db);                    \
         break;
         switch (noblk) {
             IA_L64W(1) IA_L64W(2) IA_L64W(3) IA_L64W(4) IA_L64W(5) IA_L64W(6) IA_L64W(7) IA_L64W(8)

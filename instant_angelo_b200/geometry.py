@@ -9,6 +9,7 @@ hash-grid launches + three fused-MLP launches; the 12 tap evaluations compute th
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -148,6 +149,39 @@ class VolumeSDF(BaseImplicitGeometry):
             rv.append(laplace)
         rv = [v if self.training else v.detach() for v in rv]
         return rv[0] if len(rv) == 1 else rv
+
+    # ---- fused-head path (used by NeuSModel.forward_ when the colour head supports it) ------------------------------
+    def supports_fused_head(self) -> bool:
+        """True when forward(with_grad, with_feature, with_laplace) can hand the centre evaluation's last hidden layer to
+        the colour head (ops.sdf_head) instead of materialising `feature`: tensor-core MLP with a wide output layer,
+        finite-difference gradients, no output activations."""
+        from . import _lib as L
+        act = self.network.output_activation_name
+        return (os.environ.get("IA_NO_FUSED_HEAD") is None and self.network.precision == L.IA_MLP_TC_F16
+                and self.n_output_dims > 8 and self.grad_type == "finite_difference"
+                and "sdf_activation" not in self.config and "feature_activation" not in self.config
+                and (act is None or str(act).lower() == "none"))
+
+    def forward_hidden(self, points, rand_directions: Optional[torch.Tensor] = None):
+        """Same evaluations as forward(points, with_grad=True, with_feature=True, with_laplace=True) (reference
+        models/geometry.py:195-275) except that the centre evaluation stops at the last hidden layer.
+        Returns (h [S,64], pts01 [S,3], grad [S,3], laplace [S,1], W_last [Fd,64], b_last [Fd])."""
+        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+            flat = self.network.flat_params()
+            pts01 = contract_to_unisphere(points, self.radius, self.contraction_type)
+            h = self._net(pts01, 0, flat)
+            eps = self._finite_difference_eps
+            grad = self._fd_gradient(points, eps, flat)
+            if rand_directions is None:
+                rand_directions = torch.randn_like(pts01)
+            normals, shifted = ops.curv_shift(grad.reshape(-1, 3), rand_directions.reshape(-1, 3), pts01.reshape(-1, 3), eps)
+            g_shift = self._fd_gradient(shifted, eps, flat)
+            laplace = ops.curv_angle(normals, g_shift).view(*pts01.shape[:-1], 1)
+            n_out, width = self.n_output_dims, self.network.n_neurons
+            n_hidden = flat.numel() - (n_out * width + n_out)
+            w_last = flat[n_hidden:n_hidden + n_out * width].view(n_out, width)
+            b_last = flat[n_hidden + n_out * width:]
+        return h, pts01, grad, laplace, w_last, b_last
 
     def forward_level(self, points):
         pts01 = contract_to_unisphere(points, self.radius, self.contraction_type)

@@ -203,10 +203,21 @@ class NeuSModel(nn.Module):
         midpoints = (t_starts + t_ends) / 2.0
         positions = t_origins + t_dirs * midpoints
         dists = t_ends - t_starts
-        sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True, with_laplace=True,
-                                                            rand_directions=rand_directions)
-        normal = F.normalize(sdf_grad, p=2, dim=-1)
-        rgb = self.texture(feature, t_dirs, normal)
+        fused_head = getattr(self.geometry, "supports_fused_head", lambda: False)() and \
+            getattr(self.texture, "supports_fused_head", lambda g: False)(self.geometry)
+        if fused_head:
+            # same arithmetic as the generic branch below; the 65-wide `feature` and the colour head's 87-wide input row
+            # are assembled in one buffer (ops.sdf_head) instead of out -> cat -> cat
+            h, pts01, sdf_grad, sdf_laplace, w_last, b_last = self.geometry.forward_hidden(positions, rand_directions)
+            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            rgb, sdf = self.texture.forward_fused_head(h, w_last, b_last, pts01, t_dirs, normal)
+            if not self.training:
+                sdf, sdf_grad, sdf_laplace, rgb, normal = (v.detach() for v in (sdf, sdf_grad, sdf_laplace, rgb, normal))
+        else:
+            sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True, with_laplace=True,
+                                                                rand_directions=rand_directions)
+            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            rgb = self.texture(feature, t_dirs, normal)
         inv_s = self.variance.inv_s.reshape(1).clip(1e-6, 1e6)
         weights, opacity, depth, comp_rgb, comp_normal, alpha = ops.composite_neus(
             sdf, normal, t_dirs, dists.reshape(-1), inv_s, self.cos_anneal_ratio, packed_info,

@@ -239,13 +239,69 @@ class _Linear64Fn(torch.autograd.Function):
         db = torch.zeros(n_out, device=h.device) if ctx.needs_input_grad[2] else None
         if dW is None and db is not None:
             dW = torch.zeros_like(W)
-        _run("ia_linear64_bwd", L.ptr(h), n, L.ptr(W), L.ptr(dout), dout.shape[1], n_out, L.ptr(dh), L.ptr(dW), L.ptr(db), L.stream(),
-             work=4.0 * n * n_out * 64, tag=f"64>{n_out}")
+        _run("ia_linear64_bwd", L.ptr(h), n, L.ptr(W), L.ptr(dout), dout.shape[1], n_out, None, 0, L.ptr(dh), L.ptr(dW), L.ptr(db),
+             L.stream(), work=4.0 * n * n_out * 64, tag=f"64>{n_out}")
         return dh, (dW if ctx.needs_input_grad[1] else None), db
 
 
 def linear64(h: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return _Linear64Fn.apply(h, W, b)
+
+
+class _SdfHeadFn(torch.autograd.Function):
+    """Output layer of the SDF network fused with the assembly of the colour head's input row
+    (reference models/geometry.py:206-207 + models/texture.py:24-27, 58):
+
+        out   = h @ W.T + b                                   [N, n_feat]   (written straight into tin[:, :n_feat])
+        tin   = cat[out, pts01*2-1, enc, normal]              [N, n_feat + 3 + n_enc + 3]
+        sdf   = out[:, 0];  rgb_raw = out[:, 1:4]
+
+    One buffer is written once instead of out / feature / network_inp being materialised one after the other, and in
+    backward the gradients that reach out[:, 0:4] through sdf / rgb_raw are added inside the linear64 kernels."""
+
+    @staticmethod
+    def forward(ctx, h, W, b, pts01, enc, normal):
+        L.require_cuda(h, W, b, pts01, enc, normal)
+        h, W, b, pts01, enc, normal = L.f32c(h), L.f32c(W), L.f32c(b), L.f32c(pts01), L.f32c(enc), L.f32c(normal)
+        n, n_feat, n_enc = h.shape[0], W.shape[0], enc.shape[1]
+        ld = n_feat + 3 + n_enc + 3
+        tin = torch.empty(n, ld, device=h.device, dtype=torch.float32)
+        sdf = torch.empty(n, device=h.device, dtype=torch.float32)
+        rgb_raw = torch.empty(n, 3, device=h.device, dtype=torch.float32)
+        s = L.stream()
+        _run("ia_linear64_fwd", L.ptr(h), n, L.ptr(W), L.ptr(b), n_feat, L.ptr(tin), ld, s, work=2.0 * n * n_feat * 64,
+             tag=f"64>{n_feat}")
+        _run("ia_head_fill_fwd", L.ptr(pts01), L.ptr(enc), n_enc, L.ptr(normal), n, n_feat, L.ptr(tin), ld, L.ptr(sdf),
+             L.ptr(rgb_raw), s)
+        ctx.save_for_backward(h, W)
+        ctx.dims = (n_feat, n_enc)
+        return tin, sdf, rgb_raw
+
+    @staticmethod
+    def backward(ctx, dtin, dsdf, drgb):
+        h, W = ctx.saved_tensors
+        n_feat, n_enc = ctx.dims
+        n = h.shape[0]
+        dtin = L.f32c(dtin)
+        dextra = torch.cat([dsdf.reshape(n, 1), drgb.reshape(n, 3)], dim=1)
+        need = ctx.needs_input_grad
+        dh = torch.empty_like(h) if need[0] else None
+        dW = torch.zeros_like(W) if (need[1] or need[2]) else None
+        db = torch.zeros(n_feat, device=h.device) if need[2] else None
+        s = L.stream()
+        _run("ia_linear64_bwd", L.ptr(h), n, L.ptr(W), L.ptr(dtin), dtin.shape[1], n_feat, L.ptr(dextra), 4, L.ptr(dh), L.ptr(dW),
+             L.ptr(db), s, work=4.0 * n * n_feat * 64, tag=f"64>{n_feat}")
+        dpts = torch.empty(n, 3, device=h.device) if need[3] else None
+        denc = torch.empty(n, n_enc, device=h.device) if need[4] else None
+        dnrm = torch.empty(n, 3, device=h.device) if need[5] else None
+        if dpts is not None or denc is not None or dnrm is not None:
+            _run("ia_head_fill_bwd", L.ptr(dtin), dtin.shape[1], n, n_feat, n_enc, L.ptr(dpts), L.ptr(denc), L.ptr(dnrm), s)
+        return dh, (dW if need[1] else None), db, dpts, denc, dnrm
+
+
+def sdf_head(h, W, b, pts01, enc, normal):
+    """-> (tin [N, n_feat+3+n_enc+3], sdf [N], rgb_raw [N,3]); see _SdfHeadFn."""
+    return _SdfHeadFn.apply(h, W, b, pts01, enc, normal)
 
 
 def mlp_apply(in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], params: torch.Tensor, desc: L.MlpDesc,

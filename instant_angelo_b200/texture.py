@@ -8,6 +8,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import ops
 from . import registry as models
 from .network_utils import get_encoding, get_mlp, update_module_step
 from .utils import get_activation
@@ -40,6 +41,22 @@ class VolumeRadiance(nn.Module):
             else:
                 color = act(color)
         return color
+
+    # ---- fused-head path: the input row [feature(Fd+3) | dirs_embd | normal] is assembled by ops.sdf_head ----------
+    def supports_fused_head(self, geometry) -> bool:
+        return (self.n_dir_dims == 3 and
+                self.n_input_dims == geometry.n_output_dims + 3 + self.encoding.n_output_dims + 3)
+
+    def forward_fused_head(self, h, w_last, b_last, pts01, dirs, normals):
+        """forward(cat[geometry_out, pts01*2-1], dirs, normals) with geometry_out = h @ w_last.T + b_last applied inside
+        the assembly.  Returns (color [S,3], sdf [S])."""
+        dirs_embd = self.encoding(((dirs + 1.0) / 2.0).view(-1, self.n_dir_dims))
+        tin, sdf, rgb_raw = ops.sdf_head(h, w_last, b_last, pts01.reshape(-1, 3), dirs_embd, normals.reshape(-1, 3))
+        color = self.network(tin).view(*dirs.shape[:-1], self.n_output_dims).float()
+        if "color_activation" in self.config:
+            act = get_activation(self.config["color_activation"])
+            color = act(color) + act(rgb_raw.view(*dirs.shape[:-1], 3)) if self.dual else act(color)
+        return color, sdf.view(*dirs.shape[:-1])
 
     def update_step(self, epoch, global_step):
         update_module_step(self.encoding, epoch, global_step)

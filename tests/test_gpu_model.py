@@ -227,3 +227,36 @@ def test_baseline_configs_run_at_full_table_size(cuda_lib, which):
     for name, p in model.named_parameters():
         if p.numel() and "encoding.params" not in name:
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+def test_fused_head_matches_generic_path(cuda_lib, golden_dir, monkeypatch):
+    """NeuSModel.forward_ takes the fused SDF-head / colour-input assembly (ops.sdf_head) when geometry and texture
+    support it; with IA_NO_FUSED_HEAD it goes through VolumeSDF.forward -> feature -> texture.forward like the
+    reference (models/neus.py:225-230).  Same outputs and gradients either way."""
+    from instant_angelo_b200.losses import training_loss
+    fx = load_golden(golden_dir, "neus_dualcolor_bg")
+    cfg = golden_model_config(**GOLDEN_CASES["neus_dualcolor_bg"])
+    gs = int(fx["global_step"])
+    batch = golden_batch(fx, "cuda")
+    c = lambda k: torch.from_numpy(fx[k]).cuda()
+    results = []
+    for disable in (False, True):
+        if disable:
+            monkeypatch.setenv("IA_NO_FUSED_HEAD", "1")
+        else:
+            monkeypatch.delenv("IA_NO_FUSED_HEAD", raising=False)
+        model = build_product(cfg, golden_state_dict(fx), gs, torch.from_numpy(fx["background_color"]), "FullyFusedMLP")
+        assert model.geometry.supports_fused_head() == (not disable)
+        out = model(batch["rays"], stratified_u=c("u_fg"), rand_directions=c("rand_directions"), stratified_u_bg=c("u_bg"))
+        terms = training_loss(model, out, batch, golden_loss_config(), gs)
+        terms["loss"].backward()
+        torch.cuda.synchronize()
+        results.append((out, terms, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (o0, t0, g0), (o1, t1, g1) = results
+    for k in ("comp_rgb_full", "opacity", "depth", "sdf_samples", "sdf_grad_samples", "weights"):
+        assert_close(o0[k], o1[k], rtol=1e-5, atol=1e-6, name=k)
+    assert_close(t0["loss"], t1["loss"], rtol=1e-5, atol=1e-7, name="loss")
+    assert set(g0) == set(g1)
+    for n in g0:
+        rt, at = grad_tol(g1[n], 1e-4)
+        assert_close(g0[n], g1[n], rtol=rt, atol=at, name="grad " + n)

@@ -591,3 +591,30 @@ def test_adamw_matches_torch(cuda_lib):
         opt.step()
         ops.adamw_step(p, grad.cuda(), m, v, 0.01, 0.9, 0.99, 1e-15, 0.01, step)
     assert_close(p, p_ref, rtol=1e-5, atol=1e-6, name="adamw")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,n_feat,n_enc", [(1, 65, 16), (1000, 65, 16), (4097, 13, 9)])
+def test_sdf_head_matches_torch(cuda_lib, n, n_feat, n_enc):
+    """ops.sdf_head = linear64 into the colour-head input row + cat[., pts*2-1, enc, normal] (reference
+    models/geometry.py:206-207, models/texture.py:26-27), with the sdf / diffuse columns' gradients merged in backward."""
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(n + n_feat)
+    mk = lambda *s: torch.randn(*s, generator=g).cuda().requires_grad_(True)
+    h, W, b, pts, enc, nrm = mk(n, 64), mk(n_feat, 64), mk(n_feat), mk(n, 3), mk(n, n_enc), mk(n, 3)
+    tin, sdf, raw = ops.sdf_head(h, W, b, pts, enc, nrm)
+    ld = n_feat + 6 + n_enc
+    wt, ws, wr = torch.randn(n, ld, generator=g).cuda(), torch.randn(n, generator=g).cuda(), torch.randn(n, 3, generator=g).cuda()
+    ((tin * wt).sum() + (sdf * ws).sum() + (raw * wr).sum()).backward()
+    got = [t.grad.clone() for t in (h, W, b, pts, enc, nrm)]
+    for t in (h, W, b, pts, enc, nrm):
+        t.grad = None
+    out = h.double() @ W.double().T + b.double()
+    tin_ref = torch.cat([out, pts.double() * 2 - 1, enc.double(), nrm.double()], dim=1)
+    ((tin_ref * wt).sum() + (out[:, 0] * ws).sum() + (out[:, 1:4] * wr).sum()).backward()
+    assert_close(tin, tin_ref.float(), rtol=1e-5, atol=1e-5, name="tin")
+    assert_close(sdf, out[:, 0].float(), rtol=1e-5, atol=1e-5, name="sdf")
+    assert_close(raw, out[:, 1:4].float(), rtol=1e-5, atol=1e-5, name="raw")
+    for name, a, t in zip(("dh", "dW", "db", "dpts", "denc", "dnrm"), got, (h, W, b, pts, enc, nrm)):
+        ref = t.grad.float()
+        assert_close(a, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()) + 1e-6, name=name)

@@ -1,9 +1,13 @@
-// Wide output layer of the width-64 networks: out[n, n_out] = h[n, 64] * W[n_out, 64]^T + b   (n_out <= 128),
-// forward and backward, fp32 FFMA.  Used for the 65-feature centre evaluation of the SDF network
-// (reference models/geometry.py:206: the full `feature` output), whose hidden layers run on the tensor-core kernel
-// (mlp_tc.cu, feature mode).  Skinny-N / skinny-K GEMMs like these are where a general GEMM library does worst
-// (cuBLAS picks a large-K SIMT kernel for dW = dY^T h: 1.5 ms at 1.5 M rows); these kernels are memory-streaming:
-// each reads h / dY once.
+// Wide output layer of the width-64 networks: out[n, n_out] = h[n, 64] * W[n_out, 64]^T + b   (n_out <= 72 on the
+// tiled kernels, <= 128 on the generic ones), forward and backward, fp32 FFMA.  Used for the 65-feature centre evaluation
+// of the SDF network (reference models/geometry.py:206: the full `feature` output), whose hidden layers run on the
+// tensor-core kernel (mlp_tc.cu, feature mode).  Skinny-N / skinny-K GEMMs like these are where a general GEMM library
+// does worst (cuBLAS picks a large-K SIMT kernel for dW = dY^T h: 1.5 ms at 1.5 M rows).
+//
+// Tiled kernels (n_out <= 72): one CTA owns 128 rows at a time; every thread keeps a 4 x 9 (forward), 4 x 8 (input
+// gradient) or 18 x 2 (weight gradient) block of accumulators in registers so that the inner loop is FFMA-bound (36 / 32
+// / 36 FMAs against 7 / 6 / 7 shared-memory wavefronts); all global traffic is staged through shared memory so that rows
+// with arbitrary leading dimensions (the colour head's 87-wide input row) are still read and written in full lines.
 #include <algorithm>
 
 #include "ia_common.cuh"
@@ -16,7 +20,238 @@ constexpr int LTHREADS = 256;
 constexpr int LPAD = 65;        // padded row length of the activation tiles (conflict-free row-per-lane access)
 constexpr int WPAD = 68;        // padded row length of the weight tile (16-byte aligned rows for float4 broadcasts)
 constexpr int MAX_NOUT = 128;
+constexpr int TILED_NOUT = 72;  // 8 column groups x 9 outputs
+constexpr int WTS = 96;         // forward: W^T row = 8 groups x 12 floats (9 used), 16-byte aligned groups
+constexpr int OLD = 73;         // output / dY staging tile leading dimension (odd: conflict-free row-per-lane access)
 
+// -------------------------------------------------------------------------------------------------------------------
+// tiled forward: thread (tr = t & 31, tc = t >> 5) -> rows {tr, tr+32, tr+64, tr+96} x outputs {9 tc .. 9 tc + 8}
+__global__ void __launch_bounds__(LTHREADS, 2)
+linear64_fwd_tiled_kernel(const float *__restrict__ h, int64_t n, const float *__restrict__ Wg, const float *__restrict__ bg,
+                          int n_out, float *__restrict__ out, int64_t ld_out)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *Wt = sm;                        // [64][WTS]: Wt[k][12 g + j] = W[9 g + j][k]
+    float *bs = Wt + LW * WTS;             // [72]
+    float *Hs = bs + TILED_NOUT;           // [LROWS][LPAD]; reused as the output tile [LROWS][OLD]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < LW * WTS; i += LTHREADS) Wt[i] = 0.f;
+    for (int i = tid; i < TILED_NOUT; i += LTHREADS) bs[i] = i < n_out ? __ldg(bg + i) : 0.f;
+    __syncthreads();
+    for (int i = tid; i < n_out * LW; i += LTHREADS) {
+        const int o = i / LW, k = i - o * LW;
+        Wt[k * WTS + 12 * (o / 9) + (o % 9)] = __ldg(Wg + i);
+    }
+    const int tr = tid & 31, tc = tid >> 5;
+    const int64_t n_tiles = (n + LROWS - 1) / LROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * LROWS;
+        __syncthreads();
+        {
+            float4 v[LROWS * (LW / 4) / LTHREADS];
+#pragma unroll
+            for (int u = 0; u < LROWS * (LW / 4) / LTHREADS; ++u) {
+                const int i = tid + u * LTHREADS, rr = i >> 4, q = i & 15;
+                v[u] = (row0 + rr < n) ? __ldg(reinterpret_cast<const float4 *>(h + (row0 + rr) * LW) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < LROWS * (LW / 4) / LTHREADS; ++u) {
+                const int i = tid + u * LTHREADS, rr = i >> 4, q = i & 15;
+                float *d = Hs + rr * LPAD + 4 * q;
+                d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+            }
+        }
+        __syncthreads();
+        float acc[4][9];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) acc[i][j] = bs[9 * tc + j];
+#pragma unroll 4
+        for (int k = 0; k < LW; ++k) {
+            float hv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hv[i] = Hs[(tr + 32 * i) * LPAD + k];
+            const float4 *w4 = reinterpret_cast<const float4 *>(Wt + k * WTS + 12 * tc);
+            const float4 wa = w4[0], wb = w4[1], wc = w4[2];
+            const float w[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 9; ++j) acc[i][j] = fmaf(hv[i], w[j], acc[i][j]);
+        }
+        __syncthreads();                   // every thread is done reading Hs: reuse it as the output tile
+        float *Os = Hs;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) Os[(tr + 32 * i) * OLD + 9 * tc + j] = acc[i][j];
+        __syncthreads();
+        for (int rr = tid >> 5; rr < LROWS; rr += LTHREADS / 32) {
+            if (row0 + rr < n) {
+                float *dst = out + (row0 + rr) * ld_out;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int o = (tid & 31) + 32 * c;
+                    if (o < n_out) dst[o] = Os[rr * OLD + o];
+                }
+            }
+        }
+    }
+}
+
+// Stage a [LROWS][<= 96] tile of dY (+ the optional extra gradient of its first n_ex columns) into shared memory.
+// One warp per row, three 32-lane column chunks; the row loop is unrolled so that 12 independent loads are in flight per
+// thread (a loop with one load -> one shared store per trip serialises the whole tile on DRAM latency).
+// Column o lands at Ds[rr * ld + 20 * (o / 18) + o % 18] when GROUPED (weight-gradient layout), else at Ds[rr * ld + o];
+// columns in [n_out, n_cols) are written as zeros.
+template <int NTHREADS, bool GROUPED>
+__device__ __forceinline__ void stage_dy(float *Ds, int ld, const float *__restrict__ dy, int64_t ld_dy,
+                                         const float *__restrict__ dex, int n_ex, int64_t row0, int64_t n, int n_out, int n_cols,
+                                         int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = NTHREADS / 32;
+#pragma unroll 4
+    for (int rr = warp; rr < LROWS; rr += NW) {
+        const bool live = row0 + rr < n;
+        const float *src = dy + (row0 + rr) * ld_dy;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int o = lane + 32 * c;
+            v[c] = (live && o < n_out) ? __ldg(src + o) : 0.f;
+        }
+        if (live && lane < n_ex) v[0] += __ldg(dex + (row0 + rr) * n_ex + lane);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int o = lane + 32 * c;
+            if (o < n_cols) Ds[rr * ld + (GROUPED ? 20 * (o / 18) + (o % 18) : o)] = v[c];
+        }
+    }
+}
+
+// tiled input gradient: thread (tr, tc) -> rows {tr + 32 i} x k in [8 tc, 8 tc + 8)
+__global__ void __launch_bounds__(LTHREADS, 2)
+linear64_bwd_input_tiled_kernel(const float *__restrict__ dy, int64_t ld_dy, const float *__restrict__ dex, int n_ex, int64_t n,
+                                const float *__restrict__ Wg, int n_out, float *__restrict__ dh)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *Ws = sm;                        // [n_out][WPAD]
+    float *Ds = Ws + TILED_NOUT * WPAD;    // [LROWS][OLD]; reused as the dh tile [LROWS][LPAD]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_out * LW; i += LTHREADS) Ws[(i / LW) * WPAD + (i % LW)] = __ldg(Wg + i);
+    const int tr = tid & 31, tc = tid >> 5;
+    const int64_t n_tiles = (n + LROWS - 1) / LROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * LROWS;
+        __syncthreads();
+        stage_dy<LTHREADS, false>(Ds, OLD, dy, ld_dy, dex, n_ex, row0, n, n_out, n_out, tid);
+        __syncthreads();
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+        for (int o = 0; o < n_out; ++o) {
+            float g[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] = Ds[(tr + 32 * i) * OLD + o];
+            const float4 *w4 = reinterpret_cast<const float4 *>(Ws + o * WPAD + 8 * tc);
+            const float4 wa = w4[0], wb = w4[1];
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(g[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+        float *Hs = Ds;                    // [LROWS][LPAD]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Hs[(tr + 32 * i) * LPAD + 8 * tc + j] = acc[i][j];
+        __syncthreads();
+        for (int i = tid; i < LROWS * (LW / 4); i += LTHREADS) {
+            const int rr = i >> 4, q = i & 15;
+            if (row0 + rr < n) {
+                const float *s = Hs + rr * LPAD + 4 * q;
+                reinterpret_cast<float4 *>(dh + (row0 + rr) * LW)[q] = make_float4(s[0], s[1], s[2], s[3]);
+            }
+        }
+    }
+}
+
+// tiled weight gradient: 128 threads; thread (tk = t & 31, to = t >> 5) -> outputs {18 to .. 18 to + 17} x k in {2 tk, 2 tk + 1};
+// accumulators persist over all tiles of the CTA, one atomic flush at the end.
+constexpr int WG_THREADS = 128;
+constexpr int DLD = 80;                    // dY tile row: 4 groups of 20 floats (18 used), 16-byte aligned groups
+
+__global__ void __launch_bounds__(WG_THREADS, 3)
+linear64_bwd_weight_tiled_kernel(const float *__restrict__ h, const float *__restrict__ dy, int64_t ld_dy,
+                                 const float *__restrict__ dex, int n_ex, int64_t n, int n_out, float *__restrict__ dW,
+                                 float *__restrict__ db)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *Hs = sm;                        // [LROWS][LW]
+    float *Ds = Hs + LROWS * LW;           // [LROWS][DLD], columns >= n_out are zero
+    const int tid = threadIdx.x, tk = tid & 31, to = tid >> 5;
+    float acc[18][2], bsum[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) acc[j][0] = acc[j][1] = bsum[j] = 0.f;
+    const int64_t n_tiles = (n + LROWS - 1) / LROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * LROWS;
+        __syncthreads();
+#pragma unroll
+        for (int u0 = 0; u0 < LROWS * (LW / 4) / WG_THREADS; u0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = tid + (u0 + u) * WG_THREADS, rr = i >> 4, q = i & 15;
+                v[u] = (row0 + rr < n) ? __ldg(reinterpret_cast<const float4 *>(h + (row0 + rr) * LW) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = tid + (u0 + u) * WG_THREADS, rr = i >> 4, q = i & 15;
+                reinterpret_cast<float4 *>(Hs + rr * LW)[q] = v[u];
+            }
+        }
+        stage_dy<WG_THREADS, true>(Ds, DLD, dy, ld_dy, dex, n_ex, row0, n, n_out, TILED_NOUT, tid);
+        __syncthreads();
+#pragma unroll 2
+        for (int rr = 0; rr < LROWS; ++rr) {
+            const float2 hv = *reinterpret_cast<const float2 *>(Hs + rr * LW + 2 * tk);
+            const float4 *d4 = reinterpret_cast<const float4 *>(Ds + rr * DLD + 20 * to);   // warp-uniform: broadcast loads
+            const float4 ga = d4[0], gb = d4[1], gc = d4[2], gd = d4[3];
+            const float2 ge = *reinterpret_cast<const float2 *>(d4 + 4);
+            const float g[18] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w, gc.x, gc.y, gc.z, gc.w,
+                                 gd.x, gd.y, gd.z, gd.w, ge.x, ge.y};
+#pragma unroll
+            for (int j = 0; j < 18; ++j) {
+                acc[j][0] = fmaf(g[j], hv.x, acc[j][0]);
+                acc[j][1] = fmaf(g[j], hv.y, acc[j][1]);
+            }
+            if (tk == 0) {
+#pragma unroll
+                for (int j = 0; j < 18; ++j) bsum[j] += g[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+        const int o = 18 * to + j;
+        if (o < n_out) {
+            atomicAdd(dW + o * LW + 2 * tk, acc[j][0]);
+            atomicAdd(dW + o * LW + 2 * tk + 1, acc[j][1]);
+            if (tk == 0 && db != nullptr) atomicAdd(db + o, bsum[j]);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// generic kernels (72 < n_out <= 128)
 // out[r][o] = b[o] + sum_k h[r][k] W[o][k].  Thread (r = t & 127, half = t >> 7) produces outputs o = half, half+2, ...
 __global__ void __launch_bounds__(LTHREADS)
 linear64_fwd_kernel(const float *__restrict__ h, int64_t n, const float *__restrict__ Wg, const float *__restrict__ bg, int n_out,
@@ -128,8 +363,6 @@ linear64_bwd_weight_kernel(const float *__restrict__ h, const float *__restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
     }
-    // rows of dY beyond n_out read as zero: pad the tile's leading dimension so that o = ty + 16a is always in bounds
-    
     const int64_t n_tiles = (n + LROWS - 1) / LROWS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * LROWS;
@@ -181,10 +414,18 @@ extern "C" int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, co
     IA_REQUIRE(n_out >= 1 && n_out <= MAX_NOUT, "linear64_fwd: n_out %d not in [1,%d]", n_out, MAX_NOUT);
     IA_REQUIRE(n >= 0 && (n == 0 || (h && W && b && out)), "linear64_fwd: NULL pointer");
     IA_REQUIRE(ld_out >= n_out, "linear64_fwd: ld_out < n_out");
+    IA_REQUIRE(((uintptr_t)h & 15) == 0, "linear64_fwd: h must be 16-byte aligned");
     if (n == 0) return IA_OK;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * 2);
+    if (n_out <= TILED_NOUT) {
+        const size_t bytes = sizeof(float) * ((size_t)LW * WTS + TILED_NOUT + (size_t)LROWS * OLD);
+        IA_CUDA_OK(cudaFuncSetAttribute(linear64_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        linear64_fwd_tiled_kernel<<<blocks, LTHREADS, bytes, (cudaStream_t)stream>>>(h, n, W, b, n_out, out, ld_out);
+        IA_LAUNCH_OK("linear64_fwd_tiled_kernel");
+        return IA_OK;
+    }
     const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + ((n_out + 3) & ~3) + (size_t)LROWS * LPAD);
     IA_CUDA_OK(cudaFuncSetAttribute(linear64_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * 2);
     linear64_fwd_kernel<<<blocks, LTHREADS, bytes, (cudaStream_t)stream>>>(h, n, W, b, n_out, out, ld_out);
     IA_LAUNCH_OK("linear64_fwd_kernel");
     return IA_OK;
@@ -198,26 +439,43 @@ extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, co
     IA_REQUIRE(n >= 0 && (n == 0 || (h && W && dout)), "linear64_bwd: NULL pointer");
     IA_REQUIRE(ld_dout >= n_out, "linear64_bwd: ld_dout < n_out");
     IA_REQUIRE(dh == nullptr || ((uintptr_t)dh & 15) == 0, "linear64_bwd: dh must be 16-byte aligned");
+    IA_REQUIRE(((uintptr_t)h & 15) == 0, "linear64_bwd: h must be 16-byte aligned");
     if (n == 0) return IA_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * 2);
+    const bool tiled = n_out <= TILED_NOUT;
     if (dh != nullptr) {
-        const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + (size_t)LROWS * (n_out + 1));
-        IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        linear64_bwd_input_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, dextra, n_extra, n, W, n_out, dh);
-        IA_LAUNCH_OK("linear64_bwd_input_kernel");
+        if (tiled) {
+            const size_t bytes = sizeof(float) * ((size_t)TILED_NOUT * WPAD + (size_t)LROWS * OLD);
+            IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_input_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            linear64_bwd_input_tiled_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, dextra, n_extra, n, W, n_out, dh);
+            IA_LAUNCH_OK("linear64_bwd_input_tiled_kernel");
+        } else {
+            const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + (size_t)LROWS * (n_out + 1));
+            IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            linear64_bwd_input_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, dextra, n_extra, n, W, n_out, dh);
+            IA_LAUNCH_OK("linear64_bwd_input_kernel");
+        }
     }
     if (dW != nullptr) {
+        if (tiled) {
+            const size_t bytes = sizeof(float) * ((size_t)LROWS * LW + (size_t)LROWS * DLD);
+            IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_weight_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            const unsigned wblocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * 3);
+            linear64_bwd_weight_tiled_kernel<<<wblocks, WG_THREADS, bytes, s>>>(h, dout, ld_dout, dextra, n_extra, n, n_out, dW, db);
+            IA_LAUNCH_OK("linear64_bwd_weight_tiled_kernel");
+            return IA_OK;
+        }
         const int noblk = (n_out + 15) / 16;
         const size_t bytes = sizeof(float) * ((size_t)LROWS * WPAD + (size_t)LROWS * (16 * noblk + 1));
         const unsigned wblocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, LROWS), (int64_t)ia_sm_count() * (bytes <= 72 * 1024 ? 3 : 2));
 #define IA_L64W(NB)                                                                                                              \
     case NB:                                                                                                                     \
         IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_weight_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
-        linear64_bwd_weight_kernel<NB><<<wblocks, LTHREADS, bytes, s>>>(h, dout, ld_dout, dextra, n_extra, n, n_out, dW, db);                    \
+        linear64_bwd_weight_kernel<NB><<<wblocks, LTHREADS, bytes, s>>>(h, dout, ld_dout, dextra, n_extra, n, n_out, dW, db);   \
         break;
         switch (noblk) {
-            IA_L64W(1) IA_L64W(2) IA_L64W(3) IA_L64W(4) IA_L64W(5) IA_L64W(6) IA_L64W(7) IA_L64W(8)
+            IA_L64W(5) IA_L64W(6) IA_L64W(7) IA_L64W(8)
         }
 #undef IA_L64W
         IA_LAUNCH_OK("linear64_bwd_weight_kernel");

@@ -161,45 +161,47 @@ curv_angle_bwd_kernel(const float *__restrict__ normals, const float *__restrict
     st3(dgshift, s, normalize3_bwd(ns, l, scale3(nrm, dd), sqrtf(dot3(gs, gs)) < NORM_EPS));
 }
 
-// ---- colour-head input assembly: one thread per (row, column) of the filled block, coalesced along the row
+// ---- colour-head input assembly: 8 rows per 256-thread CTA, one warp per row (no integer divisions, coalesced rows)
 __global__ void head_fill_fwd_kernel(const float *__restrict__ pts01, const float *__restrict__ enc, int n_enc,
                                      const float *__restrict__ normal, int64_t n, int n_feat, float *__restrict__ tin,
                                      int64_t ld, float *__restrict__ sdf, float *__restrict__ rgb_raw)
 {
-    const int w = 3 + n_enc + 3 + 4;       // filled columns + the 4 extracted ones
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * w) return;
-    const int64_t r = i / w;
-    const int c = (int)(i - r * w);
-    if (c < 3) {
-        tin[r * ld + n_feat + c] = __ldg(pts01 + 3 * r + c) * 2.0f - 1.0f;
-    } else if (c < 3 + n_enc) {
-        tin[r * ld + n_feat + c] = __ldg(enc + r * n_enc + (c - 3));
-    } else if (c < 6 + n_enc) {
-        tin[r * ld + n_feat + c] = __ldg(normal + 3 * r + (c - 3 - n_enc));
-    } else {
-        const int j = c - 6 - n_enc;       // 0: sdf, 1..3: raw diffuse
-        const float v = tin[r * ld + j];
-        if (j == 0) sdf[r] = v;
-        else if (rgb_raw != nullptr) rgb_raw[3 * r + (j - 1)] = v;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    float *row = tin + r * ld;
+    const int w = 6 + n_enc;
+    for (int c = lane; c < w; c += 32) {
+        float v;
+        if (c < 3) v = __ldg(pts01 + 3 * r + c) * 2.0f - 1.0f;
+        else if (c < 3 + n_enc) v = __ldg(enc + r * n_enc + (c - 3));
+        else v = __ldg(normal + 3 * r + (c - 3 - n_enc));
+        row[n_feat + c] = v;
+    }
+    if (lane < 4) {
+        const float v = row[lane];          // written by the preceding ia_linear64_fwd on the same stream
+        if (lane == 0) sdf[r] = v;
+        else if (rgb_raw != nullptr) rgb_raw[3 * r + (lane - 1)] = v;
     }
 }
 
 __global__ void head_fill_bwd_kernel(const float *__restrict__ dtin, int64_t ld, int64_t n, int n_feat, int n_enc,
                                      float *__restrict__ dpts01, float *__restrict__ denc, float *__restrict__ dnormal)
 {
-    const int w = 3 + n_enc + 3;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * w) return;
-    const int64_t r = i / w;
-    const int c = (int)(i - r * w);
-    const float g = __ldg(dtin + r * ld + n_feat + c);
-    if (c < 3) {
-        if (dpts01 != nullptr) dpts01[3 * r + c] = 2.0f * g;
-    } else if (c < 3 + n_enc) {
-        if (denc != nullptr) denc[r * n_enc + (c - 3)] = g;
-    } else if (dnormal != nullptr) {
-        dnormal[3 * r + (c - 3 - n_enc)] = g;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const float *row = dtin + r * ld + n_feat;
+    const int w = 6 + n_enc;
+    for (int c = lane; c < w; c += 32) {
+        const float g = __ldg(row + c);
+        if (c < 3) {
+            if (dpts01 != nullptr) dpts01[3 * r + c] = 2.0f * g;
+        } else if (c < 3 + n_enc) {
+            if (denc != nullptr) denc[r * n_enc + (c - 3)] = g;
+        } else if (dnormal != nullptr) {
+            dnormal[3 * r + (c - 3 - n_enc)] = g;
+        }
     }
 }
 
@@ -292,7 +294,7 @@ extern "C" int32_t ia_head_fill_fwd(const float *pts01, const float *enc, int32_
     IA_REQUIRE(n_enc >= 0 && (n_enc == 0 || enc != nullptr), "head_fill_fwd: enc is NULL with n_enc=%d", n_enc);
     IA_REQUIRE(n_feat >= 4 && ld_tin >= n_feat + 6 + n_enc, "head_fill_fwd: n_feat=%d ld_tin=%lld too small", n_feat, (long long)ld_tin);
     if (n == 0) return IA_OK;
-    head_fill_fwd_kernel<<<blocks_for(n * (10 + n_enc)), 256, 0, (cudaStream_t)stream>>>(pts01, enc, n_enc, normal, n, n_feat, tin,
+    head_fill_fwd_kernel<<<(unsigned)ia_ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(pts01, enc, n_enc, normal, n, n_feat, tin,
                                                                                         ld_tin, sdf, rgb_raw);
     IA_LAUNCH_OK("head_fill_fwd_kernel");
     return IA_OK;
@@ -304,7 +306,7 @@ extern "C" int32_t ia_head_fill_bwd(const float *dtin, int64_t ld_tin, int64_t n
     IA_REQUIRE(n >= 0 && (n == 0 || dtin), "head_fill_bwd: NULL pointer");
     IA_REQUIRE(n_enc >= 0 && ld_tin >= n_feat + 6 + n_enc, "head_fill_bwd: ld_tin too small");
     if (n == 0) return IA_OK;
-    head_fill_bwd_kernel<<<blocks_for(n * (6 + n_enc)), 256, 0, (cudaStream_t)stream>>>(dtin, ld_tin, n, n_feat, n_enc, dpts01, denc,
+    head_fill_bwd_kernel<<<(unsigned)ia_ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(dtin, ld_tin, n, n_feat, n_enc, dpts01, denc,
                                                                                        dnormal);
     IA_LAUNCH_OK("head_fill_bwd_kernel");
     return IA_OK;

@@ -143,15 +143,20 @@ int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, const float *
 int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
                         const float *dextra, int32_t n_extra, float *dh, float *dW, float *db, void *stream);
 
-/* Colour-head input assembly (models/geometry.py:207 `cat[feature, points*2-1]` + models/texture.py:26-27
- * `cat[features, dirs_embd, normals]`).  The caller lets ia_linear64_fwd write the n_feat geometry outputs into columns
- * [0, n_feat) of tin (row stride ld_tin); this call fills columns [n_feat, n_feat+3+n_enc+3) with (pts01*2-1 | enc | normal)
- * and copies column 0 to sdf[n] and columns 1..3 to rgb_raw[n,3] (the dual-colour head's diffuse term).
- * Backward: dpts01 = 2 dtin[:, n_feat:n_feat+3], denc, dnormal = the matching column blocks (each may be NULL). */
-int32_t ia_head_fill_fwd(const float *pts01, const float *enc, int32_t n_enc, const float *normal, int64_t n, int32_t n_feat,
-                         float *tin, int64_t ld_tin, float *sdf, float *rgb_raw, void *stream);
-int32_t ia_head_fill_bwd(const float *dtin, int64_t ld_tin, int64_t n, int32_t n_feat, int32_t n_enc, float *dpts01, float *denc,
-                         float *dnormal, void *stream);
+/* SDF output layer fused with the colour head's input row (models/geometry.py:206-207 `feature = cat[out, points*2-1]`
+ * + models/texture.py:26-27 `cat[features, dirs_embd, normals]`):
+ *   tin[n, ld_tin] = [ h W^T + b (n_feat <= 72 cols) | pts01*2-1 (3) | enc (n_enc <= 26) | normal (3) ],
+ *   sdf[n] = column 0, rgb_raw[n,3] = columns 1..3 (the dual-colour head's diffuse term; may be NULL).
+ * One kernel writes whole rows; nothing of `out` / `feature` / `network_inp` is materialised separately.
+ * Backward: dtin[n, ld_tin] is the colour MLP's input gradient; dextra[n, n_extra] (gradients reaching columns
+ * 0..n_extra-1 through sdf / rgb_raw) is added on the fly.  dh[n,64] required; dW/db ACCUMULATED (may be NULL);
+ * dpts01 = 2 dtin[:, n_feat:n_feat+3], denc, dnormal = the matching column blocks (each may be NULL). */
+int32_t ia_sdf_head_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_feat, const float *pts01,
+                        const float *enc, int32_t n_enc, const float *normal, float *tin, int64_t ld_tin, float *sdf,
+                        float *rgb_raw, void *stream);
+int32_t ia_sdf_head_bwd(const float *h, int64_t n, const float *W, const float *dtin, int64_t ld_tin, int32_t n_feat,
+                        int32_t n_enc, const float *dextra, int32_t n_extra, float *dh, float *dW, float *db,
+                        float *dpts01, float *denc, float *dnormal, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Finite-difference / curvature stages  fused elementwise stages of VolumeSDF.forward

@@ -22,13 +22,21 @@ constexpr int WPAD = 68;        // padded row length of the weight tile (16-byte
 constexpr int MAX_NOUT = 128;
 constexpr int TILED_NOUT = 72;  // 8 column groups x 9 outputs
 constexpr int WTS = 96;         // forward: W^T row = 8 groups x 12 floats (9 used), 16-byte aligned groups
-constexpr int OLD = 73;         // output / dY staging tile leading dimension (odd: conflict-free row-per-lane access)
+constexpr int OLD = 97;         // output / dY staging tile leading dimension (odd: conflict-free row-per-lane access); up to 96 columns
+
+// Optional tail of the colour head's input row (reference models/geometry.py:207 + models/texture.py:26-27): columns
+// [n_out, n_out + 3 + n_enc + 3) of `out` = (pts01*2-1 | enc | normal); column 0 / columns 1..3 are also copied out.
+struct HeadTail {
+    const float *pts01, *enc, *normal;   // [n,3], [n,n_enc], [n,3]; pts01 == nullptr: no tail
+    int n_enc;
+    float *sdf, *rgb_raw;                // [n], [n,3] (rgb_raw may be nullptr)
+};
 
 // -------------------------------------------------------------------------------------------------------------------
 // tiled forward: thread (tr = t & 31, tc = t >> 5) -> rows {tr, tr+32, tr+64, tr+96} x outputs {9 tc .. 9 tc + 8}
 __global__ void __launch_bounds__(LTHREADS, 2)
 linear64_fwd_tiled_kernel(const float *__restrict__ h, int64_t n, const float *__restrict__ Wg, const float *__restrict__ bg,
-                          int n_out, float *__restrict__ out, int64_t ld_out)
+                          int n_out, float *__restrict__ out, int64_t ld_out, const HeadTail T)
 {
     extern __shared__ __align__(16) float sm[];
     float *Wt = sm;                        // [64][WTS]: Wt[k][12 g + j] = W[9 g + j][k]
@@ -61,6 +69,22 @@ linear64_fwd_tiled_kernel(const float *__restrict__ h, int64_t n, const float *_
                 d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
             }
         }
+        // tail columns of this tile: one element per lane for each of the warp's 16 rows, fetched before the FMA loop
+        const int n_tail = T.pts01 != nullptr ? 6 + T.n_enc : 0;
+        float tail[LROWS / (LTHREADS / 32)];
+        if (n_tail > 0) {
+            const int c = tid & 31;
+#pragma unroll
+            for (int u = 0; u < LROWS / (LTHREADS / 32); ++u) {
+                const int64_t r = row0 + (tid >> 5) + u * (LTHREADS / 32);
+                // Raw loads only, branch-free source select: the first use of a loaded value stalls the (in-order) warp, so
+                // any arithmetic on tail[u] here would serialise the 16 rows on DRAM latency (measured: +0.45 ms per 1.5 M
+                // rows).  The pts01*2-1 affine is applied when the values are written to the output tile.
+                const float *src = c < 3 ? T.pts01 + 3 * r + c
+                                         : (c < 3 + T.n_enc ? T.enc + r * T.n_enc + (c - 3) : T.normal + 3 * r + (c - 3 - T.n_enc));
+                tail[u] = __ldg((r < n && c < n_tail) ? src : T.pts01);
+            }
+        }
         __syncthreads();
         float acc[4][9];
 #pragma unroll
@@ -85,15 +109,28 @@ linear64_fwd_tiled_kernel(const float *__restrict__ h, int64_t n, const float *_
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 9; ++j) Os[(tr + 32 * i) * OLD + 9 * tc + j] = acc[i][j];
+            for (int j = 0; j < 9; ++j)
+                if (9 * tc + j < n_out) Os[(tr + 32 * i) * OLD + 9 * tc + j] = acc[i][j];
+        if (n_tail > 0 && (tid & 31) < n_tail) {
+#pragma unroll
+            for (int u = 0; u < LROWS / (LTHREADS / 32); ++u)
+                Os[((tid >> 5) + u * (LTHREADS / 32)) * OLD + n_out + (tid & 31)] = (tid & 31) < 3 ? tail[u] * 2.0f - 1.0f : tail[u];
+        }
         __syncthreads();
+        const int n_cols = n_out + n_tail;
         for (int rr = tid >> 5; rr < LROWS; rr += LTHREADS / 32) {
-            if (row0 + rr < n) {
-                float *dst = out + (row0 + rr) * ld_out;
+            const int64_t r = row0 + rr;
+            if (r < n) {
+                float *dst = out + r * ld_out;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const int o = (tid & 31) + 32 * c;
-                    if (o < n_out) dst[o] = Os[rr * OLD + o];
+                    if (o < n_cols) dst[o] = Os[rr * OLD + o];
+                }
+                if (n_tail > 0 && (tid & 31) < 4) {
+                    const float v = Os[rr * OLD + (tid & 31)];
+                    if ((tid & 31) == 0) T.sdf[r] = v;
+                    else if (T.rgb_raw != nullptr) T.rgb_raw[3 * r + (tid & 31) - 1] = v;
                 }
             }
         }
@@ -134,7 +171,8 @@ __device__ __forceinline__ void stage_dy(float *Ds, int ld, const float *__restr
 // tiled input gradient: thread (tr, tc) -> rows {tr + 32 i} x k in [8 tc, 8 tc + 8)
 __global__ void __launch_bounds__(LTHREADS, 2)
 linear64_bwd_input_tiled_kernel(const float *__restrict__ dy, int64_t ld_dy, const float *__restrict__ dex, int n_ex, int64_t n,
-                                const float *__restrict__ Wg, int n_out, float *__restrict__ dh)
+                                const float *__restrict__ Wg, int n_out, float *__restrict__ dh, int n_tail_enc,
+                                float *__restrict__ dpts01, float *__restrict__ denc, float *__restrict__ dnormal)
 {
     extern __shared__ __align__(16) float sm[];
     float *Ws = sm;                        // [n_out][WPAD]
@@ -146,8 +184,25 @@ linear64_bwd_input_tiled_kernel(const float *__restrict__ dy, int64_t ld_dy, con
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * LROWS;
         __syncthreads();
-        stage_dy<LTHREADS, false>(Ds, OLD, dy, ld_dy, dex, n_ex, row0, n, n_out, n_out, tid);
+        const int n_tail = n_tail_enc >= 0 ? 6 + n_tail_enc : 0;     // tail columns [n_out, n_out + n_tail) of the same rows
+        stage_dy<LTHREADS, false>(Ds, OLD, dy, ld_dy, dex, n_ex, row0, n, n_out + n_tail, n_out + n_tail, tid);
         __syncthreads();
+        if (n_tail > 0) {
+            const int c = tid & 31;
+            for (int rr = tid >> 5; rr < LROWS; rr += LTHREADS / 32) {
+                const int64_t r = row0 + rr;
+                if (r < n && c < n_tail) {
+                    const float g = Ds[rr * OLD + n_out + c];
+                    if (c < 3) {
+                        if (dpts01 != nullptr) dpts01[3 * r + c] = 2.0f * g;
+                    } else if (c < 3 + n_tail_enc) {
+                        if (denc != nullptr) denc[r * n_tail_enc + (c - 3)] = g;
+                    } else if (dnormal != nullptr) {
+                        dnormal[3 * r + (c - 3 - n_tail_enc)] = g;
+                    }
+                }
+            }
+        }
         float acc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -408,8 +463,30 @@ linear64_bwd_weight_kernel(const float *__restrict__ h, const float *__restrict_
 
 }  // namespace
 
+static int linear64_fwd_impl(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out, int64_t ld_out,
+                             const HeadTail &T, void *stream);
+
 extern "C" int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out,
                                    int64_t ld_out, void *stream)
+{
+    HeadTail T{};
+    return linear64_fwd_impl(h, n, W, b, n_out, out, ld_out, T, stream);
+}
+
+extern "C" int32_t ia_sdf_head_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_feat, const float *pts01,
+                                   const float *enc, int32_t n_enc, const float *normal, float *tin, int64_t ld_tin, float *sdf,
+                                   float *rgb_raw, void *stream)
+{
+    IA_REQUIRE(n_feat >= 4 && n_feat <= TILED_NOUT, "sdf_head_fwd: n_feat %d not in [4,%d]", n_feat, TILED_NOUT);
+    IA_REQUIRE(n_enc >= 0 && 6 + n_enc <= 32 && n_feat + 6 + n_enc <= 96, "sdf_head_fwd: n_enc %d too wide", n_enc);
+    IA_REQUIRE(n == 0 || (pts01 && normal && sdf && (n_enc == 0 || enc)), "sdf_head_fwd: NULL pointer");
+    IA_REQUIRE(ld_tin >= n_feat + 6 + n_enc, "sdf_head_fwd: ld_tin too small");
+    HeadTail T{pts01, enc, normal, n_enc, sdf, rgb_raw};
+    return linear64_fwd_impl(h, n, W, b, n_feat, tin, ld_tin, T, stream);
+}
+
+static int linear64_fwd_impl(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out, int64_t ld_out,
+                             const HeadTail &T, void *stream)
 {
     IA_REQUIRE(n_out >= 1 && n_out <= MAX_NOUT, "linear64_fwd: n_out %d not in [1,%d]", n_out, MAX_NOUT);
     IA_REQUIRE(n >= 0 && (n == 0 || (h && W && b && out)), "linear64_fwd: NULL pointer");
@@ -420,7 +497,7 @@ extern "C" int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, co
     if (n_out <= TILED_NOUT) {
         const size_t bytes = sizeof(float) * ((size_t)LW * WTS + TILED_NOUT + (size_t)LROWS * OLD);
         IA_CUDA_OK(cudaFuncSetAttribute(linear64_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        linear64_fwd_tiled_kernel<<<blocks, LTHREADS, bytes, (cudaStream_t)stream>>>(h, n, W, b, n_out, out, ld_out);
+        linear64_fwd_tiled_kernel<<<blocks, LTHREADS, bytes, (cudaStream_t)stream>>>(h, n, W, b, n_out, out, ld_out, T);
         IA_LAUNCH_OK("linear64_fwd_tiled_kernel");
         return IA_OK;
     }
@@ -431,8 +508,30 @@ extern "C" int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, co
     return IA_OK;
 }
 
+static int linear64_bwd_impl(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
+                             const float *dextra, int32_t n_extra, float *dh, float *dW, float *db, int n_tail_enc, float *dpts01,
+                             float *denc, float *dnormal, void *stream);
+
 extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
                                    const float *dextra, int32_t n_extra, float *dh, float *dW, float *db, void *stream)
+{
+    return linear64_bwd_impl(h, n, W, dout, ld_dout, n_out, dextra, n_extra, dh, dW, db, -1, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int32_t ia_sdf_head_bwd(const float *h, int64_t n, const float *W, const float *dtin, int64_t ld_tin, int32_t n_feat,
+                                   int32_t n_enc, const float *dextra, int32_t n_extra, float *dh, float *dW, float *db,
+                                   float *dpts01, float *denc, float *dnormal, void *stream)
+{
+    IA_REQUIRE(n_feat >= 4 && n_feat <= TILED_NOUT, "sdf_head_bwd: n_feat %d not in [4,%d]", n_feat, TILED_NOUT);
+    IA_REQUIRE(n_enc >= 0 && 6 + n_enc <= 32 && n_feat + 6 + n_enc <= 96, "sdf_head_bwd: n_enc %d too wide", n_enc);
+    IA_REQUIRE(ld_tin >= n_feat + 6 + n_enc, "sdf_head_bwd: ld_tin too small");
+    IA_REQUIRE(dh != nullptr, "sdf_head_bwd: dh is NULL (the tail gradients are produced by the input-gradient kernel)");
+    return linear64_bwd_impl(h, n, W, dtin, ld_tin, n_feat, dextra, n_extra, dh, dW, db, n_enc, dpts01, denc, dnormal, stream);
+}
+
+static int linear64_bwd_impl(const float *h, int64_t n, const float *W, const float *dout, int64_t ld_dout, int32_t n_out,
+                             const float *dextra, int32_t n_extra, float *dh, float *dW, float *db, int n_tail_enc, float *dpts01,
+                             float *denc, float *dnormal, void *stream)
 {
     IA_REQUIRE(n_extra >= 0 && n_extra <= n_out && (n_extra == 0 || dextra != nullptr), "linear64_bwd: bad dextra / n_extra=%d", n_extra);
     IA_REQUIRE(n_out >= 1 && n_out <= MAX_NOUT, "linear64_bwd: n_out %d not in [1,%d]", n_out, MAX_NOUT);
@@ -448,7 +547,8 @@ extern "C" int32_t ia_linear64_bwd(const float *h, int64_t n, const float *W, co
         if (tiled) {
             const size_t bytes = sizeof(float) * ((size_t)TILED_NOUT * WPAD + (size_t)LROWS * OLD);
             IA_CUDA_OK(cudaFuncSetAttribute(linear64_bwd_input_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            linear64_bwd_input_tiled_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, dextra, n_extra, n, W, n_out, dh);
+            linear64_bwd_input_tiled_kernel<<<blocks, LTHREADS, bytes, s>>>(dout, ld_dout, dextra, n_extra, n, W, n_out, dh, n_tail_enc, dpts01,
+                                                                            denc, dnormal);
             IA_LAUNCH_OK("linear64_bwd_input_tiled_kernel");
         } else {
             const size_t bytes = sizeof(float) * ((size_t)n_out * WPAD + (size_t)LROWS * (n_out + 1));

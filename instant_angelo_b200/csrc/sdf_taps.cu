@@ -161,50 +161,6 @@ curv_angle_bwd_kernel(const float *__restrict__ normals, const float *__restrict
     st3(dgshift, s, normalize3_bwd(ns, l, scale3(nrm, dd), sqrtf(dot3(gs, gs)) < NORM_EPS));
 }
 
-// ---- colour-head input assembly: 8 rows per 256-thread CTA, one warp per row (no integer divisions, coalesced rows)
-__global__ void head_fill_fwd_kernel(const float *__restrict__ pts01, const float *__restrict__ enc, int n_enc,
-                                     const float *__restrict__ normal, int64_t n, int n_feat, float *__restrict__ tin,
-                                     int64_t ld, float *__restrict__ sdf, float *__restrict__ rgb_raw)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= n) return;
-    float *row = tin + r * ld;
-    const int w = 6 + n_enc;
-    for (int c = lane; c < w; c += 32) {
-        float v;
-        if (c < 3) v = __ldg(pts01 + 3 * r + c) * 2.0f - 1.0f;
-        else if (c < 3 + n_enc) v = __ldg(enc + r * n_enc + (c - 3));
-        else v = __ldg(normal + 3 * r + (c - 3 - n_enc));
-        row[n_feat + c] = v;
-    }
-    if (lane < 4) {
-        const float v = row[lane];          // written by the preceding ia_linear64_fwd on the same stream
-        if (lane == 0) sdf[r] = v;
-        else if (rgb_raw != nullptr) rgb_raw[3 * r + (lane - 1)] = v;
-    }
-}
-
-__global__ void head_fill_bwd_kernel(const float *__restrict__ dtin, int64_t ld, int64_t n, int n_feat, int n_enc,
-                                     float *__restrict__ dpts01, float *__restrict__ denc, float *__restrict__ dnormal)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= n) return;
-    const float *row = dtin + r * ld + n_feat;
-    const int w = 6 + n_enc;
-    for (int c = lane; c < w; c += 32) {
-        const float g = __ldg(row + c);
-        if (c < 3) {
-            if (dpts01 != nullptr) dpts01[3 * r + c] = 2.0f * g;
-        } else if (c < 3 + n_enc) {
-            if (denc != nullptr) denc[r * n_enc + (c - 3)] = g;
-        } else if (dnormal != nullptr) {
-            dnormal[3 * r + (c - 3 - n_enc)] = g;
-        }
-    }
-}
-
 inline unsigned blocks_for(int64_t n) { return (unsigned)ia_ceil_div(n, 256); }
 
 }  // namespace
@@ -284,30 +240,5 @@ extern "C" int32_t ia_curv_angle_bwd(const float *normals, const float *gshift, 
     if (n == 0) return IA_OK;
     curv_angle_bwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(normals, gshift, n, dlaplace, dnormals, dgshift);
     IA_LAUNCH_OK("curv_angle_bwd_kernel");
-    return IA_OK;
-}
-
-extern "C" int32_t ia_head_fill_fwd(const float *pts01, const float *enc, int32_t n_enc, const float *normal, int64_t n,
-                                    int32_t n_feat, float *tin, int64_t ld_tin, float *sdf, float *rgb_raw, void *stream)
-{
-    IA_REQUIRE(n >= 0 && (n == 0 || (pts01 && normal && tin && sdf)), "head_fill_fwd: NULL pointer");
-    IA_REQUIRE(n_enc >= 0 && (n_enc == 0 || enc != nullptr), "head_fill_fwd: enc is NULL with n_enc=%d", n_enc);
-    IA_REQUIRE(n_feat >= 4 && ld_tin >= n_feat + 6 + n_enc, "head_fill_fwd: n_feat=%d ld_tin=%lld too small", n_feat, (long long)ld_tin);
-    if (n == 0) return IA_OK;
-    head_fill_fwd_kernel<<<(unsigned)ia_ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(pts01, enc, n_enc, normal, n, n_feat, tin,
-                                                                                        ld_tin, sdf, rgb_raw);
-    IA_LAUNCH_OK("head_fill_fwd_kernel");
-    return IA_OK;
-}
-
-extern "C" int32_t ia_head_fill_bwd(const float *dtin, int64_t ld_tin, int64_t n, int32_t n_feat, int32_t n_enc, float *dpts01,
-                                    float *denc, float *dnormal, void *stream)
-{
-    IA_REQUIRE(n >= 0 && (n == 0 || dtin), "head_fill_bwd: NULL pointer");
-    IA_REQUIRE(n_enc >= 0 && ld_tin >= n_feat + 6 + n_enc, "head_fill_bwd: ld_tin too small");
-    if (n == 0) return IA_OK;
-    head_fill_bwd_kernel<<<(unsigned)ia_ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(dtin, ld_tin, n, n_feat, n_enc, dpts01, denc,
-                                                                                       dnormal);
-    IA_LAUNCH_OK("head_fill_bwd_kernel");
     return IA_OK;
 }

@@ -268,11 +268,8 @@ class _SdfHeadFn(torch.autograd.Function):
         tin = torch.empty(n, ld, device=h.device, dtype=torch.float32)
         sdf = torch.empty(n, device=h.device, dtype=torch.float32)
         rgb_raw = torch.empty(n, 3, device=h.device, dtype=torch.float32)
-        s = L.stream()
-        _run("ia_linear64_fwd", L.ptr(h), n, L.ptr(W), L.ptr(b), n_feat, L.ptr(tin), ld, s, work=2.0 * n * n_feat * 64,
-             tag=f"64>{n_feat}")
-        _run("ia_head_fill_fwd", L.ptr(pts01), L.ptr(enc), n_enc, L.ptr(normal), n, n_feat, L.ptr(tin), ld, L.ptr(sdf),
-             L.ptr(rgb_raw), s)
+        _run("ia_sdf_head_fwd", L.ptr(h), n, L.ptr(W), L.ptr(b), n_feat, L.ptr(pts01), L.ptr(enc), n_enc, L.ptr(normal), L.ptr(tin), ld,
+             L.ptr(sdf), L.ptr(rgb_raw), L.stream(), work=2.0 * n * n_feat * 64, tag=f"64>{n_feat}")
         ctx.save_for_backward(h, W)
         ctx.dims = (n_feat, n_enc)
         return tin, sdf, rgb_raw
@@ -285,18 +282,15 @@ class _SdfHeadFn(torch.autograd.Function):
         dtin = L.f32c(dtin)
         dextra = torch.cat([dsdf.reshape(n, 1), drgb.reshape(n, 3)], dim=1)
         need = ctx.needs_input_grad
-        dh = torch.empty_like(h) if need[0] else None
+        dh = torch.empty_like(h)
         dW = torch.zeros_like(W) if (need[1] or need[2]) else None
         db = torch.zeros(n_feat, device=h.device) if need[2] else None
-        s = L.stream()
-        _run("ia_linear64_bwd", L.ptr(h), n, L.ptr(W), L.ptr(dtin), dtin.shape[1], n_feat, L.ptr(dextra), 4, L.ptr(dh), L.ptr(dW),
-             L.ptr(db), s, work=4.0 * n * n_feat * 64, tag=f"64>{n_feat}")
         dpts = torch.empty(n, 3, device=h.device) if need[3] else None
         denc = torch.empty(n, n_enc, device=h.device) if need[4] else None
         dnrm = torch.empty(n, 3, device=h.device) if need[5] else None
-        if dpts is not None or denc is not None or dnrm is not None:
-            _run("ia_head_fill_bwd", L.ptr(dtin), dtin.shape[1], n, n_feat, n_enc, L.ptr(dpts), L.ptr(denc), L.ptr(dnrm), s)
-        return dh, (dW if need[1] else None), db, dpts, denc, dnrm
+        _run("ia_sdf_head_bwd", L.ptr(h), n, L.ptr(W), L.ptr(dtin), dtin.shape[1], n_feat, n_enc, L.ptr(dextra), 4, L.ptr(dh), L.ptr(dW),
+             L.ptr(db), L.ptr(dpts), L.ptr(denc), L.ptr(dnrm), L.stream(), work=4.0 * n * n_feat * 64, tag=f"64>{n_feat}")
+        return (dh if need[0] else None), (dW if need[1] else None), db, dpts, denc, dnrm
 
 
 def sdf_head(h, W, b, pts01, enc, normal):

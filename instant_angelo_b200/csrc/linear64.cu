@@ -525,6 +525,7 @@ extern "C" int32_t ia_sdf_head_bwd(const float *h, int64_t n, const float *W, co
     IA_REQUIRE(n_feat >= 4 && n_feat <= TILED_NOUT, "sdf_head_bwd: n_feat %d not in [4,%d]", n_feat, TILED_NOUT);
     IA_REQUIRE(n_enc >= 0 && 6 + n_enc <= 32 && n_feat + 6 + n_enc <= 96, "sdf_head_bwd: n_enc %d too wide", n_enc);
     IA_REQUIRE(ld_tin >= n_feat + 6 + n_enc, "sdf_head_bwd: ld_tin too small");
+    if (n == 0) return IA_OK;
     IA_REQUIRE(dh != nullptr, "sdf_head_bwd: dh is NULL (the tail gradients are produced by the input-gradient kernel)");
     return linear64_bwd_impl(h, n, W, dtin, ld_tin, n_feat, dextra, n_extra, dh, dW, db, n_enc, dpts01, denc, dnormal, stream);
 }

@@ -260,3 +260,28 @@ def test_fused_head_matches_generic_path(cuda_lib, golden_dir, monkeypatch):
     for n in g0:
         rt, at = grad_tol(g1[n], 1e-4)
         assert_close(g0[n], g1[n], rtol=rt, atol=at, name="grad " + n)
+
+
+@pytest.mark.parametrize("mlp_otype", ["VanillaMLP", "FullyFusedMLP"])
+def test_step_with_zero_marched_samples(cuda_lib, mlp_otype):
+    """Every ray misses the AABB and the background grid is empty: zero foreground and background samples.  nerfacc
+    returns empty tensors there and the reference's step still runs (comp_rgb = background colour); so must this path,
+    forward and backward, with finite (zero) gradients."""
+    from instant_angelo_b200.losses import training_loss
+    cfg = golden_model_config(texture="volume-dual-color", learned_background=True)
+    sd = mr.RefNeuSModel(cfg).state_dict()
+    bgc = torch.tensor([0.2, 0.5, 0.7])
+    model = build_product(cfg, {k: v.detach().clone() for k, v in sd.items()}, 30, bgc, mlp_otype)
+    model.occupancy_grid_bg.set_binary(torch.zeros(256, 256, 256, dtype=torch.bool))
+    n = 32
+    o = torch.tensor([[5.0, 0.0, 0.0]]).repeat(n, 1)
+    d = torch.nn.functional.normalize(torch.tensor([[1.0, 0.2, 0.1]]).repeat(n, 1), dim=-1)
+    rays = torch.cat([o, d], dim=1).cuda()
+    out = model(rays)
+    assert int(out["num_samples_full"]) == 0 and out["ray_indices"].numel() == 0
+    assert_close(out["comp_rgb_full"], bgc.cuda().expand(n, 3), rtol=0, atol=1e-6, name="comp_rgb_full")
+    assert float(out["opacity"].abs().max()) == 0.0
+    batch = {"rays": rays, "rgb": torch.rand(n, 3).cuda()}
+    terms = training_loss(model, out, batch, golden_loss_config(), 30)
+    terms["loss"].backward()       # means over zero samples are nan in the reference too; what matters is that nothing throws
+    torch.cuda.synchronize()

@@ -618,3 +618,53 @@ def test_sdf_head_matches_torch(cuda_lib, n, n_feat, n_enc):
     for name, a, t in zip(("dh", "dW", "db", "dpts", "denc", "dnrm"), got, (h, W, b, pts, enc, nrm)):
         ref = t.grad.float()
         assert_close(a, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()) + 1e-6, name=name)
+
+
+@pytest.mark.gpu
+def test_empty_inputs_are_accepted_everywhere(cuda_lib):
+    """Zero rows / zero rays (a batch whose rays all miss): every operator returns an empty result of the right shape and
+    a zero / empty gradient, as the nerfacc and tcnn bindings do (the C ABI sees NULL data pointers with n = 0)."""
+    from instant_angelo_b200 import _lib as L, ops
+    dev = "cuda"
+    z = lambda *s: torch.zeros(*s, device=dev, requires_grad=True)
+    plan = ops.make_grid_plan(16, 2, 19, 32, 1.3195079107728942)
+    table = (torch.rand(plan.n_params, device=dev) * 1e-2).requires_grad_(True)
+    for group in (1, 6):
+        x = z(0, 3)
+        y = ops.hashgrid_encode(x, table, plan, 16, group=group)
+        assert y.shape == (0, 32)
+        y.sum().backward()
+        assert float(table.grad.abs().max()) == 0.0
+    assert ops.sh_encode(z(0, 3), 4).shape == (0, 16)
+    for prec in (L.IA_MLP_FP32, L.IA_MLP_TC_F16):
+        desc = ops.make_mlp_desc(3, 32, 2, 65, L.IA_ACT_SOFTPLUS100, 2.0, -1.0, prec)
+        params = (torch.randn(L.load().ia_mlp_param_count(desc), device=dev) * 0.1).requires_grad_(True)
+        for nou in (1, 65):
+            out = ops.mlp_apply(z(0, 3), z(0, 32), params, desc, nou)
+            assert out.shape == (0, nou)
+            out.sum().backward()
+            assert float(params.grad.abs().max()) == 0.0
+    W, b = (torch.randn(65, 64, device=dev)).requires_grad_(True), z(65)
+    tin, sdf, raw = ops.sdf_head(z(0, 64), W, b, z(0, 3), z(0, 16), z(0, 3))
+    assert tin.shape == (0, 87) and sdf.shape == (0,) and raw.shape == (0, 3)
+    (tin.sum() + sdf.sum() + raw.sum()).backward()
+    assert float(W.grad.abs().max()) == 0.0
+    taps = ops.fd_taps(z(0, 3), 1e-3, 1.5)
+    assert taps.shape == (0, 6, 3)
+    assert ops.fd_grad(z(0, 6), 1e-3).shape == (0, 3)
+    nrm, sh = ops.curv_shift(z(0, 3), z(0, 3), z(0, 3), 1e-3)
+    assert ops.curv_angle(nrm, sh).shape[0] == 0
+    # zero rays
+    o, d = torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev)
+    t0, t1 = ops.aabb_intersect(o, d, [-1.5] * 3 + [1.5] * 3)
+    assert t0.shape == (0,)
+    gd = ops.make_grid_desc([-1.5] * 3 + [1.5] * 3, [128] * 3, L.IA_AABB)
+    bitfield = torch.full((128 ** 3 // 32,), -1, dtype=torch.int32, device=dev)
+    packed, ri, ts, te = ops.march(o, d, t0, t1, gd, bitfield, 0.01, 0.0)
+    assert packed.shape == (0, 2) and ri.numel() == 0
+    # rays without samples: compositing of empty segments gives zero opacity and passes zero gradients
+    packed = torch.zeros(4, 2, dtype=torch.int32, device=dev)
+    w, op, dep, rgb, n_, _ = ops.composite_neus(z(0), z(0, 3), z(0, 3), z(0), torch.ones(1, device=dev, requires_grad=True), 1.0, packed,
+                                                t_mid=z(0), rgb=z(0, 3), nrm=z(0, 3))
+    assert w.numel() == 0 and float(op.abs().max()) == 0.0 and rgb.shape == (4, 3)
+    (op.sum() + rgb.sum()).backward()

@@ -88,6 +88,18 @@ int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const float *table, c
                                 const ia_grid_plan *plan_host, int32_t active_levels, int32_t group, float *dtable,
                                 float *dx, void *stream);
 
+/* Second-order adjoints of ia_hashgrid_bwd_input (dx = J(x; table)^T dy), needed when the SDF normals are autograd's
+ * d sdf / d x with create_graph=True (grad_type: analytic, models/geometry.py:214-218; tcnn: kernel_grid_backward_input's
+ * own backward, kernel_grid_backward_input_backward_grid).  v[n,3] = dL/d(dx):
+ *   ia_hashgrid_jvp:                  out[n, L*F] = dL/d(dy)  = J(x; table) v              (masked levels: zeros)
+ *   ia_hashgrid_bwd_input_bwd_table:  dtable (ACCUMULATED)   += d(v^T J(x; table)^T dy) / d(table)
+ * d/dx of dx (mixed second derivatives of the trilinear interpolant) is not provided: positions carry no gradient on
+ * the training path. */
+int32_t ia_hashgrid_jvp(const float *x, int64_t n, const float *table, const float *v, const ia_grid_plan *plan,
+                        int32_t active_levels, float *out, void *stream);
+int32_t ia_hashgrid_bwd_input_bwd_table(const float *x, int64_t n, const float *v, const float *dy,
+                                        const ia_grid_plan *plan, int32_t active_levels, float *dtable, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Spherical harmonics                  replaces tcnn.Encoding(otype=SphericalHarmonics) built at
  *                                      models/network_utils.py:90-91, called at models/texture.py:25,52,129,134

@@ -198,6 +198,117 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     }
 }
 
+// ---- second-order adjoints of the input gradient (grad_type: analytic, reference models/geometry.py:214-218: the
+// normals are autograd's d sdf / d x with create_graph=True, so the loss back-propagates through
+// dx = J(x; table)^T dy, tcnn's kernel_grid_backward_input).  With v = dL/d(dx) [N,3]:
+//   d(dy)[l,f]            = scale_l * sum_axis v_axis * d interp_{l,f} / d axis          (hashgrid_jvp_kernel, gather)
+//   d(table)[corner c, f] += scale_l * dy[l,f] * sum_axis v_axis * d w_c / d axis       (hashgrid_bwd_input_bwd_table_kernel)
+// Same (point, x-corner) lane-pair mapping and tile staging as the first-order kernels.
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const float *__restrict__ v,
+                    const GridParams P, float *__restrict__ out)
+{
+    __shared__ float tile[HG_TILE * HG_ROW];
+    const int tid = threadIdx.x;
+    const int pl = tid >> 1;
+    const uint32_t xc = tid & 1;
+    const int64_t base = (int64_t)blockIdx.x * HG_TILE;
+    const int64_t p = base + pl;
+    const bool valid = p < n;
+    float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+    if (valid) {
+        px = __ldg(x + 3 * p); py = __ldg(x + 3 * p + 1); pz = __ldg(x + 3 * p + 2);
+        vx = __ldg(v + 3 * p); vy = __ldg(v + 3 * p + 1); vz = __ldg(v + 3 * p + 2);
+    }
+    for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
+    __syncthreads();
+#pragma unroll 2
+    for (int l = 0; l < P.active; ++l) {
+        const float scale = P.scale[l];
+        const uint32_t res = P.res[l], size = P.size[l];
+        const bool hashed = P.hashed[l] != 0;
+        const float2 *__restrict__ tl = table + P.offset[l];
+        const CellCoords c = locate(px, py, pz, scale);
+        const uint32_t cx = c.ix + xc;
+        const float wx = xc ? c.wx : 1.f - c.wx;
+        float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+        if (valid) {
+            v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));
+            v10 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed));
+            v01 = __ldg(tl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed));
+            v11 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed));
+        }
+        const float uy = 1.f - c.wy, uz = 1.f - c.wz;
+        // coefficients of the four corners of this x side in sum_axis v_axis * d w / d axis
+        const float sgn = xc ? 1.f : -1.f;
+        const float c00 = vx * sgn * uy * uz - vy * wx * uz - vz * wx * uy;
+        const float c10 = vx * sgn * c.wy * uz + vy * wx * uz - vz * wx * c.wy;
+        const float c01 = vx * sgn * uy * c.wz - vy * wx * c.wz + vz * wx * uy;
+        const float c11 = vx * sgn * c.wy * c.wz + vy * wx * c.wz + vz * wx * c.wy;
+        float a0 = scale * (c00 * v00.x + c10 * v10.x + c01 * v01.x + c11 * v11.x);
+        float a1 = scale * (c00 * v00.y + c10 * v10.y + c01 * v01.y + c11 * v11.y);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        if (xc == 0) *reinterpret_cast<float2 *>(&tile[pl * HG_ROW + 2 * l]) = make_float2(a0, a1);
+    }
+    __syncthreads();
+    const int row2 = P.n_levels;
+    float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
+    for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
+        const int r = i / row2, c2 = i - r * row2;
+        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+    }
+}
+
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_bwd_input_bwd_table_kernel(const float *__restrict__ x, int64_t n, const float *__restrict__ v,
+                                    const float *__restrict__ dy, const GridParams P, float2 *__restrict__ dtable)
+{
+    __shared__ float tile[HG_TILE * HG_ROW];
+    const int tid = threadIdx.x;
+    const int pl = tid >> 1;
+    const uint32_t xc = tid & 1;
+    const int64_t base = (int64_t)blockIdx.x * HG_TILE;
+    const int64_t p = base + pl;
+    const bool valid = p < n;
+    const int row2 = P.n_levels;
+    const float2 *__restrict__ dy2 = reinterpret_cast<const float2 *>(dy);
+    for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
+        const int r = i / row2, c2 = i - r * row2;
+        float2 g = make_float2(0.f, 0.f);
+        if (base + r < n) g = __ldg(dy2 + (base + r) * row2 + c2);
+        *reinterpret_cast<float2 *>(&tile[r * HG_ROW + 2 * c2]) = g;
+    }
+    float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+    if (valid) {
+        px = __ldg(x + 3 * p); py = __ldg(x + 3 * p + 1); pz = __ldg(x + 3 * p + 2);
+        vx = __ldg(v + 3 * p); vy = __ldg(v + 3 * p + 1); vz = __ldg(v + 3 * p + 2);
+    }
+    __syncthreads();
+    if (!valid) return;
+    for (int l = 0; l < P.active; ++l) {
+        const float2 g = *reinterpret_cast<const float2 *>(&tile[pl * HG_ROW + 2 * l]);
+        if (g.x == 0.f && g.y == 0.f) continue;
+        const float scale = P.scale[l];
+        const uint32_t res = P.res[l], size = P.size[l];
+        const bool hashed = P.hashed[l] != 0;
+        float2 *__restrict__ dl = dtable + P.offset[l];
+        const CellCoords c = locate(px, py, pz, scale);
+        const uint32_t cx = c.ix + xc;
+        const float wx = xc ? c.wx : 1.f - c.wx;
+        const float uy = 1.f - c.wy, uz = 1.f - c.wz;
+        const float sgn = xc ? 1.f : -1.f;
+        const float c00 = scale * (vx * sgn * uy * uz - vy * wx * uz - vz * wx * uy);
+        const float c10 = scale * (vx * sgn * c.wy * uz + vy * wx * uz - vz * wx * c.wy);
+        const float c01 = scale * (vx * sgn * uy * c.wz - vy * wx * c.wz + vz * wx * uy);
+        const float c11 = scale * (vx * sgn * c.wy * c.wz + vy * wx * c.wz + vz * wx * c.wy);
+        atomicAdd(dl + entry_index(cx, c.iy, c.iz, res, size, hashed), make_float2(c00 * g.x, c00 * g.y));
+        atomicAdd(dl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed), make_float2(c10 * g.x, c10 * g.y));
+        atomicAdd(dl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed), make_float2(c01 * g.x, c01 * g.y));
+        atomicAdd(dl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed), make_float2(c11 * g.x, c11 * g.y));
+    }
+}
+
 // Backward for points that arrive in GROUPS of G consecutive, spatially close rows (the 6 finite-difference taps of
 // one sample, reference models/geometry.py:221-233): at the coarse levels all taps of a group fall into the same
 // cell, so their corner contributions are summed in registers and scattered ONCE (4 REDs per x-corner instead of
@@ -457,6 +568,34 @@ extern "C" int32_t ia_hashgrid_bwd_input(const float *x, int64_t n, const float 
 {
     IA_REQUIRE(n == 0 || dx != nullptr, "hashgrid_bwd_input: dx is NULL");
     return ia_hashgrid_bwd(x, n, table, dy, plan, active_levels, nullptr, dx, stream);
+}
+
+extern "C" int32_t ia_hashgrid_jvp(const float *x, int64_t n, const float *table, const float *v, const ia_grid_plan *plan,
+                                   int32_t active_levels, float *out, void *stream)
+{
+    GridParams P;
+    int rc = fill_params(plan, active_levels, &P);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && table && v && out)), "hashgrid_jvp: NULL pointer with n=%lld", (long long)n);
+    if (n == 0) return IA_OK;
+    hashgrid_jvp_kernel<<<(unsigned)ia_ceil_div(n, HG_TILE), HG_THREADS, 0, (cudaStream_t)stream>>>(
+        x, n, reinterpret_cast<const float2 *>(table), v, P, out);
+    IA_LAUNCH_OK("hashgrid_jvp_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_bwd_input_bwd_table(const float *x, int64_t n, const float *v, const float *dy,
+                                                   const ia_grid_plan *plan, int32_t active_levels, float *dtable, void *stream)
+{
+    GridParams P;
+    int rc = fill_params(plan, active_levels, &P);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && v && dy && dtable)), "hashgrid_bwd_input_bwd_table: NULL pointer with n=%lld", (long long)n);
+    if (n == 0) return IA_OK;
+    hashgrid_bwd_input_bwd_table_kernel<<<(unsigned)ia_ceil_div(n, HG_TILE), HG_THREADS, 0, (cudaStream_t)stream>>>(
+        x, n, v, dy, P, reinterpret_cast<float2 *>(dtable));
+    IA_LAUNCH_OK("hashgrid_bwd_input_bwd_table_kernel");
+    return IA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

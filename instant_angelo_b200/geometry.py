@@ -97,6 +97,42 @@ class VolumeSDF(BaseImplicitGeometry):
     def _net(self, pts01, n_out_used, flat, group=1):
         return fused_encode_mlp(self.encoding, self.network, pts01.reshape(-1, 3), n_out_used, flat, group)
 
+    def _analytic_eval(self, pts01):
+        """grad_type 'analytic' (reference models/geometry.py:198-218): the centre evaluation together with
+        d sdf / d points by the chain rule, kept differentiable (create_graph) so that the eikonal / rendering losses
+        back-propagate through the normals.  Per sample: hash-grid forward (kernel) -> network as torch operators
+        (VanillaMLP.forward_twice_differentiable) -> d sdf / d(network input) by autograd -> J_enc^T (.) through
+        ops.hashgrid_input_grad, whose own backward is the pair of second-order hash-grid kernels.
+        Returns (out [S, n_output_dims], grad [*, 3] w.r.t. the un-normalised points)."""
+        from .network_utils import Encoding, ProgressiveBandHashGrid
+        enc_mod = self.encoding
+        inner = enc_mod.encoding
+        x = pts01.reshape(-1, 3)
+        if isinstance(inner, ProgressiveBandHashGrid):
+            grid, active = inner.encoding, inner.active_levels        # the tcnn-style Encoding holding .params
+        elif isinstance(inner, Encoding) and inner.otype == "HashGrid":
+            grid, active = inner, inner.plan.n_levels
+        else:
+            raise NotImplementedError("grad_type='analytic' is implemented for (ProgressiveBand)HashGrid encodings")
+        enc = ops.hashgrid_encode(x, grid.params, grid.plan, active)
+        parts = ([x * enc_mod.xyz_scale + enc_mod.xyz_offset] if enc_mod.include_xyz else []) + [enc]
+        e = torch.cat(parts, dim=-1)
+        if not e.requires_grad:
+            e.requires_grad_(True)
+        out = self.network.forward_twice_differentiable(e).float()
+        sdf = out[:, 0]
+        if "sdf_activation" in self.config:
+            sdf = get_activation(self.config["sdf_activation"])(sdf + float(self.config["sdf_bias"]))
+        keep = self.training
+        (g_e,) = torch.autograd.grad(sdf, e, grad_outputs=torch.ones_like(sdf), create_graph=keep, retain_graph=True)
+        n_xyz = 3 if enc_mod.include_xyz else 0
+        g01 = ops.hashgrid_input_grad(x, grid.params, g_e[:, n_xyz:].contiguous(), grid.plan, active)
+        if enc_mod.include_xyz:
+            g01 = g01 + g_e[:, :3] * enc_mod.xyz_scale
+        # points01 = (points + r) / (2 r)   (AABB contraction, models/geometry.py:24)
+        grad = (g01 / (2.0 * self.radius)).view(*pts01.shape[:-1], 3)
+        return out, grad
+
     def _fd_gradient(self, world_pts, eps, flat):
         """geometry.py:219-234: six taps clamped to the AABB in world space, central differences."""
         lead = world_pts.shape[:-1]
@@ -108,16 +144,17 @@ class VolumeSDF(BaseImplicitGeometry):
                 rand_directions: Optional[torch.Tensor] = None):
         if with_auxiliary_feature:
             raise NotImplementedError("with_auxiliary_feature is not used by any shipped config")
-        if with_grad and self.grad_type == "analytic":
-            raise NotImplementedError(
-                "grad_type='analytic' needs second-order hash-grid/MLP adjoints (SURVEY section 8f rank 1); run the "
-                "B200 path with model.geometry.grad_type=finite_difference")
-        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+        analytic = with_grad and self.grad_type == "analytic"
+        with torch.set_grad_enabled((self.training and torch.is_grad_enabled()) or analytic):
             flat = self.network.flat_params()
             points_ = points
             pts01 = contract_to_unisphere(points, self.radius, self.contraction_type)
             need_full = with_feature
-            out = self._net(pts01, self.n_output_dims if need_full else 1, flat)
+            grad = None
+            if analytic:
+                out, grad = self._analytic_eval(pts01)
+            else:
+                out = self._net(pts01, self.n_output_dims if need_full else 1, flat)
             out = out.view(*pts01.shape[:-1], out.shape[-1])
             sdf = out[..., 0]
             feature = None
@@ -127,8 +164,7 @@ class VolumeSDF(BaseImplicitGeometry):
                 sdf = get_activation(self.config["sdf_activation"])(sdf + float(self.config["sdf_bias"]))
             if with_feature and "feature_activation" in self.config:
                 feature = get_activation(self.config["feature_activation"])(feature)
-            grad = None
-            if with_grad:
+            if with_grad and not analytic:
                 grad = self._fd_gradient(points_, self._finite_difference_eps, flat)
             laplace = None
             if with_laplace:

@@ -237,6 +237,21 @@ class VanillaMLP(nn.Module):
             raise NotImplementedError("Only support cuda inputs.")
         return self.run(None, x.float())
 
+    def forward_twice_differentiable(self, x: torch.Tensor) -> torch.Tensor:
+        """The same network as plain torch operators (exactly reference models/network_utils.py:108-113), for the one
+        place that differentiates THROUGH a derivative of the network: grad_type 'analytic' (models/geometry.py:214-218).
+        The fused kernels implement first-order adjoints only; the second-order MLP adjoint is the next step of
+        SURVEY.md section 8f rank 1 (the hash-grid second-order adjoints are kernels already)."""
+        if not x.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        h = x.float()
+        lins = self.linears()
+        for i, lin in enumerate(lins):
+            h = torch.nn.functional.linear(h, lin.effective_weight(), lin.bias)
+            if i < len(lins) - 1:
+                h = torch.nn.functional.softplus(h, beta=100) if self.sphere_init else torch.relu(h)
+        return self._post(h)
+
 
 def get_mlp(n_input_dims: int, n_output_dims: int, config) -> VanillaMLP:
     """reference models/network_utils.py:177-185.  otype VanillaMLP -> fp32 arithmetic; the tcnn otypes

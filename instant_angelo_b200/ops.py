@@ -140,6 +140,50 @@ def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, plan: L.GridPlan, acti
     return _HashGridFn.apply(x, table, plan, int(active_levels), int(group))
 
 
+class _HashGridInputGradFn(torch.autograd.Function):
+    """dx = J(x; table)^T dy as a differentiable operator (the analytic SDF normal of reference models/geometry.py:214-218,
+    where autograd runs tcnn's backward with create_graph=True).  Backward: d(dy) = J v (ia_hashgrid_jvp) and
+    d(table) (ia_hashgrid_bwd_input_bwd_table); no gradient w.r.t. x (sample positions are not trainable)."""
+
+    @staticmethod
+    def forward(ctx, x, table, dy, plan, active_levels):
+        L.require_cuda(x, table, dy)
+        x, dy = L.f32c(x), L.f32c(dy)
+        n = x.shape[0]
+        dx = torch.empty(n, 3, device=x.device, dtype=torch.float32)
+        _run("ia_hashgrid_bwd_input", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(plan), active_levels, L.ptr(dx), L.stream(),
+             tag="analytic normal", work=n * hashgrid_bytes_per_point(plan, active_levels, "bwd_input"))
+        ctx.save_for_backward(x, table, dy)
+        ctx.plan, ctx.active = plan, active_levels
+        return dx
+
+    @staticmethod
+    def backward(ctx, v):
+        x, table, dy = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("second derivative of the hash grid w.r.t. the sample positions is not on the B200 path")
+        v = L.f32c(v)
+        n = x.shape[0]
+        dtable = ddy = None
+        if ctx.needs_input_grad[1]:
+            dtable = torch.zeros_like(table)
+            _run("ia_hashgrid_bwd_input_bwd_table", L.ptr(x), n, L.ptr(v), L.ptr(dy), C.byref(ctx.plan), ctx.active, L.ptr(dtable),
+                 L.stream(), work=n * hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_table"))
+        if ctx.needs_input_grad[2]:
+            ddy = torch.empty_like(dy)
+            _run("ia_hashgrid_jvp", L.ptr(x), n, L.ptr(table), L.ptr(v), C.byref(ctx.plan), ctx.active, L.ptr(ddy), L.stream(),
+                 work=n * hashgrid_bytes_per_point(ctx.plan, ctx.active, "fwd"))
+        return None, dtable, ddy, None, None
+
+
+def hashgrid_input_grad(x: torch.Tensor, table: torch.Tensor, dy: torch.Tensor, plan: L.GridPlan,
+                        active_levels: Optional[int] = None) -> torch.Tensor:
+    """[N,3] = J(x; table)^T dy, differentiable w.r.t. table and dy (see _HashGridInputGradFn)."""
+    if active_levels is None:
+        active_levels = plan.n_levels
+    return _HashGridInputGradFn.apply(x, table, dy, plan, int(active_levels))
+
+
 # ---------------------------------------------------------------------------------------------
 # spherical harmonics  (tcnn.Encoding(SphericalHarmonics), reference models/texture.py:25)
 # ---------------------------------------------------------------------------------------------

@@ -177,9 +177,10 @@ class _FakeSystem:
         return self._cls.training_step(self, batch, 0)
 
 
-def run_case(models, neus_sys, name: str, texture: str, learned_background: bool, global_step: int, seed: int):
+def run_case(models, neus_sys, name: str, texture: str, learned_background: bool, global_step: int, seed: int,
+             grad_type: str = "finite_difference"):
     torch.manual_seed(seed)
-    mcfg = to_config(golden_model_config(texture=texture, learned_background=learned_background))
+    mcfg = to_config(golden_model_config(texture=texture, learned_background=learned_background, grad_type=grad_type))
     cfg = to_config({"model": mcfg, "system": {"loss": golden_loss_config()}})
     cfg.model.dynamic_ray_sampling = False
     model = models.make("neus", cfg.model)
@@ -223,7 +224,7 @@ def run_case(models, neus_sys, name: str, texture: str, learned_background: bool
 
     fx = {"global_step": np.int64(global_step), "rays": rays.numpy(), "rgb": rgb.numpy(), "u_fg": _RNG["u_fg"].numpy(),
           "u_bg": _RNG["u_bg"].numpy(), "background_color": model.background_color.numpy(),
-          "rand_directions": drawn["rand_directions"].numpy(), "pts": pts.numpy(),
+          "rand_directions": drawn["rand_directions"].numpy(), "pts": pts.detach().numpy(),
           "pts_normal": batch["pts_normal"].numpy(), "pts_weights": batch["pts_weights"].numpy(),
           "loss": loss.detach().numpy()}
     for k, v in out.items():
@@ -247,6 +248,7 @@ def main():
     models, neus_sys = load_reference()
     run_case(models, neus_sys, "neus_dualcolor_bg", "volume-dual-color", True, 25, 100)
     run_case(models, neus_sys, "neus_v3_nobg", "volume-dual-colorV3", False, 60, 200)
+    run_case(models, neus_sys, "neus_analytic_bg", "volume-dual-color", True, 40, 300, grad_type="analytic")
 
 
 if __name__ == "__main__":

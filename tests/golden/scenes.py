@@ -14,7 +14,8 @@ def golden_encoding_config():
             "update_steps": 10}
 
 
-def golden_model_config(texture: str = "volume-dual-color", learned_background: bool = True, feature_dim: int = 65):
+def golden_model_config(texture: str = "volume-dual-color", learned_background: bool = True, feature_dim: int = 65,
+                        grad_type: str = "finite_difference"):
     enc = golden_encoding_config()
     mlp_geo = {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none", "n_neurons": 64,
                "n_hidden_layers": 2, "sphere_init": True, "sphere_init_radius": 0.5, "weight_norm": True}
@@ -32,7 +33,7 @@ def golden_model_config(texture: str = "volume-dual-color", learned_background: 
         "grid_prune": True, "grid_prune_occ_thre": 0.001, "dynamic_ray_sampling": False, "batch_image_sampling": True,
         "randomized": True, "ray_chunk": 2048, "cos_anneal_end": 100, "learned_background": learned_background,
         "background_color": "random", "variance": {"init_val": 0.3, "modulate": False},
-        "geometry": {"name": "volume-sdf", "radius": 1.5, "feature_dim": feature_dim, "grad_type": "finite_difference",
+        "geometry": {"name": "volume-sdf", "radius": 1.5, "feature_dim": feature_dim, "grad_type": grad_type,
                      "finite_difference_eps": "progressive", "isosurface": None, "xyz_encoding_config": enc,
                      "mlp_network_config": mlp_geo},
         "texture": tex,

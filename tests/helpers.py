@@ -11,6 +11,8 @@ from tests.golden.scenes import golden_loss_config, golden_model_config, sphere_
 GOLDEN_CASES = {
     "neus_dualcolor_bg": dict(texture="volume-dual-color", learned_background=True),
     "neus_v3_nobg": dict(texture="volume-dual-colorV3", learned_background=False),
+    # the shipped default of the reference configs: autograd normals (create_graph) + FD curvature taps
+    "neus_analytic_bg": dict(texture="volume-dual-color", learned_background=True, grad_type="analytic"),
 }
 
 

@@ -668,3 +668,41 @@ def test_empty_inputs_are_accepted_everywhere(cuda_lib):
                                                 t_mid=z(0), rgb=z(0, 3), nrm=z(0, 3))
     assert w.numel() == 0 and float(op.abs().max()) == 0.0 and rgb.shape == (4, 3)
     (op.sum() + rgb.sum()).backward()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_name", ["sparse_2p19", "small_mixed"])
+@pytest.mark.parametrize("active", [None, 4])
+def test_hashgrid_input_grad_second_order(cuda_lib, cfg_name, active):
+    """ops.hashgrid_input_grad = J(x; table)^T dy (the analytic SDF normal, reference models/geometry.py:214-218) and its
+    own adjoints (ia_hashgrid_jvp, ia_hashgrid_bwd_input_bwd_table) against torch's double backward through the oracle."""
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS[cfg_name]
+    plan_ref, plan = tc.grid_plan(**cfg), ops.make_grid_plan(**cfg)
+    act = active if active is None else min(active, cfg["n_levels"])
+    n = 600
+    g = torch.Generator().manual_seed(21)
+    x = _points(n, 13)[4:].clone()                       # drop the points that sit exactly on cell faces
+    n = x.shape[0]
+    table = (torch.randn(plan_ref.n_params, generator=g) * 0.1).requires_grad_(True)
+    dy = torch.randn(n, plan_ref.n_output_dims, generator=g).requires_grad_(True)
+    v = torch.randn(n, 3, generator=g)
+
+    xr = x.clone().requires_grad_(True)
+    y_ref = tc.hashgrid_forward(xr, table, plan_ref, act)
+    (dx_ref,) = torch.autograd.grad(y_ref, xr, dy, create_graph=True)
+    (dx_ref * v).sum().backward()
+
+    tg = table.detach().cuda().requires_grad_(True)
+    dg = dy.detach().cuda().requires_grad_(True)
+    dx = ops.hashgrid_input_grad(x.cuda(), tg, dg, plan, act)
+    (dx * v.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    rt, at = grad_tol(dx_ref.detach(), 1e-4)
+    assert_close(dx, dx_ref.detach(), rtol=rt, atol=at, name="dx")
+    rt, at = grad_tol(dy.grad, 1e-4)
+    assert_close(dg.grad, dy.grad, rtol=rt, atol=at, name="d(dy) = J v")
+    if act is not None:
+        assert torch.count_nonzero(dg.grad[:, act * 2:]) == 0, "masked levels receive exactly zero"
+    rt, at = grad_tol(table.grad, 1e-4)
+    assert_close(tg.grad, table.grad, rtol=rt, atol=at, name="d(table)")

@@ -124,7 +124,8 @@ def build_b200(args, rank, world, device):
     from instant_angelo_b200.dp import FusedAdamW, ParamArena
 
     torch.manual_seed(42)
-    cfg = neuralangelo_colmap_sparse("finite_difference", mlp_otype="FullyFusedMLP" if args.mlp == "tc" else "VanillaMLP")
+    cfg = neuralangelo_colmap_sparse(getattr(args, "grad_type", "finite_difference"),
+                                     mlp_otype="FullyFusedMLP" if args.mlp == "tc" else "VanillaMLP")
     model = make("neus", cfg.model).to(device)
     model.train()
     for grid in (model.occupancy_grid, model.occupancy_grid_bg):
@@ -424,12 +425,12 @@ def run_b200(args):
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "neuralangelo-colmap_sparse.yaml, grad_type=finite_difference, synthetic 512x512 cameras around an "
+        "config": {"workload": f"neuralangelo-colmap_sparse.yaml, grad_type={args.grad_type}, synthetic 512x512 cameras around an "
                                "analytic sphere (BASELINE.json configs[1])",
                    "rays_per_gpu_per_step": n_rays, "global_rays_per_step": n_rays * world, "num_samples_per_ray": 512,
                    "num_samples_per_ray_bg": 256, "hash_levels_active": 16, "log2_hashmap_size": 19, "global_step": GLOBAL_STEP0,
                    "mean_fg_samples_per_ray": fg_total / total_rays, "mean_samples_per_ray_full": full_total / total_rays,
-                   "samples_per_s": full_total / (ms_total / 1e3), "hash_point_evals_per_s": (13 * fg_total + (full_total - fg_total)) / (ms_total / 1e3),
+                   "samples_per_s": full_total / (ms_total / 1e3), "hash_point_evals_per_s": ((13 if args.grad_type == "finite_difference" else 7) * fg_total + (full_total - fg_total)) / (ms_total / 1e3),
                    "mlp": ("tcgen05 tensor cores, 3xf16-split operands + fp32 accumulate (fp32-equivalent, parity-tested at 1e-3); the 65-wide "
                            "centre evaluation returns the last hidden layer from the same kernel and applies the output layer with "
                            "the streaming fp32 linear64 kernels") if args.mlp == "tc" else "fp32 FFMA kernels",
@@ -530,7 +531,7 @@ def run_reference(args):
     from instant_angelo_b200.configs import neuralangelo_colmap_sparse
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = neuralangelo_colmap_sparse("finite_difference")
+    cfg = neuralangelo_colmap_sparse(getattr(args, "grad_type", "finite_difference"))
     ref = build_oracle(cfg)
     n = args.cpu_rays if args.cpu_rays > 0 else 512
     K, W = args.steps, args.warmup
@@ -547,12 +548,12 @@ def run_reference(args):
         total_samples += ns
     dt = time.perf_counter() - t0
     value = n * K / dt
-    sample = (f"{n} rays per step of neuralangelo-colmap_sparse (finite_difference), {total_samples / max(n * K, 1):.1f} samples/ray, "
+    sample = (f"{n} rays per step of neuralangelo-colmap_sparse ({args.grad_type}), {total_samples / max(n * K, 1):.1f} samples/ray, "
               f"CPU oracle forward + losses + backward, {cores} threads")
     line = {"impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "neuralangelo-colmap_sparse.yaml, grad_type=finite_difference, synthetic 512x512 cameras around an "
+            "config": {"workload": f"neuralangelo-colmap_sparse.yaml, grad_type={args.grad_type}, synthetic 512x512 cameras around an "
                                    "analytic sphere (BASELINE.json configs[1])", "rays_per_step_sample": n,
                        "note": "reference GPU path (tinycudann + nerfacc) is not installable in this image; CPU oracle port timed instead"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(), "sample": sample},
@@ -585,6 +586,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--grad-type", dest="grad_type", default="finite_difference", choices=["finite_difference", "analytic"],
+                    help="model.geometry.grad_type: finite_difference = the BASELINE north-star workload (default); analytic = the "
+                         "reference YAML's shipped value (autograd normals with second-order adjoints + 6 FD curvature taps)")
     ap.add_argument("--mlp", default="tc", choices=["fp32", "tc"],
                     help="MLP arithmetic: tc = tcgen05 tensor cores with 3xf16-split operands (fp32-equivalent, default); fp32 = FFMA kernels")
     ap.add_argument("--cpu-rays", type=int, default=0,

@@ -1,0 +1,36 @@
+"""hash-grid kernels on tap-like (coherent) points: 1.55 M samples x 6 taps at eps = finest cell."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C, torch
+from instant_angelo_b200 import ops, _lib as L
+dev = "cuda"; S = 1550000
+plan = ops.make_grid_plan(16, 2, 19, 32, 1.3195079107728942)
+g = torch.Generator(device=dev).manual_seed(3)
+# samples along rays through a shell around the sphere (coherent), taps at +-eps
+o = torch.nn.functional.normalize(torch.randn(8192, 3, device=dev, generator=g), dim=-1)
+d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(8192, 3, device=dev, generator=g), dim=-1)
+t = torch.linspace(0.2, 1.2, S // 8192 + 1, device=dev)[None, :, None]
+pts = (o[:, None] + d[:, None] * t).reshape(-1, 3)[:S]
+eps = 2 * 1.5 / 2048 * 1.0
+off = torch.tensor([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], device=dev, dtype=torch.float32) * eps
+x = ((pts[:, None, :] + off).clamp(-1.5, 1.5) / 3.0 + 0.5).reshape(-1, 3).contiguous()
+n = x.shape[0]
+table = torch.randn(plan.n_params, device=dev, generator=g) * 0.1
+dy = torch.randn(n, 32, device=dev, generator=g)
+out = torch.empty(n, 32, device=dev); dx = torch.empty(n, 3, device=dev); dt = torch.zeros_like(table)
+lib, s = L.load(), L.stream()
+def timed(fn, reps=5):
+    ts = []
+    for _ in range(reps + 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return sorted(ts[2:])[len(ts[2:]) // 2]
+P = C.byref(plan)
+print("n =", n)
+print("fwd                 %.3f ms" % timed(lambda: lib.ia_hashgrid_fwd(x.data_ptr(), n, table.data_ptr(), P, 16, out.data_ptr(), s)))
+print("bwd input           %.3f ms" % timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), P, 16, None, dx.data_ptr(), s)))
+print("bwd table           %.3f ms" % timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), P, 16, dt.data_ptr(), None, s)))
+print("bwd table+input     %.3f ms" % timed(lambda: lib.ia_hashgrid_bwd(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), P, 16, dt.data_ptr(), dx.data_ptr(), s)))
+print("grouped table       %.3f ms" % timed(lambda: lib.ia_hashgrid_bwd_grouped(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), P, 16, 6, dt.data_ptr(), None, s)))
+print("grouped table+input %.3f ms" % timed(lambda: lib.ia_hashgrid_bwd_grouped(x.data_ptr(), n, table.data_ptr(), dy.data_ptr(), P, 16, 6, dt.data_ptr(), dx.data_ptr(), s)))
+print("jvp                 %.3f ms" % timed(lambda: lib.ia_hashgrid_jvp(x.data_ptr(), n, table.data_ptr(), dx.data_ptr(), P, 16, out.data_ptr(), s)))

@@ -13,7 +13,8 @@ t = torch.linspace(0.2, 1.2, S // 8192 + 1, device=dev)[None, :, None]
 pts = (o[:, None] + d[:, None] * t).reshape(-1, 3)[:S]
 eps = 2 * 1.5 / 2048 * 1.0
 off = torch.tensor([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], device=dev, dtype=torch.float32) * eps
-x = ((pts[:, None, :] + off).clamp(-1.5, 1.5) / 3.0 + 0.5).reshape(-1, 3).contiguous()
+comp = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0      # 3.0: the curvature tap set (Appendix C-1 compresses the scene 3x)
+x = (((pts / comp)[:, None, :] + off).clamp(-1.5, 1.5) / 3.0 + 0.5).reshape(-1, 3).contiguous()
 n = x.shape[0]
 table = torch.randn(plan.n_params, device=dev, generator=g) * 0.1
 dy = torch.randn(n, 32, device=dev, generator=g)

@@ -285,3 +285,63 @@ def test_step_with_zero_marched_samples(cuda_lib, mlp_otype):
     terms = training_loss(model, out, batch, golden_loss_config(), 30)
     terms["loss"].backward()       # means over zero samples are nan in the reference too; what matters is that nothing throws
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("grad_type", ["analytic", "finite_difference"])
+@pytest.mark.parametrize("mlp_otype", ["VanillaMLP", "FullyFusedMLP"])
+def test_baseline_config1_geometry_block_matches_oracle(cuda_lib, grad_type, mlp_otype):
+    """BASELINE.json configs[0]: the geometry block of configs/neus-colmap.yaml (feature_dim 13, ONE hidden layer, radius
+    2.5, 16 levels at 2^19, `grad_type: analytic` as shipped) at its full table size: sdf, normals, features and all
+    parameter gradients of an eikonal + feature loss against the oracle on 4096 points."""
+    from instant_angelo_b200 import configs, make
+    from instant_angelo_b200.config import to_primitive
+    cfg = to_primitive(configs.neus_colmap_geometry(grad_type))
+    ref = mr.RefVolumeSDF(cfg)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for name, p in ref.named_parameters():
+            if name.endswith(".params"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            elif "weight" in name:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    ref.train()
+    ref.update_step(0, 3000)
+    cfg_p = {**cfg, "mlp_network_config": {**cfg["mlp_network_config"], "otype": mlp_otype}}
+    geo = make("volume-sdf", cfg_p).cuda()
+    from instant_angelo_b200.nerfacc_api import ContractionType
+    geo.contraction_type = ContractionType.AABB
+    missing, unexpected = geo.load_state_dict({k: v.detach().clone() for k, v in ref.state_dict().items()}, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    geo.train()
+    geo.update_step(0, 3000)
+    pts = (torch.rand(4096, 3, generator=g) - 0.5) * 4.6          # inside the +-2.5 box
+    w_f = torch.randn(4096, 16, generator=g) * 0.1
+
+    def loss_of(sdf, grad, feat, w):
+        return ((grad.norm(dim=-1) - 1.0) ** 2).mean() + (sdf * w[:, 0]).mean() + (feat * w).mean()
+
+    sdf_r, grad_r, feat_r = ref(pts.clone(), with_grad=True, with_feature=True)
+    loss_of(sdf_r, grad_r, feat_r, w_f).backward()
+    sdf, grad, feat = geo(pts.cuda(), with_grad=True, with_feature=True)
+    loss_of(sdf, grad, feat, w_f.cuda()).backward()
+    torch.cuda.synchronize()
+    # The shipped (analytic) variant is held to 1e-3 element-wise.  Finite differences with this config's fixed
+    # eps = 1e-3 on a 5-unit box are ill-conditioned in fp32: the +/- taps of an axis carry gradients of +/- g/(2 eps) whose
+    # table contributions cancel to ~eps of their size, so two correct fp32 evaluations with different summation orders
+    # differ by ~1e-6/eps = 1e-3 of an entry.  That variant is held to 2e-2 of the largest gradient element-wise and to
+    # 2e-3 in relative L2 norm.
+    tol = 1e-3 if grad_type == "analytic" else 2e-2
+    assert_close(sdf, sdf_r.detach(), rtol=1e-3, atol=1e-5, name="sdf")
+    assert_close(feat, feat_r.detach(), rtol=1e-3, atol=1e-5, name="feature")
+    rt, at = grad_tol(grad_r.detach(), tol)
+    assert_close(grad, grad_r.detach(), rtol=rt, atol=at, name="sdf_grad")
+    want = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    checked = 0
+    for n, p in geo.named_parameters():
+        if n in want:
+            rt, at = grad_tol(want[n], tol)
+            assert_close(p.grad, want[n], rtol=rt, atol=at, name="grad " + n)
+            rel_l2 = float((p.grad.cpu().double() - want[n].double()).norm() / want[n].double().norm().clamp_min(1e-30))
+            assert rel_l2 < 2e-3, f"grad {n}: relative L2 error {rel_l2:.2e}"
+            checked += 1
+    assert checked >= 5

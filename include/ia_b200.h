@@ -145,6 +145,20 @@ int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *
                    const float *params, const float *dout, int32_t n_out_used, int64_t ld_dout,
                    float *din0, float *din1, float *dparams, void *stream);
 
+/* Flat effective parameter vector of a VanillaMLP (models/network_utils.py:115-134) in one launch: per layer
+ * W = g * v / ||v||_row when g != NULL (torch weight_norm, dim=0), else W = v; layout as above (W block, then bias).
+ * Backward writes dg[n_out] / dv[n_out, n_in] / db[n_out] (each may be NULL) from dflat; pointers are device pointers,
+ * the descriptor itself is read on the host. */
+#define IA_WN_MAX_LAYERS 4
+typedef struct ia_wn_desc {
+    int32_t n_layers;
+    int32_t n_out[IA_WN_MAX_LAYERS], n_in[IA_WN_MAX_LAYERS];
+    const float *g[IA_WN_MAX_LAYERS], *v[IA_WN_MAX_LAYERS], *b[IA_WN_MAX_LAYERS];
+    float *dg[IA_WN_MAX_LAYERS], *dv[IA_WN_MAX_LAYERS], *db[IA_WN_MAX_LAYERS];
+} ia_wn_desc;
+int32_t ia_weightnorm_flat_fwd(const ia_wn_desc *desc_host, float *flat, void *stream);
+int32_t ia_weightnorm_flat_bwd(const ia_wn_desc *desc_host, const float *dflat, void *stream);
+
 /* Wide output layer for the feature mode above: out[n, n_out] = h[n, 64] W[n_out, 64]^T + b (n_out <= 128), fp32.
  * Backward: dh[n,64] = dout W (may be NULL); dW[n_out,64] += dout^T h and db[n_out] += sum dout (ACCUMULATED; may be NULL). */
 int32_t ia_linear64_fwd(const float *h, int64_t n, const float *W, const float *b, int32_t n_out, float *out,

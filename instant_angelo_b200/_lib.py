@@ -54,6 +54,15 @@ class CompositeArgs(C.Structure):
                 ("nrm", C.c_void_p)]
 
 
+IA_WN_MAX_LAYERS = 4
+
+
+class WnDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("n_out", C.c_int32 * IA_WN_MAX_LAYERS), ("n_in", C.c_int32 * IA_WN_MAX_LAYERS),
+                ("g", C.c_void_p * IA_WN_MAX_LAYERS), ("v", C.c_void_p * IA_WN_MAX_LAYERS), ("b", C.c_void_p * IA_WN_MAX_LAYERS),
+                ("dg", C.c_void_p * IA_WN_MAX_LAYERS), ("dv", C.c_void_p * IA_WN_MAX_LAYERS), ("db", C.c_void_p * IA_WN_MAX_LAYERS)]
+
+
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 
@@ -75,6 +84,8 @@ SIGNATURES = {
     "ia_mlp_param_count": (_I64, [C.POINTER(MlpDesc)]),
     "ia_mlp_fwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _I32, _P, _I64, _P]),
     "ia_mlp_bwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P]),
+    "ia_weightnorm_flat_fwd": (_I32, [C.POINTER(WnDesc), _P, _P]),
+    "ia_weightnorm_flat_bwd": (_I32, [C.POINTER(WnDesc), _P, _P]),
     "ia_linear64_fwd": (_I32, [_P, _I64, _P, _P, _I32, _P, _I64, _P]),
     "ia_linear64_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _P]),
     "ia_sdf_head_fwd": (_I32, [_P, _I64, _P, _P, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P, _P]),

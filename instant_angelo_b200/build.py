@@ -20,7 +20,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libia_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["capi.cu", "hashgrid.cu", "sh.cu", "march.cu", "composite.cu", "mlp.cu", "mlp_fp32.cu", "mlp_tc.cu", "adam.cu", "sdf_taps.cu", "linear64.cu"]
+SOURCES = ["capi.cu", "hashgrid.cu", "sh.cu", "march.cu", "composite.cu", "mlp.cu", "mlp_fp32.cu", "mlp_tc.cu", "adam.cu", "sdf_taps.cu", "linear64.cu", "weightnorm.cu"]
 EXTRA = {"march.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 

@@ -206,8 +206,12 @@ class VanillaMLP(nn.Module):
 
     def flat_params(self) -> torch.Tensor:
         """Effective weights (weight-norm folded) in the ABI's flat layout; differentiable."""
+        lins = self.linears()
+        if lins[0].bias.is_cuda:
+            # one launch (and one in backward) instead of norm / div / mul / cat per layer
+            return ops.weightnorm_flat([(lin.weight_g if lin.weight_norm else None, lin.raw_weight(), lin.bias) for lin in lins])
         parts = []
-        for lin in self.linears():
+        for lin in lins:
             parts.append(lin.effective_weight().reshape(-1))
             parts.append(lin.bias)
         return torch.cat(parts)

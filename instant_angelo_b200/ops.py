@@ -259,6 +259,60 @@ class _MLPFn(torch.autograd.Function):
         return d0, d1, dp, None, None
 
 
+class _WeightNormFlatFn(torch.autograd.Function):
+    """Flat effective parameters [W0 b0 W1 b1 ...] of a VanillaMLP from its per-layer (weight_g | None, weight_v | weight,
+    bias) tensors in one launch, with the weight-norm adjoint in backward (reference models/network_utils.py:115-134)."""
+
+    @staticmethod
+    def forward(ctx, has_g, *tensors):
+        n_layers = len(has_g)
+        assert n_layers <= L.IA_WN_MAX_LAYERS
+        d = L.WnDesc()
+        d.n_layers = n_layers
+        it = iter(tensors)
+        keep, total = [], 0
+        for i, hg in enumerate(has_g):
+            g = L.f32c(next(it)) if hg else None
+            v, b = L.f32c(next(it)), L.f32c(next(it))
+            L.require_cuda(g, v, b)
+            d.n_out[i], d.n_in[i] = v.shape[0], v.shape[1]
+            d.g[i], d.v[i], d.b[i] = L.ptr(g), L.ptr(v), L.ptr(b)
+            total += v.numel() + b.numel()
+            keep += ([g] if hg else []) + [v, b]
+        flat = torch.empty(total, device=tensors[0].device, dtype=torch.float32)
+        _run("ia_weightnorm_flat_fwd", C.byref(d), L.ptr(flat), L.stream())
+        ctx.save_for_backward(*keep)
+        ctx.has_g = has_g
+        return flat
+
+    @staticmethod
+    def backward(ctx, dflat):
+        dflat = L.f32c(dflat)
+        saved = list(ctx.saved_tensors)
+        d = L.WnDesc()
+        d.n_layers = len(ctx.has_g)
+        grads, k = [], 0
+        for i, hg in enumerate(ctx.has_g):
+            g = saved[k] if hg else None
+            v, b = saved[k + hg], saved[k + hg + 1]
+            k += 2 + hg
+            d.n_out[i], d.n_in[i] = v.shape[0], v.shape[1]
+            d.g[i], d.v[i], d.b[i] = L.ptr(g), L.ptr(v), L.ptr(b)
+            dg = torch.empty_like(g) if hg else None
+            dv, db = torch.empty_like(v), torch.empty_like(b)
+            d.dg[i], d.dv[i], d.db[i] = L.ptr(dg), L.ptr(dv), L.ptr(db)
+            grads += ([dg] if hg else []) + [dv, db]
+        _run("ia_weightnorm_flat_bwd", C.byref(d), L.ptr(dflat), L.stream())
+        return (None, *grads)
+
+
+def weightnorm_flat(layers) -> torch.Tensor:
+    """layers: [(weight_g or None, weight_v / weight [out, in], bias [out]), ...] -> flat [sum(out*in + out)]."""
+    has_g = tuple(int(g is not None) for g, _, _ in layers)
+    tensors = [t for g, v, b in layers for t in ((g, v, b) if g is not None else (v, b))]
+    return _WeightNormFlatFn.apply(has_g, *tensors)
+
+
 class _Linear64Fn(torch.autograd.Function):
     """out = h @ W.T + b for h [N,64], W [n_out,64] (the wide output layer behind the tensor-core feature mode)."""
 

@@ -706,3 +706,33 @@ def test_hashgrid_input_grad_second_order(cuda_lib, cfg_name, active):
         assert torch.count_nonzero(dg.grad[:, act * 2:]) == 0, "masked levels receive exactly zero"
     rt, at = grad_tol(table.grad, 1e-4)
     assert_close(tg.grad, table.grad, rtol=rt, atol=at, name="d(table)")
+
+
+@pytest.mark.gpu
+def test_weightnorm_flat_matches_torch(cuda_lib):
+    """ops.weightnorm_flat = cat[(g * v / ||v||_row).flatten(), b, ...] (torch weight_norm folded, reference
+    models/network_utils.py:115-134) and its adjoint, mixed weight-normed / plain layers."""
+    from instant_angelo_b200 import ops
+    g_ = torch.Generator().manual_seed(3)
+    shapes = [(64, 35, True), (64, 64, True), (65, 64, True)], [(64, 87, False), (64, 64, False), (3, 64, False)], [(64, 24, True), (8, 64, False)]
+    for layers in shapes:
+        leaves, ref_leaves = [], []
+        for n_out, n_in, wn in layers:
+            v = torch.randn(n_out, n_in, generator=g_)
+            b = torch.randn(n_out, generator=g_)
+            gg = torch.rand(n_out, 1, generator=g_) + 0.5 if wn else None
+            ref_leaves.append(tuple(None if t is None else t.clone().double().requires_grad_(True) for t in (gg, v, b)))
+            leaves.append(tuple(None if t is None else t.clone().cuda().requires_grad_(True) for t in (gg, v, b)))
+        flat = ops.weightnorm_flat(leaves)
+        parts = []
+        for gg, v, b in ref_leaves:
+            parts += [(v if gg is None else v * (gg / v.norm(dim=1, keepdim=True))).reshape(-1), b]
+        flat_ref = torch.cat(parts)
+        w = torch.randn(flat_ref.numel(), generator=g_)
+        (flat * w.cuda()).sum().backward()
+        (flat_ref * w.double()).sum().backward()
+        assert_close(flat, flat_ref.float(), rtol=1e-6, atol=1e-6, name="flat")
+        for (gg, v, b), (gr, vr, br) in zip(leaves, ref_leaves):
+            for a, r, nm in ((gg, gr, "dg"), (v, vr, "dv"), (b, br, "db")):
+                if a is not None:
+                    assert_close(a.grad, r.grad.float(), rtol=1e-5, atol=1e-6, name=nm)

@@ -408,9 +408,11 @@ def run_b200(args):
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peaks["source"] + " (sustained bf16 GEMM)", "launches": calls,
                 "avg_launch_ms": ms / max(calls, 1), "algorithmic_flop_per_launch": work / max(calls, 1),
-                "note": "algorithmic FLOP = 2*MAC of the unpadded fp32 network (x2 for backward); the kernel issues 3 f16 MMAs per "
-                        "product (fp32-equivalent split) and is bound by its per-row activation epilogue (MUFU/FP32/smem), not by "
-                        "the tensor pipe: see DESIGN.md section 4.2 and profiles/r01_ncu_mlp_tc.md"}
+                "note": "algorithmic FLOP = 2*MAC of the unpadded fp32 network (x2 for backward).  The kernel issues 3 f16 MMAs "
+                        "per product (fp32-equivalent hi/lo split), pads K to 16 and recomputes the forward inside backward: for "
+                        "35->64->64->1 that is 5.2x the algorithmic FLOP on the tensor pipe (ncu: tensor pipe active 16.8 %). It "
+                        "is bound by its per-row activation epilogues and the serial MMA issue, not by the tensor pipe: see "
+                        "DESIGN.md section 4.2 and profiles/r01_ncu_mlp_tc.md"}
     else:
         achieved = work / (ms / 1e3) / 1e9
         peak = peaks["hbm_gbs"]

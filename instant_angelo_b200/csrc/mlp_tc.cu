@@ -647,6 +647,43 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// Sum 32 per-lane values over the 32 lanes of a warp, for 32 different quantities at once: butterfly that halves the
+// number of values a lane carries at every step (16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5).  Returns, on lane
+// L, the warp-wide total of element L.
+__device__ __forceinline__ float warp_sum32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// dW_last[o][16 cg + j] += sum over the warp's 32 rows of dy[o] * h[j], two outputs (32 products) per butterfly
+template <int NOU>
+__device__ __forceinline__ void accumulate_dwl(float *__restrict__ dwl, const float (&dy)[NOU > 0 ? NOU : 1], const float (&h)[16],
+                                               int cg, int lane)
+{
+#pragma unroll
+    for (int o = 0; o < NOU; o += 2) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            v[j] = dy[o] * h[j];
+            v[16 + j] = (o + 1 < NOU) ? dy[o + 1 < NOU ? o + 1 : o] * h[j] : 0.f;
+        }
+        const float tot = warp_sum32(v, lane);
+        const int oo = o + (lane >> 4);
+        if (oo < NOU) atomicAdd(&dwl[oo * W + 16 * cg + (lane & 15)], tot);
+    }
+}
+
 // read this thread's share of a dW accumulator (M = 64 layout: output row o = 16*(lane quarter) + lane for lane < 16;
 // 16-column chunk ci is handled by column group ci % CG) and add it, unscaled, to the padded smem accumulator
 __device__ __forceinline__ void drain_dw(Ctx &c, float *__restrict__ acc_smem, int n_cols, int ld, float inv_scale)
@@ -809,14 +846,7 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
 #pragma unroll
                     for (int j = 0; j < 16; ++j) gwl[o][j] = fmaf(dy[o], h[j], gwl[o][j]);
             } else {
-#pragma unroll 1
-                for (int o = 0; o < NOU; ++o) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float s = warp_sum(dy[o] * h[j]);
-                        if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
-                    }
-                }
+                accumulate_dwl<NOU>(dwl, dy, h, c.cg, lane);
             }
             store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
         }
@@ -1148,14 +1178,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
     #pragma unroll
                         for (int j = 0; j < 16; ++j) gwl[o][j] = fmaf(dy[o], h[j], gwl[o][j]);
                 } else {
-    #pragma unroll 1
-                    for (int o = 0; o < NOU; ++o) {
-    #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float s = warp_sum(dy[o] * h[j]);
-                            if (lane == 0) atomicAdd(&dwl[o * W + 16 * c.cg + j], s);
-                        }
-                    }
+                    accumulate_dwl<NOU>(dwl, dy, h, c.cg, lane);
                 }
                 store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
             }

@@ -69,6 +69,15 @@ class VolumeDensity(BaseImplicitGeometry):
             feature = get_activation(self.config["feature_activation"])(feature)
         return density, feature
 
+    def density(self, points):
+        """forward(points)[0] without the feature columns (the output layer evaluates column 0 only): what the
+        background marching's visibility pruning (models/neus.py:144-149 sigma_fn) and occ_eval_fn_bg (:103-106) consume."""
+        points = contract_to_unisphere(points, self.radius, self.contraction_type)
+        density = self.encoding_with_network(points.reshape(-1, self.n_input_dims), n_out_used=1).reshape(*points.shape[:-1]).float()
+        if "density_activation" in self.config:
+            density = get_activation(self.config["density_activation"])(density + float(self.config["density_bias"]))
+        return density
+
     def forward_level(self, points):
         points = contract_to_unisphere(points, self.radius, self.contraction_type)
         density = self.encoding_with_network(points.reshape(-1, self.n_input_dims), n_out_used=1).reshape(*points.shape[:-1])

@@ -106,8 +106,7 @@ class NeuSModel(nn.Module):
         return ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).view(-1, 1).clip(0.0, 1.0)
 
     def occ_eval_fn_bg(self, x):
-        density, _ = self.geometry_bg(x)
-        return density[..., None] * self.render_step_size_bg
+        return self.geometry_bg.density(x)[..., None] * self.render_step_size_bg
 
     def update_step(self, epoch, global_step, occ_inputs: Optional[dict] = None, update_occupancy: bool = True):
         update_module_step(self.geometry, epoch, global_step)
@@ -147,8 +146,7 @@ class NeuSModel(nn.Module):
         def sigma_fn(t_starts, t_ends, ray_indices):
             ri = ray_indices.long()
             positions = rays_o[ri] + rays_d[ri] * (t_starts + t_ends) / 2.0
-            density, _ = self.geometry_bg(positions)
-            return density[..., None]
+            return self.geometry_bg.density(positions)[..., None]
 
         _, t_max = ray_aabb_intersect(rays_o, rays_d, self._aabb_host)
         near_plane = torch.where(t_max > 1e9, self.near_plane_bg, t_max)

@@ -647,6 +647,18 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// Power-of-two tile scale from the tile's gradient bound x > 0: x = m * 2^e with m in [0.5, 1) (frexp), e clamped to
+// [-60, 60]; scale = 2^(6-e), inv_scale = 2^(e-6).  Exponent-field arithmetic: frexpf / ldexpf are library routines with
+// denormal branches, and every thread of the CTA runs this once per tile.
+__device__ __forceinline__ void pow2_scale(float x, float &scale, float &inv_scale)
+{
+    x = fmaxf(x, 1e-30f);                                         // normal number
+    int e = ((__float_as_int(x) >> 23) & 0xff) - 126;
+    e = max(min(e, 60), -60);
+    scale = __int_as_float((127 + 6 - e) << 23);
+    inv_scale = __int_as_float((127 - 6 + e) << 23);
+}
+
 // Sum 32 per-lane values over the 32 lanes of a warp, for 32 different quantities at once: butterfly that halves the
 // number of values a lane carries at every step (16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5).  Returns, on lane
 // L, the warp-wide total of element L.
@@ -810,10 +822,8 @@ mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__
         dymax = 0.f;
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) dymax = fmaxf(dymax, red[w]);
-        int e = 0;
-        frexpf(fmaxf(dymax * wmax, 1e-30f), &e);                 // dymax*wmax = m * 2^e, m in [0.5, 1)
-        e = max(min(e, 60), -60);
-        const float scale = ldexpf(1.0f, 6 - e), inv_scale = ldexpf(1.0f, e - 6);
+        float scale, inv_scale;
+        pow2_scale(dymax * wmax, scale, inv_scale);
         float h[16];
         const float *bL = b0;
         if (D.nh == 2) {
@@ -1067,11 +1077,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
         float m = 0.f;
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) m = fmaxf(m, red[w]);
-        int e = 0;
-        frexpf(fmaxf(m * wmax, 1e-30f), &e);
-        e = max(min(e, 60), -60);
-        scale = ldexpf(1.0f, 6 - e);
-        inv_scale = ldexpf(1.0f, e - 6);
+        pow2_scale(m * wmax, scale, inv_scale);
     };
 
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;

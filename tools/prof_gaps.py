@@ -6,7 +6,7 @@ import torch, argparse
 import bench
 from torch.profiler import profile, ProfilerActivity
 
-args = argparse.Namespace(mlp="tc", rays=8192, steps=3, warmup=3)
+args = argparse.Namespace(mlp="tc", rays=8192, steps=3, warmup=3, grad_type="finite_difference")
 dev = torch.device("cuda", 0)
 cfg, model, arena, var_arena, opt, opt_var = bench.build_b200(args, 0, 1, dev)
 batches = [(b.to(dev), g.to(dev)) for b, g in bench.make_batches(10, 8192, 0, pin=False)]

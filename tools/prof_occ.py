@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, argparse
 import bench
 from torch.profiler import profile, ProfilerActivity
-args = argparse.Namespace(mlp="tc", rays=8192, steps=3, warmup=3)
+args = argparse.Namespace(mlp="tc", rays=8192, steps=3, warmup=3, grad_type="finite_difference")
 dev = torch.device("cuda", 0)
 cfg, model, arena, var_arena, opt, opt_var = bench.build_b200(args, 0, 1, dev)
 torch.cuda.synchronize()

@@ -243,8 +243,6 @@ def hashgrid_microbench(device, peaks):
         del table_t
     res["fwd_grid"] = grid
     # L2 / HBM random 32-byte-sector gather peaks: table resident in the 126 MB L2 vs. larger than it
-    lib.ia_debug_sector_gather.restype = C.c_int32
-    lib.ia_debug_sector_gather.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     big = torch.randn((1 << 30) // 4, device=device, generator=g)            # 1 GiB
     sink = torch.empty(1 << 22, device=device)
     gather = {}

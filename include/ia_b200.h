@@ -302,6 +302,18 @@ int32_t ia_adamw_step(float *param, const float *grad, float *exp_avg, float *ex
                       float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                       float grad_scale, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Measurement aids (not part of the drop-in surface; used by bench.py and tools/)
+ * ------------------------------------------------------------------------------------------------ */
+/* Random 32-byte-sector gather micro-benchmark (the L2 peak "must be measured on the box"): n_threads
+ * (multiple of 256) threads issue `iters` independent 8-byte loads each at pseudo-random sector-aligned addresses inside
+ * [table, table + 32 n_sectors); out[n_threads] is practically never written. */
+int32_t ia_debug_sector_gather(const float *table, int64_t n_sectors, int64_t n_threads, int32_t iters, float *out,
+                               void *stream);
+/* Cycle accounting of the tensor-core MLP kernels (thread 0 of every CTA): enable != 0 starts it; out8_host (may be NULL)
+ * receives {barrier wait, MMA issue, MMA completion wait, tile total, tiles, wait m0, wait m1, wait m2} and clears them. */
+int32_t ia_debug_tc_timing(int32_t enable, unsigned long long *out8_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,8 @@ SIGNATURES = {
     "ia_composite_fwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_composite_bwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_adamw_step": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _P]),
+    "ia_debug_sector_gather": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
+    "ia_debug_tc_timing": (_I32, [_I32, C.POINTER(C.c_ulonglong)]),
 }
 
 _lib = None

@@ -43,7 +43,6 @@ struct TcDims {
     float s0, o0;
     int nh, n_out, nou, act;
     int pW0, pb0, pW1, pb1, pWl, pbl;
-    int dbg;   // timing experiments only (IA_TC_DBG): 1 no global input loads, 2 identity activations, 4 no drains, 8 no dX stores
 };
 
 struct SmemPlan {  // byte offsets
@@ -477,7 +476,7 @@ __device__ __forceinline__ void load_input_regs(const Ctx &c, const TcDims &D, c
     for (int q = 0; q < MAX_IN_CHUNKS; ++q) {
         const int c8 = c.cg + CG * q;
         if (c8 * 8 >= D.K0) break;
-        if (valid && !(D.dbg & 1) && vec && c8 * 8 + 8 <= D.n_in1) {
+        if (valid && vec && c8 * 8 + 8 <= D.n_in1) {
             const float4 *src = reinterpret_cast<const float4 *>(in1 + row * D.n_in1 + 8 * c8);
             const float4 a = __ldg(src), b = __ldg(src + 1);
             R.v[q][0] = a.x; R.v[q][1] = a.y; R.v[q][2] = a.z; R.v[q][3] = a.w;
@@ -487,7 +486,7 @@ __device__ __forceinline__ void load_input_regs(const Ctx &c, const TcDims &D, c
             for (int j = 0; j < 8; ++j) {
                 const int col = 8 * c8 + j;
                 float v = 0.f;
-                if (valid && !(D.dbg & 1)) {
+                if (valid) {
                     if (col < D.n_in1) v = __ldg(in1 + row * D.n_in1 + col);
                     else if (col < D.din) v = fmaf(__ldg(in0 + row * D.n_in0 + (col - D.n_in1)), D.s0, D.o0);
                     else if (col == D.din) v = 1.0f;
@@ -1167,7 +1166,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
     #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int k = 16 * c.cg + j;
-                    h[j] = (D.dbg & 2) ? h[j] + b1[k] : act_fwd<ACT>(h[j] + b1[k]);
+                    h[j] = act_fwd<ACT>(h[j] + b1[k]);
                     float dh = 0.f;
                     if constexpr (NOU == 0) {
                         dh = dhf[j];
@@ -1175,7 +1174,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
     #pragma unroll
                         for (int o = 0; o < NOU; ++o) dh = fmaf(dy[o], wl[o * W + k], dh);
                     }
-                    dz[j] = dh * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(h[j])) * scale;
+                    dz[j] = dh * act_bwd_from_out<ACT>(h[j]) * scale;
                 }
                 if (NOU == 0) {
                 } else if (REG_DWL) {
@@ -1202,7 +1201,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
                 float h[16];
                 tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
     #pragma unroll
-                for (int j = 0; j < 16; ++j) h[j] = (D.dbg & 2) ? h[j] + b0[16 * c.cg + j] : act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
+                for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
                 store_cols16(c, ah_hi[nxt], ah_lo[nxt], h);
             }
             mma_wait(c, 1);      // dH1 in PD2, dW1 in PD1; the dZ buffer is free to be overwritten
@@ -1216,11 +1215,11 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
                     const uint32_t off = (uint32_t)(2 * c.cg + half) * 2048u + (uint32_t)c.r * 16u;
                     load_split8(smem + ah_hi[cur], smem + ah_lo[cur], off, hh);
     #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * ((D.dbg & 2) ? 1.f : act_bwd_from_out<ACT>(hh[j]));
+                    for (int j = 0; j < 8; ++j) a[j] = v[8 * half + j] * act_bwd_from_out<ACT>(hh[j]);
                     store_split8(smem + c.P.dz_hi, smem + c.P.dz_lo, off, a);
                 }
             }
-            if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
+            drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
             // ---- phase 2
             ws_publish(c, [&]() { issue_phase2(cur, nxt, has_next); });
             tile_scale(scale, inv_scale);       // scale of tile i+1 (red was written before the barrier)
@@ -1230,7 +1229,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
                 if (n2tile < n_tiles) load_input_regs(c, D, in0, in1, n2row, n2row < n, Rn);
             }
             mma_wait(c, 0);
-            if (want_dx && !(D.dbg & 8)) {
+            if (want_dx) {
                 for (int ci = c.cg; ci * 16 < D.din; ci += CG) {
                     const int c0 = 16 * ci;
                     float v[16];
@@ -1239,7 +1238,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const floa
                 }
             }
             mma_wait(c, 1);
-            if (!(D.dbg & 4)) drain_dw_at(c, PD1, dw0, D.K0, ld0, inv_cur);
+            drain_dw_at(c, PD1, dw0, D.K0, ld0, inv_cur);
             if (threadIdx.x == 0 && g_tc_timing_on) {
                 atomicAdd(&g_tc_cycles[3], (unsigned long long)(clock64() - tile_t0));
                 atomicAdd(&g_tc_cycles[4], 1ull);
@@ -1306,7 +1305,6 @@ int make_dims(const ia_mlp_desc *d, int32_t n_out_used, TcDims *D)
     if (D->nh == 2) { D->pW1 = p; p += W * W; D->pb1 = p; p += W; }
     D->pWl = p; p += d->n_out * W;
     D->pbl = p;
-    D->dbg = getenv("IA_TC_DBG") ? atoi(getenv("IA_TC_DBG")) : 0;
     return IA_OK;
 }
 

@@ -285,8 +285,14 @@ __device__ __forceinline__ void stage_weight(char *smem, uint32_t hi_off, uint32
 
 // optional cycle accounting (tools/prof_mlp.py --timing): [0] barrier wait, [1] MMA issue, [2] MMA completion wait,
 // [3] whole tile, [4] tiles; accumulated by thread 0 of every CTA when enabled through ia_debug_tc_timing()
+// Compiled out unless the library is built with -DIA_TC_TIMING=1: even a never-taken `if (g_tc_timing_on)` costs the hot
+// loops a global load, registers and scheduling freedom (removing the sibling debug toggles was worth 4 % of the step).
+#ifndef IA_TC_TIMING
+#define IA_TC_TIMING 0
+#endif
 __device__ unsigned long long g_tc_cycles[8];
-__device__ int g_tc_timing_on = 0;
+__device__ int g_tc_timing_flag = 0;
+#define g_tc_timing_on (IA_TC_TIMING && g_tc_timing_flag)
 
 struct Ctx {
     char *smem;
@@ -1316,7 +1322,11 @@ extern "C" int32_t ia_debug_tc_timing(int32_t enable, unsigned long long *out8_h
     if (out8_host) cudaMemcpyFromSymbol(out8_host, g_tc_cycles, sizeof(unsigned long long) * 8);
     unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(g_tc_cycles, zero, sizeof(zero));
-    cudaMemcpyToSymbol(g_tc_timing_on, &enable, sizeof(int));
+    cudaMemcpyToSymbol(g_tc_timing_flag, &enable, sizeof(int));
+    if (enable && !IA_TC_TIMING) {
+        ia_set_error("ia_debug_tc_timing: library built without -DIA_TC_TIMING=1");
+        return IA_ERR_UNSUPPORTED;
+    }
     return 0;
 }
 

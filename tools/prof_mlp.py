@@ -27,7 +27,7 @@ e0.record(); y = ops.mlp_apply(a, b, flat, desc, nou); e1.record(); y.backward(g
 torch.cuda.synchronize()
 print(f"{case} prec={prec} n={n}: fwd {e0.elapsed_time(e1):.3f} ms, bwd {e1.elapsed_time(e2):.3f} ms")
 
-if "--timing" in sys.argv:
+if "--timing" in sys.argv:   # needs `IA_TC_TIMING=1 python -m instant_angelo_b200.build` (force a rebuild of mlp_tc.cu)
     import ctypes as C
     lib = L.load()
     buf = (C.c_ulonglong * 8)()

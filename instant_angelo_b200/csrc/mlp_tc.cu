@@ -566,11 +566,22 @@ __device__ __forceinline__ void store_cols16(Ctx &c, uint32_t hi_off, uint32_t l
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
-template <int ACT, int NOU>
+// SPEC = 1 pins the input shape of the SDF network (3 xyz + 32 hash features -> K0 = 48, two hidden layers) at compile
+// time: the staging loops, vector-path tests and K loops of the dominant launches (18.7 M tap rows per step) become
+// straight-line code.  SPEC = 0 reads everything from TcDims.
+template <int SPEC>
+__device__ __forceinline__ TcDims specialise(TcDims D)
+{
+    if (SPEC == 1) { D.n_in0 = 3; D.n_in1 = 32; D.din = 35; D.K0 = 48; D.nh = 2; }
+    return D;
+}
+
+template <int ACT, int NOU, int SPEC = 0>
 __global__ void __launch_bounds__(THREADS, (NOU <= 3 ? 2 : 1))
-mlp_tc_fwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
+mlp_tc_fwd_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                   const float *__restrict__ params, float *__restrict__ out, int64_t ld_out)
 {
+    const TcDims D = specialise<SPEC>(Din);
     extern __shared__ __align__(1024) char smem[];
     Ctx c;
     c.smem = smem;
@@ -972,12 +983,13 @@ __device__ __forceinline__ void drain_dw_at(Ctx &c, uint32_t col0, float *__rest
     }
 }
 
-template <int ACT, int NOU>
+template <int ACT, int NOU, int SPEC = 0>
 __global__ void __launch_bounds__(THREADS_WS, 1)
-mlp_tc_bwd_pipe_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
+mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                        const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
                        float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams)
 {
+    const TcDims D = specialise<SPEC>(Din);
     extern __shared__ __align__(1024) char smem[];
     Ctx c;
     c.smem = smem;
@@ -1361,11 +1373,23 @@ int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
         mlp_tc_fwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, out, ld_out);    \
     } while (0)
     const bool sp = D.act == IA_ACT_SOFTPLUS100;
+    const bool geo = sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;     // the SDF network's input shape
+#define IA_TC_FWD_GEO(NOU)                                                                                                        \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_fwd_kernel<IA_ACT_SOFTPLUS100, NOU, 1>,                                            \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));                              \
+        mlp_tc_fwd_kernel<IA_ACT_SOFTPLUS100, NOU, 1><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, \
+                                                                                                          out, ld_out);          \
+    } while (0)
+    if (geo && D.nou == 0) IA_TC_FWD_GEO(0);
+    else if (geo && D.nou == 1) IA_TC_FWD_GEO(1);
+    else
     if (D.nou == 0) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_FWD(IA_ACT_RELU, 0); }
     else if (D.nou == 1) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_FWD(IA_ACT_RELU, 1); }
     else if (D.nou <= 3) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_FWD(IA_ACT_RELU, 3); }
     else { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_FWD(IA_ACT_RELU, 8); }
 #undef IA_TC_FWD
+#undef IA_TC_FWD_GEO
     IA_LAUNCH_OK("mlp_tc_fwd_kernel");
     return IA_OK;
 }
@@ -1409,11 +1433,23 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
         }                                                                                                                         \
     } while (0)
     const bool sp = D.act == IA_ACT_SOFTPLUS100;
+    const bool geo = pipe && sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;
+#define IA_TC_BWD_GEO(NOU)                                                                                                        \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<IA_ACT_SOFTPLUS100, NOU, 1>,                                       \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));                              \
+        mlp_tc_bwd_pipe_kernel<IA_ACT_SOFTPLUS100, NOU, 1><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(               \
+            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams);                                                          \
+    } while (0)
+    if (geo && D.nou == 0) IA_TC_BWD_GEO(0);
+    else if (geo && D.nou == 1) IA_TC_BWD_GEO(1);
+    else
     if (D.nou == 0) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_BWD(IA_ACT_RELU, 0); }
     else if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
     else if (D.nou <= 3) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_BWD(IA_ACT_RELU, 3); }
     else { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_BWD(IA_ACT_RELU, 8); }
 #undef IA_TC_BWD
+#undef IA_TC_BWD_GEO
     IA_LAUNCH_OK("mlp_tc_bwd_kernel");
     return IA_OK;
 }

@@ -37,8 +37,10 @@ __device__ __forceinline__ uint32_t entry_index(uint32_t cx, uint32_t cy, uint32
     // the level.  Hashed levels have a power-of-two size (2^log2_hashmap_size) => mask; dense levels can
     // exceed `size` only on the upper boundary (corner == res), by less than one `size`.
     if (hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);
+    // idx <= res + res^2 + res^3 < 2 * size (size = res^3 rounded up to a multiple of 8), so tcnn's `idx % size` is one
+    // conditional subtraction -- no integer division on the gather path
     uint32_t idx = cx + cy * res + cz * res * res;
-    return idx >= size ? idx % size : idx;
+    return idx >= size ? idx - size : idx;
 }
 
 struct CellCoords {

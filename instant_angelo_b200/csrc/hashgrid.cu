@@ -112,7 +112,7 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     const int row2 = P.n_levels;  // float2 per output row (F = 2)
     float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
-        const int r = i / row2, c2 = i - r * row2;
+        const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;     // 16 levels: shift, no integer division
         if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
     }
 }
@@ -257,7 +257,7 @@ hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     const int row2 = P.n_levels;
     float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
-        const int r = i / row2, c2 = i - r * row2;
+        const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;     // 16 levels: shift, no integer division
         if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
     }
 }

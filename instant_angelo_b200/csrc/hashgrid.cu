@@ -79,9 +79,11 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         py = __ldg(x + 3 * p + 1);
         pz = __ldg(x + 3 * p + 2);
     }
-    // masked (inactive) levels are exact zeros
-    for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
-    __syncthreads();
+    // masked (inactive) levels are exact zeros; with every level active each tile entry is overwritten below
+    if (P.active < P.n_levels) {
+        for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
+        __syncthreads();
+    }
 
 #pragma unroll 4
     for (int l = 0; l < P.active; ++l) {

@@ -573,6 +573,7 @@ template <int SPEC>
 __device__ __forceinline__ TcDims specialise(TcDims D)
 {
     if (SPEC == 1) { D.n_in0 = 3; D.n_in1 = 32; D.din = 35; D.K0 = 48; D.nh = 2; }
+    if (SPEC == 2) { D.n_in0 = 0; D.n_in1 = 87; D.din = 87; D.K0 = 96; D.nh = 2; }      // colour head: 65+3 features | SH(4) | normal
     return D;
 }
 
@@ -732,12 +733,13 @@ __device__ __forceinline__ void drain_dw(Ctx &c, float *__restrict__ acc_smem, i
     }
 }
 
-template <int ACT, int NOU>
+template <int ACT, int NOU, int SPEC = 0>
 __global__ void __launch_bounds__(THREADS, 1)
-mlp_tc_bwd_kernel(const TcDims D, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
+mlp_tc_bwd_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                   const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
                   float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams)
 {
+    const TcDims D = specialise<SPEC>(Din);
     extern __shared__ __align__(1024) char smem[];
     Ctx c;
     c.smem = smem;
@@ -1441,9 +1443,14 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
         mlp_tc_bwd_pipe_kernel<IA_ACT_SOFTPLUS100, NOU, 1><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(               \
             D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams);                                                          \
     } while (0)
+    const bool tex = !pipe && !sp && D.n_in0 == 0 && D.n_in1 == 87 && D.nh == 2 && D.K0 == 96 && D.nou == 3;
     if (geo && D.nou == 0) IA_TC_BWD_GEO(0);
     else if (geo && D.nou == 1) IA_TC_BWD_GEO(1);
-    else
+    else if (tex) {
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<IA_ACT_RELU, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));
+        mlp_tc_bwd_kernel<IA_ACT_RELU, 3, 2><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout, ld_dout,
+                                                                                                 din0, din1, dparams);
+    } else
     if (D.nou == 0) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_BWD(IA_ACT_RELU, 0); }
     else if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
     else if (D.nou <= 3) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_BWD(IA_ACT_RELU, 3); }

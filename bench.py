@@ -348,6 +348,8 @@ def run_b200(args):
     if rank == 0 and os.environ.get("IA_BENCH_VERBOSE"):
         print("host ms per step:", [round(1e3 * (b - a), 1) for a, b in zip(host_t[:-1], host_t[1:])], file=sys.stderr)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0 and os.environ.get("IA_BENCH_VERBOSE"):
+        print(f"device ms (events) {ms_total:.1f}; host loop ms {1e3 * (host_t[-1] - host_t[0]):.1f}", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     prof.enabled = False
     launches = prof.launches

@@ -57,9 +57,15 @@ def neuralangelo_colmap_sparse(grad_type: str = "analytic", log2_hashmap_size: i
     optimizer = {"name": "AdamW", "args": {"lr": 0.01, "betas": [0.9, 0.99], "eps": 1e-15},
                  "params": {"geometry": {"lr": 0.01}, "texture": {"lr": 0.01}, "geometry_bg": {"lr": 0.01},
                             "texture_bg": {"lr": 0.01}, "variance": {"lr": 0.001}}}
-    return to_config({"seed": 42, "model": model, "system": {"name": "neus-system", "loss": loss, "optimizer": optimizer,
-                                                              "warmup_steps": 500},
-                      "trainer": {"max_steps": 20000}})
+    warmup_steps, max_steps = 500, 20000
+    scheduler = {"name": "SequentialLR", "interval": "step", "milestones": [warmup_steps],
+                 "schedulers": [{"name": "LinearLR", "args": {"start_factor": 0.01, "end_factor": 1.0, "total_iters": warmup_steps}},
+                                {"name": "ExponentialLR", "args": {"gamma": 0.1 ** (1.0 / (max_steps - warmup_steps))}}]}
+    return to_config({"seed": 42, "model": model,
+                      "dataset": {"name": "colmap", "apply_mask": False},
+                      "system": {"name": "neus-system", "loss": loss, "optimizer": optimizer, "warmup_steps": warmup_steps,
+                                 "scheduler": scheduler},
+                      "trainer": {"max_steps": max_steps}})
 
 
 def neuralangelo_colmap_dense(grad_type: str = "analytic", log2_hashmap_size: int = 19) -> Config:

@@ -60,8 +60,10 @@ class FusedAdamW:
     schedule: LinearLR(0.01 -> 1, warmup_steps) then ExponentialLR(gamma) (configs/...sparse.yaml:134-165)."""
 
     def __init__(self, arena: ParamArena, lr: float = 0.01, betas=(0.9, 0.99), eps: float = 1e-15, weight_decay: float = 0.01,
-                 warmup_steps: int = 500, max_steps: int = 20000, decay_factor: float = 0.1):
+                 warmup_steps: int = 500, max_steps: int = 20000, decay_factor: float = 0.1, schedule=None):
+        """`schedule(t) -> factor` (systems.parse_scheduler) replaces the built-in warm-up + exponential decay."""
         self.arena, self.lr, self.betas, self.eps, self.wd = arena, lr, betas, eps, weight_decay
+        self.schedule = schedule
         self.m = torch.zeros_like(arena.data)
         self.v = torch.zeros_like(arena.data)
         self.t = 0
@@ -69,6 +71,8 @@ class FusedAdamW:
         self.gamma = decay_factor ** (1.0 / max(max_steps - warmup_steps, 1))
 
     def lr_at(self, step: int) -> float:
+        if self.schedule is not None:
+            return self.lr * float(self.schedule(step))
         if step < self.warmup_steps:
             return self.lr * (0.01 + (1.0 - 0.01) * step / self.warmup_steps)
         return self.lr * self.gamma ** (step - self.warmup_steps)

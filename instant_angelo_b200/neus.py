@@ -237,6 +237,10 @@ class NeuSModel(nn.Module):
             out_bg = {"comp_rgb": self.background_color[None, :].expand(*comp_rgb.shape),
                       "num_samples": torch.zeros_like(out["num_samples"]),
                       "rays_valid": torch.zeros_like(out["rays_valid"])}
+        # host-side copies of the marched sample counts (already read back by the marcher): systems.NeuSSystem's
+        # dynamic ray sampling (reference systems/neus.py:125-128) uses them instead of num_samples_full.item()
+        self.last_num_samples = len(t_starts)
+        self.last_num_samples_full = len(t_starts) + (len(marched_bg[1]) if marched_bg is not None else 0)
         out_full = {"comp_rgb": out["comp_rgb"] + out_bg["comp_rgb"] * (1.0 - out["opacity"]),
                     "num_samples": out["num_samples"] + out_bg["num_samples"],
                     "rays_valid": out["rays_valid"] | out_bg["rays_valid"]}

@@ -51,3 +51,42 @@ class SphereScene:
         """Sparse 'SfM' points on the surface with normals and confidences (batch['pts*'], systems/neus.py:63-71)."""
         nrm = F.normalize(torch.randn(n, 3, generator=gen), dim=-1)
         return (nrm * self.sphere_radius).contiguous(), nrm.contiguous(), torch.rand(n, generator=gen)
+
+
+class SphereDataset:
+    """The synthetic scene with the attribute surface of the reference's ColmapDatasetBase (datasets/colmap.py:297-316)
+    that NeuSSystem.preprocess_data reads: all_c2w [N,3,4], all_images [N,H,W,3], all_fg_masks [N,H,W], directions [H,W,3],
+    all_points / all_points_confidence / pts3d_normal (sparse 'SfM' points on the surface), all_fg_indexs / all_bg_indexs
+    (image, y, x) triples, w, h, img_wh, has_mask, apply_mask.  Tensors live on `device`, as the reference keeps its
+    dataset on the training GPU (datasets/colmap.py: `.to(self.rank)`)."""
+
+    def __init__(self, n_cameras: int = 32, width: int = 512, height: int = 512, focal: float = 560.0, cam_radius: float = 1.0,
+                 sphere_radius: float = 0.5, n_points: int = 65536, seed: int = 42, device="cpu", apply_mask: bool = False):
+        from .systems import get_ray_directions, get_rays
+        scene = SphereScene(n_cameras, width, height, focal, cam_radius, sphere_radius, seed)
+        self.w, self.h, self.img_wh = width, height, (width, height)
+        self.has_mask, self.apply_mask = True, apply_mask
+        self.directions = get_ray_directions(width, height, focal, focal, width / 2, height / 2)
+        self.all_c2w = scene.c2w.float()
+        images, masks = [], []
+        for i in range(n_cameras):
+            rays_o, rays_d = get_rays(self.directions, self.all_c2w[i])
+            rays_d = F.normalize(rays_d, p=2, dim=-1)
+            b = (rays_o * rays_d).sum(-1)
+            disc = b * b - ((rays_o * rays_o).sum(-1) - sphere_radius ** 2)
+            hit = disc > 0
+            t = -b - torch.sqrt(disc.clamp_min(0))
+            n = F.normalize(rays_o + t[:, None] * rays_d, dim=-1)
+            images.append(torch.where(hit[:, None], 0.5 + 0.5 * n, torch.ones_like(n)).view(height, width, 3))
+            masks.append(hit.float().view(height, width))
+        self.all_images, self.all_fg_masks = torch.stack(images), torch.stack(masks)
+        g = torch.Generator().manual_seed(seed + 1)
+        self.all_points, self.pts3d_normal, self.all_points_confidence = scene.surface_points(n_points, g)
+        fg = self.all_fg_masks > 0.5
+        self.all_fg_indexs, self.all_bg_indexs = torch.nonzero(fg), torch.nonzero(~fg)
+        for k in ("directions", "all_c2w", "all_images", "all_fg_masks", "all_points", "pts3d_normal", "all_points_confidence",
+                  "all_fg_indexs", "all_bg_indexs"):
+            setattr(self, k, getattr(self, k).to(device))
+
+    def __len__(self):
+        return len(self.all_images)

@@ -53,6 +53,9 @@ def test_builders_match_reference_yaml(yaml_name, builder):
 
     check(ref["model"], got["model"], "model")
     check(ref["system"]["loss"], got["system"]["loss"], "system.loss")
+    check(ref["system"]["optimizer"], got["system"]["optimizer"], "system.optimizer")
+    check(ref["system"]["scheduler"], got["system"]["scheduler"], "system.scheduler")
+    assert ref["trainer"]["max_steps"] == got["trainer"]["max_steps"] and ref["system"]["warmup_steps"] == got["system"]["warmup_steps"]
 
 
 def test_schedules_and_progressive_levels():

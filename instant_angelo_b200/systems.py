@@ -141,6 +141,53 @@ class OptimizerGroups:
 
     def __init__(self, arenas: List[ParamArena], optimizers: List[FusedAdamW], param_groups: List[dict]):
         self.arenas, self.optimizers, self.param_groups = arenas, optimizers, param_groups
+        self._where = {}            # id(param) -> (optimizer, offset into its arena)
+        for a, o in zip(arenas, optimizers):
+            for p, off in zip(a.params, a.offsets):
+                self._where[id(p)] = (o, off)
+
+    # ---- torch.optim.AdamW.state_dict() layout, so that Lightning checkpoints of the reference resume here and back ----
+    def state_dict(self) -> dict:
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                hit = self._where.get(id(p))
+                if hit is not None and hit[0].t > 0:
+                    o, off = hit
+                    n = p.numel()
+                    state[idx] = {"step": torch.tensor(float(o.t)), "exp_avg": o.m[off:off + n].view_as(p).clone(),
+                                  "exp_avg_sq": o.v[off:off + n].view_as(p).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({"name": g["name"], "lr": g["lr"], "betas": g["betas"], "eps": g["eps"],
+                           "weight_decay": g["weight_decay"], "amsgrad": False, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: dict) -> None:
+        flat = [p for g in self.param_groups for p in g["params"]]
+        n_saved = sum(len(g["params"]) for g in sd["param_groups"])
+        if n_saved != len(flat):
+            raise ValueError(f"loaded state dict contains {n_saved} parameters, the optimizer has {len(flat)}")
+        steps = set()
+        for idx, st in sd["state"].items():
+            p = flat[int(idx)]
+            hit = self._where.get(id(p))
+            if hit is None:
+                continue
+            o, off = hit
+            n = p.numel()
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {idx}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+            o.m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            o.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add((id(o), int(float(st["step"]))))
+        for o in self.optimizers:
+            mine = {t for oid, t in steps if oid == id(o)}
+            if len(mine) > 1:
+                raise ValueError(f"parameters of one fused group were saved at different step counts {sorted(mine)}")
+            if mine:
+                o.t = mine.pop()
 
     def zero_grad(self) -> None:
         for a in self.arenas:
@@ -193,7 +240,7 @@ def parse_optimizer(config, model, schedule: Optional[Callable[[int], float]] = 
                 fresh.append(p)
         buckets.setdefault(key, []).extend(fresh)
         param_groups.append({"name": gname, "lr": key[0], "betas": betas, "eps": key[2], "weight_decay": wd,
-                             "numel": sum(p.numel() for p in fresh)})
+                             "numel": sum(p.numel() for p in fresh), "params": list(params)})
     arenas, opts = [], []
     for (lr, betas, eps, wd), params in buckets.items():
         if not params:
@@ -429,6 +476,43 @@ class NeuSSystem:
         self.optimizers.step(self.scheduler_step_count(), grad_scale=1.0 / world_size)
         self.global_step += 1
         return loss.detach()
+
+    # ---- Lightning checkpoint layout (reference: ModelCheckpoint of launch.py:86-90, loaded by trainer.fit(ckpt_path=...)) ----
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Keys as LightningModule.state_dict() of the reference system: 'model.' + the model's own keys."""
+        return {"model." + k: v for k, v in self.model.state_dict().items()}
+
+    def save_checkpoint(self, path: str) -> None:
+        ckpt = {"epoch": self.current_epoch, "global_step": self.global_step, "pytorch-lightning_version": "1.7.7",
+                "state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
+                "optimizer_states": [], "lr_schedulers": [], "train_num_rays": self.train_num_rays}
+        if self.optimizers is not None:
+            osd = self.optimizers.state_dict()
+            osd["state"] = {i: {k: v.detach().cpu() for k, v in st.items()} for i, st in osd["state"].items()}
+            ckpt["optimizer_states"] = [osd]
+        torch.save(ckpt, path)
+
+    def load_checkpoint(self, path_or_dict, strict: bool = True, load_optimizer: bool = True) -> None:
+        """Accepts a checkpoint written by the reference (Lightning `.ckpt`: tcnn's flat `...encoding.params`, weight-norm
+        `weight_g/weight_v`, nerfacc's occupancy buffers) or by save_checkpoint.  Derived device state (the marching
+        bitfields) is rebuilt; parameters keep living in their optimizer arenas (copied in place)."""
+        ckpt = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location="cpu", weights_only=False)
+        sd = {k[len("model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("model.")}
+        missing, unexpected = self.model.load_state_dict(sd, strict=False)
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"checkpoint does not match the model: missing {list(missing)}, unexpected {list(unexpected)}")
+        for name in ("occupancy_grid", "occupancy_grid_bg"):
+            grid = getattr(self.model, name, None)
+            if grid is not None and grid.occs.is_cuda:
+                grid.repack()
+        self.global_step = int(ckpt.get("global_step", 0))
+        self.current_epoch = int(ckpt.get("epoch", 0))
+        if "train_num_rays" in ckpt:
+            self.train_num_rays = int(ckpt["train_num_rays"])
+        if load_optimizer and ckpt.get("optimizer_states"):
+            if self.optimizers is None:
+                self.configure_optimizers()
+            self.optimizers.load_state_dict(ckpt["optimizer_states"][0])
 
     def seed_everything(self, seed: int, rank: int = 0) -> None:
         """Data-parallel replicas: the occupancy grids refresh from an identically seeded device generator on every rank

@@ -217,3 +217,120 @@ def test_training_step_matches_reference_training_step(golden_dir, case):
     g = oracle.geometry.encoding.encoding.encoding.params.grad
     assert_close(g, fx["grad.geometry.encoding.encoding.encoding.params"], rtol=1e-3,
                  atol=1e-4 * float(np.abs(fx["grad.geometry.encoding.encoding.encoding.params"]).max()), name="table grad")
+
+
+def _tiny_system():
+    cfg = configs.neuralangelo_colmap_sparse("finite_difference")
+    for blk in (cfg.model.geometry, cfg.model.geometry_bg):
+        blk.xyz_encoding_config["log2_hashmap_size"] = 8
+    torch.manual_seed(3)
+    system = NeuSSystem(cfg)
+    system.configure_optimizers()
+    return cfg, system
+
+
+def _reference_adamw(cfg, model):
+    """torch.optim.AdamW exactly as the reference's parse_optimizer builds it (systems/utils.py:314-326)."""
+    from instant_angelo_b200.systems import get_parameters
+    oc = cfg.system.optimizer
+    groups = [{"params": get_parameters(model, n), "name": n, **a} for n, a in oc.params.items()]
+    return torch.optim.AdamW(groups, **oc.args)
+
+
+def test_optimizer_state_dict_is_interchangeable_with_torch_adamw():
+    cfg, system = _tiny_system()
+    groups = system.optimizers
+    ref_opt = _reference_adamw(cfg, system.model)
+    g = torch.Generator().manual_seed(5)
+    for a in groups.arenas:
+        a.grad.copy_(torch.randn(a.grad.shape, generator=g))
+    before = [a.data.clone() for a in groups.arenas]
+    ref_opt.step()                                                  # one real AdamW step on the arena-backed parameters
+    for a, b in zip(groups.arenas, before):
+        assert not torch.equal(a.data, b)
+    # torch -> fused: moments land at the parameters' arena offsets
+    groups.load_state_dict(ref_opt.state_dict())
+    assert all(o.t == 1 for o in groups.optimizers)
+    for a, o in zip(groups.arenas, groups.optimizers):
+        for p, off in zip(a.params, a.offsets):
+            st = ref_opt.state[p]
+            assert torch.equal(o.m[off:off + p.numel()].view_as(p), st["exp_avg"])
+            assert torch.equal(o.v[off:off + p.numel()].view_as(p), st["exp_avg_sq"])
+    # fused -> torch: a fresh reference optimizer accepts the layout and holds the same moments
+    sd = groups.state_dict()
+    assert [g_["name"] for g_ in sd["param_groups"]] == ["geometry", "texture", "geometry_bg", "texture_bg", "variance"]
+    ref2 = _reference_adamw(cfg, system.model)
+    ref2.load_state_dict(sd)
+    for p in system.model.parameters():
+        if p.numel() and p.requires_grad:
+            assert torch.equal(ref2.state[p]["exp_avg"], ref_opt.state[p]["exp_avg"])
+            assert float(ref2.state[p]["step"]) == 1.0
+    assert [g_["lr"] for g_ in ref2.param_groups] == [0.01, 0.01, 0.01, 0.01, 0.001]
+    with pytest.raises(ValueError):
+        bad = ref_opt.state_dict()
+        bad["param_groups"] = bad["param_groups"][:-1]
+        groups.load_state_dict(bad)
+
+
+def test_checkpoint_roundtrip_in_lightning_layout(tmp_path):
+    cfg, system = _tiny_system()
+    g = torch.Generator().manual_seed(9)
+    for o in system.optimizers.optimizers:
+        o.m.copy_(torch.randn(o.m.shape, generator=g))
+        o.v.copy_(torch.rand(o.v.shape, generator=g))
+        o.t = 37
+    system.global_step, system.train_num_rays = 37, 1234
+    system.model.occupancy_grid.occs.copy_(torch.rand(system.model.occupancy_grid.occs.shape, generator=g))
+    system.model.occupancy_grid._binary.copy_(system.model.occupancy_grid.occs.view(128, 128, 128) > 0.5)
+    path = str(tmp_path / "last.ckpt")
+    system.save_checkpoint(path)
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    assert {"epoch", "global_step", "state_dict", "optimizer_states", "lr_schedulers"} <= set(ckpt)
+    keys = set(ckpt["state_dict"])
+    for k in ("model.geometry.encoding.encoding.encoding.params", "model.geometry.network.layers.0.weight_g",
+              "model.geometry.network.layers.4.weight_v", "model.variance.variance", "model.occupancy_grid._binary",
+              "model.occupancy_grid.occs", "model.occupancy_grid_bg.resolution", "model.scene_aabb"):
+        assert k in keys, k
+    assert not [k for k in keys if "bitfield" in k or "_fd_signs" in k], "derived state must not be persisted"
+
+    _, fresh = _tiny_system()
+    with torch.no_grad():
+        for p in fresh.model.parameters():
+            p.add_(1.0)
+    arena_ptrs = [a.data.data_ptr() for a in fresh.optimizers.arenas]
+    fresh.load_checkpoint(path)
+    assert fresh.global_step == 37 and fresh.train_num_rays == 1234
+    for (k, a), (_, b) in zip(system.model.state_dict().items(), fresh.model.state_dict().items()):
+        assert torch.equal(a, b), k
+    for a1, o1, o2 in zip(system.optimizers.arenas, system.optimizers.optimizers, fresh.optimizers.optimizers):
+        assert o2.t == 37
+        for p, off in zip(a1.params, a1.offsets):           # (alignment padding between segments is not state)
+            sl = slice(off, off + p.numel())
+            assert torch.equal(o1.m[sl], o2.m[sl]) and torch.equal(o1.v[sl], o2.v[sl])
+    # parameters were copied in place: they still live in the optimizer arenas
+    assert arena_ptrs == [a.data.data_ptr() for a in fresh.optimizers.arenas]
+    for a in fresh.optimizers.arenas:
+        for p, off in zip(a.params, a.offsets):
+            assert p.data_ptr() == a.data[off:].data_ptr()
+    # a checkpoint that does not fit is refused
+    bad = dict(ckpt, state_dict={k: v for k, v in ckpt["state_dict"].items() if "variance" not in k})
+    with pytest.raises(RuntimeError, match="missing"):
+        fresh.load_checkpoint(bad)
+
+
+def test_reference_checkpoint_keys_load(golden_dir):
+    """state_dict keys written by the reference's own modules (tests/golden/*.npz 'param.*' = named_parameters of the
+    reference NeuSModel with tcnn's flat table layout) load under the Lightning 'model.' prefix."""
+    from tests.helpers import GOLDEN_CASES, golden_state_dict, load_golden
+    from tests.golden.scenes import golden_model_config
+    fx = load_golden(golden_dir, "neus_dualcolor_bg")
+    cfg = to_config({"model": golden_model_config(**GOLDEN_CASES["neus_dualcolor_bg"])})
+    system = NeuSSystem(cfg)
+    ref_sd = golden_state_dict(fx)
+    ckpt = {"state_dict": {"model." + k: v for k, v in ref_sd.items()}, "global_step": 25, "epoch": 0}
+    system.load_checkpoint(ckpt, strict=False, load_optimizer=False)
+    own = dict(system.model.named_parameters())
+    assert set(ref_sd) == set(own), set(ref_sd) ^ set(own)
+    for k, v in ref_sd.items():
+        assert torch.equal(own[k].detach(), v), k
+    assert system.global_step == 25

@@ -67,6 +67,56 @@ def test_dp_arena_allreduce_world2():
     assert [r[2] for r in res] == [(0, 5), (5, 10)]
 
 
+def _worker_system(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from instant_angelo_b200 import configs
+    from instant_angelo_b200.synthetic import SphereDataset
+    from instant_angelo_b200.systems import NeuSSystem
+    cfg = configs.neuralangelo_colmap_sparse("finite_difference")
+    for blk in (cfg.model.geometry, cfg.model.geometry_bg):
+        blk.xyz_encoding_config["log2_hashmap_size"] = 8
+    torch.manual_seed(100 + rank)                     # replicas start from different weights ...
+    system = NeuSSystem(cfg, dataset=SphereDataset(3, 16, 12, focal=10.0, n_points=50), device_sampling=True)
+    groups = system.configure_optimizers()
+    groups.broadcast_params(0)                        # ... and agree after the broadcast of both arenas
+    same = True
+    for a in groups.arenas:
+        got = [torch.zeros_like(a.data) for _ in range(world)]
+        dist.all_gather(got, a.data)
+        same &= torch.equal(got[0], got[1])
+    # per-rank ray streams (seed + 1000 * rank), so the ranks render different shards of the image set
+    system.seed_everything(42, rank)
+    b = {}
+    system.preprocess_data(b, "train")
+    rays = [torch.zeros_like(b["rays"]) for _ in range(world)]
+    dist.all_gather(rays, b["rays"].contiguous())
+    distinct = not torch.equal(rays[0], rays[1])
+    # one all-reduce(sum) per arena; the mean's 1/world is the optimizer's grad_scale
+    groups.zero_grad()
+    for a in groups.arenas:
+        a.grad.fill_(float(rank + 1))
+    groups.all_reduce()
+    summed = all(bool((a.grad == 3.0).all()) for a in groups.arenas)
+    views = all(p.grad.data_ptr() == a.grad[off:].data_ptr() for a in groups.arenas for p, off in zip(a.params, a.offsets))
+    q.put((rank, bool(same), bool(distinct), bool(summed), bool(views), len(groups.arenas)))
+    dist.destroy_process_group()
+
+
+def test_system_optimizer_groups_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_system, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert [r[1:] for r in res] == [(True, True, True, True, 2)] * 2
+
+
 def test_shard_and_lr_schedule():
     from instant_angelo_b200.dp import FusedAdamW, ParamArena, shard_rays
     assert [shard_rays(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]

@@ -310,6 +310,10 @@ int32_t ia_adamw_step(float *param, const float *grad, float *exp_avg, float *ex
  * [table, table + 32 n_sectors); out[n_threads] is practically never written. */
 int32_t ia_debug_sector_gather(const float *table, int64_t n_sectors, int64_t n_threads, int32_t iters, float *out,
                                void *stream);
+/* A/B switch of ia_hashgrid_fwd: on = 1 launches the one-loop kernel (dense / hashed index chosen per level under a
+ * predicate), on = 0 the split-loop kernel (default when the plan's dense levels come first), on = -1 lets the environment
+ * variable IA_HASHGRID_FWD_GENERIC decide.  Both compute the same indices and the same interpolation expression. */
+int32_t ia_debug_hashgrid_fwd_generic(int32_t on);
 /* Cycle accounting of the tensor-core MLP kernels (thread 0 of every CTA): enable != 0 starts it; out8_host (may be NULL)
  * receives {barrier wait, MMA issue, MMA completion wait, tile total, tiles, wait m0, wait m1, wait m2} and clears them. */
 int32_t ia_debug_tc_timing(int32_t enable, unsigned long long *out8_host);

@@ -112,6 +112,7 @@ SIGNATURES = {
     "ia_composite_bwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_adamw_step": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _P]),
     "ia_debug_sector_gather": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
+    "ia_debug_hashgrid_fwd_generic": (_I32, [_I32]),
     "ia_debug_tc_timing": (_I32, [_I32, C.POINTER(C.c_ulonglong)]),
 }
 

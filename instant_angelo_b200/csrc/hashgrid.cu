@@ -11,6 +11,7 @@
 // Outputs / incoming gradients are transposed through a padded shared-memory tile so that global
 // traffic on the [n, L*F] side is fully coalesced.
 #include <math.h>
+#include <stdlib.h>
 
 #include "ia_common.cuh"
 
@@ -23,6 +24,7 @@ constexpr int HG_ROW = 34;       // padded floats per tile row (32 + 2): conflic
 struct GridParams {
     int32_t n_levels;
     int32_t active;
+    int32_t n_dense;   // leading levels with a dense (un-hashed) index when every later level is hashed; -1 otherwise
     float scale[IA_MAX_LEVELS];
     uint32_t res[IA_MAX_LEVELS];
     uint32_t size[IA_MAX_LEVELS];
@@ -109,6 +111,95 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
         if (xc == 0) *reinterpret_cast<float2 *>(&tile[pl * HG_ROW + 2 * l]) = make_float2(a0, a1);
     }
+    __syncthreads();
+
+    const int row2 = P.n_levels;  // float2 per output row (F = 2)
+    float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
+    for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
+        const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;     // 16 levels: shift, no integer division
+        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+    }
+}
+
+// The four corner indices of one x side of a cell.  Same values as entry_index() corner by corner ((iy+1)*P == iy*P + P
+// modulo 2^32; the dense index of a y/z neighbour is the base index plus res / res^2), with the dense-or-hashed choice
+// made at compile time: the caller walks the dense levels and the hashed levels in two loops, so neither path issues
+// the other's instructions (under a per-thread predicate both did: 48 of the 129 instructions per level and lane).
+template <bool HASHED>
+__device__ __forceinline__ void corner_indices(uint32_t cx, uint32_t iy, uint32_t iz, uint32_t res, uint32_t size,
+                                               uint32_t &i00, uint32_t &i10, uint32_t &i01, uint32_t &i11)
+{
+    if (HASHED) {
+        const uint32_t m = size - 1u;
+        const uint32_t hy0 = iy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = iz * 805459861u, hz1 = hz0 + 805459861u;
+        i00 = (cx ^ hy0 ^ hz0) & m;
+        i10 = (cx ^ hy1 ^ hz0) & m;
+        i01 = (cx ^ hy0 ^ hz1) & m;
+        i11 = (cx ^ hy1 ^ hz1) & m;
+    } else {
+        const uint32_t r2 = res * res;
+        const uint32_t b = cx + iy * res + iz * r2;
+        i00 = b;
+        i10 = b + res;
+        i01 = b + r2;
+        i11 = b + res + r2;
+        i00 = i00 >= size ? i00 - size : i00;
+        i10 = i10 >= size ? i10 - size : i10;
+        i01 = i01 >= size ? i01 - size : i01;
+        i11 = i11 >= size ? i11 - size : i11;
+    }
+}
+
+template <bool HASHED>
+__device__ __forceinline__ void fwd_level(int l, const GridParams &P, const float2 *__restrict__ table, float px, float py,
+                                          float pz, uint32_t xc, float *tile_row)
+{
+    const float scale = P.scale[l];
+    const uint32_t off = P.offset[l];
+    const CellCoords c = locate(px, py, pz, scale);
+    const float wx = xc ? c.wx : 1.f - c.wx;
+    uint32_t i00, i10, i01, i11;
+    corner_indices<HASHED>(c.ix + xc, c.iy, c.iz, P.res[l], P.size[l], i00, i10, i01, i11);
+    // one 32-bit add per corner (level offset + entry), widened once by the address computation
+    const float2 v00 = __ldg(table + (off + i00));
+    const float2 v10 = __ldg(table + (off + i10));
+    const float2 v01 = __ldg(table + (off + i01));
+    const float2 v11 = __ldg(table + (off + i11));
+    const float w00 = wx * (1.f - c.wy) * (1.f - c.wz), w10 = wx * c.wy * (1.f - c.wz);
+    const float w01 = wx * (1.f - c.wy) * c.wz, w11 = wx * c.wy * c.wz;
+    float a0 = w00 * v00.x + w10 * v10.x + w01 * v01.x + w11 * v11.x;
+    float a1 = w00 * v00.y + w10 * v10.y + w01 * v01.y + w11 * v11.y;
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    if (xc == 0) *reinterpret_cast<float2 *>(tile_row + 2 * l) = make_float2(a0, a1);
+}
+
+// hashgrid_fwd_kernel with fewer instructions per (point, level, lane) -- the kernel is issue bound on the coherent points
+// of a training step (ncu: issue slots 91 % busy, profiles/r01_ncu_hashgrid_step.md): dense and hashed levels in separate
+// loops (P.n_dense), 32-bit entry offsets, and rows past n computed on a copy of the last point instead of predicating
+// every load (they are not written out).  Same indices and the same interpolation expression as hashgrid_fwd_kernel.
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const GridParams P,
+                          float *__restrict__ out)
+{
+    __shared__ float tile[HG_TILE * HG_ROW];
+    const int tid = threadIdx.x;
+    const int pl = tid >> 1;
+    const uint32_t xc = tid & 1;
+    const int64_t base = (int64_t)blockIdx.x * HG_TILE;
+    const int64_t p = base + pl < n ? base + pl : n - 1;      // n >= 1
+    const float px = __ldg(x + 3 * p), py = __ldg(x + 3 * p + 1), pz = __ldg(x + 3 * p + 2);
+    if (P.active < P.n_levels) {
+        for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
+        __syncthreads();
+    }
+    float *tile_row = tile + pl * HG_ROW;
+    const int nd = P.n_dense < P.active ? P.n_dense : P.active;
+#pragma unroll 2
+    for (int l = 0; l < nd; ++l) fwd_level<false>(l, P, table, px, py, pz, xc, tile_row);
+#pragma unroll 4
+    for (int l = nd; l < P.active; ++l) fwd_level<true>(l, P, table, px, py, pz, xc, tile_row);
     __syncthreads();
 
     const int row2 = P.n_levels;  // float2 per output row (F = 2)
@@ -447,6 +538,12 @@ int fill_params(const ia_grid_plan *plan, int32_t active_levels, GridParams *P)
         IA_REQUIRE(!plan->hashed[l] || (plan->size[l] & (plan->size[l] - 1)) == 0,
                    "hashgrid: hashed level %d has a non power-of-two size %u", l, plan->size[l]);
     }
+    // tcnn's levels grow monotonically, so the dense ones come first; any other plan keeps the generic kernels
+    int nd = 0;
+    while (nd < plan->n_levels && !plan->hashed[nd]) ++nd;
+    P->n_dense = nd;
+    for (int l = nd; l < plan->n_levels; ++l)
+        if (!plan->hashed[l]) P->n_dense = -1;
     return IA_OK;
 }
 
@@ -496,6 +593,14 @@ extern "C" int32_t ia_hashgrid_plan(int32_t n_levels, int32_t n_features, int32_
     return IA_OK;
 }
 
+static int g_fwd_generic = -1;   // -1: environment decides
+
+extern "C" int32_t ia_debug_hashgrid_fwd_generic(int32_t on)
+{
+    g_fwd_generic = on;
+    return IA_OK;
+}
+
 extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table, const ia_grid_plan *plan,
                                    int32_t active_levels, float *out, void *stream)
 {
@@ -505,8 +610,15 @@ extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table
     IA_REQUIRE(n >= 0 && (n == 0 || (x && table && out)), "hashgrid_fwd: NULL pointer with n=%lld", (long long)n);
     if (n == 0) return IA_OK;
     const int64_t blocks = ia_ceil_div(n, HG_TILE);
-    hashgrid_fwd_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
-        x, n, reinterpret_cast<const float2 *>(table), P, out);
+    // the one-loop kernel stays selectable for A/B runs: IA_HASHGRID_FWD_GENERIC=1 or ia_debug_hashgrid_fwd_generic(1)
+    static const bool generic_env = getenv("IA_HASHGRID_FWD_GENERIC") != nullptr;
+    const bool generic = g_fwd_generic < 0 ? generic_env : g_fwd_generic != 0;
+    if (P.n_dense >= 0 && !generic)
+        hashgrid_fwd_split_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
+            x, n, reinterpret_cast<const float2 *>(table), P, out);
+    else
+        hashgrid_fwd_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
+            x, n, reinterpret_cast<const float2 *>(table), P, out);
     IA_LAUNCH_OK("hashgrid_fwd_kernel");
     return IA_OK;
 }

@@ -183,6 +183,37 @@ def train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
     return terms["loss"], out
 
 
+def step_roofline(fg_per_ray, bg_per_ray, rays_per_s, peaks, grad_type="finite_difference"):
+    """Whole-step roofline of SURVEY.md section 8d: rays/s <= min(HBM bytes/s / algorithmic bytes per ray,
+    tensor FLOP/s / algorithmic FLOP per ray), from the measured samples per ray.  Algorithmic work per sample (fp32
+    tables and encodings, 16 levels x 2 features; unpadded 2*MAC of the networks as this path evaluates them: the 12 tap
+    evaluations compute the SDF column only; backward = 2x forward):
+      foreground sample, finite differences: 13 encodes (1164 B forward + 1164 B table gradient each) + 6 input gradients
+        (1176 B: the curvature taps move with the parameters); 35>64>64>65 centre + 12 x 35>64>64>1 taps + 87>64>64>3 colour
+      foreground sample, analytic: 7 encodes, 1 input gradient + its two second-order adjoints, centre network twice over
+      background sample: 1 encode (forward + table gradient); 35>64>8 density + 24>64>64>3 colour."""
+    enc_f, enc_bt, enc_bi = 1164.0, 1164.0, 1176.0
+    mlp = lambda din, nh, nout: 2.0 * (din * 64 + (64 * 64 if nh == 2 else 0) + 64 * nout)
+    centre, tap, colour = mlp(35, 2, 65), mlp(35, 2, 1), mlp(87, 2, 3)
+    if grad_type == "finite_difference":
+        fg_bytes = 13 * (enc_f + enc_bt) + 6 * enc_bi
+        fg_flop = 3.0 * (centre + 12 * tap + colour)
+    else:
+        fg_bytes = 7 * (enc_f + enc_bt) + 6 * enc_bi + (enc_bi + enc_f + enc_bt)
+        fg_flop = 3.0 * (2 * centre + 6 * tap + colour)
+    bg_bytes = enc_f + enc_bt
+    bg_flop = 3.0 * (mlp(35, 1, 8) + mlp(24, 2, 3))
+    bytes_per_ray = fg_per_ray * fg_bytes + bg_per_ray * bg_bytes + 24 + 32
+    flop_per_ray = fg_per_ray * fg_flop + bg_per_ray * bg_flop
+    by_hbm = peaks["hbm_gbs"] * 1e9 / bytes_per_ray
+    by_tensor = peaks["bf16_tflops_sustained"] * 1e12 / flop_per_ray
+    bound = "hbm" if by_hbm <= by_tensor else "tensor"
+    roof = min(by_hbm, by_tensor)
+    return {"bound": bound, "rays_per_s_roofline": roof, "frac": rays_per_s / roof, "algorithmic_bytes_per_ray": bytes_per_ray,
+            "algorithmic_flop_per_ray": flop_per_ray, "rays_per_s_by_hbm": by_hbm, "rays_per_s_by_tensor": by_tensor,
+            "note": "per GPU; the 2^19-entry tables are L2 resident, so the HBM line is the SURVEY 8d reporting convention, not a hard bound"}
+
+
 def hashgrid_microbench(device, peaks):
     """Secondary BASELINE metric: hash-grid G point-evals/s (16 levels, F=2, 2^19 entries/level, 2^22 incoherent points)."""
     from instant_angelo_b200 import ops
@@ -410,7 +441,7 @@ def run_b200(args):
                 "avg_launch_ms": ms / max(calls, 1), "algorithmic_flop_per_launch": work / max(calls, 1),
                 "note": "algorithmic FLOP = 2*MAC of the unpadded fp32 network (x2 for backward).  The kernel issues 3 f16 MMAs "
                         "per product (fp32-equivalent hi/lo split), pads K to 16 and recomputes the forward inside backward: for "
-                        "35->64->64->1 that is 5.2x the algorithmic FLOP on the tensor pipe (ncu: tensor pipe active 16.8 %). It "
+                        "35->64->64->1 that is 5.2x the algorithmic FLOP on the tensor pipe (ncu: tensor pipe active 22.8 %). It "
                         "is bound by its per-row activation epilogues and the serial MMA issue, not by the tensor pipe: see "
                         "DESIGN.md section 4.2 and profiles/r01_ncu_mlp_tc.md"}
     else:
@@ -420,6 +451,10 @@ def run_b200(args):
                 "traffic": traffic, "peak_source": peaks["source"], "launches": calls, "avg_launch_ms": ms / max(calls, 1),
                 "algorithmic_bytes_per_launch": work / max(calls, 1)}
 
+    try:        # reporting only: never lose the bench line over it
+        step_roof = step_roofline(fg_total / total_rays, (full_total - fg_total) / total_rays, value / world, peaks, args.grad_type)
+    except Exception as e:  # pragma: no cover
+        step_roof = {"error": repr(e)}
     cpu = cpu_baseline_leg(cfg, model, args) if world == 1 and not args.no_cpu_baseline else None
     hg = hashgrid_microbench(device, peaks) if world == 1 else None
 
@@ -443,6 +478,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches,
         "roofline": roof,
+        "step_roofline": step_roof,
         "cpu_baseline": cpu,
         "kernels": per_kernel,
         "hashgrid_microbench": hg,

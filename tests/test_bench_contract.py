@@ -30,3 +30,22 @@ def test_reference_arm_other_ranks_exit_quietly():
                         "--warmup", "1", "--cpu-rays", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     assert p.stdout.strip() == ""
+
+
+def test_step_roofline_arithmetic():
+    """The whole-step roofline of SURVEY.md 8d from samples per ray (host arithmetic only)."""
+    import bench
+    peaks = {"hbm_gbs": 6553.9, "bf16_tflops_sustained": 1344.2}
+    r = bench.step_roofline(189.9, 80.8, 292946.0, peaks)
+    fg_bytes = 13 * (1164 + 1164) + 6 * 1176
+    assert fg_bytes == 37320
+    want_bytes = 189.9 * fg_bytes + 80.8 * 2328 + 56
+    assert abs(r["algorithmic_bytes_per_ray"] - want_bytes) < 1e-6
+    fg_flop = 3 * (20992 + 12 * 12800 + 19712)
+    bg_flop = 3 * (5504 + 11648)
+    assert abs(r["algorithmic_flop_per_ray"] - (189.9 * fg_flop + 80.8 * bg_flop)) < 1e-3
+    assert r["bound"] == "hbm" and abs(r["rays_per_s_roofline"] - 6553.9e9 / want_bytes) < 1e-3
+    assert 0.30 < r["frac"] < 0.36
+    assert r["rays_per_s_by_tensor"] > 10 * r["rays_per_s_by_hbm"]
+    a = bench.step_roofline(189.9, 80.8, 190918.0, peaks, "analytic")
+    assert a["algorithmic_bytes_per_ray"] < r["algorithmic_bytes_per_ray"]

@@ -65,6 +65,7 @@ def neuralangelo_colmap_sparse(grad_type: str = "analytic", log2_hashmap_size: i
                       "dataset": {"name": "colmap", "apply_mask": False},
                       "system": {"name": "neus-system", "loss": loss, "optimizer": optimizer, "warmup_steps": warmup_steps,
                                  "scheduler": scheduler},
+                      "export": {"chunk_size": 2097152, "export_vertex_color": True},
                       "trainer": {"max_steps": max_steps}})
 
 

@@ -47,6 +47,25 @@ class BaseImplicitGeometry(nn.Module):
     def regularizations(self, out):
         return {}
 
+    def forward_level(self, points):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def isosurface(self):
+        """reference models/geometry.py:80-113: marching cubes over the +-radius box on the lattice of `isosurface.resolution`
+        steps per 2 units, at the reference's fixed threshold 0.001; the SDF blocks are evaluated by forward_level on the
+        parameters' device and meshed there (isosurface.py)."""
+        isocfg = self.config.get("isosurface", None)
+        if isocfg is None:
+            raise NotImplementedError
+        assert isocfg["method"] in ["mc", "CuMCubes"]
+        from .isosurface import MarchingCubeHelper
+        r = self.radius
+        device = next(self.parameters()).device
+        helper = MarchingCubeHelper(lambda x: -self.forward_level(x), [(-r, r), (-r, r), (-r, r)], int(isocfg["resolution"]),
+                                    block_res=int(isocfg.get("block_res", 256)), method=isocfg["method"], device=device)
+        return helper(threshold=0.001)
+
 
 @models.register("volume-density")
 class VolumeDensity(BaseImplicitGeometry):

@@ -127,6 +127,28 @@ class NeuSModel(nn.Module):
                                                     occ_thre=self.config.get("grid_prune_occ_thre_bg", 0.01),
                                                     indices=oi.get("indices_bg"), jitter=oi.get("jitter_bg"))
 
+    # ---- reference models/neus.py:113-115, 308-318 -----------------------------------------------------------------
+    def isosurface(self):
+        return self.geometry.isosurface()
+
+    @torch.no_grad()
+    def export(self, export_config):
+        mesh = self.isosurface()
+        if export_config.get("export_vertex_color", False) and mesh["v_pos"].shape[0] > 0:
+            device = self.scene_aabb.device
+            chunk = int(export_config.get("chunk_size", 2097152))
+            was_training = self.geometry.training
+            self.geometry.eval()
+            rgb, nrm = [], []
+            for i in range(0, mesh["v_pos"].shape[0], chunk):
+                pts = mesh["v_pos"][i:i + chunk].to(device).float().contiguous()
+                _, sdf_grad, features = self.geometry(pts, with_grad=True, with_feature=True)
+                nrm.append(F.normalize(sdf_grad, p=2, dim=-1).cpu())
+                rgb.append(torch.sigmoid(features[..., 1:4]).cpu())
+            self.geometry.train(was_training)
+            mesh["v_rgb"], mesh["v_norm"] = torch.cat(rgb, dim=0), torch.cat(nrm, dim=0)
+        return mesh
+
     # ---- reference models/neus.py:117-139 (stand-alone; forward_ uses the fused kernel) ---------------
     def get_alpha(self, sdf, normal, dirs, dists):
         inv_s = self.variance.inv_s.reshape(1).clip(1e-6, 1e6)

@@ -514,6 +514,16 @@ class NeuSSystem:
                 self.configure_optimizers()
             self.optimizers.load_state_dict(ckpt["optimizer_states"][0])
 
+    # ---- systems/neus.py:305-310 ------------------------------------------------------------------------------------
+    def export(self, path: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """model.export(config.export) and, when `path` is given, the mesh as a Wavefront OBJ with vertex colours."""
+        from .isosurface import save_obj
+        export_cfg = self.config.get("export", None) or {"chunk_size": 2097152, "export_vertex_color": True}
+        mesh = self.model.export(export_cfg)
+        if path is not None:
+            save_obj(path, **mesh)
+        return mesh
+
     def seed_everything(self, seed: int, rank: int = 0) -> None:
         """Data-parallel replicas: the occupancy grids refresh from an identically seeded device generator on every rank
         (so they stay replica-identical without the reference's per-forward buffer broadcast), while the

@@ -68,3 +68,26 @@ def test_system_validation_step_eval_mode(cuda_lib):
     out2 = system.validation_step(batch2)
     assert torch.equal(system.out["comp_rgb_full"], o["comp_rgb_full"]) and float(out2["psnr"]) == float(out["psnr"])
     assert torch.equal(system.model.background_color, torch.ones(3, device="cuda"))
+
+
+def test_system_export_mesh(cuda_lib, tmp_path):
+    """Export path (systems/neus.py:305-310 -> models/neus.py:308-318 -> models/geometry.py:80-113) on the kernels: the
+    sphere-initialised SDF of a fresh model meshes into one closed, outward-oriented surface whose vertices sit on the
+    0.001 level of the network that produced them."""
+    from tests.test_isosurface import _manifold_stats, _signed_volume
+    system = _system(n_cameras=2, size=64)
+    system.config.model.geometry.isosurface["resolution"] = 40
+    system.config.model.geometry.isosurface["block_res"] = 32         # several blocks
+    for _ in range(2):
+        system.fit_step()                                              # sets the progressive levels / finite-difference eps
+    path = tmp_path / "mesh.obj"
+    mesh = system.export(str(path))
+    nv, nf = mesh["v_pos"].shape[0], mesh["t_pos_idx"].shape[0]
+    assert nv > 100 and nf > 100 and mesh["v_rgb"].shape == (nv, 3) and mesh["v_norm"].shape == (nv, 3)
+    assert _signed_volume(mesh["v_pos"], mesh["t_pos_idx"]) > 0
+    system.model.eval()
+    with torch.no_grad():
+        sdf = system.model.geometry(mesh["v_pos"].cuda().contiguous(), with_grad=False, with_feature=False)
+    assert float((sdf - 0.001).abs().max()) < 2e-2                     # linear interpolation on a 0.05 lattice
+    assert torch.isfinite(mesh["v_rgb"]).all() and (mesh["v_norm"].norm(dim=-1) - 1).abs().max() < 1e-4
+    assert sum(1 for l in path.read_text().splitlines() if l.startswith("f ")) == nf

@@ -5,8 +5,6 @@ get_ray_directions / get_rays (models/ray_utils.py:9-43) and per-step pixel samp
 (systems/neus.py:49-55, 95); everything is generated on the CPU with a seeded torch.Generator."""
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn.functional as F
 

@@ -74,7 +74,7 @@ def test_system_export_mesh(cuda_lib, tmp_path):
     """Export path (systems/neus.py:305-310 -> models/neus.py:308-318 -> models/geometry.py:80-113) on the kernels: the
     sphere-initialised SDF of a fresh model meshes into one closed, outward-oriented surface whose vertices sit on the
     0.001 level of the network that produced them."""
-    from tests.test_isosurface import _manifold_stats, _signed_volume
+    from tests.test_isosurface import _signed_volume
     system = _system(n_cameras=2, size=64)
     system.config.model.geometry.isosurface["resolution"] = 40
     system.config.model.geometry.isosurface["block_res"] = 32         # several blocks

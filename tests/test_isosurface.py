@@ -142,7 +142,6 @@ def test_geometry_isosurface_and_model_export_wiring(monkeypatch):
     """BaseImplicitGeometry.isosurface / NeuSModel.export (reference models/geometry.py:80-113, models/neus.py:308-318) with
     the network evaluations replaced by an analytic sphere (the kernels need a GPU): lattice, sign convention,
     threshold 0.001, chunked vertex attributes."""
-    import types
     from instant_angelo_b200 import configs, make
     from instant_angelo_b200.config import to_config
     cfg = configs.neuralangelo_colmap_sparse("finite_difference")

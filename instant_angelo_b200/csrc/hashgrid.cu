@@ -39,10 +39,17 @@ __device__ __forceinline__ uint32_t entry_index(uint32_t cx, uint32_t cy, uint32
     // the level.  Hashed levels have a power-of-two size (2^log2_hashmap_size) => mask; dense levels can
     // exceed `size` only on the upper boundary (corner == res), by less than one `size`.
     if (hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);
-    // idx <= res + res^2 + res^3 < 2 * size (size = res^3 rounded up to a multiple of 8), so tcnn's `idx % size` is one
-    // conditional subtraction -- no integer division on the gather path
+    // For x in [0,1]: idx <= res + res^2 + res^3 < 2 * size (size = res^3 rounded up to a multiple of 8), so tcnn's
+    // `idx % size` is one conditional subtraction -- no integer division on the gather path.  Points outside the unit cube
+    // (e.g. un-clamped COLMAP points handed to VolumeSDF by the sparse-point losses) give negative / huge cell
+    // coordinates whose uint32 stride sum wraps anywhere: they take the (never hot) modulo so that the index stays
+    // inside the level exactly as tcnn's does.
     uint32_t idx = cx + cy * res + cz * res * res;
-    return idx >= size ? idx - size : idx;
+    if (idx >= size) {
+        idx -= size;
+        if (idx >= size) idx %= size;
+    }
+    return idx;
 }
 
 struct CellCoords {
@@ -148,6 +155,11 @@ __device__ __forceinline__ void corner_indices(uint32_t cx, uint32_t iy, uint32_
         i10 = i10 >= size ? i10 - size : i10;
         i01 = i01 >= size ? i01 - size : i01;
         i11 = i11 >= size ? i11 - size : i11;
+        // out-of-cube points (see entry_index): a | b >= max(a, b), so one test covers the four corners; a false positive
+        // only takes the modulo of values that are already in range
+        if ((i00 | i10 | i01 | i11) >= size) {
+            i00 = (b % size); i10 = ((b + res) % size); i01 = ((b + r2) % size); i11 = ((b + res + r2) % size);
+        }
     }
 }
 

@@ -309,6 +309,87 @@ def estimate_normals(pts: torch.Tensor, radius: float = 0.1, max_nn: int = 30, c
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# dense prior: COLMAP's dense/fused.ply (datasets/colmap.py:246-256 reads it with `plyfile`, which is not installable here)
+# ---------------------------------------------------------------------------------------------------------------------
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
+              "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
+              "double": "f8", "float64": "f8"}
+
+
+def read_ply_vertices(path: str) -> Dict[str, np.ndarray]:
+    """The `vertex` element of a PLY file as {property: array} (ascii, binary_little_endian and binary_big_endian; scalar
+    properties only -- what COLMAP's stereo fusion and the reference's MVS preprocessing write)."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt, elements = None, []
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: unterminated PLY header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] in ("comment", "obj_info"):
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append((tok[1], int(tok[2]), []))
+            elif tok[0] == "property":
+                if tok[1] == "list":
+                    elements[-1][2].append((tok[-1], None))
+                else:
+                    if tok[1] not in _PLY_TYPES:
+                        raise ValueError(f"{path}: unknown PLY property type {tok[1]!r}")
+                    elements[-1][2].append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        if not elements or elements[0][0] != "vertex":
+            raise ValueError(f"{path}: the first PLY element must be `vertex`")
+        _, count, props = elements[0]
+        if any(t is None for _, t in props):
+            raise ValueError(f"{path}: list properties on the vertex element are not supported")
+        if fmt == "ascii":
+            rows = np.loadtxt(f, dtype=np.float64, max_rows=count, ndmin=2) if count else np.zeros((0, len(props)))
+            return {name: rows[:, i].astype(t) for i, (name, t) in enumerate(props)}
+        if fmt not in ("binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{path}: unsupported PLY format {fmt!r}")
+        order = "<" if fmt == "binary_little_endian" else ">"
+        dt = np.dtype([(name, order + t) for name, t in props])
+        rec = np.frombuffer(f.read(count * dt.itemsize), dtype=dt, count=count)
+        return {name: np.ascontiguousarray(rec[name]).astype(rec[name].dtype.newbyteorder("=")) for name, _ in props}
+
+
+def write_ply_vertices(path: str, props: Dict[str, np.ndarray]) -> None:
+    """binary_little_endian PLY with one `vertex` element (fixtures; float32 / uint8 properties)."""
+    names = list(props)
+    n = len(props[names[0]])
+    dt = np.dtype([(k, "<u1" if props[k].dtype == np.uint8 else "<f4") for k in names])
+    rec = np.zeros(n, dtype=dt)
+    for k in names:
+        rec[k] = props[k]
+    with open(path, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\n")
+        f.write(f"element vertex {n}\n".encode())
+        for k in names:
+            f.write(f"property {'uchar' if props[k].dtype == np.uint8 else 'float'} {k}\n".encode())
+        f.write(b"end_header\n")
+        f.write(rec.tobytes())
+
+
+def load_dense_prior(path: str) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """datasets/colmap.py:246-256: points, the PLY's own normals and its `confidence` column (ones when absent)."""
+    assert os.path.exists(path), f"Please check whether {path} exists"
+    v = read_ply_vertices(path)
+    for k in ("x", "y", "z", "nx", "ny", "nz"):
+        if k not in v:
+            raise KeyError(f"{path}: vertex property {k!r} missing (the dense prior needs positions and normals)")
+    pts = torch.from_numpy(np.stack([v["x"], v["y"], v["z"]], axis=1).astype(np.float32))
+    nrm = torch.from_numpy(np.stack([v["nx"], v["ny"], v["nz"]], axis=1).astype(np.float32))
+    conf = torch.from_numpy(v["confidence"].astype(np.float32)) if "confidence" in v else torch.ones(pts.shape[0])
+    return pts, nrm, conf
+
+
 def colmap_to_c2w(qvec, tvec) -> torch.Tensor:
     """world->camera (q, t) of images.bin -> camera->world [3,4] in the OpenGL convention (datasets/colmap.py:217-221)."""
     R = qvec2rotmat(qvec)
@@ -373,10 +454,14 @@ class ColmapDataset:
                 images.append(img.contiguous())
                 masks.append(mask)
         all_c2w = torch.stack(c2ws, dim=0)
-        xyz, _, err = read_points3d_arrays(os.path.join(root, "sparse/0/points3D.bin"))
-        pts3d = torch.from_numpy(xyz).float()
-        conf = torch.from_numpy(error_to_confidence(err)).float()
-        normals = estimate_normals(pts3d, radius=0.1, max_nn=30)
+        if config.get("dense_pcd_path", None) is not None:
+            # dense MVS prior with its own oriented normals and confidences (datasets/colmap.py:246-256)
+            pts3d, normals, conf = load_dense_prior(os.path.join(root, config["dense_pcd_path"]))
+        else:
+            xyz, _, err = read_points3d_arrays(os.path.join(root, "sparse/0/points3D.bin"))
+            pts3d = torch.from_numpy(xyz).float()
+            conf = torch.from_numpy(error_to_confidence(err)).float()
+            normals = estimate_normals(pts3d, radius=0.1, max_nn=30)
         all_c2w, pts3d, normals = normalize_poses(all_c2w, pts3d, config["up_est_method"], config["center_est_method"], normals)
         if split == "test":
             n = int(config["n_test_traj_steps"])

@@ -25,10 +25,37 @@ def binary_cross_entropy(inp, target):
     return -(target * torch.log(inp) + (1 - target) * torch.log(1 - inp)).mean()
 
 
+def flatten_eff_distloss(w: torch.Tensor, m: torch.Tensor, interval: torch.Tensor, ray_id: torch.Tensor) -> torch.Tensor:
+    """Mip-NeRF 360 distortion loss over packed samples, the O(S) prefix-sum form of `torch_efficient_distloss`
+    (an un-vendored pip dependency of the reference, imported at systems/neus.py:15, used at :163-171):
+
+        loss = ( sum_i w_i^2 interval_i / 3  +  2 sum_i w_i (m_i W_i - WM_i) ) / n_rays,
+        W_i / WM_i = sums of w_j / w_j m_j over the samples j < i of the same ray, n_rays = ray_id.max() + 1.
+
+    Samples are sorted by ray (nerfacc's packed order).  Every shipped config has lambda_distortion = 0, so this is off
+    the hot path: plain tensor operations, float64 prefix sums, gradients by autograd."""
+    if w.numel() == 0:
+        return w.sum() * 0.0
+    w, m, interval = w.reshape(-1), m.reshape(-1), interval.reshape(-1)
+    ray_id = ray_id.reshape(-1)
+    n_rays = (ray_id.max() + 1).to(w.dtype)
+    wd, md = w.double(), m.double()
+    wm = wd * md
+    w_ex, wm_ex = torch.cumsum(wd, 0) - wd, torch.cumsum(wm, 0) - wm          # exclusive prefix over the whole batch
+    first = torch.ones_like(ray_id, dtype=torch.bool)
+    first[1:] = ray_id[1:] != ray_id[:-1]
+    idx = torch.arange(ray_id.numel(), device=ray_id.device)
+    start = torch.cummax(torch.where(first, idx, torch.zeros_like(idx)), 0).values   # index of the ray's first sample
+    w_prefix, wm_prefix = w_ex - w_ex[start], wm_ex - wm_ex[start]
+    loss_uni = (interval.double() * wd * wd).sum() / 3.0
+    loss_bi = 2.0 * (wd * (md * w_prefix - wm_prefix)).sum()
+    return ((loss_uni + loss_bi) / n_rays.double()).to(w.dtype)
+
+
 def training_loss(model, out: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], loss_cfg, global_step: int,
-                  has_mask: bool = False) -> Dict[str, torch.Tensor]:
+                  has_mask: bool = False, current_epoch: int = 0) -> Dict[str, torch.Tensor]:
     """reference systems/neus.py:130-194.  Returns every term plus 'loss'."""
-    c = lambda v: C(v, global_step)
+    c = lambda v: C(v, global_step, current_epoch)
     terms = {}
     # mean over the valid rays' channels, as F.mse_loss / F.l1_loss on comp_rgb_full[valid] (systems/neus.py:134-138),
     # written as a masked sum so that no boolean compaction (a host read-back per use) sits inside the step;
@@ -54,6 +81,13 @@ def training_loss(model, out: Dict[str, torch.Tensor], batch: Dict[str, torch.Te
         assert "sdf_laplace_samples" in out, "Need geometry.grad_type='finite_difference' to get SDF Laplace samples"
         terms["curvature"] = out["sdf_laplace_samples"].abs().mean()
         loss = loss + terms["curvature"] * c(loss_cfg["lambda_curvature"])
+    # systems/neus.py:161-171 (inactive in every shipped config: lambda_distortion = lambda_distortion_bg = 0)
+    if c(loss_cfg.get("lambda_distortion", 0.0)) > 0:
+        terms["distortion"] = flatten_eff_distloss(out["weights"], out["points"], out["intervals"], out["ray_indices"])
+        loss = loss + terms["distortion"] * c(loss_cfg["lambda_distortion"])
+    if getattr(model, "learned_background", False) and c(loss_cfg.get("lambda_distortion_bg", 0.0)) > 0:
+        terms["distortion_bg"] = flatten_eff_distloss(out["weights_bg"], out["points_bg"], out["intervals_bg"], out["ray_indices_bg"])
+        loss = loss + terms["distortion_bg"] * c(loss_cfg["lambda_distortion_bg"])
     if c(loss_cfg["lambda_sdf_l1"]) > 0 and batch.get("pts") is not None:
         sdf_p, grad_p = model.geometry(batch["pts"], with_grad=True, with_feature=False)
         terms["sdf_l1"] = (F.l1_loss(sdf_p, torch.zeros_like(sdf_p)) * batch["pts_weights"]).mean(dim=0)   # Appendix C-11

@@ -129,12 +129,16 @@ class _Linear(nn.Module):
     def __init__(self, dim_in: int, dim_out: int, weight_norm: bool):
         super().__init__()
         self.dim_in, self.dim_out, self.weight_norm = dim_in, dim_out, weight_norm
-        self.bias = nn.Parameter(torch.zeros(dim_out))
+        # registration order = torch's: nn.Linear registers (weight, bias); nn.utils.weight_norm then deletes `weight` and
+        # appends (weight_g, weight_v), leaving (bias, weight_g, weight_v).  torch.optim state dicts index parameters by
+        # position, so a reference checkpoint's optimizer_states only land on the right tensors with this order.
         if weight_norm:
+            self.bias = nn.Parameter(torch.zeros(dim_out))
             self.weight_g = nn.Parameter(torch.ones(dim_out, 1))
             self.weight_v = nn.Parameter(torch.empty(dim_out, dim_in))
         else:
             self.weight = nn.Parameter(torch.empty(dim_out, dim_in))
+            self.bias = nn.Parameter(torch.zeros(dim_out))
 
     def raw_weight(self) -> torch.Tensor:
         return self.weight_v if self.weight_norm else self.weight

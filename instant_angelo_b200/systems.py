@@ -147,7 +147,7 @@ class OptimizerGroups:
                 self._where[id(p)] = (o, off)
 
     # ---- torch.optim.AdamW.state_dict() layout, so that Lightning checkpoints of the reference resume here and back ----
-    def state_dict(self) -> dict:
+    def state_dict(self, lr_factor: float = 1.0) -> dict:
         state, groups, idx = {}, [], 0
         for g in self.param_groups:
             ids = []
@@ -160,8 +160,13 @@ class OptimizerGroups:
                                   "exp_avg_sq": o.v[off:off + n].view_as(p).clone()}
                 ids.append(idx)
                 idx += 1
-            groups.append({"name": g["name"], "lr": g["lr"], "betas": g["betas"], "eps": g["eps"],
-                           "weight_decay": g["weight_decay"], "amsgrad": False, "params": ids})
+            # every key torch.optim.AdamW keeps in a param group (torch 1.13 ... 2.x): Optimizer.load_state_dict REPLACES the
+            # live groups with the saved ones, so a missing key is a KeyError in the reference's next optimizer.step().
+            # `lr` is the scheduled rate at the saved step and `initial_lr` the base rate, as torch's schedulers leave them.
+            groups.append({"name": g["name"], "lr": g["lr"] * float(lr_factor), "betas": g["betas"], "eps": g["eps"],
+                           "weight_decay": g["weight_decay"], "amsgrad": False, "maximize": False, "foreach": None,
+                           "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": True,
+                           "initial_lr": g["lr"], "params": ids})
         return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd: dict) -> None:
@@ -249,6 +254,32 @@ def parse_optimizer(config, model, schedule: Optional[Callable[[int], float]] = 
         arenas.append(arena)
         opts.append(FusedAdamW(arena, lr=lr, betas=betas, eps=eps, weight_decay=wd, schedule=schedule))
     return OptimizerGroups(arenas, opts, param_groups)
+
+
+def torch_scheduler_state(config, base_lrs: List[float], n_steps: int) -> dict:
+    """`scheduler.state_dict()` of the torch scheduler the reference's parse_scheduler (systems/utils.py:329-346) builds,
+    after `n_steps` scheduler steps -- the entry Lightning stores under `lr_schedulers` in a `.ckpt`.  Built by stepping
+    real torch scheduler objects over a throw-away optimizer with the same groups, so the layout is whatever the installed
+    torch writes (nested `_schedulers`, `_milestones`, `last_epoch`, `_last_lr`)."""
+    import warnings
+    from torch.optim import lr_scheduler as S
+    dummy = torch.optim.SGD([{"params": [nn.Parameter(torch.zeros(1))], "lr": float(lr)} for lr in base_lrs], lr=0.1)
+
+    def build(c):
+        name = c["name"]
+        if name == "SequentialLR":
+            return S.SequentialLR(dummy, [build(x) for x in c["schedulers"]], milestones=[int(m) for m in c["milestones"]])
+        if name == "Chained":
+            return S.ChainedScheduler([build(x) for x in c["schedulers"]])
+        return getattr(S, name)(dummy, **dict(to_primitive(c.get("args", {}))))
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sched = build(config)
+        for _ in range(int(n_steps)):
+            dummy.step()
+            sched.step()
+        return sched.state_dict()
 
 
 class PSNR(nn.Module):
@@ -422,7 +453,7 @@ class NeuSSystem:
         if pts is None or pts.numel() == 0:
             loss_batch["pts"] = None
         terms = training_loss(self.model, out, loss_batch, sys_cfg.loss, self.global_step,
-                              has_mask=bool(getattr(self.dataset, "has_mask", False)))
+                              has_mask=bool(getattr(self.dataset, "has_mask", False)), current_epoch=self.current_epoch)
         for k, v in terms.items():
             if k != "loss":
                 self.log(f"train/loss_{k}", v)
@@ -483,13 +514,24 @@ class NeuSSystem:
         return {"model." + k: v for k, v in self.model.state_dict().items()}
 
     def save_checkpoint(self, path: str) -> None:
+        """Lightning 1.7 `.ckpt` layout: `state_dict` under the `model.` prefix, `optimizer_states[0]` as
+        torch.optim.AdamW.state_dict() with every param-group key torch expects (incl. `initial_lr` and the scheduled
+        `lr`), `lr_schedulers[0]` as the SequentialLR / ChainedScheduler state after the steps taken so far, and the fit
+        loop's step counters."""
         ckpt = {"epoch": self.current_epoch, "global_step": self.global_step, "pytorch-lightning_version": "1.7.7",
                 "state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
-                "optimizer_states": [], "lr_schedulers": [], "train_num_rays": self.train_num_rays}
+                "optimizer_states": [], "lr_schedulers": [], "train_num_rays": self.train_num_rays,
+                "loops": {"fit_loop": {"epoch_loop.batch_progress": {"total": {"ready": self.global_step, "completed": self.global_step}},
+                                       "epoch_loop.state_dict": {"_batches_that_stepped": self.global_step}}}}
         if self.optimizers is not None:
-            osd = self.optimizers.state_dict()
+            t = self.scheduler_step_count()
+            factor = float(self._scheduler["factor"](t)) if self._scheduler is not None else 1.0
+            osd = self.optimizers.state_dict(lr_factor=factor)
             osd["state"] = {i: {k: v.detach().cpu() for k, v in st.items()} for i, st in osd["state"].items()}
             ckpt["optimizer_states"] = [osd]
+            if self._scheduler is not None:
+                base = [g["lr"] for g in self.optimizers.param_groups]
+                ckpt["lr_schedulers"] = [torch_scheduler_state(self.config.system.scheduler, base, t)]
         torch.save(ckpt, path)
 
     def load_checkpoint(self, path_or_dict, strict: bool = True, load_optimizer: bool = True) -> None:

@@ -126,3 +126,75 @@ def test_colmap_dataset_feeds_preprocess_data():
     system.dataset = t
     system.preprocess_data(v, "test")
     assert v["rays"].shape == (96, 6)
+
+
+def test_ply_reader_formats(tmp_path):
+    g = np.random.default_rng(0)
+    props = {"x": g.normal(size=50).astype(np.float32), "y": g.normal(size=50).astype(np.float32),
+             "z": g.normal(size=50).astype(np.float32), "nx": g.normal(size=50).astype(np.float32),
+             "ny": g.normal(size=50).astype(np.float32), "nz": g.normal(size=50).astype(np.float32),
+             "red": g.integers(0, 255, 50).astype(np.uint8), "confidence": g.random(50).astype(np.float32)}
+    p = str(tmp_path / "le.ply")
+    ds.write_ply_vertices(p, props)
+    got = ds.read_ply_vertices(p)
+    assert list(got) == list(props)
+    for k in props:
+        assert np.array_equal(got[k], props[k]) and got[k].dtype == props[k].dtype, k
+    # ascii, with a comment and a trailing face element that must be ignored
+    a = tmp_path / "a.ply"
+    lines = ["ply", "format ascii 1.0", "comment made by hand", "element vertex 3", "property float x", "property float y",
+             "property double z", "property uchar red", "element face 1", "property list uchar int vertex_indices", "end_header",
+             "0 1 2.5 7", "1 0 -2 255", "0.5 0.5 0.25 0", "3 0 1 2"]
+    a.write_text("\n".join(lines) + "\n")
+    got = ds.read_ply_vertices(str(a))
+    assert got["z"].dtype == np.float64 and got["red"].tolist() == [7, 255, 0] and got["x"].tolist() == [0.0, 1.0, 0.5]
+    # big endian
+    be = tmp_path / "be.ply"
+    rec = np.zeros(4, dtype=np.dtype([("x", ">f4"), ("y", ">f4"), ("z", ">f4")]))
+    rec["x"], rec["y"], rec["z"] = [1, 2, 3, 4], [5, 6, 7, 8], [-1, -2, -3, -4]
+    be.write_bytes(b"ply\nformat binary_big_endian 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\nend_header\n" + rec.tobytes())
+    got = ds.read_ply_vertices(str(be))
+    assert got["z"].tolist() == [-1.0, -2.0, -3.0, -4.0]
+    (tmp_path / "bad.ply").write_bytes(b"plx\n")
+    with pytest.raises(ValueError):
+        ds.read_ply_vertices(str(tmp_path / "bad.ply"))
+
+
+def test_dense_prior_branch(tmp_path):
+    """config.dense_pcd_path (configs/neuralangelo-colmap_dense.yaml: dense/fused.ply): points, the PLY's own normals
+    and confidences replace the sparse points + estimated normals (reference datasets/colmap.py:246-256)."""
+    root = tmp_path / "scene"
+    root.mkdir()
+    for sub in ("sparse", "images"):
+        os.symlink(os.path.join(SCENE, sub), root / sub)
+    (root / "dense").mkdir()
+    g = np.random.default_rng(1)
+    n = 37
+    xyz = g.normal(size=(n, 3)).astype(np.float32) * 0.3 + np.array([0.3, -0.2, 0.1], np.float32)
+    nrm = g.normal(size=(n, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    conf = g.random(n).astype(np.float32)
+    ds.write_ply_vertices(str(root / "dense" / "fused.ply"),
+                          {"x": xyz[:, 0], "y": xyz[:, 1], "z": xyz[:, 2], "nx": nrm[:, 0], "ny": nrm[:, 1], "nz": nrm[:, 2],
+                           "confidence": conf})
+    base = {"name": "colmap", "root_dir": str(root), "img_downscale": 2, "up_est_method": "camera", "center_est_method": "lookat",
+            "n_test_traj_steps": 5, "apply_mask": False}
+    d = ds.ColmapDataset(to_config({**base, "dense_pcd_path": "dense/fused.ply"}), "train")
+    assert d.all_points.shape == (n, 3) and d.pts3d_normal.shape == (n, 3)
+    assert np.allclose(d.all_points_confidence.numpy(), conf)
+    # the same rigid normalisation the sparse branch applies: normals are the PLY's, rotated, still unit length
+    imgs = ds.read_images_binary(os.path.join(SCENE, "sparse/0/images.bin"))
+    c2w = torch.stack([ds.colmap_to_c2w(i.qvec, i.tvec) for i in imgs.values()])
+    _, want_p, want_n = ds.normalize_poses(c2w, torch.from_numpy(xyz), "camera", "lookat", torch.from_numpy(nrm))
+    assert torch.allclose(d.all_points, want_p.float(), atol=1e-6) and torch.allclose(d.pts3d_normal, want_n.float(), atol=1e-6)
+    assert torch.allclose(d.pts3d_normal.norm(dim=-1), torch.ones(n), atol=1e-5)
+    # without a confidence column: ones
+    ds.write_ply_vertices(str(root / "dense" / "noconf.ply"),
+                          {"x": xyz[:, 0], "y": xyz[:, 1], "z": xyz[:, 2], "nx": nrm[:, 0], "ny": nrm[:, 1], "nz": nrm[:, 2]})
+    d2 = ds.ColmapDataset(to_config({**base, "dense_pcd_path": "dense/noconf.ply"}), "train")
+    assert torch.equal(d2.all_points_confidence, torch.ones(n))
+    with pytest.raises(AssertionError, match="exists"):
+        ds.ColmapDataset(to_config({**base, "dense_pcd_path": "dense/missing.ply"}), "train")
+    # sparse branch unchanged when the key is null (the sparse YAMLs)
+    d3 = ds.ColmapDataset(to_config({**base, "dense_pcd_path": None}), "train")
+    assert d3.all_points.shape == (400, 3)

@@ -115,6 +115,74 @@ def test_hashgrid_grouped_backward(cuda_lib, cfg_name, active):
     assert_close(tg2.grad, table.grad, rtol=1e-4, atol=1e-5, name="dtable (grouped, table only)")
 
 
+@pytest.mark.parametrize("cfg_name", ["sparse_2p19", "small_mixed"])
+def test_hashgrid_points_outside_unit_cube(cuda_lib, cfg_name):
+    """tcnn's index is total: for x outside [0,1] the cell coordinates are negative / beyond the grid, the uint32 stride
+    sum wraps and `% size` (dense levels) / the hash mask (hashed levels) keep it inside the level.  The sparse-point
+    losses hand un-clamped COLMAP points to VolumeSDF (reference systems/neus.py:178-186 -> models/geometry.py:200-206),
+    so the kernels must neither read nor scatter outside the table: forward, table/input gradients, grouped backward and
+    the second-order adjoints against the oracle on x in [-2, 3], with canaries around the table gradient."""
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS[cfg_name]
+    plan_ref, plan = tc.grid_plan(**cfg), ops.make_grid_plan(**cfg)
+    g = torch.Generator().manual_seed(23)
+    n = 6 * 211
+    x = (torch.rand(n, 3, generator=g) * 5.0 - 2.0)
+    x[::5] = torch.rand(x[::5].shape, generator=g)            # a share of in-range points
+    x[1] = torch.tensor([-2.0, 3.0, -0.5])
+    x[2] = torch.tensor([1.0 + 1e-6, -1e-6, 0.37])
+    x = x.contiguous().requires_grad_(True)
+    table = (torch.randn(plan_ref.n_params, generator=g) * 0.1).requires_grad_(True)
+    dy = torch.randn(n, plan_ref.n_output_dims, generator=g)
+    y_ref = tc.hashgrid_forward(x, table, plan_ref)
+    y_ref.backward(dy)
+    for group in (1, 6):
+        xg = x.detach().cuda().requires_grad_(True)
+        pad = 4096
+        guard = torch.zeros(plan.n_params + 2 * pad, device="cuda")
+        guard[pad:pad + plan.n_params] = table.detach().cuda()
+        tg = guard[pad:pad + plan.n_params].requires_grad_(True)
+        y = ops.hashgrid_encode(xg, tg, plan, None, group=group)
+        y.backward(dy.cuda())
+        torch.cuda.synchronize()
+        assert_close(y, y_ref, rtol=1e-5, atol=1e-6, name=f"enc outside cube (group {group})")
+        assert_close(tg.grad, table.grad, rtol=1e-4, atol=1e-5, name=f"dtable outside cube (group {group})")
+        rt, at = grad_tol(x.grad, 1e-4)
+        assert_close(xg.grad, x.grad, rtol=rt, atol=at, name=f"dx outside cube (group {group})")
+    # raw ABI with canaries around dtable: nothing may be scattered outside [0, n_params)
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    pad = 1 << 16
+    buf = torch.zeros(plan.n_params + 2 * pad, device="cuda")
+    dt = buf[pad:pad + plan.n_params]
+    xc, tcu, dyc = x.detach().cuda(), table.detach().cuda(), dy.cuda()
+    v = torch.randn(n, 3, generator=g).cuda()
+    s = L.stream()
+    L.check(cuda_lib.ia_hashgrid_bwd(xc.data_ptr(), n, tcu.data_ptr(), dyc.data_ptr(), C.byref(plan), plan.n_levels, dt.data_ptr(), None, s))
+    L.check(cuda_lib.ia_hashgrid_bwd_grouped(xc.data_ptr(), n, tcu.data_ptr(), dyc.data_ptr(), C.byref(plan), plan.n_levels, 6, dt.data_ptr(), None, s))
+    L.check(cuda_lib.ia_hashgrid_bwd_input_bwd_table(xc.data_ptr(), n, v.data_ptr(), dyc.data_ptr(), C.byref(plan), plan.n_levels, dt.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert float(buf[:pad].abs().max()) == 0.0 and float(buf[pad + plan.n_params:].abs().max()) == 0.0, "scatter outside the table"
+    # second-order adjoints (grad_type analytic) on the same points
+    xr = x.detach().clone()
+    tr = table.detach().clone().requires_grad_(True)
+    dyr = dy.clone().requires_grad_(True)
+    xr.requires_grad_(True)
+    (dx_ref,) = torch.autograd.grad(tc.hashgrid_forward(xr, tr, plan_ref), xr, dyr, create_graph=True)
+    (dx_ref * v.cpu()).sum().backward()
+    tg2 = table.detach().cuda().requires_grad_(True)
+    dyg = dy.cuda().requires_grad_(True)
+    dxg = ops.hashgrid_input_grad(xc, tg2, dyg, plan)
+    (dxg * v).sum().backward()
+    torch.cuda.synchronize()
+    rt, at = grad_tol(dx_ref, 1e-4)
+    assert_close(dxg, dx_ref, rtol=rt, atol=at, name="J^T dy outside cube")
+    rt, at = grad_tol(dyr.grad, 1e-4)
+    assert_close(dyg.grad, dyr.grad, rtol=rt, atol=at, name="jvp outside cube")
+    rt, at = grad_tol(tr.grad, 1e-4)
+    assert_close(tg2.grad, tr.grad, rtol=rt, atol=at, name="second-order dtable outside cube")
+
+
 def test_hashgrid_abi_entry_points_and_errors(cuda_lib):
     """ia_hashgrid_bwd_table / ia_hashgrid_bwd_input agree with the fused ia_hashgrid_bwd; bad args fail loudly."""
     import ctypes as C
@@ -264,6 +332,95 @@ def test_mlp(cuda_lib, case, n, precision):
     want = torch.cat([t.grad.reshape(-1) if t.grad is not None else torch.zeros_like(t).reshape(-1) for pair in eff for t in pair])
     rt, at = grad_tol(want, 2e-4)
     assert_close(flat.grad, want, rtol=rt, atol=at, name="d params")
+
+
+MLP_CASES_LARGE = dict(MLP_CASES, v3_cam=(0, 80, 2, 3, False, False, 3))
+
+
+def _mlp_ref64(a, b, Ws, bs, softplus, nou):
+    """float64 torch reference of VanillaMLP.forward (reference models/network_utils.py:96-113) on cat[a*2-1, b];
+    also returns, per row, the smallest |pre-activation| over the hidden units (distance to the nearest ReLU kink)."""
+    h = (torch.cat([a * 2 - 1, b], 1) if a is not None else b).double()
+    zmin = torch.full((h.shape[0],), float("inf"), device=h.device, dtype=torch.float64)
+    for i, (w, bias) in enumerate(zip(Ws, bs)):
+        h = h @ w.double().t() + bias.double()
+        if i < len(Ws) - 1:
+            zmin = torch.minimum(zmin, h.detach().abs().min(dim=1).values)
+            h = torch.nn.functional.softplus(h, beta=100) if softplus else torch.relu(h)
+    return h[:, :nou], zmin
+
+
+def _assert_rel(got, want, name, rtol=1e-3, floor=1e-3, l2=1e-4):
+    """north_star tolerance: |got - want| <= rtol * |want| on every entry above floor * max|want| (smaller entries are held to
+    rtol * floor * max|want| absolute), and relative L2 error below `l2`."""
+    got, want = got.detach().double(), want.detach().double()
+    assert got.shape == want.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    if want.numel() == 0:
+        return
+    scale = float(want.abs().max())
+    if scale == 0.0:
+        assert float(got.abs().max()) == 0.0, f"{name}: expected exact zeros"
+        return
+    err = (got - want).abs()
+    tol = rtol * torch.clamp(want.abs(), min=floor * scale)
+    bad = err > tol
+    if bool(bad.any()):
+        i = int(torch.argmax(err - tol))
+        raise AssertionError(f"{name}: {int(bad.sum())}/{want.numel()} entries out of tolerance; worst flat index {i}: got "
+                             f"{float(got.reshape(-1)[i]):.8g} want {float(want.reshape(-1)[i]):.8g} (max|want| {scale:.3g})")
+    rel_l2 = float((got - want).norm() / want.norm().clamp_min(1e-300))
+    assert rel_l2 < l2, f"{name}: relative L2 error {rel_l2:.3g} >= {l2}"
+
+
+@pytest.mark.parametrize("case", list(MLP_CASES_LARGE))
+@pytest.mark.parametrize("n", [50_000, 1_000_003])
+@pytest.mark.parametrize("dout_scale", [1.0, 1e-4])
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_mlp_large_n(cuda_lib, case, n, dout_scale, precision):
+    """The regime bench.py runs: hundreds of 128-row tiles per persistent CTA (cross-tile dW accumulation, per-tile
+    power-of-two gradient rescale, the software pipeline's steady state, a ragged last tile), against a float64 torch
+    reference of the same network.  Tolerance 1e-3 relative per entry (entries > 1e-3 of the tensor's max) and 1e-4
+    relative L2.
+
+    ReLU networks: the gradient is discontinuous where a hidden pre-activation crosses zero.  With ~1e8 hidden units
+    per case a handful lie within rounding distance (1e-6) of the kink, and there fp32 (either kernel) and float64
+    legitimately pick different sides -- a whole row of d(input) then differs by O(1).  (This is what the round-1
+    probe's `v3_weight n=50000 din1 9.8e-02` line was: one row, on the kink.)  Rows whose float64 pre-activations come
+    within 1e-5 of zero get a zero incoming gradient, so they take part in the forward comparison only."""
+    from instant_angelo_b200 import _lib as L
+    from instant_angelo_b200 import ops
+    n0, n1, nh, nout, softplus, _wn, nou = MLP_CASES_LARGE[case]
+    prec = L.IA_MLP_FP32 if precision == "fp32" else L.IA_MLP_TC_F16
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(sum(map(ord, case)) + n)
+    din = n0 + n1
+    dims = [din] + [64] * nh + [nout]
+    Ws = [(torch.randn(dims[i + 1], dims[i], device=dev, generator=g) * (1.5 / dims[i] ** 0.5)).requires_grad_(True)
+          for i in range(len(dims) - 1)]
+    bs = [(torch.randn(dims[i + 1], device=dev, generator=g) * 0.1).requires_grad_(True) for i in range(len(dims) - 1)]
+    a = torch.rand(n, n0, device=dev, generator=g).requires_grad_(True) if n0 else None
+    b = (torch.randn(n, n1, device=dev, generator=g) * 0.3).requires_grad_(True)
+    go = torch.randn(n, nou, device=dev, generator=g) * dout_scale
+    y64, zmin = _mlp_ref64(a, b, Ws, bs, softplus, nou)
+    if not softplus:
+        on_kink = zmin < 1e-5
+        assert int(on_kink.sum()) < max(8, n // 1000), "kink mask should only remove a handful of rows"
+        go = torch.where(on_kink[:, None], torch.zeros_like(go), go)
+    y64.backward(go.double())
+    want_p = torch.cat([t.grad.reshape(-1) for pair in zip(Ws, bs) for t in pair])
+
+    flat = torch.cat([t.detach().reshape(-1) for pair in zip(Ws, bs) for t in pair]).requires_grad_(True)
+    desc = ops.make_mlp_desc(n0, n1, nh, nout, L.IA_ACT_SOFTPLUS100 if softplus else L.IA_ACT_RELU, 2.0, -1.0, prec)
+    ag = a.detach().clone().requires_grad_(True) if n0 else None
+    bg = b.detach().clone().requires_grad_(True)
+    y = ops.mlp_apply(ag, bg, flat, desc, nou)
+    y.backward(go)
+    torch.cuda.synchronize()
+    _assert_rel(y, y64, "mlp out")
+    _assert_rel(bg.grad, b.grad, "d in1")
+    if n0:
+        _assert_rel(ag.grad, a.grad, "d in0")
+    _assert_rel(flat.grad, want_p, "d params")
 
 
 def test_mlp_rejects_unsupported(cuda_lib):

@@ -334,3 +334,133 @@ def test_reference_checkpoint_keys_load(golden_dir):
     for k, v in ref_sd.items():
         assert torch.equal(own[k].detach(), v), k
     assert system.global_step == 25
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# checkpoint written by the reference's own objects (tests/golden/make_golden_checkpoint.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _load_ref_checkpoint():
+    import gzip
+    import io
+    with gzip.open(os.path.join(GOLD, "ref_checkpoint.ckpt.gz"), "rb") as f:
+        return torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=False)
+
+
+def _ref_checkpoint_system():
+    from tests.golden.make_golden_checkpoint import checkpoint_config
+    torch.manual_seed(11)
+    system = NeuSSystem(checkpoint_config())
+    system.configure_optimizers()
+    return system
+
+
+def test_parameter_order_is_torchs():
+    """torch.optim state dicts index parameters by position: VanillaMLP must yield its parameters in the order of the
+    reference's nn.Sequential of nn.Linear (weight, bias) / weight-normed nn.Linear (bias, weight_g, weight_v)
+    (reference models/network_utils.py:115-134)."""
+    import torch.nn as nn
+    from instant_angelo_b200.network_utils import VanillaMLP
+    for wn in (False, True):
+        cfg = {"n_neurons": 64, "n_hidden_layers": 2, "sphere_init": wn, "weight_norm": wn}
+        ours = [n for n, _ in VanillaMLP(7, 5, cfg).named_parameters()]
+        lin = lambda i, o: nn.utils.weight_norm(nn.Linear(i, o)) if wn else nn.Linear(i, o)
+        ref = nn.Module()
+        ref.layers = nn.Sequential(lin(7, 64), nn.ReLU(), lin(64, 64), nn.ReLU(), lin(64, 5))
+        assert ours == [n for n, _ in ref.named_parameters()], (wn, ours)
+
+
+def test_reference_written_checkpoint_loads():
+    """A Lightning-layout checkpoint whose state_dict / optimizer_states / lr_schedulers were produced by the reference's
+    models, the reference's parse_optimizer (a real torch.optim.AdamW) and parse_scheduler after three training steps."""
+    ckpt = _load_ref_checkpoint()
+    system = _ref_checkpoint_system()
+    system.load_checkpoint(ckpt)                                    # strict: every key of the reference must be consumed
+    assert system.global_step == 3 and system.current_epoch == 0
+    own = dict(system.model.named_parameters())
+    ref_params = {k[len("model."):]: v for k, v in ckpt["state_dict"].items()}
+    for k, p in own.items():
+        assert torch.equal(p.detach(), ref_params[k]), k
+    assert torch.equal(system.model.occupancy_grid._binary, ref_params["occupancy_grid._binary"])
+    assert torch.equal(system.model.occupancy_grid_bg.occs, ref_params["occupancy_grid_bg.occs"])
+    # the reference's parameter order (names recorded by the generator) is the order this model yields them in
+    groups = system.optimizers
+    flat = [p for g in groups.param_groups for p in g["params"]]
+    names = {id(p): n for n, p in system.model.named_parameters()}
+    assert [names[id(p)] for p in flat] == ckpt["_param_names"]
+    # optimizer moments land on the tensors they belong to
+    osd = ckpt["optimizer_states"][0]
+    assert all(o.t == 3 for o in groups.optimizers)
+    hit = 0
+    for idx, st in osd["state"].items():
+        o, off = groups._where[id(flat[idx])]
+        n = flat[idx].numel()
+        assert torch.equal(o.m[off:off + n].view_as(flat[idx]), st["exp_avg"]), ckpt["_param_names"][idx]
+        assert torch.equal(o.v[off:off + n].view_as(flat[idx]), st["exp_avg_sq"]), ckpt["_param_names"][idx]
+        hit += 1
+    assert hit == len(osd["state"]) >= 25
+    # the closed-form schedule continues where the reference's SequentialLR stood
+    lrs = dict(zip([g["name"] for g in groups.param_groups], ckpt["_lrs"]))
+    t = system.scheduler_step_count()
+    for o in groups.optimizers:
+        want = lrs["variance"] if abs(o.lr - 0.001) < 1e-12 else lrs["geometry"]
+        assert abs(o.lr_at(t) - want) < 1e-12
+
+
+def test_checkpoint_resumes_in_the_reference(tmp_path):
+    """here -> reference: the optimizer_states / lr_schedulers entries written by save_checkpoint load into the REAL torch
+    objects the reference builds (AdamW with the reference's groups, SequentialLR[LinearLR, ExponentialLR]), step without
+    a KeyError, and continue the schedule from the saved step instead of restarting the warm-up."""
+    from torch.optim.lr_scheduler import ExponentialLR, LinearLR, SequentialLR
+    system = _ref_checkpoint_system()
+    system.load_checkpoint(_load_ref_checkpoint())
+    system.global_step = 700                                         # past the 500-step warm-up milestone
+    for o in system.optimizers.optimizers:
+        o.t = 700
+    path = str(tmp_path / "resume.ckpt")
+    system.save_checkpoint(path)
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    assert ckpt["loops"]["fit_loop"]["epoch_loop.state_dict"]["_batches_that_stepped"] == 700
+    cfg = system.config
+    ref_opt = _reference_adamw(cfg, system.model)
+    sc = cfg.system.scheduler
+    subs = [LinearLR(ref_opt, **dict(sc.schedulers[0].args)), ExponentialLR(ref_opt, **dict(sc.schedulers[1].args))]
+    ref_sched = SequentialLR(ref_opt, subs, milestones=list(sc.milestones))
+    ref_opt.load_state_dict(ckpt["optimizer_states"][0])
+    ref_sched.load_state_dict(ckpt["lr_schedulers"][0])
+    gamma = float(sc.schedulers[1].args.gamma)
+    assert abs(ref_opt.param_groups[0]["lr"] - 0.01 * gamma ** 200) < 1e-12
+    assert ref_opt.param_groups[0]["initial_lr"] == 0.01 and ref_opt.param_groups[4]["initial_lr"] == 0.001
+    for p in system.model.parameters():
+        if p.requires_grad and p.numel():
+            p.grad = torch.zeros_like(p)
+    ref_opt.step()                                                   # KeyError here if a param-group key were missing
+    ref_sched.step()
+    assert abs(ref_opt.param_groups[0]["lr"] - 0.01 * gamma ** 201) < 1e-12
+    assert abs(ref_opt.param_groups[4]["lr"] - 0.001 * gamma ** 201) < 1e-13
+    some = next(p for p in system.model.parameters() if p.requires_grad and p.numel())
+    assert float(ref_opt.state[some]["step"]) == 701.0
+
+
+def test_distortion_loss_matches_definition():
+    """flatten_eff_distloss (reference systems/neus.py:163-171 via torch_efficient_distloss) against the O(S^2) definition
+    sum_ij w_i w_j |m_i - m_j| + sum_i w_i^2 interval_i / 3 per ray, averaged over ray_id.max() + 1 rays."""
+    from instant_angelo_b200.losses import flatten_eff_distloss, training_loss
+    g = torch.Generator().manual_seed(0)
+    counts = [5, 0, 1, 9, 3]
+    ray_id = torch.cat([torch.full((c,), i) for i, c in enumerate(counts)])
+    S = ray_id.numel()
+    w = torch.rand(S, generator=g).requires_grad_(True)
+    interval = torch.rand(S, generator=g) * 0.1
+    m = torch.cat([torch.sort(torch.rand(c, generator=g)).values for c in counts])
+    want = 0.0
+    for i in range(len(counts)):
+        sel = ray_id == i
+        wi, mi, ii = w[sel].double(), m[sel].double(), interval[sel].double()
+        want = want + (wi[:, None] * wi[None, :] * (mi[:, None] - mi[None, :]).abs()).sum() + (wi * wi * ii).sum() / 3.0
+    want = want / len(counts)
+    got = flatten_eff_distloss(w, m, interval, ray_id)
+    assert abs(float(got) - float(want)) < 1e-6 * max(1.0, abs(float(want)))
+    (gw,) = torch.autograd.grad(got, w)
+    (gw_ref,) = torch.autograd.grad(want, w)
+    assert torch.allclose(gw, gw_ref.float(), rtol=1e-5, atol=1e-7)
+    assert float(flatten_eff_distloss(w[:0], m[:0], interval[:0], ray_id[:0])) == 0.0

@@ -457,11 +457,12 @@ hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
         const bool hashed = P.hashed[l] != 0;
         float2 *__restrict__ dl = WITH_TABLE ? dtable + P.offset[l] : nullptr;
         const float2 *__restrict__ tl = WITH_INPUT ? table + P.offset[l] : nullptr;
-        uint32_t px = 0xFFFFFFFFu, py = 0, pz = 0;     // pending cell
+        uint32_t px = 0, py = 0, pz = 0;               // pending cell (any uint32 is a legal coordinate: points outside the
+        bool pending = false;                           // unit cube have negative cells, so no in-band sentinel)
         float2 a00 = make_float2(0.f, 0.f), a10 = a00, a01 = a00, a11 = a00;
         float2 v00 = a00, v10 = a00, v01 = a00, v11 = a00;
         auto flush = [&]() {
-            if (WITH_TABLE && px != 0xFFFFFFFFu) {
+            if (WITH_TABLE && pending) {
                 const uint32_t cx = px + xc;
                 if (a00.x != 0.f || a00.y != 0.f) atomicAdd(dl + entry_index(cx, py, pz, res, size, hashed), a00);
                 if (a10.x != 0.f || a10.y != 0.f) atomicAdd(dl + entry_index(cx, py + 1, pz, res, size, hashed), a10);
@@ -475,10 +476,11 @@ hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
             const int p = grp * G + k;
             if (base + p >= n) continue;
             const CellCoords c = locate(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2], scale);
-            const bool same = c.ix == px && c.iy == py && c.iz == pz;
+            const bool same = pending && c.ix == px && c.iy == py && c.iz == pz;
             if (!same) {
                 flush();
                 px = c.ix; py = c.iy; pz = c.iz;
+                pending = true;
                 if (WITH_INPUT) {
                     const uint32_t cx = c.ix + xc;
                     v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));

@@ -37,6 +37,8 @@ class ParamArena:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.grad[off:off + p.numel()].view_as(p)
+                # kernels whose gradient is a scatter (the hash tables) accumulate into this slice directly (ops._grad_sink)
+                p._ia_grad_inplace = True
 
     def zero_grad(self) -> None:
         self.grad.zero_()

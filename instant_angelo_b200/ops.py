@@ -90,6 +90,7 @@ class _HashGridFn(torch.autograd.Function):
              work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
         ctx.save_for_backward(x, table)
         ctx.plan, ctx.active, ctx.group = plan, active_levels, group
+        ctx.sink_param = table if getattr(table, "_ia_grad_inplace", False) else None
         return out
 
     @staticmethod
@@ -98,7 +99,10 @@ class _HashGridFn(torch.autograd.Function):
         need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dy = L.f32c(dy)
         n = x.shape[0]
-        dtable = torch.zeros_like(table) if need_t else None
+        # table gradient: scattered (atomic adds) straight into the parameter's slice of the gradient arena when there is
+        # one -- no table-sized zero-filled temporary and no autograd accumulation pass per hash-grid call
+        sink = _grad_sink(ctx.sink_param) if need_t else None
+        dtable = (sink if sink is not None else torch.zeros_like(table)) if need_t else None
         dx = torch.empty_like(x) if need_x else None
         if n > 0 and (need_t or need_x):
             work = (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_table") if need_t else 0) + \
@@ -112,7 +116,21 @@ class _HashGridFn(torch.autograd.Function):
                      L.ptr(dtable), L.ptr(dx), L.stream(), tag=tag, work=n * work)
         elif need_x:
             dx.zero_()
-        return dx, dtable, None, None, None
+        return dx, (None if sink is not None else dtable), None, None, None
+
+
+def _grad_sink(param) -> Optional[torch.Tensor]:
+    """Called inside a backward: the tensor a hash-grid backward may accumulate d(table) into directly -- `param.grad` when
+    `param` is a leaf that opted in (dp.ParamArena sets `_ia_grad_inplace` on the parameters it re-homes; their .grad is a
+    persistent, zeroed view of the gradient arena).  Autograd then receives None for that input: the adds have already
+    happened.  Not taken under create_graph (grad mode is on inside such a backward), where autograd must see the value;
+    parameters that opt in must be differentiated with .backward(), not torch.autograd.grad()."""
+    if param is None or not param.is_leaf or torch.is_grad_enabled():
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape or g.device != param.device:
+        return None
+    return g
 
 
 def hashgrid_bytes_per_point(plan: L.GridPlan, active_levels: int, which: str = "fwd", param_bytes: int = 4,
@@ -155,6 +173,7 @@ class _HashGridInputGradFn(torch.autograd.Function):
              tag="analytic normal", work=n * hashgrid_bytes_per_point(plan, active_levels, "bwd_input"))
         ctx.save_for_backward(x, table, dy)
         ctx.plan, ctx.active = plan, active_levels
+        ctx.sink_param = table if getattr(table, "_ia_grad_inplace", False) else None
         return dx
 
     @staticmethod
@@ -166,9 +185,12 @@ class _HashGridInputGradFn(torch.autograd.Function):
         n = x.shape[0]
         dtable = ddy = None
         if ctx.needs_input_grad[1]:
-            dtable = torch.zeros_like(table)
+            sink = _grad_sink(ctx.sink_param)
+            dtable = sink if sink is not None else torch.zeros_like(table)
             _run("ia_hashgrid_bwd_input_bwd_table", L.ptr(x), n, L.ptr(v), L.ptr(dy), C.byref(ctx.plan), ctx.active, L.ptr(dtable),
                  L.stream(), work=n * hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_table"))
+            if sink is not None:
+                dtable = None
         if ctx.needs_input_grad[2]:
             ddy = torch.empty_like(dy)
             _run("ia_hashgrid_jvp", L.ptr(x), n, L.ptr(table), L.ptr(v), C.byref(ctx.plan), ctx.active, L.ptr(ddy), L.stream(),

@@ -229,6 +229,115 @@ def test_baseline_configs_run_at_full_table_size(cuda_lib, which):
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
 
 
+def _scale_close(got, want, name, rtol=1e-3, l2=1e-3):
+    """1e-3 relative (north_star), read per tensor: every entry within rtol * (|want| + max|want|) ... i.e. relative to the
+    entry for large entries and to the tensor's scale for small ones (finite-difference quantities divide fp32 rounding noise
+    of the SDF by 2 eps ~ 3e-3, which bounds their ABSOLUTE error), plus an aggregate relative-L2 bound."""
+    g = got.detach().cpu().double()
+    w = want.detach().cpu().double() if isinstance(want, torch.Tensor) else torch.as_tensor(np.asarray(want)).double()
+    assert g.shape == w.shape, f"{name}: shape {tuple(g.shape)} vs {tuple(w.shape)}"
+    if w.numel() == 0:
+        return
+    scale = float(w.abs().max())
+    if scale == 0.0:
+        assert float(g.abs().max()) == 0.0, f"{name}: expected exact zeros"
+        return
+    err = (g - w).abs()
+    tol = rtol * (w.abs() + scale)
+    if bool((err > tol).any()):
+        i = int(torch.argmax(err - tol))
+        raise AssertionError(f"{name}: {int((err > tol).sum())}/{w.numel()} entries out of tolerance; worst flat index {i}: got "
+                             f"{float(g.reshape(-1)[i]):.8g} want {float(w.reshape(-1)[i]):.8g}, max|want| {scale:.3g}")
+    rel_l2 = float((g - w).norm() / w.norm().clamp_min(1e-300))
+    assert rel_l2 < l2, f"{name}: relative L2 error {rel_l2:.3g} >= {l2}"
+
+
+@pytest.mark.parametrize("which,gs", [("sparse", 19000), ("dense_2p21", 19000), ("wreflection", 12000), ("sparse", 7000)])
+@pytest.mark.parametrize("mlp_otype", ["FullyFusedMLP", "VanillaMLP"])
+def test_baseline_configs_full_size_match_oracle(cuda_lib, which, gs, mlp_otype):
+    """BASELINE.json configs[1..3] at their REAL sizes -- 16 levels, 2^19 (2^21 for the dense stress config) entries per
+    level, 512 / 256 / 1024 samples per ray budget, background model on, UniSDF V3 heads for the reflection config -- one
+    training step on 256 rays through the CPU oracle (oracle/model_ref.py) and through the CUDA path with identical weights,
+    occupancy grids and random draws: marched samples bit-exact; rendered outputs, SDF, normals, curvature, every loss term
+    and every parameter gradient (both hash tables included) within 1e-3.  FullyFusedMLP = the tcgen05 kernels bench.py runs."""
+    import copy
+    from instant_angelo_b200 import configs
+    from instant_angelo_b200.config import to_primitive
+    from instant_angelo_b200.losses import training_loss
+    from instant_angelo_b200.synthetic import SphereScene
+    torch.manual_seed(0)
+    if which == "sparse":
+        cfg = configs.neuralangelo_colmap_sparse("finite_difference")
+    elif which == "dense_2p21":
+        cfg = configs.neuralangelo_colmap_dense("finite_difference", log2_hashmap_size=21)
+        cfg.model.num_samples_per_ray = 256
+    else:
+        cfg = configs.neuralangelo_colmap_sparse_wreflection("finite_difference")
+    mcfg = to_primitive(cfg.model)
+    loss_cfg = to_primitive(cfg.system.loss)
+    ref = mr.RefNeuSModel(copy.deepcopy(mcfg))
+    g = torch.Generator().manual_seed(31)
+    with torch.no_grad():          # "trained-like" weights: every table entry and every weight matters
+        for name, p in ref.named_parameters():
+            if name.endswith(".params") and p.numel():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif "weight" in name:
+                p.add_(torch.randn(p.shape, generator=g) * 0.03)
+    ref.train()
+    bgc = torch.rand(3, generator=g)
+    model = build_product(mcfg, {k: v.detach().clone() for k, v in ref.state_dict().items()}, gs, bgc, mlp_otype)
+    # occupancy grids: refreshed by the product from its own SDF / density (all cells, step 0), shared with the oracle
+    model.update_step(0, 0)
+    model.update_step(0, gs, update_occupancy=False)
+    ref.occupancy_grid.binary = model.occupancy_grid.binary.cpu().clone()
+    ref.occupancy_grid_bg.binary = model.occupancy_grid_bg.binary.cpu().clone()
+    ref.update_step(0, gs, update_occupancy=False)
+    ref.background_color = bgc
+    n_rays = 256
+    scene = SphereScene(seed=3)
+    rays, rgb = scene.sample(n_rays, g)
+    pts, nrm, conf = scene.surface_points(n_rays, g)
+    pts[:8] = pts[:8] * 2.5                     # sparse points outside the +-1.5 box, as real COLMAP points are
+    u_fg, u_bg = torch.rand(n_rays, generator=g), torch.rand(n_rays, generator=g)
+    probe = ref.forward_(rays, stratified_u=u_fg, rand_directions=None, stratified_u_bg=u_bg)
+    S = probe["sdf_samples"].shape[0]
+    assert S > 5000, f"only {S} foreground samples marched"
+    rnd = torch.randn(S, 3, generator=g)
+    batch = {"rays": rays, "rgb": rgb, "pts": pts, "pts_normal": nrm, "pts_weights": conf}
+    ref.zero_grad()
+    out_ref = ref.forward_(rays, stratified_u=u_fg, rand_directions=rnd, stratified_u_bg=u_bg)
+    terms_ref = mr.training_loss(ref, out_ref, batch, loss_cfg, gs)
+    terms_ref["loss"].backward()
+
+    cb = {k: v.cuda() for k, v in batch.items()}
+    out = model(cb["rays"], stratified_u=u_fg.cuda(), rand_directions=rnd.cuda(), stratified_u_bg=u_bg.cuda())
+    terms = training_loss(model, out, cb, cfg.system.loss, gs)
+    terms["loss"].backward()
+    torch.cuda.synchronize()
+    for k in ("ray_indices", "ray_indices_bg"):
+        assert np.array_equal(out[k].cpu().numpy(), out_ref[k].numpy()), f"{k} must be bit-exact"
+    assert int(out["num_samples_full"].item()) == int(out_ref["num_samples_full"].item())
+    assert np.array_equal(out["rays_valid_full"].cpu().numpy(), out_ref["rays_valid_full"].numpy())
+    for k in ("points", "intervals", "points_bg", "intervals_bg"):
+        assert_close(out[k], out_ref[k], rtol=1e-6, atol=1e-7, name=k)
+    for k in ("comp_rgb", "comp_normal", "opacity", "depth", "sdf_samples", "sdf_grad_samples", "sdf_laplace_samples", "weights",
+              "comp_rgb_full", "comp_rgb_bg", "opacity_bg", "depth_bg", "weights_bg"):
+        _scale_close(out[k], out_ref[k], k)
+    assert set(terms) == set(terms_ref)
+    for k, v in terms_ref.items():
+        assert_close(terms[k], v.detach(), rtol=1e-3, atol=1e-6, name="loss term " + k)
+    want = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    checked = 0
+    for n, p in model.named_parameters():
+        if n in want:
+            assert p.grad is not None, f"{n} received no gradient"
+            _scale_close(p.grad, want[n], "grad " + n)
+            checked += 1
+    assert checked == len(want) >= 20
+    active = model.geometry.encoding.encoding.active_levels
+    assert active == min(16, 4 + (gs - 5000) // 1000)
+
+
 def test_fused_head_matches_generic_path(cuda_lib, golden_dir, monkeypatch):
     """NeuSModel.forward_ takes the fused SDF-head / colour-input assembly (ops.sdf_head) when geometry and texture
     support it; with IA_NO_FUSED_HEAD it goes through VolumeSDF.forward -> feature -> texture.forward like the

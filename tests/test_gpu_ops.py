@@ -183,6 +183,48 @@ def test_hashgrid_points_outside_unit_cube(cuda_lib, cfg_name):
     assert_close(tg2.grad, tr.grad, rtol=rt, atol=at, name="second-order dtable outside cube")
 
 
+def test_hashgrid_scatters_into_the_gradient_arena(cuda_lib):
+    """Parameters re-homed by dp.ParamArena receive their table gradient by atomic adds straight into the arena slice
+    (ops._grad_sink): same values as autograd's zero-filled temporary + accumulate, added on top of what is already there,
+    for the plain, the grouped and the second-order backward; create_graph falls back to the autograd path."""
+    from instant_angelo_b200 import ops
+    from instant_angelo_b200.dp import ParamArena
+    cfg = GRID_CFGS["small_mixed"]
+    plan = ops.make_grid_plan(**cfg)
+    g = torch.Generator().manual_seed(41)
+    n = 6 * 100
+    x = torch.rand(n, 3, generator=g).cuda()
+    t0 = (torch.randn(plan.n_params, generator=g) * 0.1).cuda()
+    dy = torch.randn(n, 16, generator=g).cuda()
+    dy2 = torch.randn(n, 16, generator=g).cuda()
+    v = torch.randn(n, 3, generator=g).cuda()
+
+    def run(table):
+        ops.hashgrid_encode(x, table, plan).backward(dy)
+        ops.hashgrid_encode(x, table, plan, 5, group=6).backward(dy2)
+        (ops.hashgrid_input_grad(x, table, dy, plan) * v).sum().backward()
+
+    plain = torch.nn.Parameter(t0.clone())
+    run(plain)
+    homed = torch.nn.Parameter(t0.clone())
+    other = torch.nn.Parameter(torch.ones(7, device="cuda"))
+    arena = ParamArena([other, homed])
+    assert homed.grad.data_ptr() == arena.grad[arena.offsets[1]:].data_ptr()
+    arena.grad.fill_(0.25)                      # pre-existing gradient: the kernels must ADD
+    grad_view = homed.grad
+    run(homed)
+    torch.cuda.synchronize()
+    assert homed.grad is grad_view and homed.grad.data_ptr() == arena.grad[arena.offsets[1]:].data_ptr(), "autograd replaced .grad"
+    assert_close(homed.grad - 0.25, plain.grad, rtol=1e-5, atol=1e-6, name="arena-resident table gradient")
+    assert float((arena.grad[:7] - 0.25).abs().max()) == 0.0
+    # create_graph: autograd needs the value -> no in-place accumulation
+    arena.zero_grad()
+    y = ops.hashgrid_input_grad(x, homed, dy, plan)
+    (gt,) = torch.autograd.grad((y * v).sum(), homed, create_graph=True)
+    assert gt is not None and float(arena.grad.abs().max()) == 0.0
+    assert float(gt.abs().max()) > 0.0
+
+
 def test_hashgrid_abi_entry_points_and_errors(cuda_lib):
     """ia_hashgrid_bwd_table / ia_hashgrid_bwd_input agree with the fused ia_hashgrid_bwd; bad args fail loudly."""
     import ctypes as C

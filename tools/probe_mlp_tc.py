@@ -8,13 +8,20 @@ CASES = {"geometry_sdf": (3, 32, 2, 65, True, 1), "texture": (0, 87, 2, 3, False
          "bg_geometry": (3, 32, 1, 8, False, 8), "bg_texture": (0, 24, 2, 3, False, 3), "v3_cam": (0, 80, 2, 3, False, 3)}
 
 
+ZMIN = {}
+
+
 def ref64(a, b, Ws, bs, softplus, nou):
+    """float64 reference; ZMIN['z'] = per row, the smallest |pre-activation| over all hidden units (distance to a ReLU kink)."""
     x = torch.cat([a * 2 - 1, b], 1) if a is not None else b
     h = x.double()
+    zmin = torch.full((h.shape[0],), float("inf"), device=h.device, dtype=torch.float64)
     for i, (w, bias) in enumerate(zip(Ws, bs)):
         h = h @ w.double().t() + bias.double()
         if i < len(Ws) - 1:
+            zmin = torch.minimum(zmin, h.detach().abs().min(dim=1).values)
             h = torch.nn.functional.softplus(h, beta=100) if softplus else torch.relu(h)
+    ZMIN["z"] = zmin
     return h[:, :nou]
 
 
@@ -47,6 +54,14 @@ def main():
                 torch.cuda.synchronize()
                 rel = lambda got, want: float((got.double() - want.double()).abs().max() / want.double().abs().max().clamp_min(1e-30))
                 res[pname] = (rel(y, y64), rel(bg.grad, g64["in1"]), rel(ag.grad, g64["in0"]) if n0 else 0.0, rel(fp.grad, g64["params"]))
+                if res[pname][1] > 1e-3:
+                    # which row carries the d(in1) outlier, and how far its nearest hidden pre-activation is from the ReLU kink
+                    row_err = (bg.grad.double() - g64["in1"].double()).abs().max(dim=1).values
+                    r = int(row_err.argmax())
+                    off = row_err.clone(); off[r] = 0
+                    print(f"    {pname}: worst d(in1) row {r}: min |pre-activation| of that row in float64 = {float(ZMIN['z'][r]):.3e} "
+                          f"(rows within 1e-5 of a kink: {int((ZMIN['z'] < 1e-5).sum())}); max rel err over all OTHER rows = "
+                          f"{float(off.max() / g64['in1'].double().abs().max()):.1e}", flush=True)
             print(f"{name:13s} n={n:6d}  fp32: out {res['fp32'][0]:.1e} din1 {res['fp32'][1]:.1e} din0 {res['fp32'][2]:.1e} dpar {res['fp32'][3]:.1e}"
                   f"   tc: out {res['tc'][0]:.1e} din1 {res['tc'][1]:.1e} din0 {res['tc'][2]:.1e} dpar {res['tc'][3]:.1e}", flush=True)
             worst = max(worst, *res["tc"])

@@ -40,6 +40,7 @@ import torch  # noqa: E402
 GLOBAL_STEP0 = 19000          # all 16 levels active (start_level 4 + (19000-5000)//1000 >= 16), curvature weight 0.5
 RAYS_PER_GPU = 8192           # max_train_num_rays of the config
 OCC_WARMUP_UPDATES = 16
+AR_EVENTS = None              # list of (start, end) CUDA events around the gradient all-reduce while the timed region runs
 
 
 def measured_peaks():
@@ -118,14 +119,63 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    # --config: (BASELINE.json configs[] index, reference YAML, what differs from configs[1])
+    "sparse": (1, "neuralangelo-colmap_sparse.yaml", "2^19-entry tables, 512 (+256 background) samples/ray budget"),
+    "dense21": (2, "neuralangelo-colmap_dense.yaml", "2^21-entry tables (198 MB per grid: not L2 resident), 256 samples/ray, "
+                                                      "dual-colour background head"),
+    "wreflection": (3, "neuralangelo-colmap_sparse-wreflection.yaml", "UniSDF V3 colour heads (two 87->64->64->3 heads + 71->64->1 "
+                                                                      "weight net, SH degree 3), 1024 samples/ray"),
+}
+
+
+def _set_mlp_otype(node, otype):
+    for k in list(node.keys()):
+        v = node[k]
+        if hasattr(v, "keys"):
+            if "n_neurons" in v and "otype" in v:
+                v["otype"] = otype
+            else:
+                _set_mlp_otype(v, otype)
+
+
+def workload_config(args):
+    """The reference configuration `--config` names, with model.geometry.grad_type and the MLP arithmetic of the arm."""
+    from instant_angelo_b200 import configs
+    name = getattr(args, "config", "sparse")
+    grad_type = getattr(args, "grad_type", "finite_difference")
+    if name == "sparse":
+        cfg = configs.neuralangelo_colmap_sparse(grad_type)
+    elif name == "dense21":
+        cfg = configs.neuralangelo_colmap_dense(grad_type, log2_hashmap_size=21)
+        cfg.model.num_samples_per_ray = 256
+    elif name == "wreflection":
+        cfg = configs.neuralangelo_colmap_sparse_wreflection(grad_type)
+    else:
+        raise ValueError(name)
+    _set_mlp_otype(cfg.model, "FullyFusedMLP" if getattr(args, "mlp", "tc") == "tc" else "VanillaMLP")
+    return cfg
+
+
+def workload_description(args, cfg, world):
+    """`config` of the JSON line: static facts of the workload only, identical for the B200 arm and the reference arm."""
+    name = getattr(args, "config", "sparse")
+    idx, yaml, what = WORKLOADS[name]
+    return {"workload": f"{yaml}, grad_type={args.grad_type}, synthetic 512x512 cameras around an analytic sphere "
+                        f"(BASELINE.json configs[{idx}]: {what})",
+            "config_name": name, "rays_per_gpu_per_step": args.rays, "global_rays_per_step": args.rays * world,
+            "num_samples_per_ray": int(cfg.model.num_samples_per_ray), "num_samples_per_ray_bg": int(cfg.model.num_samples_per_ray_bg),
+            "hash_levels_active": 16, "log2_hashmap_size": int(cfg.model.geometry.xyz_encoding_config.log2_hashmap_size),
+            "global_step": GLOBAL_STEP0, "grad_type": args.grad_type,
+            "l2": "per-step working set (hash tables + >1 GB of per-sample activations) exceeds the 126 MB L2; no explicit flush"}
+
+
 def build_b200(args, rank, world, device):
     from instant_angelo_b200 import make
-    from instant_angelo_b200.configs import neuralangelo_colmap_sparse
     from instant_angelo_b200.dp import FusedAdamW, ParamArena
 
     torch.manual_seed(42)
-    cfg = neuralangelo_colmap_sparse(getattr(args, "grad_type", "finite_difference"),
-                                     mlp_otype="FullyFusedMLP" if args.mlp == "tc" else "VanillaMLP")
+    cfg = workload_config(args)
     model = make("neus", cfg.model).to(device)
     model.train()
     for grid in (model.occupancy_grid, model.occupancy_grid_bg):
@@ -176,14 +226,31 @@ def train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
     terms = training_loss(model, out, batch, cfg.system.loss, gs)
     terms["loss"].backward()
     if world > 1:
+        if AR_EVENTS is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         arena.all_reduce()
         var_arena.all_reduce()
+        if AR_EVENTS is not None:
+            b.record()
+            AR_EVENTS.append((a, b))
     opt.step(gs, grad_scale=1.0 / world)
     opt_var.step(gs, grad_scale=1.0 / world)
     return terms["loss"], out
 
 
-def step_roofline(fg_per_ray, bg_per_ray, rays_per_s, peaks, grad_type="finite_difference"):
+def mlp_flops_of(module) -> float:
+    """2*MAC of one forward evaluation of every width-64 network under `module` (unpadded)."""
+    from instant_angelo_b200.network_utils import VanillaMLP
+    total = 0.0
+    for m in module.modules():
+        if isinstance(m, VanillaMLP):
+            total += 2.0 * (m.n_input_dims * 64 + (64 * 64 if m.n_hidden_layers == 2 else 0) + 64 * m.n_output_dims)
+    return total
+
+
+def step_roofline(fg_per_ray, bg_per_ray, rays_per_s, peaks, grad_type="finite_difference", colour_flop=None, bg_flop=None,
+                  tables_l2_resident=True):
     """Whole-step roofline of SURVEY.md section 8d: rays/s <= min(HBM bytes/s / algorithmic bytes per ray,
     tensor FLOP/s / algorithmic FLOP per ray), from the measured samples per ray.  Algorithmic work per sample (fp32
     tables and encodings, 16 levels x 2 features; unpadded 2*MAC of the networks as this path evaluates them: the 12 tap
@@ -194,7 +261,7 @@ def step_roofline(fg_per_ray, bg_per_ray, rays_per_s, peaks, grad_type="finite_d
       background sample: 1 encode (forward + table gradient); 35>64>8 density + 24>64>64>3 colour."""
     enc_f, enc_bt, enc_bi = 1164.0, 1164.0, 1176.0
     mlp = lambda din, nh, nout: 2.0 * (din * 64 + (64 * 64 if nh == 2 else 0) + 64 * nout)
-    centre, tap, colour = mlp(35, 2, 65), mlp(35, 2, 1), mlp(87, 2, 3)
+    centre, tap, colour = mlp(35, 2, 65), mlp(35, 2, 1), (mlp(87, 2, 3) if colour_flop is None else colour_flop)
     if grad_type == "finite_difference":
         fg_bytes = 13 * (enc_f + enc_bt) + 6 * enc_bi
         fg_flop = 3.0 * (centre + 12 * tap + colour)
@@ -202,7 +269,7 @@ def step_roofline(fg_per_ray, bg_per_ray, rays_per_s, peaks, grad_type="finite_d
         fg_bytes = 7 * (enc_f + enc_bt) + 6 * enc_bi + (enc_bi + enc_f + enc_bt)
         fg_flop = 3.0 * (2 * centre + 6 * tap + colour)
     bg_bytes = enc_f + enc_bt
-    bg_flop = 3.0 * (mlp(35, 1, 8) + mlp(24, 2, 3))
+    bg_flop = 3.0 * ((mlp(35, 1, 8) + mlp(24, 2, 3)) if bg_flop is None else bg_flop)
     bytes_per_ray = fg_per_ray * fg_bytes + bg_per_ray * bg_bytes + 24 + 32
     flop_per_ray = fg_per_ray * fg_flop + bg_per_ray * bg_flop
     by_hbm = peaks["hbm_gbs"] * 1e9 / bytes_per_ray
@@ -211,7 +278,8 @@ def step_roofline(fg_per_ray, bg_per_ray, rays_per_s, peaks, grad_type="finite_d
     roof = min(by_hbm, by_tensor)
     return {"bound": bound, "rays_per_s_roofline": roof, "frac": rays_per_s / roof, "algorithmic_bytes_per_ray": bytes_per_ray,
             "algorithmic_flop_per_ray": flop_per_ray, "rays_per_s_by_hbm": by_hbm, "rays_per_s_by_tensor": by_tensor,
-            "note": "per GPU; the 2^19-entry tables are L2 resident, so the HBM line is the SURVEY 8d reporting convention, not a hard bound"}
+            "note": ("per GPU; the 2^19-entry tables are L2 resident, so the HBM line is the SURVEY 8d reporting convention, not a hard bound"
+                     if tables_l2_resident else "per GPU; the 2^21-entry tables (198 MB per grid) do not fit the 126 MB L2: the HBM line binds")}
 
 
 def hashgrid_microbench(device, peaks):
@@ -362,9 +430,12 @@ def run_b200(args):
     gc.disable()         # collector from pausing the launch thread inside the timed regions
     barrier()
     sampler.mark()
+    global AR_EVENTS
+    AR_EVENTS = [] if world > 1 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     counts = []
+    step_events = [e0]
     host_t = [time.perf_counter()]
     for i in range(W, W + K):
         batch, bg = unpack_batch(*dev_batches[i])
@@ -374,8 +445,37 @@ def run_b200(args):
         host_t.append(time.perf_counter())
         if i - W + 1 == PROF_STEPS:
             prof.timing = False
+        if i < W + K - 1:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            step_events.append(ev)
     e1.record()
+    step_events.append(e1)
     barrier()
+    ar_events, AR_EVENTS = AR_EVENTS, None
+    # per-step device times of this rank, then (min, median, max) over steps of the per-step MAX over ranks, the spread
+    # between ranks, and the all-reduce's share: a straggler, unequal sample counts and a real collective cost look different
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(step_events[:-1], step_events[1:])], device=device, dtype=torch.float64)
+    ar_ms = torch.tensor([a.elapsed_time(b) for a, b in (ar_events or [])], device=device, dtype=torch.float64)
+    if world > 1:
+        all_steps = [torch.empty_like(step_ms) for _ in range(world)]
+        dist.all_gather(all_steps, step_ms)
+        all_steps = torch.stack(all_steps)                        # [world, K]
+        all_ar = [torch.empty_like(ar_ms) for _ in range(world)]
+        dist.all_gather(all_ar, ar_ms)
+        all_ar = torch.stack(all_ar)
+    else:
+        all_steps, all_ar = step_ms[None], ar_ms[None]
+    per_step_max = all_steps.max(dim=0).values
+    step_stats = {"min_ms": float(per_step_max.min()), "median_ms": float(per_step_max.median()), "max_ms": float(per_step_max.max()),
+                  "per_rank_mean_ms": [float(v) for v in all_steps.mean(dim=1)],
+                  "note": "device time between consecutive step boundaries (CUDA events); min/median/max over the K timed steps "
+                          "of the per-step maximum over ranks"}
+    if world > 1 and all_ar.numel():
+        step_stats["allreduce_ms"] = {"mean_over_ranks_and_steps": float(all_ar.mean()), "min_rank_mean": float(all_ar.mean(dim=1).min()),
+                                      "max_rank_mean": float(all_ar.mean(dim=1).max()),
+                                      "note": "events around the gradient all-reduce on each rank: includes the wait for the slowest "
+                                              "rank to arrive, so min_rank_mean is the collective's own cost"}
     if rank == 0 and os.environ.get("IA_BENCH_VERBOSE"):
         print("host ms per step:", [round(1e3 * (b - a), 1) for a, b in zip(host_t[:-1], host_t[1:])], file=sys.stderr)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -426,13 +526,14 @@ def run_b200(args):
     dom = max(summary, key=lambda k: summary[k][1])     # the (entry point, shape) with the largest total device time
     calls, ms, work = summary[dom]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
+    tpath = next((p_ for p_ in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json"))
+                  if os.path.exists(p_)), None)
+    if tpath is not None:
         with open(tpath) as f:
             tj = json.load(f)
         if dom in tj:       # DRAM bytes of the ncu capture, rescaled from its row count to this run's average launch
-            flop_per_row = 2.0 * 2 * (35 * 64 + 64 * 64 + 64 * 1)
-            traffic = tj[dom]["dram_bytes_per_row"] * (work / max(calls, 1)) / flop_per_row
+            unit_per_row = tj[dom].get("work_per_row", 2.0 * 2 * (35 * 64 + 64 * 64 + 64 * 1))
+            traffic = tj[dom]["dram_bytes_per_row"] * (work / max(calls, 1)) / unit_per_row
     if dom.startswith("ia_mlp"):
         achieved = work / (ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
@@ -452,34 +553,44 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": work / max(calls, 1)}
 
     try:        # reporting only: never lose the bench line over it
-        step_roof = step_roofline(fg_total / total_rays, (full_total - fg_total) / total_rays, value / world, peaks, args.grad_type)
+        step_roof = step_roofline(fg_total / total_rays, (full_total - fg_total) / total_rays, value / world, peaks, args.grad_type,
+                                  colour_flop=mlp_flops_of(model.texture),
+                                  bg_flop=mlp_flops_of(model.geometry_bg) + mlp_flops_of(model.texture_bg),
+                                  tables_l2_resident=int(cfg.model.geometry.xyz_encoding_config.log2_hashmap_size) <= 19)
     except Exception as e:  # pragma: no cover
         step_roof = {"error": repr(e)}
     cpu = cpu_baseline_leg(cfg, model, args) if world == 1 and not args.no_cpu_baseline else None
+    cpu1 = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu1 = cpu_config1_protocol()
+        except Exception as e:  # pragma: no cover
+            cpu1 = {"error": repr(e)}
     hg = hashgrid_microbench(device, peaks) if world == 1 else None
 
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"neuralangelo-colmap_sparse.yaml, grad_type={args.grad_type}, synthetic 512x512 cameras around an "
-                               "analytic sphere (BASELINE.json configs[1])",
-                   "rays_per_gpu_per_step": n_rays, "global_rays_per_step": n_rays * world, "num_samples_per_ray": 512,
-                   "num_samples_per_ray_bg": 256, "hash_levels_active": 16, "log2_hashmap_size": 19, "global_step": GLOBAL_STEP0,
-                   "mean_fg_samples_per_ray": fg_total / total_rays, "mean_samples_per_ray_full": full_total / total_rays,
-                   "samples_per_s": full_total / (ms_total / 1e3), "hash_point_evals_per_s": ((13 if args.grad_type == "finite_difference" else 7) * fg_total + (full_total - fg_total)) / (ms_total / 1e3),
-                   "mlp": ("tcgen05 tensor cores, 3xf16-split operands + fp32 accumulate (fp32-equivalent, parity-tested at 1e-3); the 65-wide "
-                           "centre evaluation returns the last hidden layer from the same kernel and applies the output layer with "
-                           "the streaming fp32 linear64 kernels") if args.mlp == "tc" else "fp32 FFMA kernels",
-                   "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
-                   "l2": "per-step working set (hash tables 112 MB + >1 GB of per-sample activations) exceeds the 126 MB L2; no explicit flush",
-                   "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)"},
+        "config": workload_description(args, cfg, world),
+        "workload_measured": {
+            "mean_fg_samples_per_ray": fg_total / total_rays, "mean_samples_per_ray_full": full_total / total_rays,
+            "samples_per_s": full_total / (ms_total / 1e3),
+            "hash_point_evals_per_s": ((13 if args.grad_type == "finite_difference" else 7) * fg_total + (full_total - fg_total)) / (ms_total / 1e3)},
+        "implementation": {
+            "mlp": ("tcgen05 tensor cores, 3xf16-split operands + fp32 accumulate (fp32-equivalent, parity-tested at 1e-3); the 65-wide "
+                    "centre evaluation returns the last hidden layer from the same kernel and applies the output layer with "
+                    "the streaming fp32 linear64 kernels") if args.mlp == "tc" else "fp32 FFMA kernels",
+            "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
+            "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)"},
+        "step_ms": step_stats,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
         "gpu_launches": launches,
         "roofline": roof,
         "step_roofline": step_roof,
         "cpu_baseline": cpu,
+        "cpu_baseline_config1": cpu1,
         "kernels": per_kernel,
         "hashgrid_microbench": hg,
     }
@@ -559,6 +670,46 @@ def cpu_baseline_leg(cfg, model, args):
                       f"through the CPU oracle (oracle/model_ref.py, PyTorch fp32, {cores} threads); warm-up run {t1 - t0:.1f} s, timed run {t2 - t1:.1f} s"}
 
 
+def cpu_config1_protocol():
+    """BASELINE.md section 2, CPU row: BASELINE.json configs[0] -- the geometry block of configs/neus-colmap.yaml (16-level
+    2^19 hash grid -> 35->64->13 sphere-initialised MLP, grad_type analytic as shipped) on an analytic-sphere scene,
+    R = 4096 rays x 128 samples/ray, forward + eikonal/SDF loss + backward through the CPU oracle with all host threads;
+    2 warm-ups, median of 5 perf_counter runs."""
+    from instant_angelo_b200 import configs
+    from instant_angelo_b200.config import to_primitive
+    from oracle import model_ref as mr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    geo = mr.RefVolumeSDF(to_primitive(configs.neus_colmap_geometry("analytic")))
+    geo.train()
+    geo.update_step(0, 20000)
+    g = torch.Generator().manual_seed(1)
+    R, S = 4096, 128
+    o = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * 2.0
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(R, 3, generator=g), dim=-1)
+    t = torch.linspace(0.5, 3.5, S)[None, :, None]
+    pts = (o[:, None, :] + d[:, None, :] * t).reshape(-1, 3).clamp(-2.5, 2.5)
+    target = pts.norm(dim=-1) - 0.5                                  # analytic sphere SDF
+
+    def run():
+        geo.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        sdf, grad = geo(pts, with_grad=True, with_feature=False)
+        loss = ((grad.norm(dim=-1) - 1.0) ** 2).mean() + (sdf - target).abs().mean()
+        loss.backward()
+        return time.perf_counter() - t0
+
+    for _ in range(2):
+        run()
+    ts = sorted(run() for _ in range(5))
+    med = ts[2]
+    return {"value": R / med, "unit": "rays/s", "samples_per_s": R * S / med, "hash_point_evals_per_s": R * S / med,
+            "seconds_median_of_5": med, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+            "sample": f"BASELINE.json configs[0]: neus-colmap.yaml geometry block, {R} rays x {S} samples/ray, analytic normals, "
+                      f"forward + backward, CPU oracle, {cores} threads, 2 warm-ups, median of 5"}
+
+
 def run_reference(args):
     """Reference arm: the reference's path cannot run here (tinycudann / nerfacc are CUDA-only third-party packages
     that are not installable offline), so this times the CPU oracle restatement of the SAME workload on all host
@@ -566,10 +717,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from instant_angelo_b200.configs import neuralangelo_colmap_sparse
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = neuralangelo_colmap_sparse(getattr(args, "grad_type", "finite_difference"))
+    cfg = workload_config(args)
     ref = build_oracle(cfg)
     n = args.cpu_rays if args.cpu_rays > 0 else 512
     K, W = args.steps, args.warmup
@@ -586,14 +736,14 @@ def run_reference(args):
         total_samples += ns
     dt = time.perf_counter() - t0
     value = n * K / dt
-    sample = (f"{n} rays per step of neuralangelo-colmap_sparse ({args.grad_type}), {total_samples / max(n * K, 1):.1f} samples/ray, "
-              f"CPU oracle forward + losses + backward, {cores} threads")
+    sample = (f"each step is a bounded sample of {n} rays of the workload ({WORKLOADS[args.config][1]}, {args.grad_type}), "
+              f"{total_samples / max(n * K, 1):.1f} samples/ray, CPU oracle forward + losses + backward, {cores} threads")
     line = {"impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"neuralangelo-colmap_sparse.yaml, grad_type={args.grad_type}, synthetic 512x512 cameras around an "
-                                   "analytic sphere (BASELINE.json configs[1])", "rays_per_step_sample": n,
-                       "note": "reference GPU path (tinycudann + nerfacc) is not installable in this image; CPU oracle port timed instead"},
+            "config": workload_description(args, cfg, args.gpus),
+            "note": "the reference's GPU path (tinycudann + nerfacc) is not installable in this image and the reference has no CPU "
+                    "implementation of its own; this arm times the CPU oracle port (oracle/) of the same workload",
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(), "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -620,10 +770,13 @@ def main():
     os.dup2(2, 1)          # stray prints of libraries go to stderr; stdout carries exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step (BASELINE config 5 sweeps 8192..131072 per GPU)")
+    ap.add_argument("--config", default="sparse", choices=sorted(WORKLOADS),
+                    help="sparse = BASELINE.json configs[1] (the metric's configuration, default); dense21 = configs[2] (2^21-entry "
+                         "tables, 256 samples/ray); wreflection = configs[3] (UniSDF V3 heads)")
     ap.add_argument("--grad-type", dest="grad_type", default="finite_difference", choices=["finite_difference", "analytic"],
                     help="model.geometry.grad_type: finite_difference = the BASELINE north-star workload (default); analytic = the "
                          "reference YAML's shipped value (autograd normals with second-order adjoints + 6 FD curvature taps)")

@@ -145,6 +145,28 @@ int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *
                    const float *params, const float *dout, int32_t n_out_used, int64_t ld_dout,
                    float *din0, float *din1, float *dparams, void *stream);
 
+/* Fused VolumeSDF evaluation: out = network(cat[x*in0_scale+in0_offset, hashgrid(x)]) -- the composition
+ * `self.network(self.encoding(points))` of models/geometry.py:206 (centre), :233 (six finite-difference taps) and :266 (six
+ * curvature taps), i.e. the 13 evaluations per sample of SURVEY.md section 8(b) -- with the hash-grid gather done inside the
+ * tensor-core MLP kernel's operand staging: thread (row, column group) gathers its four levels and writes the fp16 hi/lo
+ * pair straight into the UMMA operand layout, so the [n, L*F] encoding never exists in HBM (neither in forward nor as a
+ * saved tensor: backward re-gathers it).  desc: precision IA_MLP_TC_F16, n_in0 == 3 (the xyz pass-through of
+ * CompositeEncoding, models/network_utils.py:75-78), n_in1 == L*F, L % 4 == 0.  x: [n,3] in the encoder's [0,1] coordinates
+ * (any value is legal: tcnn's wrap-around indexing).  n_out_used as for ia_mlp_fwd (0: last hidden layer [n, 64]). */
+int32_t ia_sdf_taps_fused_fwd(const ia_mlp_desc *desc_host, const ia_grid_plan *plan_host, int32_t active_levels,
+                              const float *x, int64_t n, const float *table, const float *params, int32_t n_out_used,
+                              float *out, int64_t ld_out, void *stream);
+
+/* Backward of the above (two-hidden-layer Softplus networks = VolumeSDF): dparams and dtable are ACCUMULATED; the
+ * position gradient comes in two parts, dx_enc[n,3] through the encoding and dx_direct[n,3] through the xyz pass-through
+ * (each overwritten, each may be NULL; d out / d x = dx_enc + dx_direct).  `group` as for ia_hashgrid_bwd_grouped (6: rows
+ * are the six taps of one sample).  denc_ws: caller-provided [n, L*F] fp32 workspace for the gradient w.r.t. the encoding
+ * on its way from the MLP kernel to the table scatter (required unless dtable and dx_enc are both NULL). */
+int32_t ia_sdf_taps_fused_bwd(const ia_mlp_desc *desc_host, const ia_grid_plan *plan_host, int32_t active_levels,
+                              const float *x, int64_t n, const float *table, const float *params, const float *dout,
+                              int32_t n_out_used, int64_t ld_dout, int32_t group, float *dtable, float *dx_enc,
+                              float *dx_direct, float *dparams, float *denc_ws, void *stream);
+
 /* Flat effective parameter vector of a VanillaMLP (models/network_utils.py:115-134) in one launch: per layer
  * W = g * v / ||v||_row when g != NULL (torch weight_norm, dim=0), else W = v; layout as above (W block, then bias).
  * Backward writes dg[n_out] / dv[n_out, n_in] / db[n_out] (each may be NULL) from dflat; pointers are device pointers,

@@ -84,6 +84,9 @@ SIGNATURES = {
     "ia_mlp_param_count": (_I64, [C.POINTER(MlpDesc)]),
     "ia_mlp_fwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _I32, _P, _I64, _P]),
     "ia_mlp_bwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P]),
+    "ia_sdf_taps_fused_fwd": (_I32, [C.POINTER(MlpDesc), C.POINTER(GridPlan), _I32, _P, _I64, _P, _P, _I32, _P, _I64, _P]),
+    "ia_sdf_taps_fused_bwd": (_I32, [C.POINTER(MlpDesc), C.POINTER(GridPlan), _I32, _P, _I64, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P,
+                                     _P, _P, _P]),
     "ia_weightnorm_flat_fwd": (_I32, [C.POINTER(WnDesc), _P, _P]),
     "ia_weightnorm_flat_bwd": (_I32, [C.POINTER(WnDesc), _P, _P]),
     "ia_linear64_fwd": (_I32, [_P, _I64, _P, _P, _I32, _P, _I64, _P]),

@@ -14,62 +14,13 @@
 #include <stdlib.h>
 
 #include "ia_common.cuh"
+#include "hashgrid_device.cuh"
 
 namespace {
 
 constexpr int HG_TILE = 128;     // points per CTA
 constexpr int HG_THREADS = 256;  // 2 lanes per point
 constexpr int HG_ROW = 34;       // padded floats per tile row (32 + 2): conflict-free float2 stores
-
-struct GridParams {
-    int32_t n_levels;
-    int32_t active;
-    int32_t n_dense;   // leading levels with a dense (un-hashed) index when every later level is hashed; -1 otherwise
-    float scale[IA_MAX_LEVELS];
-    uint32_t res[IA_MAX_LEVELS];
-    uint32_t size[IA_MAX_LEVELS];
-    uint32_t offset[IA_MAX_LEVELS];
-    uint32_t hashed[IA_MAX_LEVELS];
-};
-
-__device__ __forceinline__ uint32_t entry_index(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t res, uint32_t size,
-                                                bool hashed)
-{
-    // tcnn grid_index(): dense stride index, or coherent prime hash when the dense grid would overflow
-    // the level.  Hashed levels have a power-of-two size (2^log2_hashmap_size) => mask; dense levels can
-    // exceed `size` only on the upper boundary (corner == res), by less than one `size`.
-    if (hashed) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);
-    // For x in [0,1]: idx <= res + res^2 + res^3 < 2 * size (size = res^3 rounded up to a multiple of 8), so tcnn's
-    // `idx % size` is one conditional subtraction -- no integer division on the gather path.  Points outside the unit cube
-    // (e.g. un-clamped COLMAP points handed to VolumeSDF by the sparse-point losses) give negative / huge cell
-    // coordinates whose uint32 stride sum wraps anywhere: they take the (never hot) modulo so that the index stays
-    // inside the level exactly as tcnn's does.
-    uint32_t idx = cx + cy * res + cz * res * res;
-    if (idx >= size) {
-        idx -= size;
-        if (idx >= size) idx %= size;
-    }
-    return idx;
-}
-
-struct CellCoords {
-    uint32_t ix, iy, iz;
-    float wx, wy, wz;
-};
-
-__device__ __forceinline__ CellCoords locate(float px, float py, float pz, float scale)
-{
-    CellCoords c;
-    float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
-    float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
-    c.wx = fx - gx;
-    c.wy = fy - gy;
-    c.wz = fz - gz;
-    c.ix = (uint32_t)(int)gx;
-    c.iy = (uint32_t)(int)gy;
-    c.iz = (uint32_t)(int)gz;
-    return c;
-}
 
 __global__ void __launch_bounds__(HG_THREADS)
 hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const GridParams P,
@@ -88,6 +39,7 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         py = __ldg(x + 3 * p + 1);
         pz = __ldg(x + 3 * p + 2);
     }
+    const bool oob = point_outside(px, py, pz);
     // masked (inactive) levels are exact zeros; with every level active each tile entry is overwritten below
     if (P.active < P.n_levels) {
         for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
@@ -105,10 +57,13 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         const float wx = xc ? c.wx : 1.f - c.wx;
         float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
         if (valid) {
-            v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));
-            v10 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed));
-            v01 = __ldg(tl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed));
-            v11 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed));
+            uint32_t i00, i10, i01, i11;
+            if (!oob) corner4<false>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+            else corner4<true>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+            v00 = __ldg(tl + i00);
+            v10 = __ldg(tl + i10);
+            v01 = __ldg(tl + i01);
+            v11 = __ldg(tl + i11);
         }
         const float w00 = wx * (1.f - c.wy) * (1.f - c.wz), w10 = wx * c.wy * (1.f - c.wz);
         const float w01 = wx * (1.f - c.wy) * c.wz, w11 = wx * c.wy * c.wz;
@@ -155,24 +110,20 @@ __device__ __forceinline__ void corner_indices(uint32_t cx, uint32_t iy, uint32_
         i10 = i10 >= size ? i10 - size : i10;
         i01 = i01 >= size ? i01 - size : i01;
         i11 = i11 >= size ? i11 - size : i11;
-        // out-of-cube points (see entry_index): a | b >= max(a, b), so one test covers the four corners; a false positive
-        // only takes the modulo of values that are already in range
-        if ((i00 | i10 | i01 | i11) >= size) {
-            i00 = (b % size); i10 = ((b + res) % size); i01 = ((b + r2) % size); i11 = ((b + res + r2) % size);
-        }
     }
 }
 
 template <bool HASHED>
 __device__ __forceinline__ void fwd_level(int l, const GridParams &P, const float2 *__restrict__ table, float px, float py,
-                                          float pz, uint32_t xc, float *tile_row)
+                                          float pz, uint32_t xc, float *tile_row, bool oob)
 {
     const float scale = P.scale[l];
     const uint32_t off = P.offset[l];
     const CellCoords c = locate(px, py, pz, scale);
     const float wx = xc ? c.wx : 1.f - c.wx;
     uint32_t i00, i10, i01, i11;
-    corner_indices<HASHED>(c.ix + xc, c.iy, c.iz, P.res[l], P.size[l], i00, i10, i01, i11);
+    if (HASHED || !oob) corner_indices<HASHED>(c.ix + xc, c.iy, c.iz, P.res[l], P.size[l], i00, i10, i01, i11);
+    else corner4<true>(c.ix + xc, c.iy, c.iz, P.res[l], P.size[l], false, i00, i10, i01, i11);
     // one 32-bit add per corner (level offset + entry), widened once by the address computation
     const float2 v00 = __ldg(table + (off + i00));
     const float2 v10 = __ldg(table + (off + i10));
@@ -208,10 +159,11 @@ hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const float2 *
     }
     float *tile_row = tile + pl * HG_ROW;
     const int nd = P.n_dense < P.active ? P.n_dense : P.active;
+    const bool oob = point_outside(px, py, pz);
 #pragma unroll 2
-    for (int l = 0; l < nd; ++l) fwd_level<false>(l, P, table, px, py, pz, xc, tile_row);
+    for (int l = 0; l < nd; ++l) fwd_level<false>(l, P, table, px, py, pz, xc, tile_row, oob);
 #pragma unroll 4
-    for (int l = nd; l < P.active; ++l) fwd_level<true>(l, P, table, px, py, pz, xc, tile_row);
+    for (int l = nd; l < P.active; ++l) fwd_level<true>(l, P, table, px, py, pz, xc, tile_row, false);
     __syncthreads();
 
     const int row2 = P.n_levels;  // float2 per output row (F = 2)
@@ -251,6 +203,7 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     }
     __syncthreads();
 
+    const bool oob = point_outside(px, py, pz);
     float gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll 2
     for (int l = 0; l < P.active; ++l) {
@@ -261,10 +214,9 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         const uint32_t cx = c.ix + xc;
         const float wx = xc ? c.wx : 1.f - c.wx;
         const float2 g = *reinterpret_cast<const float2 *>(&tile[pl * HG_ROW + 2 * l]);
-        const uint32_t i00 = entry_index(cx, c.iy, c.iz, res, size, hashed);
-        const uint32_t i10 = entry_index(cx, c.iy + 1, c.iz, res, size, hashed);
-        const uint32_t i01 = entry_index(cx, c.iy, c.iz + 1, res, size, hashed);
-        const uint32_t i11 = entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed);
+        uint32_t i00, i10, i01, i11;
+        if (!oob) corner4<false>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+        else corner4<true>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
         const float uy = 1.f - c.wy, uz = 1.f - c.wz;
         if (WITH_TABLE) {
             if (valid && (g.x != 0.f || g.y != 0.f)) {
@@ -329,6 +281,7 @@ hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     }
     for (int i = tid; i < HG_TILE * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
     __syncthreads();
+    const bool oob = point_outside(px, py, pz);
 #pragma unroll 2
     for (int l = 0; l < P.active; ++l) {
         const float scale = P.scale[l];
@@ -340,10 +293,13 @@ hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         const float wx = xc ? c.wx : 1.f - c.wx;
         float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
         if (valid) {
-            v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));
-            v10 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed));
-            v01 = __ldg(tl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed));
-            v11 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed));
+            uint32_t i00, i10, i01, i11;
+            if (!oob) corner4<false>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+            else corner4<true>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+            v00 = __ldg(tl + i00);
+            v10 = __ldg(tl + i10);
+            v01 = __ldg(tl + i01);
+            v11 = __ldg(tl + i11);
         }
         const float uy = 1.f - c.wy, uz = 1.f - c.wz;
         // coefficients of the four corners of this x side in sum_axis v_axis * d w / d axis
@@ -393,6 +349,7 @@ hashgrid_bwd_input_bwd_table_kernel(const float *__restrict__ x, int64_t n, cons
     }
     __syncthreads();
     if (!valid) return;
+    const bool oob = point_outside(px, py, pz);
     for (int l = 0; l < P.active; ++l) {
         const float2 g = *reinterpret_cast<const float2 *>(&tile[pl * HG_ROW + 2 * l]);
         if (g.x == 0.f && g.y == 0.f) continue;
@@ -409,10 +366,13 @@ hashgrid_bwd_input_bwd_table_kernel(const float *__restrict__ x, int64_t n, cons
         const float c10 = scale * (vx * sgn * c.wy * uz + vy * wx * uz - vz * wx * c.wy);
         const float c01 = scale * (vx * sgn * uy * c.wz - vy * wx * c.wz + vz * wx * uy);
         const float c11 = scale * (vx * sgn * c.wy * c.wz + vy * wx * c.wz + vz * wx * c.wy);
-        atomicAdd(dl + entry_index(cx, c.iy, c.iz, res, size, hashed), make_float2(c00 * g.x, c00 * g.y));
-        atomicAdd(dl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed), make_float2(c10 * g.x, c10 * g.y));
-        atomicAdd(dl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed), make_float2(c01 * g.x, c01 * g.y));
-        atomicAdd(dl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed), make_float2(c11 * g.x, c11 * g.y));
+        uint32_t i00, i10, i01, i11;
+        if (!oob) corner4<false>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+        else corner4<true>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+        atomicAdd(dl + i00, make_float2(c00 * g.x, c00 * g.y));
+        atomicAdd(dl + i10, make_float2(c10 * g.x, c10 * g.y));
+        atomicAdd(dl + i01, make_float2(c01 * g.x, c01 * g.y));
+        atomicAdd(dl + i11, make_float2(c11 * g.x, c11 * g.y));
     }
 }
 
@@ -422,6 +382,76 @@ hashgrid_bwd_input_bwd_table_kernel(const float *__restrict__ x, int64_t n, cons
 // 4*G).  One thread owns (group, x-corner, 4 levels); the taps of the group are walked sequentially and the pending
 // cell is flushed whenever the cell changes.  Same result as hashgrid_bwd_kernel up to fp32 summation order.
 constexpr int HGG_GROUPS = 32;   // groups per CTA (256 threads = 32 groups x 2 x-corners x 4 level slots)
+
+// The level walk of one thread of hashgrid_bwd_grouped_kernel: (group grp, x side xc, levels ls, ls+4, ...).  TOTAL: some tap
+// of the group lies outside the unit cube, cells may lie outside the grid (cold instance, see point_outside()).
+template <int G, bool WITH_TABLE, bool WITH_INPUT, bool TOTAL>
+__device__ __forceinline__ void grouped_walk(const GridParams &P, const float *tile, const float *xs, int grp, int ls, uint32_t xc,
+                                             int n_valid, const float2 *__restrict__ table, float2 *__restrict__ dtable,
+                                             float (&gx)[G], float (&gy)[G], float (&gz)[G])
+{
+    for (int l = ls; l < P.active; l += 4) {
+        const float scale = P.scale[l];
+        const uint32_t res = P.res[l], size = P.size[l];
+        const bool hashed = P.hashed[l] != 0;
+        float2 *__restrict__ dl = WITH_TABLE ? dtable + P.offset[l] : nullptr;
+        const float2 *__restrict__ tl = WITH_INPUT ? table + P.offset[l] : nullptr;
+        uint32_t px = 0, py = 0, pz = 0;               // pending cell (any uint32 is a legal coordinate: points outside the
+        bool pending = false;                           // unit cube have negative cells, so no in-band sentinel)
+        float2 a00 = make_float2(0.f, 0.f), a10 = a00, a01 = a00, a11 = a00;
+        float2 v00 = a00, v10 = a00, v01 = a00, v11 = a00;
+        auto flush = [&]() {
+            if (WITH_TABLE && pending) {
+                uint32_t i00, i10, i01, i11;
+                corner4<TOTAL>(px + xc, py, pz, res, size, hashed, i00, i10, i01, i11);
+                if (a00.x != 0.f || a00.y != 0.f) atomicAdd(dl + i00, a00);
+                if (a10.x != 0.f || a10.y != 0.f) atomicAdd(dl + i10, a10);
+                if (a01.x != 0.f || a01.y != 0.f) atomicAdd(dl + i01, a01);
+                if (a11.x != 0.f || a11.y != 0.f) atomicAdd(dl + i11, a11);
+            }
+            a00 = a10 = a01 = a11 = make_float2(0.f, 0.f);
+        };
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const int p = grp * G + k;
+            if (p >= n_valid) continue;
+            const CellCoords c = locate(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2], scale);
+            const bool same = pending && c.ix == px && c.iy == py && c.iz == pz;
+            if (!same) {
+                flush();
+                px = c.ix; py = c.iy; pz = c.iz;
+                pending = true;
+                if (WITH_INPUT) {
+                    uint32_t i00, i10, i01, i11;
+                    corner4<TOTAL>(c.ix + xc, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
+                    v00 = __ldg(tl + i00);
+                    v10 = __ldg(tl + i10);
+                    v01 = __ldg(tl + i01);
+                    v11 = __ldg(tl + i11);
+                }
+            }
+            const float2 g = *reinterpret_cast<const float2 *>(&tile[p * HG_ROW + 2 * l]);
+            const float wx = xc ? c.wx : 1.f - c.wx;
+            const float uy = 1.f - c.wy, uz = 1.f - c.wz;
+            if (WITH_TABLE) {
+                const float w00 = wx * uy * uz, w10 = wx * c.wy * uz, w01 = wx * uy * c.wz, w11 = wx * c.wy * c.wz;
+                a00.x += w00 * g.x; a00.y += w00 * g.y;
+                a10.x += w10 * g.x; a10.y += w10 * g.y;
+                a01.x += w01 * g.x; a01.y += w01 * g.y;
+                a11.x += w11 * g.x; a11.y += w11 * g.y;
+            }
+            if (WITH_INPUT) {
+                const float d00 = v00.x * g.x + v00.y * g.y, d10 = v10.x * g.x + v10.y * g.y;
+                const float d01 = v01.x * g.x + v01.y * g.y, d11 = v11.x * g.x + v11.y * g.y;
+                const float sx = uy * uz * d00 + c.wy * uz * d10 + uy * c.wz * d01 + c.wy * c.wz * d11;
+                gx[k] += scale * (xc ? sx : -sx);
+                gy[k] += scale * wx * (uz * (d10 - d00) + c.wz * (d11 - d01));
+                gz[k] += scale * wx * (uy * (d01 - d00) + c.wy * (d11 - d10));
+            }
+        }
+        flush();
+    }
+}
 
 template <int G, bool WITH_TABLE, bool WITH_INPUT>
 __global__ void __launch_bounds__(HG_THREADS)
@@ -450,66 +480,15 @@ hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
     float gx[G], gy[G], gz[G];
 #pragma unroll
     for (int k = 0; k < G; ++k) gx[k] = gy[k] = gz[k] = 0.f;
-
-    for (int l = ls; l < P.active; l += 4) {
-        const float scale = P.scale[l];
-        const uint32_t res = P.res[l], size = P.size[l];
-        const bool hashed = P.hashed[l] != 0;
-        float2 *__restrict__ dl = WITH_TABLE ? dtable + P.offset[l] : nullptr;
-        const float2 *__restrict__ tl = WITH_INPUT ? table + P.offset[l] : nullptr;
-        uint32_t px = 0, py = 0, pz = 0;               // pending cell (any uint32 is a legal coordinate: points outside the
-        bool pending = false;                           // unit cube have negative cells, so no in-band sentinel)
-        float2 a00 = make_float2(0.f, 0.f), a10 = a00, a01 = a00, a11 = a00;
-        float2 v00 = a00, v10 = a00, v01 = a00, v11 = a00;
-        auto flush = [&]() {
-            if (WITH_TABLE && pending) {
-                const uint32_t cx = px + xc;
-                if (a00.x != 0.f || a00.y != 0.f) atomicAdd(dl + entry_index(cx, py, pz, res, size, hashed), a00);
-                if (a10.x != 0.f || a10.y != 0.f) atomicAdd(dl + entry_index(cx, py + 1, pz, res, size, hashed), a10);
-                if (a01.x != 0.f || a01.y != 0.f) atomicAdd(dl + entry_index(cx, py, pz + 1, res, size, hashed), a01);
-                if (a11.x != 0.f || a11.y != 0.f) atomicAdd(dl + entry_index(cx, py + 1, pz + 1, res, size, hashed), a11);
-            }
-            a00 = a10 = a01 = a11 = make_float2(0.f, 0.f);
-        };
+    const int n_valid = (int)(n - base < TP ? n - base : TP);
+    bool oob = false;
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
-            const int p = grp * G + k;
-            if (base + p >= n) continue;
-            const CellCoords c = locate(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2], scale);
-            const bool same = pending && c.ix == px && c.iy == py && c.iz == pz;
-            if (!same) {
-                flush();
-                px = c.ix; py = c.iy; pz = c.iz;
-                pending = true;
-                if (WITH_INPUT) {
-                    const uint32_t cx = c.ix + xc;
-                    v00 = __ldg(tl + entry_index(cx, c.iy, c.iz, res, size, hashed));
-                    v10 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz, res, size, hashed));
-                    v01 = __ldg(tl + entry_index(cx, c.iy, c.iz + 1, res, size, hashed));
-                    v11 = __ldg(tl + entry_index(cx, c.iy + 1, c.iz + 1, res, size, hashed));
-                }
-            }
-            const float2 g = *reinterpret_cast<const float2 *>(&tile[p * HG_ROW + 2 * l]);
-            const float wx = xc ? c.wx : 1.f - c.wx;
-            const float uy = 1.f - c.wy, uz = 1.f - c.wz;
-            if (WITH_TABLE) {
-                const float w00 = wx * uy * uz, w10 = wx * c.wy * uz, w01 = wx * uy * c.wz, w11 = wx * c.wy * c.wz;
-                a00.x += w00 * g.x; a00.y += w00 * g.y;
-                a10.x += w10 * g.x; a10.y += w10 * g.y;
-                a01.x += w01 * g.x; a01.y += w01 * g.y;
-                a11.x += w11 * g.x; a11.y += w11 * g.y;
-            }
-            if (WITH_INPUT) {
-                const float d00 = v00.x * g.x + v00.y * g.y, d10 = v10.x * g.x + v10.y * g.y;
-                const float d01 = v01.x * g.x + v01.y * g.y, d11 = v11.x * g.x + v11.y * g.y;
-                const float sx = uy * uz * d00 + c.wy * uz * d10 + uy * c.wz * d01 + c.wy * c.wz * d11;
-                gx[k] += scale * (xc ? sx : -sx);
-                gy[k] += scale * wx * (uz * (d10 - d00) + c.wz * (d11 - d01));
-                gz[k] += scale * wx * (uy * (d01 - d00) + c.wy * (d11 - d10));
-            }
-        }
-        flush();
+    for (int k = 0; k < G; ++k) {
+        const int p = grp * G + k;
+        oob = oob || (p < n_valid && point_outside(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]));
     }
+    if (!oob) grouped_walk<G, WITH_TABLE, WITH_INPUT, false>(P, tile, xs, grp, ls, xc, n_valid, table, dtable, gx, gy, gz);
+    else grouped_walk<G, WITH_TABLE, WITH_INPUT, true>(P, tile, xs, grp, ls, xc, n_valid, table, dtable, gx, gy, gz);
     if (WITH_INPUT) {
         // the 8 lanes (4 level slots x 2 x-corners) of a group hold partial sums: butterfly over the low 3 lane bits
 #pragma unroll
@@ -533,32 +512,6 @@ hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
             }
         }
     }
-}
-
-int fill_params(const ia_grid_plan *plan, int32_t active_levels, GridParams *P)
-{
-    IA_REQUIRE(plan != nullptr, "hashgrid: plan is NULL");
-    IA_REQUIRE(plan->n_features == 2, "hashgrid: only n_features_per_level == 2 is supported (got %d)", plan->n_features);
-    IA_REQUIRE(plan->n_levels >= 1 && plan->n_levels <= 16, "hashgrid: n_levels must be in [1,16] (got %d)", plan->n_levels);
-    IA_REQUIRE(active_levels >= 0 && active_levels <= plan->n_levels, "hashgrid: active_levels %d out of range", active_levels);
-    P->n_levels = plan->n_levels;
-    P->active = active_levels;
-    for (int l = 0; l < plan->n_levels; ++l) {
-        P->scale[l] = plan->scale[l];
-        P->res[l] = plan->res[l];
-        P->size[l] = plan->size[l];
-        P->offset[l] = plan->offset[l];
-        P->hashed[l] = plan->hashed[l];
-        IA_REQUIRE(!plan->hashed[l] || (plan->size[l] & (plan->size[l] - 1)) == 0,
-                   "hashgrid: hashed level %d has a non power-of-two size %u", l, plan->size[l]);
-    }
-    // tcnn's levels grow monotonically, so the dense ones come first; any other plan keeps the generic kernels
-    int nd = 0;
-    while (nd < plan->n_levels && !plan->hashed[nd]) ++nd;
-    P->n_dense = nd;
-    for (int l = nd; l < plan->n_levels; ++l)
-        if (!plan->hashed[l]) P->n_dense = -1;
-    return IA_OK;
 }
 
 }  // namespace

@@ -25,6 +25,7 @@
 #include <algorithm>
 
 #include "ia_common.cuh"
+#include "hashgrid_device.cuh"
 
 namespace {
 
@@ -521,6 +522,42 @@ __device__ __forceinline__ void stage_input(Ctx &c, const TcDims &D, const float
     store_input_regs(c, D, R, c.P.ax_hi, c.P.ax_lo);
 }
 
+// ---- fused encoder: the first-layer input row is cat[hash-grid features (2 per level) | x*s0+o0 | 1 | 0], with the features
+// gathered here instead of read from an [n, L*F] tensor (reference models/geometry.py:206, 233, 266: network(encoding(x))).
+// Thread (r, cg) owns 8-column chunks cg, cg+4, ...: a feature chunk is 4 consecutive levels, so the warps of column group cg
+// gather levels 4cg .. 4cg+3 (n_in1 is a multiple of 8 on this path).  x: [n,3] in the encoder's [0,1] coordinates.
+__device__ __forceinline__ void gather_input_regs(const Ctx &c, const TcDims &D, const GridParams &G, const float2 *__restrict__ table,
+                                                  const float *__restrict__ x, int64_t row_clamped, InRegs &R)
+{
+    const float px = __ldg(x + 3 * row_clamped), py = __ldg(x + 3 * row_clamped + 1), pz = __ldg(x + 3 * row_clamped + 2);
+    const bool oob = point_outside(px, py, pz);
+#pragma unroll
+    for (int q = 0; q < MAX_IN_CHUNKS; ++q) {
+        const int c8 = c.cg + CG * q;
+        if (c8 * 8 >= D.K0) break;
+        if (c8 * 8 < D.n_in1) {
+#pragma unroll
+            for (int lv = 0; lv < 4; ++lv) {
+                const int l = 4 * c8 + lv;
+                float f0 = 0.f, f1 = 0.f;
+                if (l < G.active) {                                                      // masked levels: exact zeros
+                    if (!oob) hg_gather_level<false>(G, table, l, px, py, pz, f0, f1);
+                    else hg_gather_level<true>(G, table, l, px, py, pz, f0, f1);
+                }
+                R.v[q][2 * lv] = f0;
+                R.v[q][2 * lv + 1] = f1;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = 8 * c8 + j - D.n_in1;       // 0..2: xyz, 3: the constant one, then zero padding
+                R.v[q][j] = col == 0 ? fmaf(px, D.s0, D.o0) : col == 1 ? fmaf(py, D.s0, D.o0) : col == 2 ? fmaf(pz, D.s0, D.o0)
+                                                                                               : col == 3 ? 1.0f : 0.f;
+            }
+        }
+    }
+}
+
 // this thread's 16-column share of d(input): internal columns [16ci, 16ci+16) of the dX accumulator -> din1 / din0
 __device__ __forceinline__ void write_dx16(const TcDims &D, int c0, const float (&v)[16], float inv_scale, int64_t row,
                                            float *__restrict__ din0, float *__restrict__ din1)
@@ -577,10 +614,11 @@ __device__ __forceinline__ TcDims specialise(TcDims D)
     return D;
 }
 
-template <int ACT, int NOU, int SPEC = 0>
+template <int ACT, int NOU, int SPEC = 0, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS, (NOU <= 3 ? 2 : 1))
 mlp_tc_fwd_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
-                  const float *__restrict__ params, float *__restrict__ out, int64_t ld_out)
+                  const float *__restrict__ params, float *__restrict__ out, int64_t ld_out, const GridParams G,
+                  const float2 *__restrict__ table)
 {
     const TcDims D = specialise<SPEC>(Din);
     extern __shared__ __align__(1024) char smem[];
@@ -607,7 +645,13 @@ mlp_tc_fwd_kernel(const TcDims Din, const float *__restrict__ in0, const float *
         const int64_t row = tile * ROWS + c.r;
         const bool valid = row < n;
         const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
-        stage_input(c, D, in0, in1, row, valid);
+        if constexpr (FUSED) {
+            InRegs R;
+            gather_input_regs(c, D, G, table, in0, valid ? row : n - 1, R);      // rows past n: a copy of the last row, not written
+            store_input_regs(c, D, R, c.P.ax_hi, c.P.ax_lo);
+        } else {
+            stage_input(c, D, in0, in1, row, valid);
+        }
         run_mma(c, [&]() { issue_gemm(c.tmem + D0_COL, AX, BW0, idesc_fwd, D.K0 / 16); });
         float h[16];
         hidden_cols<ACT>(c, b0, h);
@@ -985,11 +1029,12 @@ __device__ __forceinline__ void drain_dw_at(Ctx &c, uint32_t col0, float *__rest
     }
 }
 
-template <int ACT, int NOU, int SPEC = 0>
+template <int ACT, int NOU, int SPEC = 0, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS_WS, 1)
 mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                        const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
-                       float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams)
+                       float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams, const GridParams G,
+                       const float2 *__restrict__ table)
 {
     const TcDims D = specialise<SPEC>(Din);
     extern __shared__ __align__(1024) char smem[];
@@ -1147,7 +1192,8 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             const int64_t row = tile * ROWS + c.r;
             const bool valid = row < n;
             InRegs R0;
-            load_input_regs(c, D, in0, in1, row, valid, R0);
+            if constexpr (FUSED) gather_input_regs(c, D, G, table, in0, valid ? row : n - 1, R0);
+            else load_input_regs(c, D, in0, in1, row, valid, R0);
             store_input_regs(c, D, R0, ax_hi[0], ax_lo[0]);
             const float m = load_dy(row, valid);
             if (lane == 0) red[warp] = m;
@@ -1166,7 +1212,10 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
         {
             const int64_t ntile0 = tile + gridDim.x;
             const int64_t nrow0 = ntile0 * ROWS + c.r;
-            if (ntile0 < n_tiles) load_input_regs(c, D, in0, in1, nrow0, nrow0 < n, Rn);
+            if (ntile0 < n_tiles) {
+                if constexpr (FUSED) gather_input_regs(c, D, G, table, in0, nrow0 < n ? nrow0 : n - 1, Rn);
+                else load_input_regs(c, D, in0, in1, nrow0, nrow0 < n, Rn);
+            }
         }
         for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
             const int cur = it & 1, nxt = cur ^ 1;
@@ -1246,7 +1295,10 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             {
                 const int64_t n2tile = ntile + gridDim.x;          // prefetch the input rows of tile i+2
                 const int64_t n2row = n2tile * ROWS + c.r;
-                if (n2tile < n_tiles) load_input_regs(c, D, in0, in1, n2row, n2row < n, Rn);
+                if (n2tile < n_tiles) {
+                    if constexpr (FUSED) gather_input_regs(c, D, G, table, in0, n2row < n ? n2row : n - 1, Rn);
+                    else load_input_regs(c, D, in0, in1, n2row, n2row < n, Rn);
+                }
             }
             mma_wait(c, 0);
             if (want_dx) {
@@ -1348,6 +1400,113 @@ int ia_mlp_fwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, 
 int ia_mlp_bwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, const float *, const float *, int32_t, int64_t,
                     float *, float *, float *, void *);
 
+namespace {
+
+int launch_fwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n, const float *params, float *out, int64_t ld_out,
+                  const GridParams *G, const float2 *table, void *stream)
+{
+    const SmemPlan P = make_plan(D, false);
+    IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_fwd: needs %u B of shared memory", P.total);
+    const int64_t n_tiles = ia_ceil_div(n, ROWS);
+    const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));   // TMEM: 2 x 256 columns
+    const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
+    static const GridParams no_grid = {};
+    const GridParams &GP = G ? *G : no_grid;
+#define IA_TC_FWD(ACT, NOU, SPEC, FUSED)                                                                                          \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_fwd_kernel<ACT, NOU, SPEC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        (int)P.total));                                                                           \
+        mlp_tc_fwd_kernel<ACT, NOU, SPEC, FUSED><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, out, \
+                                                                                                     ld_out, GP, table);          \
+    } while (0)
+    const bool sp = D.act == IA_ACT_SOFTPLUS100;
+    const bool geo = sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;     // the SDF network's input shape
+    if (G != nullptr) {
+        // fused encoder: the SDF network (Softplus) and the background density network (ReLU), SDF column / feature mode
+        if (geo && D.nou == 0) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0, 1, true);
+        else if (geo && D.nou == 1) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1, 1, true);
+        else if (sp && D.nou == 0) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0, 0, true);
+        else if (sp && D.nou == 1) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1, 0, true);
+        else if (!sp && D.nou == 1) IA_TC_FWD(IA_ACT_RELU, 1, 0, true);
+        else if (!sp && D.nou <= 8 && D.nou > 3) IA_TC_FWD(IA_ACT_RELU, 8, 0, true);
+        else {
+            ia_set_error("sdf_taps_fused_fwd: unsupported (activation, n_out_used) = (%d, %d)", D.act, D.nou);
+            return IA_ERR_UNSUPPORTED;
+        }
+    }
+    else if (geo && D.nou == 0) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0, 1, false);
+    else if (geo && D.nou == 1) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1, 1, false);
+    else if (D.nou == 0) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0, 0, false); else IA_TC_FWD(IA_ACT_RELU, 0, 0, false); }
+    else if (D.nou == 1) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1, 0, false); else IA_TC_FWD(IA_ACT_RELU, 1, 0, false); }
+    else if (D.nou <= 3) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 3, 0, false); else IA_TC_FWD(IA_ACT_RELU, 3, 0, false); }
+    else { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 8, 0, false); else IA_TC_FWD(IA_ACT_RELU, 8, 0, false); }
+#undef IA_TC_FWD
+    IA_LAUNCH_OK("mlp_tc_fwd_kernel");
+    return IA_OK;
+}
+
+int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n, const float *params, const float *dout,
+                  int64_t ld_dout, float *din0, float *din1, float *dparams, const GridParams *G, const float2 *table, void *stream)
+{
+    // software-pipelined variant when two hidden layers and the doubled X / H1 buffers fit in shared memory
+    const SmemPlan Ppipe = make_plan(D, true, true);
+    const bool pipe = D.nh == 2 && D.K0 <= 64 && Ppipe.total <= 227 * 1024 && (G != nullptr || getenv("IA_TC_NO_PIPE") == nullptr);
+    const SmemPlan P = pipe ? Ppipe : make_plan(D, true);
+    IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_bwd: needs %u B of shared memory", P.total);
+    const int64_t n_tiles = ia_ceil_div(n, ROWS);
+    const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));
+    const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
+    static const GridParams no_grid = {};
+    const GridParams &GP = G ? *G : no_grid;
+#define IA_TC_BWD_PIPE(ACT, NOU, SPEC, FUSED)                                                                                     \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)P.total));                                                                           \
+        mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(                     \
+            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, GP, table);                                               \
+    } while (0)
+#define IA_TC_BWD_GEN(ACT, NOU, SPEC)                                                                                             \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<ACT, NOU, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                        (int)P.total));                                                                           \
+        mlp_tc_bwd_kernel<ACT, NOU, SPEC><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,      \
+                                                                                              ld_dout, din0, din1, dparams);     \
+    } while (0)
+#define IA_TC_BWD(ACT, NOU)                                                                                                       \
+    do {                                                                                                                          \
+        if (pipe) IA_TC_BWD_PIPE(ACT, NOU, 0, false);                                                                             \
+        else IA_TC_BWD_GEN(ACT, NOU, 0);                                                                                          \
+    } while (0)
+    const bool sp = D.act == IA_ACT_SOFTPLUS100;
+    const bool geo = pipe && sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;
+    const bool tex = !pipe && !sp && D.n_in0 == 0 && D.n_in1 == 87 && D.nh == 2 && D.K0 == 96 && D.nou == 3;
+    if (G != nullptr) {
+        // fused encoder (in-kernel re-gather of the first-layer input): two-hidden-layer Softplus networks, i.e. VolumeSDF
+        if (!(pipe && sp && (D.nou == 0 || D.nou == 1))) {
+            ia_set_error("sdf_taps_fused_bwd: unsupported network shape (hidden layers %d, activation %d, n_out_used %d)", D.nh, D.act, D.nou);
+            return IA_ERR_UNSUPPORTED;
+        }
+        if (geo && D.nou == 0) IA_TC_BWD_PIPE(IA_ACT_SOFTPLUS100, 0, 1, true);
+        else if (geo && D.nou == 1) IA_TC_BWD_PIPE(IA_ACT_SOFTPLUS100, 1, 1, true);
+        else if (D.nou == 0) IA_TC_BWD_PIPE(IA_ACT_SOFTPLUS100, 0, 0, true);
+        else IA_TC_BWD_PIPE(IA_ACT_SOFTPLUS100, 1, 0, true);
+    }
+    else if (geo && D.nou == 0) IA_TC_BWD_PIPE(IA_ACT_SOFTPLUS100, 0, 1, false);
+    else if (geo && D.nou == 1) IA_TC_BWD_PIPE(IA_ACT_SOFTPLUS100, 1, 1, false);
+    else if (tex) IA_TC_BWD_GEN(IA_ACT_RELU, 3, 2);
+    else if (D.nou == 0) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_BWD(IA_ACT_RELU, 0); }
+    else if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
+    else if (D.nou <= 3) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_BWD(IA_ACT_RELU, 3); }
+    else { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_BWD(IA_ACT_RELU, 8); }
+#undef IA_TC_BWD
+#undef IA_TC_BWD_GEN
+#undef IA_TC_BWD_PIPE
+    IA_LAUNCH_OK("mlp_tc_bwd_kernel");
+    return IA_OK;
+}
+
+}  // namespace
+
 int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, int64_t n, const float *params,
                   int32_t n_out_used, float *out, int64_t ld_out, void *stream)
 {
@@ -1364,36 +1523,7 @@ int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
     IA_REQUIRE(ld_out >= (n_out_used == 0 ? W : n_out_used), "mlp_tc_fwd: ld_out too small");
     IA_REQUIRE(n_out_used != 0 || (ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0), "mlp_tc_fwd: feature output must be 16-byte aligned");
     if (n == 0) return IA_OK;
-    const SmemPlan P = make_plan(D, false);
-    IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_fwd: needs %u B of shared memory", P.total);
-    const int64_t n_tiles = ia_ceil_div(n, ROWS);
-    const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));   // TMEM: 2 x 256 columns
-    const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
-#define IA_TC_FWD(ACT, NOU)                                                                                                       \
-    do {                                                                                                                          \
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_fwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total)); \
-        mlp_tc_fwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, out, ld_out);    \
-    } while (0)
-    const bool sp = D.act == IA_ACT_SOFTPLUS100;
-    const bool geo = sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;     // the SDF network's input shape
-#define IA_TC_FWD_GEO(NOU)                                                                                                        \
-    do {                                                                                                                          \
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_fwd_kernel<IA_ACT_SOFTPLUS100, NOU, 1>,                                            \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));                              \
-        mlp_tc_fwd_kernel<IA_ACT_SOFTPLUS100, NOU, 1><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, \
-                                                                                                          out, ld_out);          \
-    } while (0)
-    if (geo && D.nou == 0) IA_TC_FWD_GEO(0);
-    else if (geo && D.nou == 1) IA_TC_FWD_GEO(1);
-    else
-    if (D.nou == 0) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_FWD(IA_ACT_RELU, 0); }
-    else if (D.nou == 1) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_FWD(IA_ACT_RELU, 1); }
-    else if (D.nou <= 3) { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_FWD(IA_ACT_RELU, 3); }
-    else { if (sp) IA_TC_FWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_FWD(IA_ACT_RELU, 8); }
-#undef IA_TC_FWD
-#undef IA_TC_FWD_GEO
-    IA_LAUNCH_OK("mlp_tc_fwd_kernel");
-    return IA_OK;
+    return launch_fwd_tc(D, in0, in1, n, params, out, ld_out, nullptr, nullptr, stream);
 }
 
 int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, int64_t n, const float *params,
@@ -1412,51 +1542,68 @@ int ia_mlp_bwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, i
     IA_REQUIRE(ld_dout >= (n_out_used == 0 ? W : n_out_used), "mlp_tc_bwd: ld_dout too small");
     IA_REQUIRE(n_out_used != 0 || (ld_dout % 4 == 0 && ((uintptr_t)dout & 15) == 0), "mlp_tc_bwd: feature gradient must be 16-byte aligned");
     if (n == 0) return IA_OK;
-    // software-pipelined variant when two hidden layers and the doubled X / H1 buffers fit in shared memory
-    const SmemPlan Ppipe = make_plan(D, true, true);
-    const bool pipe = D.nh == 2 && D.K0 <= 64 && Ppipe.total <= 227 * 1024 && getenv("IA_TC_NO_PIPE") == nullptr;
-    const SmemPlan P = pipe ? Ppipe : make_plan(D, true);
-    IA_REQUIRE(P.total <= 227 * 1024, "mlp_tc_bwd: needs %u B of shared memory", P.total);
-    const int64_t n_tiles = ia_ceil_div(n, ROWS);
-    const int per_sm = std::max(1, std::min(2, (int)((227u * 1024u) / (P.total + 1024u))));
-    const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
-#define IA_TC_BWD(ACT, NOU)                                                                                                       \
-    do {                                                                                                                          \
-        if (pipe) {                                                                                                               \
-            IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                            (int)P.total));                                                                       \
-            mlp_tc_bwd_pipe_kernel<ACT, NOU><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,   \
-                                                                                                 ld_dout, din0, din1, dparams);  \
-        } else {                                                                                                                  \
-            IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<ACT, NOU>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                            (int)P.total));                                                                       \
-            mlp_tc_bwd_kernel<ACT, NOU><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout,        \
-                                                                                            ld_dout, din0, din1, dparams);       \
-        }                                                                                                                         \
-    } while (0)
-    const bool sp = D.act == IA_ACT_SOFTPLUS100;
-    const bool geo = pipe && sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;
-#define IA_TC_BWD_GEO(NOU)                                                                                                        \
-    do {                                                                                                                          \
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<IA_ACT_SOFTPLUS100, NOU, 1>,                                       \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));                              \
-        mlp_tc_bwd_pipe_kernel<IA_ACT_SOFTPLUS100, NOU, 1><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(               \
-            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams);                                                          \
-    } while (0)
-    const bool tex = !pipe && !sp && D.n_in0 == 0 && D.n_in1 == 87 && D.nh == 2 && D.K0 == 96 && D.nou == 3;
-    if (geo && D.nou == 0) IA_TC_BWD_GEO(0);
-    else if (geo && D.nou == 1) IA_TC_BWD_GEO(1);
-    else if (tex) {
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<IA_ACT_RELU, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));
-        mlp_tc_bwd_kernel<IA_ACT_RELU, 3, 2><<<blocks, THREADS, P.total, (cudaStream_t)stream>>>(D, in0, in1, n, params, dout, ld_dout,
-                                                                                                 din0, din1, dparams);
-    } else
-    if (D.nou == 0) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 0); else IA_TC_BWD(IA_ACT_RELU, 0); }
-    else if (D.nou == 1) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 1); else IA_TC_BWD(IA_ACT_RELU, 1); }
-    else if (D.nou <= 3) { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 3); else IA_TC_BWD(IA_ACT_RELU, 3); }
-    else { if (sp) IA_TC_BWD(IA_ACT_SOFTPLUS100, 8); else IA_TC_BWD(IA_ACT_RELU, 8); }
-#undef IA_TC_BWD
-#undef IA_TC_BWD_GEO
-    IA_LAUNCH_OK("mlp_tc_bwd_kernel");
+    return launch_bwd_tc(D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, nullptr, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused VolumeSDF evaluation (include/ia_b200.h: ia_sdf_taps_fused_fwd / _bwd)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+int fused_dims(const ia_mlp_desc *desc, const ia_grid_plan *plan, int32_t active_levels, int32_t n_out_used, TcDims *D, GridParams *G)
+{
+    IA_REQUIRE(desc != nullptr && plan != nullptr, "sdf_taps_fused: NULL descriptor");
+    IA_REQUIRE(desc->precision == IA_MLP_TC_F16, "sdf_taps_fused: the fused kernels are the tensor-core (IA_MLP_TC_F16) path");
+    int rc = fill_params(plan, active_levels, G);
+    if (rc) return rc;
+    IA_REQUIRE(desc->n_in0 == 3, "sdf_taps_fused: the network input must be cat[xyz pass-through (3), encoding] (n_in0 = %d)", desc->n_in0);
+    IA_REQUIRE(desc->n_in1 == plan->n_levels * plan->n_features, "sdf_taps_fused: n_in1 = %d but the grid has %d x %d features",
+               desc->n_in1, plan->n_levels, plan->n_features);
+    IA_REQUIRE(plan->n_levels % 4 == 0, "sdf_taps_fused: n_levels must be a multiple of 4 (got %d)", plan->n_levels);
+    if (n_out_used > MAX_OUT) {
+        ia_set_error("sdf_taps_fused: more than %d fused outputs; request n_out_used = 0 (last hidden layer)", MAX_OUT);
+        return IA_ERR_UNSUPPORTED;
+    }
+    return make_dims(desc, n_out_used, D);
+}
+}  // namespace
+
+extern "C" int32_t ia_sdf_taps_fused_fwd(const ia_mlp_desc *desc, const ia_grid_plan *plan, int32_t active_levels, const float *x,
+                                         int64_t n, const float *table, const float *params, int32_t n_out_used, float *out,
+                                         int64_t ld_out, void *stream)
+{
+    TcDims D;
+    GridParams G;
+    int rc = fused_dims(desc, plan, active_levels, n_out_used, &D, &G);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && table && params && out)), "sdf_taps_fused_fwd: NULL pointer");
+    IA_REQUIRE(ld_out >= (n_out_used == 0 ? W : n_out_used), "sdf_taps_fused_fwd: ld_out too small");
+    IA_REQUIRE(n_out_used != 0 || (ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0), "sdf_taps_fused_fwd: feature output must be 16-byte aligned");
+    if (n == 0) return IA_OK;
+    return launch_fwd_tc(D, x, nullptr, n, params, out, ld_out, &G, reinterpret_cast<const float2 *>(table), stream);
+}
+
+extern "C" int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const float *table, const float *dy,
+                                           const ia_grid_plan *plan, int32_t active_levels, int32_t group, float *dtable,
+                                           float *dx, void *stream);
+
+extern "C" int32_t ia_sdf_taps_fused_bwd(const ia_mlp_desc *desc, const ia_grid_plan *plan, int32_t active_levels, const float *x,
+                                         int64_t n, const float *table, const float *params, const float *dout, int32_t n_out_used,
+                                         int64_t ld_dout, int32_t group, float *dtable, float *dx_enc, float *dx_direct,
+                                         float *dparams, float *denc_ws, void *stream)
+{
+    TcDims D;
+    GridParams G;
+    int rc = fused_dims(desc, plan, active_levels, n_out_used, &D, &G);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && table && params && dout)), "sdf_taps_fused_bwd: NULL pointer");
+    IA_REQUIRE(ld_dout >= (n_out_used == 0 ? W : n_out_used), "sdf_taps_fused_bwd: ld_dout too small");
+    IA_REQUIRE(n_out_used != 0 || (ld_dout % 4 == 0 && ((uintptr_t)dout & 15) == 0), "sdf_taps_fused_bwd: feature gradient must be 16-byte aligned");
+    IA_REQUIRE((dtable == nullptr && dx_enc == nullptr) || denc_ws != nullptr,
+               "sdf_taps_fused_bwd: table / position gradients need the [n, L*F] workspace");
+    if (n == 0) return IA_OK;
+    rc = launch_bwd_tc(D, x, nullptr, n, params, dout, ld_dout, dx_direct, denc_ws, dparams, &G, reinterpret_cast<const float2 *>(table), stream);
+    if (rc) return rc;
+    if (dtable != nullptr || dx_enc != nullptr)
+        return ia_hashgrid_bwd_grouped(x, n, table, denc_ws, plan, active_levels, group, dtable, dx_enc, stream);
     return IA_OK;
 }

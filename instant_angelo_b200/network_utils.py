@@ -294,6 +294,20 @@ def fused_encode_mlp(encoding: CompositeEncoding, network: VanillaMLP, x: torch.
     models/network_utils.py:77: the include_xyz columns are produced inside the MLP kernel."""
     x = x.reshape(-1, encoding.n_input_dims)
     inner = encoding.encoding
+    # fused path: the gather runs inside the tensor-core MLP kernel, the [N, L*F] encoding never exists (ops.sdf_fused)
+    grid, active = None, None
+    if isinstance(inner, ProgressiveBandHashGrid):
+        grid, active = inner.encoding, inner.active_levels
+    elif isinstance(inner, Encoding) and inner.otype == "HashGrid":
+        grid, active = inner, inner.plan.n_levels
+    if grid is not None and encoding.include_xyz and x.is_cuda and network.output_activation_name in (None, "none", "None"):
+        desc = ops.make_mlp_desc(3, grid.n_output_dims, network.n_hidden_layers, network.n_output_dims, network.hidden_act,
+                                 encoding.xyz_scale, encoding.xyz_offset, network.precision)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or grid.params.requires_grad)
+        if ops.sdf_fused_supported(desc, grid.plan, needs_grad):
+            if flat is None:
+                flat = network.flat_params()
+            return ops.sdf_fused(x, grid.params, flat, desc, grid.plan, active, n_out_used, group)
     enc = inner(x, group=group) if group > 1 and isinstance(inner, (ProgressiveBandHashGrid, Encoding)) and \
         getattr(inner, "otype", "HashGrid") == "HashGrid" else inner(x)
     if encoding.include_xyz:

@@ -6,6 +6,7 @@ Each function documents the reference call it stands in for.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -16,7 +17,8 @@ from . import _lib as L
 _LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_grouped": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
              "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_linear64_fwd": 1, "ia_linear64_bwd": 2, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
              "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
-             "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0}
+             "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0,
+             "ia_sdf_taps_fused_fwd": 1, "ia_sdf_taps_fused_bwd": 2}
 
 
 class Profiler:
@@ -119,13 +121,16 @@ class _HashGridFn(torch.autograd.Function):
         return dx, (None if sink is not None else dtable), None, None, None
 
 
+_NO_GRAD_SINK = os.environ.get("IA_NO_GRAD_SINK") is not None     # A/B switch (tools / bench experiments)
+
+
 def _grad_sink(param) -> Optional[torch.Tensor]:
     """Called inside a backward: the tensor a hash-grid backward may accumulate d(table) into directly -- `param.grad` when
     `param` is a leaf that opted in (dp.ParamArena sets `_ia_grad_inplace` on the parameters it re-homes; their .grad is a
     persistent, zeroed view of the gradient arena).  Autograd then receives None for that input: the adds have already
     happened.  Not taken under create_graph (grad mode is on inside such a backward), where autograd must see the value;
     parameters that opt in must be differentiated with .backward(), not torch.autograd.grad()."""
-    if param is None or not param.is_leaf or torch.is_grad_enabled():
+    if param is None or not param.is_leaf or torch.is_grad_enabled() or _NO_GRAD_SINK:
         return None
     g = param.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape or g.device != param.device:
@@ -279,6 +284,78 @@ class _MLPFn(torch.autograd.Function):
                  dout.shape[1], L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou),
                  tag=f"{ctx.desc.n_in0 + ctx.desc.n_in1}>{ctx.nou}/{ctx.desc.n_out}")
         return d0, d1, dp, None, None
+
+
+class _SdfFusedFn(torch.autograd.Function):
+    """network(cat[x*s+o, hashgrid(x)]) in one kernel (ia_sdf_taps_fused_fwd / _bwd): reference models/geometry.py:206, 233, 266
+    `self.network(self.encoding(points))` without the [N, L*F] encoding in HBM."""
+
+    @staticmethod
+    def forward(ctx, x, table, params, desc, plan, active_levels, n_out_used, group):
+        L.require_cuda(x, table, params)
+        x, params = L.f32c(x), L.f32c(params)
+        n = x.shape[0]
+        width_out = n_out_used if n_out_used > 0 else desc.width
+        out = torch.empty(n, width_out, device=x.device, dtype=torch.float32)
+        _run("ia_sdf_taps_fused_fwd", C.byref(desc), C.byref(plan), active_levels, L.ptr(x), n, L.ptr(table), L.ptr(params), n_out_used,
+             L.ptr(out), width_out, L.stream(), tag=f"{desc.n_in0 + desc.n_in1}>{n_out_used}/{desc.n_out}",
+             work=n * mlp_flops_per_row(desc, n_out_used))
+        ctx.save_for_backward(x, table, params)
+        ctx.cfg = (desc, plan, active_levels, n_out_used, group)
+        ctx.sink_param = table if getattr(table, "_ia_grad_inplace", False) else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, table, params = ctx.saved_tensors
+        desc, plan, active, nou, group = ctx.cfg
+        dout = L.f32c(dout)
+        n = x.shape[0]
+        need_x, need_t, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        sink = _grad_sink(ctx.sink_param) if need_t else None
+        dtable = (sink if sink is not None else torch.zeros_like(table)) if need_t else None
+        dp = torch.zeros_like(params) if need_p else None
+        dx_enc = torch.empty_like(x) if need_x else None
+        dx_dir = torch.empty_like(x) if need_x else None
+        if n > 0:
+            ws = torch.empty(n, desc.n_in1, device=x.device, dtype=torch.float32) if (need_t or need_x) else None
+            tag = f"{desc.n_in0 + desc.n_in1}>{nou}/{desc.n_out}" + (f",g{group}" if group > 1 else "") + (",dx" if need_x else "")
+            _run("ia_sdf_taps_fused_bwd", C.byref(desc), C.byref(plan), active, L.ptr(x), n, L.ptr(table), L.ptr(params), L.ptr(dout), nou,
+                 dout.shape[1], group, L.ptr(dtable), L.ptr(dx_enc), L.ptr(dx_dir), L.ptr(dp), L.ptr(ws), L.stream(), tag=tag,
+                 work=2 * n * mlp_flops_per_row(desc, nou))
+            dx = dx_enc + dx_dir if need_x else None
+        else:
+            dx = torch.zeros_like(x) if need_x else None
+        return dx, (None if sink is not None else dtable), dp, None, None, None, None, None
+
+
+def sdf_fused(x: torch.Tensor, table: torch.Tensor, params: torch.Tensor, desc: L.MlpDesc, plan: L.GridPlan,
+              active_levels: Optional[int] = None, n_out_used: Optional[int] = None, group: int = 1) -> torch.Tensor:
+    """Fused hash-grid encode + tensor-core MLP on cat[x*scale+offset, encode(x)]; x [N,3] in the encoder's [0,1] coordinates.
+    n_out_used as for mlp_apply (None: all outputs; wide output layers go through the last hidden layer + linear64)."""
+    if active_levels is None:
+        active_levels = plan.n_levels
+    nou = int(desc.n_out if n_out_used is None else n_out_used)
+    if nou > 8:
+        h = _SdfFusedFn.apply(x, table, params, desc, plan, int(active_levels), 0, int(group))
+        n_hidden = params.numel() - (desc.n_out * desc.width + desc.n_out)
+        w_last = params[n_hidden:n_hidden + desc.n_out * desc.width].view(desc.n_out, desc.width)
+        b_last = params[n_hidden + desc.n_out * desc.width:]
+        return linear64(h, w_last[:nou], b_last[:nou])
+    return _SdfFusedFn.apply(x, table, params, desc, plan, int(active_levels), nou, int(group))
+
+
+def sdf_fused_supported(desc: L.MlpDesc, plan: L.GridPlan, needs_grad: bool) -> bool:
+    """Shapes the fused kernels cover (anything else takes hashgrid_encode + mlp_apply)."""
+    if os.environ.get("IA_NO_FUSED_ENCODER") is not None:
+        return False
+    ok = (desc.precision == L.IA_MLP_TC_F16 and desc.n_in0 == 3 and plan.n_features == 2 and plan.n_levels % 4 == 0
+          and desc.n_in1 == plan.n_levels * plan.n_features and desc.width == 64)
+    if not ok:
+        return False
+    if desc.hidden_act == L.IA_ACT_SOFTPLUS100:
+        return desc.n_hidden_layers == 2 or not needs_grad
+    return False
 
 
 class _WeightNormFlatFn(torch.autograd.Function):

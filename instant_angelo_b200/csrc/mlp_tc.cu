@@ -368,24 +368,27 @@ __device__ __forceinline__ void mma_issue(Ctx &c, F issue)
         }
     }
 }
-// Warp-specialised form (pipelined backward): THREADS epilogue threads + one issuer warp.  The epilogue threads publish
-// their operand writes and meet the issuer warp on named barrier 1; lane 0 of the issuer warp then issues the GEMMs while
-// every epilogue warp (including warp 0) is free to run ahead into its mbarrier waits.
-#ifndef IA_TC_WS
-#define IA_TC_WS 0     // measured on B200: the 17th warp caps ptxas at 96 registers (5 warps on one SM sub-partition) and the
-                       // spills cost more than the freed issue slots give back (0.654 vs 0.60 ms per 2^20 rows), so off
-#endif
-constexpr int THREADS_WS = THREADS + (IA_TC_WS ? 32 : 0);
-template <typename F>
+// Warp-specialised form (pipelined backward, WS = true): THREADS epilogue threads + one more warpgroup whose first warp only
+// issues MMAs.  The epilogue threads publish their operand writes and meet the issuer warp on named barrier 1; one lane of
+// the issuer warp then issues the GEMMs while every epilogue warp (including warp 0) is free to run ahead into its mbarrier
+// waits.  Without it (WS = false) the issuing lane of warp 0 is blocked for ~3.7 k cycles per tile by the back-pressure of the
+// tensor pipe's queue, and the other 15 warps wait for warp 0 at the next barrier (ncu: stall_barrier 15 %).
+// Registers: a 17th warp alone capped ptxas at 96 registers for everyone (round 1: the spills cost more than the issuer
+// bought).  Here the issuer's whole warpgroup drops to 32 registers with setmaxnreg.dec and the four epilogue warpgroups
+// raise theirs to 112 with setmaxnreg.inc: 128 * 32 + 512 * 112 = 640 * 96, exactly the allocation of a 640-thread CTA.
+constexpr int WS_EXTRA = 128;                   // setmaxnreg works on whole warpgroups
+constexpr int WS_BAR = THREADS + 32;            // named barrier 1: the epilogue threads and the issuer warp
+template <bool WS, typename F>
 __device__ __forceinline__ void ws_publish(Ctx &c, F issue)
 {
     const bool timing = threadIdx.x == 0 && g_tc_timing_on;
     const long long t0 = timing ? clock64() : 0;
     fence_async_smem();
     tc_fence_before();
-    asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS_WS) : "memory");
+    if (WS) asm volatile("bar.sync 1, %0;\n" ::"n"(WS_BAR) : "memory");
+    else asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS) : "memory");
     if (timing) atomicAdd(&g_tc_cycles[0], (unsigned long long)(clock64() - t0));
-    if (!IA_TC_WS && threadIdx.x < 32) {      // no issuer warp: one lane of warp 0 issues, then warp 0 joins the epilogue
+    if (!WS && threadIdx.x < 32) {      // no issuer warp: one lane of warp 0 issues, then warp 0 joins the epilogue
         if (elect_one()) {
             const long long t1 = timing ? clock64() : 0;
             tc_fence_after();
@@ -398,7 +401,7 @@ __device__ __forceinline__ void ws_publish(Ctx &c, F issue)
 template <typename F>
 __device__ __forceinline__ void ws_issue(Ctx &c, F issue)
 {
-    asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS_WS) : "memory");
+    asm volatile("bar.sync 1, %0;\n" ::"n"(WS_BAR) : "memory");
     if (elect_one()) {
         const bool timing = g_tc_timing_on;
         const long long t1 = timing ? clock64() : 0;
@@ -1029,8 +1032,8 @@ __device__ __forceinline__ void drain_dw_at(Ctx &c, uint32_t col0, float *__rest
     }
 }
 
-template <int ACT, int NOU, int SPEC = 0, bool FUSED = false>
-__global__ void __launch_bounds__(THREADS_WS, 1)
+template <int ACT, int NOU, int SPEC = 0, bool FUSED = false, bool WS = false>
+__global__ void __launch_bounds__(THREADS + (WS ? WS_EXTRA : 0), 1)
 mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                        const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
                        float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams, const GridParams G,
@@ -1174,8 +1177,11 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
         if (has_next) issue_gemm(c.tmem + PD0, s_buf[nxt][1], BW1, idesc_fwd, W / 16);
         mbar_commit(c, 2);
     };
-    if (IA_TC_WS && warp == THREADS / 32) {
-        // ---- optional issuer warp: mirrors the tile loop of the epilogue threads, one named-barrier rendezvous per batch
+    if (WS && warp >= THREADS / 32) {
+        // ---- the issuer's warpgroup (every warp of a warpgroup executes the same setmaxnreg, see ws_publish); its first warp
+        // mirrors the tile loop of the epilogue threads, one named-barrier rendezvous per batch; the other three idle
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+        if (warp == THREADS / 32) {
         if (tile < n_tiles) {
             ws_issue(c, issue_first0);
             ws_issue(c, issue_first1);
@@ -1186,7 +1192,9 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             ws_issue(c, [&]() { issue_phase1(cur, nxt, has_next); });
             ws_issue(c, [&]() { issue_phase2(cur, nxt, has_next); });
         }
+        }
     } else {
+        if constexpr (WS) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
         if (tile < n_tiles) {
             // ---- prologue: forward of the first tile, its incoming gradient and scale
             const int64_t row = tile * ROWS + c.r;
@@ -1197,7 +1205,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             store_input_regs(c, D, R0, ax_hi[0], ax_lo[0]);
             const float m = load_dy(row, valid);
             if (lane == 0) red[warp] = m;
-            ws_publish(c, issue_first0);
+            ws_publish<WS>(c, issue_first0);
             mma_wait(c, 0);
             tile_scale(scale, inv_scale);
             float h[16];
@@ -1205,7 +1213,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
     #pragma unroll
             for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + b0[16 * c.cg + j]);
             store_cols16(c, ah_hi[0], ah_lo[0], h);
-            ws_publish(c, issue_first1);
+            ws_publish<WS>(c, issue_first1);
         }
         // input rows of the NEXT tile are fetched into registers one phase ahead of their use (global latency hidden)
         InRegs Rn;
@@ -1257,7 +1265,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
                 store_cols16(c, c.P.dz_hi, c.P.dz_lo, dz);
             }
             // ---- phase 1
-                ws_publish(c, [&]() { issue_phase1(cur, nxt, has_next); });
+                ws_publish<WS>(c, [&]() { issue_phase1(cur, nxt, has_next); });
             const float inv_cur = inv_scale;
             // incoming gradient of the next tile: its per-warp maxima are published by the phase-2 barrier
             // (dy / dhf of tile i are dead from here on: the output-layer work of tile i happened in stage A)
@@ -1290,7 +1298,7 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             }
             drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
             // ---- phase 2
-            ws_publish(c, [&]() { issue_phase2(cur, nxt, has_next); });
+            ws_publish<WS>(c, [&]() { issue_phase2(cur, nxt, has_next); });
             tile_scale(scale, inv_scale);       // scale of tile i+1 (red was written before the barrier)
             {
                 const int64_t n2tile = ntile + gridDim.x;          // prefetch the input rows of tile i+2
@@ -1458,12 +1466,19 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
     const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
     static const GridParams no_grid = {};
     const GridParams &GP = G ? *G : no_grid;
+#define IA_TC_BWD_PIPE_WS(ACT, NOU, SPEC, FUSED, WS)                                                                              \
+    do {                                                                                                                          \
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED, WS>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));                              \
+        mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED, WS><<<blocks, THREADS + (WS ? WS_EXTRA : 0), P.total, (cudaStream_t)stream>>>( \
+            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, GP, table);                                               \
+    } while (0)
+    // the SDF-network shapes (SPEC = 1) have the warp-specialised variant; IA_TC_WS=0 selects the single-role kernel (A/B runs)
+    static const bool ws_env = getenv("IA_TC_WS") == nullptr || atoi(getenv("IA_TC_WS")) != 0;
 #define IA_TC_BWD_PIPE(ACT, NOU, SPEC, FUSED)                                                                                     \
     do {                                                                                                                          \
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)P.total));                                                                           \
-        mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED><<<blocks, THREADS_WS, P.total, (cudaStream_t)stream>>>(                     \
-            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, GP, table);                                               \
+        if (SPEC == 1 && ws_env) IA_TC_BWD_PIPE_WS(ACT, NOU, SPEC, FUSED, (SPEC == 1));                                           \
+        else IA_TC_BWD_PIPE_WS(ACT, NOU, SPEC, FUSED, false);                                                                     \
     } while (0)
 #define IA_TC_BWD_GEN(ACT, NOU, SPEC)                                                                                             \
     do {                                                                                                                          \
@@ -1501,6 +1516,7 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
 #undef IA_TC_BWD
 #undef IA_TC_BWD_GEN
 #undef IA_TC_BWD_PIPE
+#undef IA_TC_BWD_PIPE_WS
     IA_LAUNCH_OK("mlp_tc_bwd_kernel");
     return IA_OK;
 }

@@ -300,7 +300,8 @@ def fused_encode_mlp(encoding: CompositeEncoding, network: VanillaMLP, x: torch.
         grid, active = inner.encoding, inner.active_levels
     elif isinstance(inner, Encoding) and inner.otype == "HashGrid":
         grid, active = inner, inner.plan.n_levels
-    if grid is not None and encoding.include_xyz and x.is_cuda and network.output_activation_name in (None, "none", "None"):
+    if grid is not None and ops.sdf_fused_enabled() and encoding.include_xyz and x.is_cuda and \
+            network.output_activation_name in (None, "none", "None"):
         desc = ops.make_mlp_desc(3, grid.n_output_dims, network.n_hidden_layers, network.n_output_dims, network.hidden_act,
                                  encoding.xyz_scale, encoding.xyz_offset, network.precision)
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or grid.params.requires_grad)

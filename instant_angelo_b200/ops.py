@@ -345,10 +345,17 @@ def sdf_fused(x: torch.Tensor, table: torch.Tensor, params: torch.Tensor, desc: 
     return _SdfFusedFn.apply(x, table, params, desc, plan, int(active_levels), nou, int(group))
 
 
+def sdf_fused_enabled() -> bool:
+    """Whether the module layer (network_utils.fused_encode_mlp) routes VolumeSDF through the fused kernels.  Measured on a
+    B200 (profiles/r02_fused_encoder_ab.md): the in-kernel gather trades 256 B/row of HBM traffic for gather latency inside a
+    kernel that runs 16-32 warps per SM instead of the stand-alone encoder's 64, and the step is 12 % SLOWER with it (30.7 vs
+    27.2 ms), so the default stays the unfused pair; IA_FUSED_ENCODER=1 selects the fused path (e.g. when the [N, L*F]
+    activations do not fit)."""
+    return os.environ.get("IA_FUSED_ENCODER", "0") not in ("0", "")
+
+
 def sdf_fused_supported(desc: L.MlpDesc, plan: L.GridPlan, needs_grad: bool) -> bool:
     """Shapes the fused kernels cover (anything else takes hashgrid_encode + mlp_apply)."""
-    if os.environ.get("IA_NO_FUSED_ENCODER") is not None:
-        return False
     ok = (desc.precision == L.IA_MLP_TC_F16 and desc.n_in0 == 3 and plan.n_features == 2 and plan.n_levels % 4 == 0
           and desc.n_in1 == plan.n_levels * plan.n_features and desc.width == 64)
     if not ok:

@@ -531,20 +531,15 @@ def test_sdf_taps_fused_matches_unfused_and_oracle(cuda_lib, cfg_name, active, n
         Wr = [w.clone().double().requires_grad_(True) for w in Ws]
         br = [b.clone().double().requires_grad_(True) for b in bs]
         h = torch.cat([xr * 2 - 1, tc.hashgrid_forward(xr, tr, plan_ref, act)], dim=1).double()
-        for i in range(3):
-            h = h @ Wr[i].t() + br[i]
-            if i < 2:
-                if i == 1 and nou == 0:
-                    h = torch.nn.functional.softplus(h, beta=100)
-                    break
-                h = torch.nn.functional.softplus(h, beta=100)
-        y_r = h if nou == 0 else h[:, :nou]
+        h = torch.nn.functional.softplus(h @ Wr[0].t() + br[0], beta=100)
+        h = torch.nn.functional.softplus(h @ Wr[1].t() + br[1], beta=100)
+        y_r = h if nou == 0 else (h @ Wr[2].t() + br[2])[:, :nou]
         y_r.backward(go.double())
-        _assert_rel(y_f, y_r, "out (fused vs oracle)")
-        _assert_rel(dt_f, tr.grad, "d table (fused vs oracle)")
-        _assert_rel(dx_f[x.ge(0).all(1) & x.le(1).all(1)], xr.grad[x.ge(0).all(1) & x.le(1).all(1)], "d x (fused vs oracle)")
+        _assert_rel(y_f.cpu(), y_r, "out (fused vs oracle)")
+        _assert_rel(dt_f.cpu(), tr.grad, "d table (fused vs oracle)")
+        _assert_rel(dx_f.cpu(), xr.grad, "d x (fused vs oracle)")
         want_p = torch.cat([(t.grad if t.grad is not None else torch.zeros_like(t)).reshape(-1) for pair in zip(Wr, br) for t in pair])
-        _assert_rel(dp_f, want_p, "d params (fused vs oracle)")
+        _assert_rel(dp_f.cpu(), want_p, "d params (fused vs oracle)")
 
 
 def test_sdf_taps_fused_abi_errors(cuda_lib):

@@ -385,7 +385,11 @@ __device__ __forceinline__ void ws_publish(Ctx &c, F issue)
     const long long t0 = timing ? clock64() : 0;
     fence_async_smem();
     tc_fence_before();
-    if (WS) asm volatile("bar.sync 1, %0;\n" ::"n"(WS_BAR) : "memory");
+    // WS: the epilogue threads only ARRIVE -- the issuer warp is the one that waits (ws_issue).  They meet no CTA-wide barrier
+    // in the tile loop at all: everything they wait for afterwards is an mbarrier of an MMA group that the issuer commits
+    // after this rendezvous, so a slow warp (or the issuer, blocked on the tensor pipe's queue) delays nobody but itself,
+    // and the generations of the named barrier cannot mix.
+    if (WS) asm volatile("bar.arrive 1, %0;\n" ::"n"(WS_BAR) : "memory");
     else asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS) : "memory");
     if (timing) atomicAdd(&g_tc_cycles[0], (unsigned long long)(clock64() - t0));
     if (!WS && threadIdx.x < 32) {      // no issuer warp: one lane of warp 0 issues, then warp 0 joins the epilogue
@@ -495,10 +499,12 @@ __device__ __forceinline__ void load_input_regs(const Ctx &c, const TcDims &D, c
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int col = 8 * c8 + j;
+                // in0 columns are kept RAW here (scale / offset are applied by store_input_regs): the caller prefetches these
+                // registers one pipeline phase ahead, and arithmetic on a just-loaded value would stall the warp on it
                 float v = 0.f;
                 if (valid) {
                     if (col < D.n_in1) v = __ldg(in1 + row * D.n_in1 + col);
-                    else if (col < D.din) v = fmaf(__ldg(in0 + row * D.n_in0 + (col - D.n_in1)), D.s0, D.o0);
+                    else if (col < D.din) v = __ldg(in0 + row * D.n_in0 + (col - D.n_in1));
                     else if (col == D.din) v = 1.0f;
                 }
                 R.v[q][j] = v;
@@ -507,13 +513,26 @@ __device__ __forceinline__ void load_input_regs(const Ctx &c, const TcDims &D, c
     }
 }
 
-__device__ __forceinline__ void store_input_regs(Ctx &c, const TcDims &D, const InRegs &R, uint32_t hi_off, uint32_t lo_off)
+// RAW_IN0: R holds the in0 columns as loaded (load_input_regs); valid == false rows are all zeros and stay so
+template <bool RAW_IN0 = true>
+__device__ __forceinline__ void store_input_regs(Ctx &c, const TcDims &D, const InRegs &R, uint32_t hi_off, uint32_t lo_off,
+                                                 bool valid = true)
 {
 #pragma unroll
     for (int q = 0; q < MAX_IN_CHUNKS; ++q) {
         const int c8 = c.cg + CG * q;
         if (c8 * 8 >= D.K0) break;
-        store_split8(c.smem + hi_off, c.smem + lo_off, (uint32_t)c8 * 2048u + (uint32_t)c.r * 16u, R.v[q]);
+        if (RAW_IN0 && c8 * 8 + 8 > D.n_in1 && c8 * 8 < D.din) {
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = 8 * c8 + j;
+                a[j] = (valid && col >= D.n_in1 && col < D.din) ? fmaf(R.v[q][j], D.s0, D.o0) : R.v[q][j];
+            }
+            store_split8(c.smem + hi_off, c.smem + lo_off, (uint32_t)c8 * 2048u + (uint32_t)c.r * 16u, a);
+        } else {
+            store_split8(c.smem + hi_off, c.smem + lo_off, (uint32_t)c8 * 2048u + (uint32_t)c.r * 16u, R.v[q]);
+        }
     }
 }
 
@@ -522,7 +541,7 @@ __device__ __forceinline__ void stage_input(Ctx &c, const TcDims &D, const float
 {
     InRegs R;
     load_input_regs(c, D, in0, in1, row, valid, R);
-    store_input_regs(c, D, R, c.P.ax_hi, c.P.ax_lo);
+    store_input_regs<true>(c, D, R, c.P.ax_hi, c.P.ax_lo, valid);
 }
 
 // ---- fused encoder: the first-layer input row is cat[hash-grid features (2 per level) | x*s0+o0 | 1 | 0], with the features
@@ -651,7 +670,7 @@ mlp_tc_fwd_kernel(const TcDims Din, const float *__restrict__ in0, const float *
         if constexpr (FUSED) {
             InRegs R;
             gather_input_regs(c, D, G, table, in0, valid ? row : n - 1, R);      // rows past n: a copy of the last row, not written
-            store_input_regs(c, D, R, c.P.ax_hi, c.P.ax_lo);
+            store_input_regs<false>(c, D, R, c.P.ax_hi, c.P.ax_lo);
         } else {
             stage_input(c, D, in0, in1, row, valid);
         }
@@ -1037,7 +1056,7 @@ __global__ void __launch_bounds__(THREADS + (WS ? WS_EXTRA : 0), 1)
 mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
                        const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
                        float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams, const GridParams G,
-                       const float2 *__restrict__ table)
+                       const float2 *__restrict__ table, const float *__restrict__ gmax)
 {
     const TcDims D = specialise<SPEC>(Din);
     extern __shared__ __align__(1024) char smem[];
@@ -1114,42 +1133,33 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
 #pragma unroll
         for (int j = 0; j < 16; ++j) gwl[o][j] = 0.f;
 
-    // loads this thread's share of the incoming gradient of a tile and returns the tile-local max |.| of this thread
+    // One power-of-two gradient scale for the whole launch, from max |dout| (absmax pre-pass, *gmax) and the output layer's
+    // weights: |dZ| <= 2^6 everywhere, fp16 normal range with 2^10 headroom for dH.  (A per-tile scale tracked each tile's own
+    // maximum, but needed a CTA-wide exchange of the per-warp maxima in every tile; rows whose gradient is 2^-20 of the
+    // launch maximum lose relative precision, their absolute error stays at 2^-24 of the maximum.)
+    float scale, inv_scale;
+    pow2_scale(fmaxf(__ldg(gmax), 1e-30f) * wmax, scale, inv_scale);
+    // this thread's share of the incoming gradient of a tile: plain loads, consumed in stage A of that tile (a whole pipeline
+    // phase later, so the warp never waits on them)
     float dy[NO];
     float dhf[NOU == 0 ? 16 : 1];
-    auto load_dy = [&](int64_t row, bool valid) -> float {
-        float m = 0.f;
+    auto load_dy = [&](int64_t row, bool valid) {
         if constexpr (NOU == 0) {
             const float4 *src = reinterpret_cast<const float4 *>(dout + row * ld_dout + 16 * c.cg);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 t = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 dhf[4 * q] = t.x; dhf[4 * q + 1] = t.y; dhf[4 * q + 2] = t.z; dhf[4 * q + 3] = t.w;
-                m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
             }
             dy[0] = 0.f;
         } else {
 #pragma unroll
-            for (int o = 0; o < NOU; ++o) {
-                dy[o] = (valid && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
-                m = fmaxf(m, fabsf(dy[o]));
-                if (c.cg == 0) gbl[o] += dy[o];
-            }
+            for (int o = 0; o < NOU; ++o) dy[o] = (valid && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        return m;
-    };
-    auto tile_scale = [&](float &scale, float &inv_scale) {   // call after the barrier that published `red`
-        float m = 0.f;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) m = fmaxf(m, red[w]);
-        pow2_scale(m * wmax, scale, inv_scale);
     };
 
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;
     int64_t tile = blockIdx.x;
-    float scale = 1.f, inv_scale = 1.f;
     // GEMM batches, in the order the tensor pipe executes them (issue order); each group commits to its own mbarrier
     auto issue_first0 = [&]() {
         issue_gemm(c.tmem + PD0, s_buf[0][0], BW0, idesc_fwd, D.K0 / 16);
@@ -1202,12 +1212,10 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             InRegs R0;
             if constexpr (FUSED) gather_input_regs(c, D, G, table, in0, valid ? row : n - 1, R0);
             else load_input_regs(c, D, in0, in1, row, valid, R0);
-            store_input_regs(c, D, R0, ax_hi[0], ax_lo[0]);
-            const float m = load_dy(row, valid);
-            if (lane == 0) red[warp] = m;
+            store_input_regs<!FUSED>(c, D, R0, ax_hi[0], ax_lo[0], valid);
+            load_dy(row, valid);
             ws_publish<WS>(c, issue_first0);
             mma_wait(c, 0);
-            tile_scale(scale, inv_scale);
             float h[16];
             tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
     #pragma unroll
@@ -1235,10 +1243,16 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             const bool nvalid = has_next && nrow < n;
             const long long tile_t0 = (threadIdx.x == 0 && g_tc_timing_on) ? clock64() : 0;
             // ---- A: D0 = pre-activations of the last hidden layer of tile i; next tile's input goes to the other buffer
-            if (has_next) store_input_regs(c, D, Rn, ax_hi[nxt], ax_lo[nxt]);
+            if (has_next) store_input_regs<!FUSED>(c, D, Rn, ax_hi[nxt], ax_lo[nxt], nvalid);
             mma_wait(c, 2);      // second forward GEMM of tile i (issued by the prologue / the previous phase 2)
             {
                 float h[16], dz[16];
+                if constexpr (NOU > 0) {
+                    if (c.cg == 0) {
+#pragma unroll
+                        for (int o = 0; o < NOU; ++o) gbl[o] += dy[o];
+                    }
+                }
                 tmem_ld16(c.tmem + c.lane_addr + PD0 + 16u * c.cg, h);
     #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -1267,11 +1281,9 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             // ---- phase 1
                 ws_publish<WS>(c, [&]() { issue_phase1(cur, nxt, has_next); });
             const float inv_cur = inv_scale;
-            // incoming gradient of the next tile: its per-warp maxima are published by the phase-2 barrier
-            // (dy / dhf of tile i are dead from here on: the output-layer work of tile i happened in stage A)
-            float mnext = 0.f;
-            if (has_next) mnext = load_dy(nrow, nvalid);
-            if (lane == 0) red[warp] = mnext;
+            // incoming gradient of the next tile (dy / dhf of tile i are dead from here on: the output-layer work of tile i
+            // happened in stage A)
+            if (has_next) load_dy(nrow, nvalid);
             mma_wait(c, 0);
             if (has_next) {
                 // H1(i+1) = act(L0(i+1) + b0)
@@ -1299,7 +1311,6 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
             drain_dw_at(c, PD1, dw1, 72, ld1, inv_cur);
             // ---- phase 2
             ws_publish<WS>(c, [&]() { issue_phase2(cur, nxt, has_next); });
-            tile_scale(scale, inv_scale);       // scale of tile i+1 (red was written before the barrier)
             {
                 const int64_t n2tile = ntile + gridDim.x;          // prefetch the input rows of tile i+2
                 const int64_t n2row = n2tile * ROWS + c.r;
@@ -1453,6 +1464,36 @@ int launch_fwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
     return IA_OK;
 }
 
+// max |dout| over the rows of a launch (device scalar, one of 64 rotating slots so that launches in flight on different
+// streams do not share one): the pipelined backward's launch-wide gradient scale
+__global__ void absmax_kernel(const float *__restrict__ v, int64_t n, int cols, int64_t ld, float *__restrict__ out)
+{
+    float m = 0.f;
+    const int64_t total = n * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        m = fmaxf(m, fabsf(__ldg(v + r * ld + (i - r * cols))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));     // m >= 0: int order == float order
+}
+
+int absmax_slot(const float *dout, int64_t n, int cols, int64_t ld, cudaStream_t stream, float **slot_out)
+{
+    static float *slots = nullptr;
+    static unsigned next = 0;
+    if (slots == nullptr) IA_CUDA_OK(cudaMalloc(&slots, 64 * sizeof(float)));
+    float *slot = slots + (next++ & 63u);
+    IA_CUDA_OK(cudaMemsetAsync(slot, 0, sizeof(float), stream));
+    const int64_t total = n * cols;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(total, 256 * 8), (int64_t)ia_sm_count() * 8);
+    absmax_kernel<<<std::max(1u, blocks), 256, 0, stream>>>(dout, n, cols, ld, slot);
+    IA_LAUNCH_OK("absmax_kernel");
+    *slot_out = slot;
+    return IA_OK;
+}
+
 int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n, const float *params, const float *dout,
                   int64_t ld_dout, float *din0, float *din1, float *dparams, const GridParams *G, const float2 *table, void *stream)
 {
@@ -1466,12 +1507,17 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
     const unsigned blocks = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ia_sm_count() * per_sm);
     static const GridParams no_grid = {};
     const GridParams &GP = G ? *G : no_grid;
+    float *gmax = nullptr;
+    if (pipe) {
+        int rc = absmax_slot(dout, n, D.nou == 0 ? W : D.nou, ld_dout, (cudaStream_t)stream, &gmax);
+        if (rc) return rc;
+    }
 #define IA_TC_BWD_PIPE_WS(ACT, NOU, SPEC, FUSED, WS)                                                                              \
     do {                                                                                                                          \
         IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED, WS>,                                        \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.total));                              \
         mlp_tc_bwd_pipe_kernel<ACT, NOU, SPEC, FUSED, WS><<<blocks, THREADS + (WS ? WS_EXTRA : 0), P.total, (cudaStream_t)stream>>>( \
-            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, GP, table);                                               \
+            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, GP, table, gmax);                                         \
     } while (0)
     // the SDF-network shapes (SPEC = 1) have the warp-specialised variant; IA_TC_WS=0 selects the single-role kernel (A/B runs)
     static const bool ws_env = getenv("IA_TC_WS") == nullptr || atoi(getenv("IA_TC_WS")) != 0;

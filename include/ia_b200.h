@@ -65,6 +65,13 @@ int32_t ia_hashgrid_plan(int32_t n_levels, int32_t n_features, int32_t log2_hash
 int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table, const ia_grid_plan *plan_host,
                         int32_t active_levels, float *out, void *stream);
 
+/* As ia_hashgrid_fwd, for rows that arrive in groups of `group` consecutive, spatially close points (the six finite-difference
+ * taps of one sample, models/geometry.py:221-233): one thread walks the taps of a (group, level) and re-fetches the cell's
+ * corners only when a tap leaves the cell.  Same values as ia_hashgrid_fwd up to fp32 rounding of the interpolation
+ * (lerp chain instead of weight products).  group == 6 and n_levels <= 16 are specialised; anything else uses ia_hashgrid_fwd. */
+int32_t ia_hashgrid_fwd_grouped(const float *x, int64_t n, const float *table, const ia_grid_plan *plan_host,
+                                int32_t active_levels, int32_t group, float *out, void *stream);
+
 /* dtable[...] += scatter(w_corner * dy[n, L*F]) (accumulates; caller zeroes).  Autograd of the call at
  * models/network_utils.py:57 w.r.t. Encoding.params. */
 int32_t ia_hashgrid_bwd_table(const float *x, int64_t n, const float *dy, const ia_grid_plan *plan_host,

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ia_device_arch": (_I32, []),
     "ia_hashgrid_plan": (_I32, [_I32, _I32, _I32, _I32, _F, C.POINTER(GridPlan)]),
     "ia_hashgrid_fwd": (_I32, [_P, _I64, _P, C.POINTER(GridPlan), _I32, _P, _P]),
+    "ia_hashgrid_fwd_grouped": (_I32, [_P, _I64, _P, C.POINTER(GridPlan), _I32, _I32, _P, _P]),
     "ia_hashgrid_bwd_table": (_I32, [_P, _I64, _P, C.POINTER(GridPlan), _I32, _P, _P]),
     "ia_hashgrid_bwd_input": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _P, _P]),
     "ia_hashgrid_bwd": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _P, _P, _P]),

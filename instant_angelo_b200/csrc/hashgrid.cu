@@ -174,6 +174,83 @@ hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const float2 *
     }
 }
 
+// Forward for points that arrive in GROUPS of G consecutive, spatially close rows (the six finite-difference taps of one
+// sample, reference models/geometry.py:221-233).  One thread owns (group, level) and walks the G taps: the eight corner
+// values of the current cell stay in registers and are re-fetched only when a tap leaves that cell.  At the coarse levels all
+// six taps share one cell (one gather instead of six), at the finest ones each tap has its own; over the 16 levels of the
+// training grids that is ~3 gathers per (group, level) instead of 6, and the cell is located once per tap by one thread instead
+// of twice by a lane pair.  The kernel this replaces for tap rows (hashgrid_fwd_split_kernel) is instruction-issue bound there
+// (ncu: issue slots 91 % busy), so instructions are what counts.  A warp holds 16 consecutive groups x 2 levels: the dense /
+// hashed branch is warp-uniform and neighbouring lanes (neighbouring samples of a ray) read neighbouring cells.
+constexpr int HFG_GROUPS = 16;   // groups per CTA: 256 threads = 16 groups x 16 level slots
+
+template <int G, bool TOTAL>
+__device__ __forceinline__ void fwd_group_walk(const GridParams &P, int l, const float2 *__restrict__ table, const float *xs, int grp,
+                                               int n_valid, float *tile)
+{
+    const float scale = P.scale[l];
+    const float2 *__restrict__ tl = table + P.offset[l];
+    uint32_t px = 0, py = 0, pz = 0;
+    bool have = false;
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const int p = grp * G + k;
+        if (p >= n_valid) break;
+        const CellCoords c = locate(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2], scale);
+        if (!(have && c.ix == px && c.iy == py && c.iz == pz)) {
+            uint32_t i[8];
+            hg_corner8<TOTAL>(P, l, c, i);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldg(tl + i[q]);
+            px = c.ix; py = c.iy; pz = c.iz;
+            have = true;
+        }
+        const float x00a = fmaf(c.wx, v[1].x - v[0].x, v[0].x), x00b = fmaf(c.wx, v[1].y - v[0].y, v[0].y);
+        const float x10a = fmaf(c.wx, v[3].x - v[2].x, v[2].x), x10b = fmaf(c.wx, v[3].y - v[2].y, v[2].y);
+        const float x01a = fmaf(c.wx, v[5].x - v[4].x, v[4].x), x01b = fmaf(c.wx, v[5].y - v[4].y, v[4].y);
+        const float x11a = fmaf(c.wx, v[7].x - v[6].x, v[6].x), x11b = fmaf(c.wx, v[7].y - v[6].y, v[6].y);
+        const float y0a = fmaf(c.wy, x10a - x00a, x00a), y0b = fmaf(c.wy, x10b - x00b, x00b);
+        const float y1a = fmaf(c.wy, x11a - x01a, x01a), y1b = fmaf(c.wy, x11b - x01b, x01b);
+        *reinterpret_cast<float2 *>(&tile[p * HG_ROW + 2 * l]) = make_float2(fmaf(c.wz, y1a - y0a, y0a), fmaf(c.wz, y1b - y0b, y0b));
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(HG_THREADS)
+hashgrid_fwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const GridParams P,
+                            float *__restrict__ out)
+{
+    constexpr int TP = HFG_GROUPS * G;   // points per CTA
+    __shared__ float tile[TP * HG_ROW];
+    __shared__ float xs[TP * 3];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * TP;
+    for (int i = tid; i < TP * 3; i += HG_THREADS) xs[i] = (base * 3 + i < n * 3) ? __ldg(x + base * 3 + i) : 0.f;
+    if (P.active < P.n_levels)        // masked (inactive) levels are exact zeros
+        for (int i = tid; i < TP * HG_ROW; i += HG_THREADS) tile[i] = 0.f;
+    __syncthreads();
+    const int grp = tid & (HFG_GROUPS - 1), l = tid >> 4;
+    const int n_valid = (int)(n - base < TP ? n - base : TP);
+    if (l < P.active && grp * G < n_valid) {
+        bool oob = false;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const int p = grp * G + k;
+            oob = oob || (p < n_valid && point_outside(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]));
+        }
+        if (!oob) fwd_group_walk<G, false>(P, l, table, xs, grp, n_valid, tile);
+        else fwd_group_walk<G, true>(P, l, table, xs, grp, n_valid, tile);
+    }
+    __syncthreads();
+    const int row2 = P.n_levels;  // float2 per output row (F = 2)
+    float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
+    for (int i = tid; i < TP * row2; i += HG_THREADS) {
+        const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;
+        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+    }
+}
+
 template <bool WITH_TABLE, bool WITH_INPUT>
 __global__ void __launch_bounds__(HG_THREADS)
 hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table,
@@ -587,6 +664,21 @@ extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table
         hashgrid_fwd_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
             x, n, reinterpret_cast<const float2 *>(table), P, out);
     IA_LAUNCH_OK("hashgrid_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_fwd_grouped(const float *x, int64_t n, const float *table, const ia_grid_plan *plan,
+                                           int32_t active_levels, int32_t group, float *out, void *stream)
+{
+    if (group != 6 || (plan && plan->n_levels > 16)) return ia_hashgrid_fwd(x, n, table, plan, active_levels, out, stream);
+    GridParams P;
+    int rc = fill_params(plan, active_levels, &P);
+    if (rc) return rc;
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && table && out)), "hashgrid_fwd_grouped: NULL pointer with n=%lld", (long long)n);
+    if (n == 0) return IA_OK;
+    hashgrid_fwd_grouped_kernel<6><<<(unsigned)ia_ceil_div(n, HFG_GROUPS * 6), HG_THREADS, 0, (cudaStream_t)stream>>>(
+        x, n, reinterpret_cast<const float2 *>(table), P, out);
+    IA_LAUNCH_OK("hashgrid_fwd_grouped_kernel");
     return IA_OK;
 }
 

@@ -1520,7 +1520,9 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
             D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, GP, table, gmax);                                         \
     } while (0)
     // the SDF-network shapes (SPEC = 1) have the warp-specialised variant; IA_TC_WS=0 selects the single-role kernel (A/B runs)
-    static const bool ws_env = getenv("IA_TC_WS") == nullptr || atoi(getenv("IA_TC_WS")) != 0;
+    // Measured on a B200 (profiles/r02_ab_tc_bwd_ws.md): 6.73 ms/step with the issuer warpgroup against 6.44 ms without, so the
+    // single-role kernel stays the default; IA_TC_WS=1 selects the warp-specialised one.
+    static const bool ws_env = getenv("IA_TC_WS") != nullptr && atoi(getenv("IA_TC_WS")) != 0;
 #define IA_TC_BWD_PIPE(ACT, NOU, SPEC, FUSED)                                                                                     \
     do {                                                                                                                          \
         if (SPEC == 1 && ws_env) IA_TC_BWD_PIPE_WS(ACT, NOU, SPEC, FUSED, (SPEC == 1));                                           \

@@ -14,7 +14,7 @@ import torch
 from . import _lib as L
 
 # kernels launched per ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_grouped": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
+_LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_fwd_grouped": 1, "ia_hashgrid_bwd": 1, "ia_hashgrid_bwd_grouped": 1, "ia_hashgrid_bwd_table": 1, "ia_hashgrid_bwd_input": 1, "ia_sh_fwd": 1,
              "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_linear64_fwd": 1, "ia_linear64_bwd": 2, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
              "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
              "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0,
@@ -88,8 +88,12 @@ class _HashGridFn(torch.autograd.Function):
         x = L.f32c(x)
         n = x.shape[0]
         out = torch.empty(n, plan.n_levels * plan.n_features, device=x.device, dtype=torch.float32)
-        _run("ia_hashgrid_fwd", L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, L.ptr(out), L.stream(),
-             work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
+        if group == 6 and _FWD_GROUPED:
+            _run("ia_hashgrid_fwd_grouped", L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, group, L.ptr(out), L.stream(),
+                 tag="g6", work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
+        else:
+            _run("ia_hashgrid_fwd", L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, L.ptr(out), L.stream(),
+                 work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
         ctx.save_for_backward(x, table)
         ctx.plan, ctx.active, ctx.group = plan, active_levels, group
         ctx.sink_param = table if getattr(table, "_ia_grad_inplace", False) else None
@@ -121,6 +125,7 @@ class _HashGridFn(torch.autograd.Function):
         return dx, (None if sink is not None else dtable), None, None, None
 
 
+_FWD_GROUPED = os.environ.get("IA_HASHGRID_FWD_GROUPED", "1") not in ("0", "")      # A/B switch
 _NO_GRAD_SINK = os.environ.get("IA_NO_GRAD_SINK") is not None     # A/B switch (tools / bench experiments)
 
 

@@ -101,11 +101,17 @@ def test_hashgrid_grouped_backward(cuda_lib, cfg_name, active):
     dy = torch.randn(n, plan_ref.n_output_dims, generator=g)
     dy[5::7] = 0.0                                            # some rows with exactly-zero gradient
     act = active if active is None else min(active, cfg["n_levels"])
-    tc.hashgrid_forward(x, table, plan_ref, act).backward(dy)
+    y_ref = tc.hashgrid_forward(x, table, plan_ref, act)
+    y_ref.backward(dy)
     xg, tg = x.detach().cuda().requires_grad_(True), table.detach().cuda().requires_grad_(True)
-    y = ops.hashgrid_encode(xg, tg, plan, act, group=6)
+    y = ops.hashgrid_encode(xg, tg, plan, act, group=6)          # forward: ia_hashgrid_fwd_grouped (one thread walks the 6 taps)
     y.backward(dy.cuda())
     torch.cuda.synchronize()
+    assert_close(y, y_ref.detach(), rtol=1e-5, atol=1e-6, name="enc (grouped forward)")
+    if act is not None:
+        assert torch.count_nonzero(y[:, act * 2:]) == 0, "masked levels must be exact zeros"
+    y_plain = ops.hashgrid_encode(x.detach().cuda(), table.detach().cuda(), plan, act)
+    assert_close(y, y_plain, rtol=1e-5, atol=1e-6, name="enc (grouped vs plain forward)")
     assert_close(tg.grad, table.grad, rtol=1e-4, atol=1e-5, name="dtable (grouped)")
     rt, at = grad_tol(x.grad, 1e-4)
     assert_close(xg.grad, x.grad, rtol=rt, atol=at, name="dx (grouped)")

@@ -125,7 +125,11 @@ class _HashGridFn(torch.autograd.Function):
         return dx, (None if sink is not None else dtable), None, None, None
 
 
-_FWD_GROUPED = os.environ.get("IA_HASHGRID_FWD_GROUPED", "1") not in ("0", "")      # A/B switch
+# ia_hashgrid_fwd_grouped (one thread walks the six taps of a (group, level) and re-fetches corners only on a cell change) was
+# measured on a B200 against the lane-pair kernel on the tap rows of a training step: 2.68 vs 1.85 ms per step (profiles/
+# r02_ab_hashgrid_fwd_grouped.md) -- the cell-change branch diverges between the 16 groups of a warp, so the gathers are
+# issued anyway, and the walk is a chain of dependent gathers.  Off unless IA_HASHGRID_FWD_GROUPED=1.
+_FWD_GROUPED = os.environ.get("IA_HASHGRID_FWD_GROUPED", "0") not in ("0", "")
 _NO_GRAD_SINK = os.environ.get("IA_NO_GRAD_SINK") is not None     # A/B switch (tools / bench experiments)
 
 

@@ -104,8 +104,15 @@ def test_hashgrid_grouped_backward(cuda_lib, cfg_name, active):
     y_ref = tc.hashgrid_forward(x, table, plan_ref, act)
     y_ref.backward(dy)
     xg, tg = x.detach().cuda().requires_grad_(True), table.detach().cuda().requires_grad_(True)
-    y = ops.hashgrid_encode(xg, tg, plan, act, group=6)          # forward: ia_hashgrid_fwd_grouped (one thread walks the 6 taps)
+    y = ops.hashgrid_encode(xg, tg, plan, act, group=6)
     y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    # ia_hashgrid_fwd_grouped (one thread walks the 6 taps; opt-in, see ops._FWD_GROUPED) through the raw ABI
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    y = torch.empty(n, plan_ref.n_output_dims, device="cuda")
+    L.check(cuda_lib.ia_hashgrid_fwd_grouped(xg.data_ptr(), n, tg.data_ptr(), C.byref(plan), plan.n_levels if act is None else act, 6,
+                                             y.data_ptr(), L.stream()))
     torch.cuda.synchronize()
     assert_close(y, y_ref.detach(), rtol=1e-5, atol=1e-6, name="enc (grouped forward)")
     if act is not None:
@@ -164,6 +171,9 @@ def test_hashgrid_points_outside_unit_cube(cuda_lib, cfg_name):
     xc, tcu, dyc = x.detach().cuda(), table.detach().cuda(), dy.cuda()
     v = torch.randn(n, 3, generator=g).cuda()
     s = L.stream()
+    yg = torch.empty(n, plan_ref.n_output_dims, device="cuda")
+    L.check(cuda_lib.ia_hashgrid_fwd_grouped(xc.data_ptr(), n, tcu.data_ptr(), C.byref(plan), plan.n_levels, 6, yg.data_ptr(), s))
+    assert_close(yg, y_ref.detach(), rtol=1e-5, atol=1e-6, name="enc outside cube (grouped forward kernel)")
     L.check(cuda_lib.ia_hashgrid_bwd(xc.data_ptr(), n, tcu.data_ptr(), dyc.data_ptr(), C.byref(plan), plan.n_levels, dt.data_ptr(), None, s))
     L.check(cuda_lib.ia_hashgrid_bwd_grouped(xc.data_ptr(), n, tcu.data_ptr(), dyc.data_ptr(), C.byref(plan), plan.n_levels, 6, dt.data_ptr(), None, s))
     L.check(cuda_lib.ia_hashgrid_bwd_input_bwd_table(xc.data_ptr(), n, v.data_ptr(), dyc.data_ptr(), C.byref(plan), plan.n_levels, dt.data_ptr(), s))

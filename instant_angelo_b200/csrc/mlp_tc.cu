@@ -256,6 +256,23 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Operand &A, co
     }
 }
 
+// same, with the accumulate flag of the very first MMA given by the caller (accumulators that persist across tiles)
+__device__ __forceinline__ void issue_gemm_acc(uint32_t tmem_d, const Operand &A, const Operand &B, uint32_t idesc, int n_ksteps,
+                                               uint32_t accumulate_first)
+{
+    uint64_t ah = A.dhi, al = A.dlo, bh = B.dhi, bl = B.dlo;
+    umma(tmem_d, ah, bh, idesc, accumulate_first);
+    umma(tmem_d, ah, bl, idesc, 1u);
+    umma(tmem_d, al, bh, idesc, 1u);
+#pragma unroll 4
+    for (int ks = 1; ks < n_ksteps; ++ks) {
+        ah += A.kstep16; al += A.kstep16; bh += B.kstep16; bl += B.kstep16;
+        umma(tmem_d, ah, bh, idesc, 1u);
+        umma(tmem_d, ah, bl, idesc, 1u);
+        umma(tmem_d, al, bh, idesc, 1u);
+    }
+}
+
 // activation buffer [128 rows, C cols] (chunk c at c*2048, row r at r*16)
 __device__ __forceinline__ Operand act_as_A_kmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 2048u, 128u, 4096u); }
 __device__ __forceinline__ Operand act_as_mnmajor(uint32_t hi, uint32_t lo) { return make_operand(hi, lo, 128u, 2048u, 256u); }
@@ -1372,6 +1389,375 @@ mlp_tc_bwd_pipe_kernel(const TcDims Din, const float *__restrict__ in0, const fl
     teardown(c);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// backward, two tiles in flight ("duo"): the 512 threads of the CTA are two TEAMS of 256; each team runs the plain
+// recompute-forward / backward sequence on its own 128-row tile with its own operand buffers, TMEM columns, mbarriers and
+// named barrier, and the two teams share only the staged weights.  Nothing orders one team against the other, so while
+// one team sits in an epilogue (MUFU / FP32 pipes) or waits for its GEMMs, the other team's instructions and MMAs fill the
+// issue slots and the tensor pipe -- the overlap two CTAs per SM would give, which the 64 K registers / 227 KB of an SM
+// cannot hold for this kernel (ncu on the single-tile pipeline: tensor pipe 23 %, issue slots 38 %, stalls dominated by
+// dependency waits of the 4 warps per scheduler).
+//   thread (team, warp w, lane): TMEM lane quarter q = w % 4 (rows 32 q + lane), column half = w / 4 (32 columns).
+//   dW0 / dW1 accumulate in TMEM across ALL tiles of the team (launch-wide gradient scale => no per-tile rescale, no drain):
+//   TMEM columns per team: [0,64) forward / dH, [64,128) dX, [128,200) dW1, [200,248) dW0.
+// Shape: the SDF network (3 + 32 inputs, K0 = 48, two hidden layers), NOU outputs used.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TEAM = 256;
+constexpr uint32_t DUO_COLS = 512, DUO_TEAM_COLS = 256, DUO_D0 = 0, DUO_D2 = 64, DUO_W1 = 128, DUO_W0 = 200;
+
+struct DuoPlan {
+    uint32_t ax_hi[2], ax_lo[2], ah_hi[2], ah_lo[2], dz_hi[2], dz_lo[2], w0_hi, w0_lo, w1_hi, w1_lo, wl, b0, b1, bl, dwl, dbl, red,
+        mbar, tmem, ops, total;
+};
+
+__host__ __device__ inline DuoPlan make_duo_plan()
+{
+    DuoPlan p;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 127u) & ~127u; return r; };
+    for (int t = 0; t < 2; ++t) {
+        p.ax_hi[t] = take(6 * 2048); p.ax_lo[t] = take(6 * 2048);
+        p.ah_hi[t] = take(9 * 2048); p.ah_lo[t] = take(9 * 2048);
+        p.dz_hi[t] = take(8 * 2048); p.dz_lo[t] = take(8 * 2048);
+    }
+    p.w0_hi = take(6 * 1024); p.w0_lo = take(6 * 1024);
+    p.w1_hi = take(8 * 1024); p.w1_lo = take(8 * 1024);
+    p.wl = take(MAX_OUT * W * 4);
+    p.b0 = take(W * 4); p.b1 = take(W * 4); p.bl = take(MAX_OUT * 4);
+    p.dwl = take(MAX_OUT * W * 4); p.dbl = take(MAX_OUT * 4);
+    p.red = take(64 * 4);
+    p.mbar = take(64);       // 2 teams x 4 mbarriers
+    p.tmem = take(16);
+    p.ops = take(2 * 6 * sizeof(Operand) + 4 * sizeof(Operand));
+    p.total = o;
+    return p;
+}
+
+template <int ACT, int NOU>
+__global__ void __launch_bounds__(2 * TEAM, 1)
+mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const float *__restrict__ in1, int64_t n,
+                      const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
+                      float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams, const float *__restrict__ gmax)
+{
+    static_assert(NOU >= 1 && NOU <= 3, "duo backward: fused output layer with 1..3 outputs");
+    const TcDims D = specialise<1>(Din);
+    extern __shared__ __align__(1024) char smem[];
+    const DuoPlan P = make_duo_plan();
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, team = tid >> 8, tt = tid & (TEAM - 1), lane = tid & 31, wt = tt >> 5;
+    const int q = wt & 3, half = wt >> 2, r = 32 * q + lane;
+    float *dwl = reinterpret_cast<float *>(smem + P.dwl), *dbl = reinterpret_cast<float *>(smem + P.dbl);
+    float *red = reinterpret_cast<float *>(smem + P.red);
+    // ---- one-time setup by all 512 threads
+    for (int i = tid; i < W * 6; i += 2 * TEAM) {          // W0 [64][35] -> split K-major B operand, 48 columns, internal order
+        const int o = i % W, c8 = i / W;
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * c8 + j;
+            a[j] = c < D.din ? __ldg(params + D.pW0 + o * D.din + global_col(c, D.n_in0, D.n_in1)) : 0.f;
+        }
+        store_split8(smem + P.w0_hi, smem + P.w0_lo, (uint32_t)c8 * 1024u + (uint32_t)o * 16u, a);
+    }
+    for (int i = tid; i < W * 8; i += 2 * TEAM) {
+        const int o = i % W, c8 = i / W;
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = __ldg(params + D.pW1 + o * W + 8 * c8 + j);
+        store_split8(smem + P.w1_hi, smem + P.w1_lo, (uint32_t)c8 * 1024u + (uint32_t)o * 16u, a);
+    }
+    float *wl_s = reinterpret_cast<float *>(smem + P.wl);
+    float *b0_s = reinterpret_cast<float *>(smem + P.b0), *b1_s = reinterpret_cast<float *>(smem + P.b1);
+    for (int i = tid; i < NOU * W; i += 2 * TEAM) wl_s[i] = i < D.nou * W ? __ldg(params + D.pWl + i) : 0.f;
+    for (int i = tid; i < W; i += 2 * TEAM) { b0_s[i] = __ldg(params + D.pb0 + i); b1_s[i] = __ldg(params + D.pb1 + i); }
+    for (int i = tid; i < MAX_OUT * W; i += 2 * TEAM) dwl[i] = 0.f;
+    if (tid < MAX_OUT) dbl[tid] = 0.f;
+    {   // constant columns of each team's buffers: H1 chunk 8 = (1, 0, ..., 0) (bias gradient of layer 1), X chunk 5 = zeros
+        const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (tt < ROWS) {
+            store_split8(smem + P.ah_hi[team], smem + P.ah_lo[team], 8u * 2048u + (uint32_t)tt * 16u, one);
+            store_split8(smem + P.ax_hi[team], smem + P.ax_lo[team], 5u * 2048u + (uint32_t)tt * 16u, zero);
+        }
+    }
+    if (tid < 8) mbar_init(sbase + P.mbar + 8u * (uint32_t)tid, 1);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(sbase + P.tmem), "r"(DUO_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    float wmax = 0.f;
+    for (int i = tid; i < NOU * W; i += 2 * TEAM) wmax = fmaxf(wmax, fabsf(__ldg(params + D.pWl + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) red[tid >> 5] = wmax;
+    Operand *ops = reinterpret_cast<Operand *>(smem + P.ops);       // [team][6] then 4 shared weight operands
+    if (tt == 0) {
+        Operand *o = ops + 6 * team;
+        o[0] = act_as_A_kmajor(sbase + P.ax_hi[team], sbase + P.ax_lo[team]);
+        o[1] = act_as_A_kmajor(sbase + P.ah_hi[team], sbase + P.ah_lo[team]);
+        o[2] = act_as_A_kmajor(sbase + P.dz_hi[team], sbase + P.dz_lo[team]);
+        o[3] = act_as_mnmajor(sbase + P.ax_hi[team], sbase + P.ax_lo[team]);
+        o[4] = act_as_mnmajor(sbase + P.ah_hi[team], sbase + P.ah_lo[team]);
+        o[5] = act_as_mnmajor(sbase + P.dz_hi[team], sbase + P.dz_lo[team]);
+    }
+    if (tid == 0) {
+        ops[12] = w_as_B_kmajor(sbase + P.w0_hi, sbase + P.w0_lo);
+        ops[13] = w_as_B_kmajor(sbase + P.w1_hi, sbase + P.w1_lo);
+        ops[14] = w_as_B_mnmajor(sbase + P.w0_hi, sbase + P.w0_lo);
+        ops[15] = w_as_B_mnmajor(sbase + P.w1_hi, sbase + P.w1_lo);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + P.tmem) + DUO_TEAM_COLS * (uint32_t)team;
+    const uint32_t lane_addr = ((uint32_t)q * 32u) << 16;
+    wmax = 0.f;
+#pragma unroll
+    for (int w = 0; w < 2 * TEAM / 32; ++w) wmax = fmaxf(wmax, red[w]);
+    wmax = fmaxf(wmax * (float)NOU, 1e-30f);
+    float scale, inv_scale;
+    pow2_scale(fmaxf(__ldg(gmax), 1e-30f) * wmax, scale, inv_scale);
+
+    const Operand &AX = ops[6 * team + 0], &AH = ops[6 * team + 1], &ADZ = ops[6 * team + 2];
+    const Operand &XT = ops[6 * team + 3], &HT = ops[6 * team + 4], &DZT = ops[6 * team + 5];
+    const Operand &BW0 = ops[12], &BW1 = ops[13], &BW0T = ops[14], &BW1T = ops[15];
+    const uint32_t idesc_fwd = make_idesc(128, W, 0, 0), idesc_dh = make_idesc(128, W, 0, 1), idesc_dx = make_idesc(128, 48, 0, 1);
+    const uint32_t idesc_dw1 = make_idesc(64, 72, 1, 1), idesc_dw0 = make_idesc(64, 48, 1, 1);
+    const uint32_t mb0 = sbase + P.mbar + 32u * (uint32_t)team, mb1 = mb0 + 8u;
+    uint32_t ph0 = 0, ph1 = 0;
+    char *ax_hi = smem + P.ax_hi[team], *ax_lo = smem + P.ax_lo[team], *ah_hi = smem + P.ah_hi[team], *ah_lo = smem + P.ah_lo[team];
+    char *dz_hi = smem + P.dz_hi[team], *dz_lo = smem + P.dz_lo[team];
+
+    // team barrier + MMA issue by one lane of the team's first warp
+    auto team_issue = [&](auto issue) {
+        fence_async_smem();
+        tc_fence_before();
+        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + team), "n"(TEAM) : "memory");
+        if (wt == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+                issue();
+            }
+            __syncwarp();
+        }
+    };
+    auto wait0 = [&]() { mbar_wait(mb0, ph0); ph0 ^= 1u; tc_fence_after(); };
+    auto wait1 = [&]() { mbar_wait(mb1, ph1); ph1 ^= 1u; tc_fence_after(); };
+
+    // input rows: thread (r, half) owns chunks half, half + 2 (hash features) and, for half == 0, chunk 4 (xyz | 1 | 0 0 0 0)
+    float xr[2][8], xyz[3];
+    auto load_x = [&](int64_t row, bool valid) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float4 *src = reinterpret_cast<const float4 *>(in1 + row * 32 + 8 * (half + 2 * k));
+            const float4 a = valid ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f), b = valid ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xr[k][0] = a.x; xr[k][1] = a.y; xr[k][2] = a.z; xr[k][3] = a.w;
+            xr[k][4] = b.x; xr[k][5] = b.y; xr[k][6] = b.z; xr[k][7] = b.w;
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) xyz[j] = valid ? __ldg(in0 + row * 3 + j) : 0.f;
+        }
+    };
+    auto store_x = [&](bool valid) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) store_split8(ax_hi, ax_lo, (uint32_t)(half + 2 * k) * 2048u + (uint32_t)r * 16u, xr[k]);
+        if (half == 0) {
+            const float a[8] = {valid ? fmaf(xyz[0], D.s0, D.o0) : 0.f, valid ? fmaf(xyz[1], D.s0, D.o0) : 0.f,
+                                valid ? fmaf(xyz[2], D.s0, D.o0) : 0.f, valid ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f};
+            store_split8(ax_hi, ax_lo, 4u * 2048u + (uint32_t)r * 16u, a);
+        }
+    };
+
+    float gwl[NOU][32], gbl[NOU];
+#pragma unroll
+    for (int o = 0; o < NOU; ++o) {
+        gbl[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gwl[o][j] = 0.f;
+    }
+    const bool want_dx = din0 != nullptr || din1 != nullptr;
+    const int64_t n_tiles = (n + ROWS - 1) / ROWS;
+    const int64_t stride = (int64_t)gridDim.x * 2;
+    int64_t tile = (int64_t)blockIdx.x * 2 + team;
+    const bool had_tiles = tile < n_tiles;
+    float dy_next[NOU];
+    if (had_tiles) {
+        const int64_t row = tile * ROWS + r;
+        load_x(row, row < n);
+#pragma unroll
+        for (int o = 0; o < NOU; ++o) dy_next[o] = (row < n && o < D.nou) ? __ldg(dout + row * ld_dout + o) : 0.f;
+    }
+    uint32_t acc = 0u;        // 0 for the team's first tile: the persistent dW accumulators start from the first MMA
+    for (; tile < n_tiles; tile += stride) {
+        const int64_t row = tile * ROWS + r;
+        const bool valid = row < n;
+        float dy[NOU];
+#pragma unroll
+        for (int o = 0; o < NOU; ++o) dy[o] = dy_next[o];
+        // ---- X(i) -> smem; raw prefetch of tile i+1 (consumed one whole tile later)
+        store_x(valid);
+        {
+            const int64_t nrow = (tile + stride) * ROWS + r;
+            const bool nvalid = tile + stride < n_tiles && nrow < n;
+            load_x(nvalid ? nrow : 0, nvalid);
+#pragma unroll
+            for (int o = 0; o < NOU; ++o) dy_next[o] = (nvalid && o < D.nou) ? __ldg(dout + nrow * ld_dout + o) : 0.f;
+        }
+        // ---- L0 = X W0^T
+        team_issue([&]() { issue_gemm(tmem_base + DUO_D0, AX, BW0, idesc_fwd, 48 / 16); umma_commit(mb0); });
+        wait0();
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int c0 = 32 * half + 16 * pass;
+            float h[16];
+            tmem_ld16(tmem_base + lane_addr + DUO_D0 + (uint32_t)c0, h);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = act_fwd<ACT>(h[j] + b0_s[c0 + j]);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = h[8 * hf + j];
+                store_split8(ah_hi, ah_lo, (uint32_t)(c0 / 8 + hf) * 2048u + (uint32_t)r * 16u, a);
+            }
+        }
+        // ---- L1 = H1 W1^T
+        team_issue([&]() { issue_gemm(tmem_base + DUO_D0, AH, BW1, idesc_fwd, W / 16); umma_commit(mb0); });
+        wait0();
+        if (half == 0) {
+#pragma unroll
+            for (int o = 0; o < NOU; ++o) gbl[o] += dy[o];
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int c0 = 32 * half + 16 * pass;
+            float h[16], dz[16];
+            tmem_ld16(tmem_base + lane_addr + DUO_D0 + (uint32_t)c0, h);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = c0 + j;
+                h[j] = act_fwd<ACT>(h[j] + b1_s[k]);
+                float dh = 0.f;
+#pragma unroll
+                for (int o = 0; o < NOU; ++o) {
+                    dh = fmaf(dy[o], wl_s[o * W + k], dh);
+                    gwl[o][16 * pass + j] = fmaf(dy[o], h[j], gwl[o][16 * pass + j]);
+                }
+                dz[j] = dh * act_bwd_from_out<ACT>(h[j]) * scale;
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = dz[8 * hf + j];
+                store_split8(dz_hi, dz_lo, (uint32_t)(c0 / 8 + hf) * 2048u + (uint32_t)r * 16u, a);
+            }
+        }
+        // ---- dH1 = dZ2 W1 ; dW1 (+db1) += dZ2^T [H1 | 1]   (persistent accumulator)
+        team_issue([&]() {
+            issue_gemm(tmem_base + DUO_D0, ADZ, BW1T, idesc_dh, W / 16);
+            umma_commit(mb0);
+            issue_gemm_acc(tmem_base + DUO_W1, DZT, HT, idesc_dw1, ROWS / 16, acc);
+            umma_commit(mb1);
+        });
+        wait0();
+        float dz1[32];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int c0 = 32 * half + 16 * pass;
+            float v[16];
+            tmem_ld16(tmem_base + lane_addr + DUO_D0 + (uint32_t)c0, v);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float hh[8];
+                load_split8(ah_hi, ah_lo, (uint32_t)(c0 / 8 + hf) * 2048u + (uint32_t)r * 16u, hh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz1[16 * pass + 8 * hf + j] = v[8 * hf + j] * act_bwd_from_out<ACT>(hh[j]);
+            }
+        }
+        wait1();          // dW1 has read dZ2 and H1: the dZ buffer may be overwritten
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = dz1[8 * c8 + j];
+            store_split8(dz_hi, dz_lo, (uint32_t)(4 * half + c8) * 2048u + (uint32_t)r * 16u, a);
+        }
+        // ---- dX = dZ1 W0 ; dW0 (+db0) += dZ1^T [X | 1]
+        team_issue([&]() {
+            if (want_dx) issue_gemm(tmem_base + DUO_D2, ADZ, BW0T, idesc_dx, W / 16);
+            umma_commit(mb0);
+            issue_gemm_acc(tmem_base + DUO_W0, DZT, XT, idesc_dw0, ROWS / 16, acc);
+            umma_commit(mb1);
+        });
+        acc = 1u;
+        wait0();
+        if (want_dx) {
+            // internal columns [0,32): hash features -> din1 ; [32,35): xyz -> din0.  half 0: columns 0-15 and 32-47, half 1: 16-31
+            float v[16];
+            tmem_ld16(tmem_base + lane_addr + DUO_D2 + 16u * (uint32_t)half, v);
+            if (valid) write_dx16(D, 16 * half, v, inv_scale, row, din0, din1);
+            if (half == 0) {
+                tmem_ld16(tmem_base + lane_addr + DUO_D2 + 32u, v);
+                if (valid) write_dx16(D, 32, v, inv_scale, row, din0, din1);
+            }
+        }
+        wait1();          // dW0 has read X and dZ1: both buffers are free for the next tile
+    }
+    // ---- per team: drain the persistent dW accumulators (M = 64 layout: output row o = 16 q + lane for lane < 16)
+    if (had_tiles && dparams != nullptr) {
+        const int o = 16 * q + lane;
+        for (int ci = half; ci * 16 < 72; ci += 2) {
+            const int c0 = 16 * ci, m = 72 - c0 >= 16 ? 16 : 8;
+            float v[16];
+            if (m == 16) tmem_ld16(tmem_base + lane_addr + DUO_W1 + (uint32_t)c0, v);
+            else tmem_ld8(tmem_base + lane_addr + DUO_W1 + (uint32_t)c0, v);
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = c0 + j;
+                    if (j < m) {
+                        if (col < W) atomicAdd(dparams + D.pW1 + o * W + col, v[j] * inv_scale);
+                        else if (col == W) atomicAdd(dparams + D.pb1 + o, v[j] * inv_scale);
+                    }
+                }
+            }
+        }
+        for (int ci = half; ci * 16 < 48; ci += 2) {
+            const int c0 = 16 * ci;
+            float v[16];
+            tmem_ld16(tmem_base + lane_addr + DUO_W0 + (uint32_t)c0, v);
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = c0 + j;
+                    if (col < D.din) atomicAdd(dparams + D.pW0 + o * D.din + global_col(col, D.n_in0, D.n_in1), v[j] * inv_scale);
+                    else if (col == D.din) atomicAdd(dparams + D.pb0 + o, v[j] * inv_scale);
+                }
+            }
+        }
+    }
+    // ---- output-layer gradients: reduce the per-thread partial sums over the 32 rows of a warp, then over warps in smem
+#pragma unroll
+    for (int o = 0; o < NOU; ++o) {
+        const float tot = warp_sum32(gwl[o], lane);          // lane L holds the warp total of column 32 half + L
+        atomicAdd(&dwl[o * W + 32 * half + lane], tot);
+        const float sb = warp_sum(gbl[o]);
+        if (lane == 0 && half == 0) atomicAdd(&dbl[o], sb);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (dparams != nullptr) {
+        for (int i = tid; i < D.nou * W; i += 2 * TEAM) atomicAdd(dparams + D.pWl + i, dwl[i]);
+        if (tid < D.nou) atomicAdd(dparams + D.pbl + tid, dbl[tid]);
+    }
+    if (tid < 32) {
+        const uint32_t base = *reinterpret_cast<volatile uint32_t *>(smem + P.tmem);
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(base), "r"(DUO_COLS) : "memory");
+    }
+}
+
 int make_dims(const ia_mlp_desc *d, int32_t n_out_used, TcDims *D)
 {
     IA_REQUIRE(d != nullptr, "mlp_tc: desc is NULL");
@@ -1543,6 +1929,18 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
     const bool sp = D.act == IA_ACT_SOFTPLUS100;
     const bool geo = pipe && sp && D.n_in0 == 3 && D.n_in1 == 32 && D.nh == 2 && D.K0 == 48;
     const bool tex = !pipe && !sp && D.n_in0 == 0 && D.n_in1 == 87 && D.nh == 2 && D.K0 == 96 && D.nou == 3;
+    // the tap evaluations of the SDF network (one output column): two tiles in flight per CTA (mlp_tc_bwd_duo_kernel);
+    // IA_TC_DUO=0 selects the single-tile software pipeline (A/B runs)
+    static const bool duo_env = getenv("IA_TC_DUO") == nullptr || atoi(getenv("IA_TC_DUO")) != 0;
+    if (G == nullptr && geo && D.nou == 1 && duo_env) {
+        const DuoPlan DP = make_duo_plan();
+        const unsigned dblocks = (unsigned)std::min<int64_t>(ia_ceil_div(n_tiles, 2), (int64_t)ia_sm_count());
+        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP.total));
+        mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 1><<<dblocks, 2 * TEAM, DP.total, (cudaStream_t)stream>>>(
+            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, gmax);
+        IA_LAUNCH_OK("mlp_tc_bwd_duo_kernel");
+        return IA_OK;
+    }
     if (G != nullptr) {
         // fused encoder (in-kernel re-gather of the first-layer input): two-hidden-layer Softplus networks, i.e. VolumeSDF
         if (!(pipe && sp && (D.nou == 0 || D.nou == 1))) {

@@ -1439,7 +1439,8 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
                       const float *__restrict__ params, const float *__restrict__ dout, int64_t ld_dout,
                       float *__restrict__ din0, float *__restrict__ din1, float *__restrict__ dparams, const float *__restrict__ gmax)
 {
-    static_assert(NOU >= 1 && NOU <= 3, "duo backward: fused output layer with 1..3 outputs");
+    static_assert(NOU >= 0 && NOU <= 3, "duo backward: feature mode (0) or a fused output layer with 1..3 outputs");
+    constexpr int NO = NOU > 0 ? NOU : 1;
     const TcDims D = specialise<1>(Din);
     extern __shared__ __align__(1024) char smem[];
     const DuoPlan P = make_duo_plan();
@@ -1484,7 +1485,7 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(sbase + P.tmem), "r"(DUO_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
-    float wmax = 0.f;
+    float wmax = NOU == 0 ? 1.f : 0.f;      // NOU == 0: the incoming gradient is d(last hidden layer) itself
     for (int i = tid; i < NOU * W; i += 2 * TEAM) wmax = fmaxf(wmax, fabsf(__ldg(params + D.pWl + i)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
@@ -1514,7 +1515,7 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
     wmax = 0.f;
 #pragma unroll
     for (int w = 0; w < 2 * TEAM / 32; ++w) wmax = fmaxf(wmax, red[w]);
-    wmax = fmaxf(wmax * (float)NOU, 1e-30f);
+    wmax = fmaxf(wmax * (float)NO, 1e-30f);
     float scale, inv_scale;
     pow2_scale(fmaxf(__ldg(gmax), 1e-30f) * wmax, scale, inv_scale);
 
@@ -1569,19 +1570,21 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
         }
     };
 
-    float gwl[NOU][32], gbl[NOU];
+    float gwl[NO][NOU > 0 ? 32 : 1], gbl[NO];
 #pragma unroll
-    for (int o = 0; o < NOU; ++o) {
+    for (int o = 0; o < NO; ++o) {
         gbl[o] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) gwl[o][j] = 0.f;
+        for (int j = 0; j < (NOU > 0 ? 32 : 1); ++j) gwl[o][j] = 0.f;
     }
     const bool want_dx = din0 != nullptr || din1 != nullptr;
     const int64_t n_tiles = (n + ROWS - 1) / ROWS;
     const int64_t stride = (int64_t)gridDim.x * 2;
     int64_t tile = (int64_t)blockIdx.x * 2 + team;
     const bool had_tiles = tile < n_tiles;
-    float dy_next[NOU];
+    float dy_next[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) dy_next[o] = 0.f;
     if (had_tiles) {
         const int64_t row = tile * ROWS + r;
         load_x(row, row < n);
@@ -1592,20 +1595,22 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
     for (; tile < n_tiles; tile += stride) {
         const int64_t row = tile * ROWS + r;
         const bool valid = row < n;
-        float dy[NOU];
+        float dy[NO];
 #pragma unroll
-        for (int o = 0; o < NOU; ++o) dy[o] = dy_next[o];
-        // ---- X(i) -> smem; raw prefetch of tile i+1 (consumed one whole tile later)
+        for (int o = 0; o < NO; ++o) dy[o] = dy_next[o];
+        // ---- X(i) -> smem
         store_x(valid);
+        // ---- L0 = X W0^T
+        team_issue([&]() { issue_gemm(tmem_base + DUO_D0, AX, BW0, idesc_fwd, 48 / 16); umma_commit(mb0); });
         {
+            // raw prefetch of tile i+1 (consumed one whole tile later).  Issued AFTER the team barrier: the proxy fence in
+            // front of a barrier waits for outstanding loads (ncu: long-scoreboard stalls on FENCE.VIEW.ASYNC / BAR.SYNC)
             const int64_t nrow = (tile + stride) * ROWS + r;
             const bool nvalid = tile + stride < n_tiles && nrow < n;
             load_x(nvalid ? nrow : 0, nvalid);
 #pragma unroll
             for (int o = 0; o < NOU; ++o) dy_next[o] = (nvalid && o < D.nou) ? __ldg(dout + nrow * ld_dout + o) : 0.f;
         }
-        // ---- L0 = X W0^T
-        team_issue([&]() { issue_gemm(tmem_base + DUO_D0, AX, BW0, idesc_fwd, 48 / 16); umma_commit(mb0); });
         wait0();
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -1625,7 +1630,7 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
         // ---- L1 = H1 W1^T
         team_issue([&]() { issue_gemm(tmem_base + DUO_D0, AH, BW1, idesc_fwd, W / 16); umma_commit(mb0); });
         wait0();
-        if (half == 0) {
+        if (NOU > 0 && half == 0) {
 #pragma unroll
             for (int o = 0; o < NOU; ++o) gbl[o] += dy[o];
         }
@@ -1633,16 +1638,29 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
         for (int pass = 0; pass < 2; ++pass) {
             const int c0 = 32 * half + 16 * pass;
             float h[16], dz[16];
+            float dhf[NOU == 0 ? 16 : 1];
+            if constexpr (NOU == 0) {          // feature mode: d(last hidden layer) [n, 64] comes from the caller
+                const float4 *src = reinterpret_cast<const float4 *>(dout + row * ld_dout + c0);
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const float4 t4 = valid ? __ldg(src + qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dhf[4 * qq] = t4.x; dhf[4 * qq + 1] = t4.y; dhf[4 * qq + 2] = t4.z; dhf[4 * qq + 3] = t4.w;
+                }
+            }
             tmem_ld16(tmem_base + lane_addr + DUO_D0 + (uint32_t)c0, h);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int k = c0 + j;
                 h[j] = act_fwd<ACT>(h[j] + b1_s[k]);
                 float dh = 0.f;
+                if constexpr (NOU == 0) {
+                    dh = dhf[j];
+                } else {
 #pragma unroll
-                for (int o = 0; o < NOU; ++o) {
-                    dh = fmaf(dy[o], wl_s[o * W + k], dh);
-                    gwl[o][16 * pass + j] = fmaf(dy[o], h[j], gwl[o][16 * pass + j]);
+                    for (int o = 0; o < NOU; ++o) {
+                        dh = fmaf(dy[o], wl_s[o * W + k], dh);
+                        gwl[o][16 * pass + j] = fmaf(dy[o], h[j], gwl[o][16 * pass + j]);
+                    }
                 }
                 dz[j] = dh * act_bwd_from_out<ACT>(h[j]) * scale;
             }
@@ -1739,12 +1757,14 @@ mlp_tc_bwd_duo_kernel(const TcDims Din, const float *__restrict__ in0, const flo
         }
     }
     // ---- output-layer gradients: reduce the per-thread partial sums over the 32 rows of a warp, then over warps in smem
+    if constexpr (NOU > 0) {
 #pragma unroll
-    for (int o = 0; o < NOU; ++o) {
-        const float tot = warp_sum32(gwl[o], lane);          // lane L holds the warp total of column 32 half + L
-        atomicAdd(&dwl[o * W + 32 * half + lane], tot);
-        const float sb = warp_sum(gbl[o]);
-        if (lane == 0 && half == 0) atomicAdd(&dbl[o], sb);
+        for (int o = 0; o < NOU; ++o) {
+            const float tot = warp_sum32(gwl[o], lane);          // lane L holds the warp total of column 32 half + L
+            atomicAdd(&dwl[o * W + 32 * half + lane], tot);
+            const float sb = warp_sum(gbl[o]);
+            if (lane == 0 && half == 0) atomicAdd(&dbl[o], sb);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -1855,10 +1875,20 @@ int launch_fwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
 __global__ void absmax_kernel(const float *__restrict__ v, int64_t n, int cols, int64_t ld, float *__restrict__ out)
 {
     float m = 0.f;
-    const int64_t total = n * cols;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cols;
-        m = fmaxf(m, fabsf(__ldg(v + r * ld + (i - r * cols))));
+    const int64_t total = n * cols, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    if (ld == cols && ((uintptr_t)v & 15) == 0) {           // contiguous rows: one flat array, 16-byte loads
+        const float4 *v4 = reinterpret_cast<const float4 *>(v);
+        const int64_t n4 = total >> 2;
+        for (int64_t i = t0; i < n4; i += step) {
+            const float4 a = __ldg(v4 + i);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        }
+        for (int64_t i = (n4 << 2) + t0; i < total; i += step) m = fmaxf(m, fabsf(__ldg(v + i)));
+    } else {
+        for (int64_t i = t0; i < total; i += step) {
+            const int64_t r = i / cols;
+            m = fmaxf(m, fabsf(__ldg(v + r * ld + (i - r * cols))));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -1873,7 +1903,7 @@ int absmax_slot(const float *dout, int64_t n, int cols, int64_t ld, cudaStream_t
     float *slot = slots + (next++ & 63u);
     IA_CUDA_OK(cudaMemsetAsync(slot, 0, sizeof(float), stream));
     const int64_t total = n * cols;
-    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(total, 256 * 8), (int64_t)ia_sm_count() * 8);
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(total, 256 * 16), (int64_t)ia_sm_count() * 8);
     absmax_kernel<<<std::max(1u, blocks), 256, 0, stream>>>(dout, n, cols, ld, slot);
     IA_LAUNCH_OK("absmax_kernel");
     *slot_out = slot;
@@ -1932,12 +1962,18 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
     // the tap evaluations of the SDF network (one output column): two tiles in flight per CTA (mlp_tc_bwd_duo_kernel);
     // IA_TC_DUO=0 selects the single-tile software pipeline (A/B runs)
     static const bool duo_env = getenv("IA_TC_DUO") == nullptr || atoi(getenv("IA_TC_DUO")) != 0;
-    if (G == nullptr && geo && D.nou == 1 && duo_env) {
+    if (G == nullptr && geo && (D.nou == 0 || D.nou == 1) && duo_env) {
         const DuoPlan DP = make_duo_plan();
         const unsigned dblocks = (unsigned)std::min<int64_t>(ia_ceil_div(n_tiles, 2), (int64_t)ia_sm_count());
-        IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP.total));
-        mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 1><<<dblocks, 2 * TEAM, DP.total, (cudaStream_t)stream>>>(
-            D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, gmax);
+        if (D.nou == 1) {
+            IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP.total));
+            mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 1><<<dblocks, 2 * TEAM, DP.total, (cudaStream_t)stream>>>(
+                D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, gmax);
+        } else {
+            IA_CUDA_OK(cudaFuncSetAttribute(mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DP.total));
+            mlp_tc_bwd_duo_kernel<IA_ACT_SOFTPLUS100, 0><<<dblocks, 2 * TEAM, DP.total, (cudaStream_t)stream>>>(
+                D, in0, in1, n, params, dout, ld_dout, din0, din1, dparams, gmax);
+        }
         IA_LAUNCH_OK("mlp_tc_bwd_duo_kernel");
         return IA_OK;
     }

@@ -152,6 +152,22 @@ int32_t ia_mlp_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *
                    const float *params, const float *dout, int32_t n_out_used, int64_t ld_dout,
                    float *din0, float *din1, float *dparams, void *stream);
 
+/* grad_type 'analytic' (models/geometry.py:206 + :214-218: `torch.autograd.grad(sdf, points_, create_graph=True)`): the SDF
+ * network together with the derivative of its output column 0 (the SDF) w.r.t. its own inputs, on the tensor cores.
+ * Shape: precision IA_MLP_TC_F16, n_in0 == 3, n_in1 == 32, two hidden layers, IA_ACT_SOFTPLUS100 (anything else returns
+ * IA_ERR_UNSUPPORTED).  h_out[n, 64]: the last hidden layer (apply the output layer with ia_linear64_fwd / ia_sdf_head_fwd,
+ * as after ia_mlp_fwd with n_out_used == 0); g0[n, 3] = d out0 / d in0, g1[n, 32] = d out0 / d in1.  Outputs may be NULL. */
+int32_t ia_mlp_fwd_grad(const ia_mlp_desc *desc_host, const float *in0, const float *in1, int64_t n, const float *params,
+                        float *h_out, float *g0, float *g1, void *stream);
+
+/* Adjoint of ia_mlp_fwd_grad (a second-order adjoint of the network: what autograd's double backward computes for the
+ * reference): cotangents dh[n, 64], dg0[n, 3], dg1[n, 32] (each may be NULL = zero) -> din0[n, 3], din1[n, 32] (overwritten,
+ * may be NULL) and dparams (ACCUMULATED; row 0 of the output layer receives the contribution that arrives through g, the
+ * contribution through h_out belongs to the caller's output-layer backward). */
+int32_t ia_mlp_fwd_grad_bwd(const ia_mlp_desc *desc_host, const float *in0, const float *in1, int64_t n, const float *params,
+                            const float *dh, const float *dg0, const float *dg1, float *din0, float *din1, float *dparams,
+                            void *stream);
+
 /* Fused VolumeSDF evaluation: out = network(cat[x*in0_scale+in0_offset, hashgrid(x)]) -- the composition
  * `self.network(self.encoding(points))` of models/geometry.py:206 (centre), :233 (six finite-difference taps) and :266 (six
  * curvature taps), i.e. the 13 evaluations per sample of SURVEY.md section 8(b) -- with the hash-grid gather done inside the

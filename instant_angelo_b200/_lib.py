@@ -85,6 +85,8 @@ SIGNATURES = {
     "ia_mlp_param_count": (_I64, [C.POINTER(MlpDesc)]),
     "ia_mlp_fwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _I32, _P, _I64, _P]),
     "ia_mlp_bwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _P, _I32, _I64, _P, _P, _P, _P]),
+    "ia_mlp_fwd_grad": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "ia_mlp_fwd_grad_bwd": (_I32, [C.POINTER(MlpDesc), _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_sdf_taps_fused_fwd": (_I32, [C.POINTER(MlpDesc), C.POINTER(GridPlan), _I32, _P, _I64, _P, _P, _I32, _P, _I64, _P]),
     "ia_sdf_taps_fused_bwd": (_I32, [C.POINTER(MlpDesc), C.POINTER(GridPlan), _I32, _P, _I64, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P,
                                      _P, _P, _P]),

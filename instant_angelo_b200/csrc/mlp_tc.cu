@@ -1629,6 +1629,12 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
 
 }  // namespace
 
+// abs-max pre-pass into a rotating device slot, for the kernels of mlp_tc2.cu
+int ia_tc_absmax_slot(const float *v, int64_t n, int cols, int64_t ld, cudaStream_t stream, float **slot_out)
+{
+    return absmax_slot(v, n, cols, ld, stream, slot_out);
+}
+
 int ia_mlp_fwd_tc(const ia_mlp_desc *desc, const float *in0, const float *in1, int64_t n, const float *params,
                   int32_t n_out_used, float *out, int64_t ld_out, void *stream)
 {

@@ -125,7 +125,37 @@ class VolumeSDF(BaseImplicitGeometry):
     def _net(self, pts01, n_out_used, flat, group=1):
         return fused_encode_mlp(self.encoding, self.network, pts01.reshape(-1, 3), n_out_used, flat, group)
 
-    def _analytic_eval(self, pts01):
+    def _analytic_grid(self):
+        from .network_utils import Encoding, ProgressiveBandHashGrid
+        inner = self.encoding.encoding
+        if isinstance(inner, ProgressiveBandHashGrid):
+            return inner.encoding, inner.active_levels        # the tcnn-style Encoding holding .params
+        if isinstance(inner, Encoding) and inner.otype == "HashGrid":
+            return inner, inner.plan.n_levels
+        return None, None
+
+    def _analytic_hidden(self, pts01, flat=None):
+        """Kernel path of grad_type 'analytic': (last hidden layer [S,64], grad [*,3] w.r.t. the un-normalised points, flat) or
+        None when the shape is not the one ia_mlp_fwd_grad implements (then _analytic_eval differentiates torch operators)."""
+        enc_mod, net = self.encoding, self.network
+        grid, active = self._analytic_grid()
+        if grid is None or not enc_mod.include_xyz or "sdf_activation" in self.config or \
+                not (net.output_activation_name is None or str(net.output_activation_name).lower() == "none"):
+            return None
+        desc = ops.make_mlp_desc(3, grid.n_output_dims, net.n_hidden_layers, net.n_output_dims, net.hidden_act,
+                                 enc_mod.xyz_scale, enc_mod.xyz_offset, net.precision)
+        if not ops.mlp_fwd_grad_supported(desc):
+            return None
+        x = pts01.reshape(-1, 3)
+        flat = net.flat_params() if flat is None else flat
+        enc = ops.hashgrid_encode(x, grid.params, grid.plan, active)
+        h, g0, g1 = ops.mlp_fwd_grad(x, enc, flat, desc)
+        g01 = ops.hashgrid_input_grad(x, grid.params, g1, grid.plan, active) + g0
+        # points01 = (points + r) / (2 r)   (AABB contraction, models/geometry.py:24)
+        grad = (g01 / (2.0 * self.radius)).view(*pts01.shape[:-1], 3)
+        return h, grad, flat
+
+    def _analytic_eval(self, pts01, flat=None):
         """grad_type 'analytic' (reference models/geometry.py:198-218): the centre evaluation together with
         d sdf / d points by the chain rule, kept differentiable (create_graph) so that the eikonal / rendering losses
         back-propagate through the normals.  Per sample: hash-grid forward (kernel) -> network as torch operators
@@ -142,6 +172,16 @@ class VolumeSDF(BaseImplicitGeometry):
             grid, active = inner, inner.plan.n_levels
         else:
             raise NotImplementedError("grad_type='analytic' is implemented for (ProgressiveBand)HashGrid encodings")
+        hg = self._analytic_hidden(pts01, flat)
+        if hg is not None:
+            # tensor-core path: network and d sdf / d(network input) in one kernel whose backward is the second-order adjoint
+            # (ops.mlp_fwd_grad); the wide output layer by linear64 as for the first-order centre evaluation
+            h, grad, flat = hg
+            net = self.network
+            n_out, width = net.n_output_dims, net.n_neurons
+            n_hidden = flat.numel() - (n_out * width + n_out)
+            out = ops.linear64(h, flat[n_hidden:n_hidden + n_out * width].view(n_out, width), flat[n_hidden + n_out * width:])
+            return out, grad
         enc = ops.hashgrid_encode(x, grid.params, grid.plan, active)
         parts = ([x * enc_mod.xyz_scale + enc_mod.xyz_offset] if enc_mod.include_xyz else []) + [enc]
         e = torch.cat(parts, dim=-1)
@@ -180,7 +220,7 @@ class VolumeSDF(BaseImplicitGeometry):
             need_full = with_feature
             grad = None
             if analytic:
-                out, grad = self._analytic_eval(pts01)
+                out, grad = self._analytic_eval(pts01, flat)
             else:
                 out = self._net(pts01, self.n_output_dims if need_full else 1, flat)
             out = out.view(*pts01.shape[:-1], out.shape[-1])
@@ -222,20 +262,33 @@ class VolumeSDF(BaseImplicitGeometry):
         from . import _lib as L
         act = self.network.output_activation_name
         return (os.environ.get("IA_NO_FUSED_HEAD") is None and self.network.precision == L.IA_MLP_TC_F16
-                and self.n_output_dims > 8 and self.grad_type == "finite_difference"
+                and self.n_output_dims > 8 and (self.grad_type == "finite_difference" or self._analytic_kernel_ok())
                 and "sdf_activation" not in self.config and "feature_activation" not in self.config
                 and (act is None or str(act).lower() == "none"))
+
+    def _analytic_kernel_ok(self) -> bool:
+        if self.grad_type != "analytic":
+            return False
+        grid, _ = self._analytic_grid()
+        net = self.network
+        if grid is None or not self.encoding.include_xyz:
+            return False
+        desc = ops.make_mlp_desc(3, grid.n_output_dims, net.n_hidden_layers, net.n_output_dims, net.hidden_act, 1.0, 0.0, net.precision)
+        return ops.mlp_fwd_grad_supported(desc)
 
     def forward_hidden(self, points, rand_directions: Optional[torch.Tensor] = None):
         """Same evaluations as forward(points, with_grad=True, with_feature=True, with_laplace=True) (reference
         models/geometry.py:195-275) except that the centre evaluation stops at the last hidden layer.
         Returns (h [S,64], pts01 [S,3], grad [S,3], laplace [S,1], W_last [Fd,64], b_last [Fd])."""
-        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+        with torch.set_grad_enabled((self.training and torch.is_grad_enabled()) or self.grad_type == "analytic"):
             flat = self.network.flat_params()
             pts01 = contract_to_unisphere(points, self.radius, self.contraction_type)
-            h = self._net(pts01, 0, flat)
             eps = self._finite_difference_eps
-            grad = self._fd_gradient(points, eps, flat)
+            if self.grad_type == "analytic":
+                h, grad, flat = self._analytic_hidden(pts01, flat)
+            else:
+                h = self._net(pts01, 0, flat)
+                grad = self._fd_gradient(points, eps, flat)
             if rand_directions is None:
                 rand_directions = torch.randn_like(pts01)
             normals, shifted = ops.curv_shift(grad.reshape(-1, 3), rand_directions.reshape(-1, 3), pts01.reshape(-1, 3), eps)

@@ -295,6 +295,56 @@ class _MLPFn(torch.autograd.Function):
         return d0, d1, dp, None, None
 
 
+class _MLPGradFn(torch.autograd.Function):
+    """(h, g0, g1) = (last hidden layer, d out0 / d in0, d out0 / d in1) of the SDF network in one kernel, with the adjoint
+    of that triple as its backward (ia_mlp_fwd_grad / ia_mlp_fwd_grad_bwd): reference models/geometry.py:206 + :214-218,
+    `torch.autograd.grad(sdf, points_, create_graph=True)` followed by a backward through the resulting normals."""
+
+    @staticmethod
+    def forward(ctx, in0, in1, params, desc):
+        L.require_cuda(in0, in1, params)
+        in0, in1, params = L.f32c(in0), L.f32c(in1), L.f32c(params)
+        n = in1.shape[0]
+        h = torch.empty(n, desc.width, device=params.device, dtype=torch.float32)
+        g0 = torch.empty(n, desc.n_in0, device=params.device, dtype=torch.float32)
+        g1 = torch.empty(n, desc.n_in1, device=params.device, dtype=torch.float32)
+        # 2 MAC per weight: forward (W0, W1) + the gradient chain (W1^T, W0^T)
+        flops = 4 * n * (desc.width * (desc.n_in0 + desc.n_in1) + desc.width * desc.width)
+        _run("ia_mlp_fwd_grad", C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(h), L.ptr(g0), L.ptr(g1), L.stream(),
+             work=flops, tag=f"{desc.n_in0 + desc.n_in1}>h+g")
+        ctx.save_for_backward(in0, in1, params)
+        ctx.desc = desc
+        return h, g0, g1
+
+    @staticmethod
+    def backward(ctx, dh, dg0, dg1):
+        in0, in1, params = ctx.saved_tensors
+        desc = ctx.desc
+        n = in1.shape[0]
+        dh = L.f32c(dh) if dh is not None else None
+        dg0 = L.f32c(dg0) if dg0 is not None else None
+        dg1 = L.f32c(dg1) if dg1 is not None else None
+        need0, need1, needp = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d0 = torch.empty_like(in0) if need0 else None
+        d1 = torch.empty_like(in1) if need1 else None
+        dp = torch.zeros_like(params) if needp else None
+        if n > 0:
+            flops = 2 * n * (7 * desc.width * desc.width + 4 * desc.width * (desc.n_in0 + desc.n_in1))     # 4 + 2 W0-shaped, 4 + 3 W1-shaped GEMMs... per row
+            _run("ia_mlp_fwd_grad_bwd", C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dh), L.ptr(dg0), L.ptr(dg1),
+                 L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=flops, tag=f"{desc.n_in0 + desc.n_in1}>h+g")
+        return d0, d1, dp, None
+
+
+def mlp_fwd_grad_supported(desc: L.MlpDesc) -> bool:
+    return (desc.precision == L.IA_MLP_TC_F16 and desc.n_in0 == 3 and desc.n_in1 == 32 and desc.n_hidden_layers == 2
+            and desc.width == 64 and desc.hidden_act == L.IA_ACT_SOFTPLUS100 and os.environ.get("IA_ANALYTIC_TORCH") is None)
+
+
+def mlp_fwd_grad(in0: torch.Tensor, in1: torch.Tensor, params: torch.Tensor, desc: L.MlpDesc):
+    """-> (h [N,64] last hidden layer, g0 [N,3] = d out0 / d in0, g1 [N,32] = d out0 / d in1); differentiable once more."""
+    return _MLPGradFn.apply(in0, in1, params, desc)
+
+
 class _SdfFusedFn(torch.autograd.Function):
     """network(cat[x*s+o, hashgrid(x)]) in one kernel (ia_sdf_taps_fused_fwd / _bwd): reference models/geometry.py:206, 233, 266
     `self.network(self.encoding(points))` without the [N, L*F] encoding in HBM."""

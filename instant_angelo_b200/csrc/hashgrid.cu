@@ -458,6 +458,9 @@ hashgrid_bwd_input_bwd_table_kernel(const float *__restrict__ x, int64_t n, cons
 // cell, so their corner contributions are summed in registers and scattered ONCE (4 REDs per x-corner instead of
 // 4*G).  One thread owns (group, x-corner, 4 levels); the taps of the group are walked sequentially and the pending
 // cell is flushed whenever the cell changes.  Same result as hashgrid_bwd_kernel up to fp32 summation order.
+#ifndef HGG_MINB
+#define HGG_MINB 4
+#endif
 constexpr int HGG_GROUPS = 32;   // groups per CTA (256 threads = 32 groups x 2 x-corners x 4 level slots)
 
 // The level walk of one thread of hashgrid_bwd_grouped_kernel: (group grp, x side xc, levels ls, ls+4, ...).  TOTAL: some tap
@@ -531,7 +534,7 @@ __device__ __forceinline__ void grouped_walk(const GridParams &P, const float *t
 }
 
 template <int G, bool WITH_TABLE, bool WITH_INPUT>
-__global__ void __launch_bounds__(HG_THREADS)
+__global__ void __launch_bounds__(HG_THREADS, HGG_MINB)
 hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table,
                             const float *__restrict__ dy, const GridParams P, float2 *__restrict__ dtable,
                             float *__restrict__ dx)

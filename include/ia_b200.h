@@ -229,6 +229,20 @@ int32_t ia_sdf_head_bwd(const float *h, int64_t n, const float *W, const float *
                         int32_t n_enc, const float *dextra, int32_t n_extra, float *dh, float *dW, float *db,
                         float *dpts01, float *denc, float *dnormal, void *stream);
 
+/* The same input row with the SDF network's wide output layer FOLDED into the colour network's first layer: with
+ * out = Wl h + bl, colour layer 0 is z = (Wc0[:, :n_feat] Wl) h + Wc0[:, n_feat:] [pts | enc | normal] + (bc0 + Wc0[:, :n_feat] bl), so the
+ * colour network reads h directly and the [n, n_feat] geometry output (models/geometry.py:206-207) is never formed; the caller
+ * composes the two small matrices.  tin[n, ld] = [h (64) | pts01*2-1 (3) | enc (n_enc) | normal (3) | zeros up to ld] (ld % 4 == 0);
+ * the four geometry outputs used outside the colour network -- sdf = out[:, 0] and the dual-colour diffuse term out[:, 1:4]
+ * (models/texture.py:58) -- come from W4 = Wl[0:4], b4 = bl[0:4]. */
+int32_t ia_colour_in_fwd(const float *h, int64_t n, const float *W4, const float *b4, const float *pts01, const float *enc,
+                         int32_t n_enc, const float *normal, float *tin, int64_t ld, float *sdf, float *rgb_raw, void *stream);
+/* dh[n,64] = dtin[:, :64] + [dsdf | drgb] W4 (overwritten); dpts01 / denc / dnormal: column blocks of dtin (overwritten, may be
+ * NULL); dW4[4,64], db4[4] ACCUMULATED (may be NULL). */
+int32_t ia_colour_in_bwd(const float *h, int64_t n, const float *W4, const float *dtin, int64_t ld, int32_t n_enc,
+                         const float *dsdf, const float *drgb, float *dh, float *dW4, float *db4, float *dpts01, float *denc,
+                         float *dnormal, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Finite-difference / curvature stages  fused elementwise stages of VolumeSDF.forward
  *                                       (models/geometry.py:219-234 FD taps + gradient, :236-275 curvature)

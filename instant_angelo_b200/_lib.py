@@ -96,6 +96,8 @@ SIGNATURES = {
     "ia_linear64_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _P]),
     "ia_sdf_head_fwd": (_I32, [_P, _I64, _P, _P, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
     "ia_sdf_head_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "ia_colour_in_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
+    "ia_colour_in_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_fd_taps_fwd": (_I32, [_P, _I64, _F, _F, _P, _P]),
     "ia_fd_taps_bwd": (_I32, [_P, _I64, _F, _F, _P, _P, _P]),
     "ia_fd_grad_fwd": (_I32, [_P, _I64, _F, _P, _P]),

@@ -1,0 +1,190 @@
+// Input row of the colour head when the SDF network's wide output layer is FOLDED into the colour network's first layer.
+//
+// Reference: feature = cat[out, points*2-1] (models/geometry.py:206-207), network_inp = cat[feature, dirs_embd, normals]
+// (models/texture.py:26-27), colour layer 0: z = Wc0 network_inp + bc0.  With out = Wl h + bl (h = last hidden layer of the SDF
+// network) the first 65 columns of Wc0 compose with Wl:  z = (Wc0[:, :65] Wl) h + Wc0[:, 65:] [pts | enc | normal] + (bc0 + Wc0[:, :65] bl),
+// so the colour network can read h directly and the [N, 65] geometry output is never formed.  Only the four columns that are used
+// outside the colour network are: sdf = out[:, 0] and the dual-colour diffuse term out[:, 1:4] (models/texture.py:58).
+//
+//   forward : tin[N, ld] = [h (64) | pts01*2-1 (3) | enc (n_enc) | normal (3) | zero padding],  out4[N, 4] = h W4^T + b4
+//   backward: dh = dtin[:, :64] + dout4 W4;  dpts01 = 2 dtin[:, 64:67];  denc, dnormal = column blocks;  dW4 += dout4^T h;  db4 += sum dout4
+// HBM streaming: 64-row tiles staged through shared memory, every global access a whole line; dW4 accumulates in one register per
+// thread across the tiles of a persistent CTA.
+#include <algorithm>
+
+#include "ia_common.cuh"
+
+namespace {
+
+constexpr int CI_THREADS = 256;
+constexpr int CI_W = 64;
+constexpr int CI_T = 64;          // rows per tile
+constexpr int CI_HS = 68;         // smem row stride of the h tile: 16-byte aligned rows, (4 r + k) % 32 distinct for 8 rows of a warp
+
+// extras block of a row: columns [64, ld) of tin = [pts01*2-1 | enc | normal | zeros]
+__device__ __forceinline__ float extra_value(int c, int64_t row, const float *__restrict__ pts01, const float *__restrict__ enc, int n_enc,
+                                             const float *__restrict__ normal)
+{
+    if (c < 3) return fmaf(__ldg(pts01 + row * 3 + c), 2.f, -1.f);
+    if (c < 3 + n_enc) return __ldg(enc + row * n_enc + (c - 3));
+    if (c < 6 + n_enc) return __ldg(normal + row * 3 + (c - 3 - n_enc));
+    return 0.f;
+}
+
+__global__ void __launch_bounds__(CI_THREADS)
+colour_in_fwd_kernel(const float *__restrict__ h, int64_t n, const float *__restrict__ W4, const float *__restrict__ b4,
+                     const float *__restrict__ pts01, const float *__restrict__ enc, int n_enc, const float *__restrict__ normal,
+                     float *__restrict__ tin, int ld, float *__restrict__ sdf, float *__restrict__ rgb_raw)
+{
+    __shared__ __align__(16) float hs[CI_T * CI_HS];
+    __shared__ float w4s[4 * 65];
+    const int tid = threadIdx.x;
+    w4s[(tid >> 6) * 65 + (tid & 63)] = __ldg(W4 + tid);
+    const int r_dot = tid >> 2, o_dot = tid & 3;
+    const float bias = __ldg(b4 + o_dot);
+    const int n_x = ld - CI_W;
+    const int64_t n_tiles = (n + CI_T - 1) / CI_T;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * CI_T;
+        __syncthreads();                 // previous tile's dot products have read hs (and w4s is written)
+#pragma unroll
+        for (int i = 0; i < CI_T * 16 / CI_THREADS; ++i) {
+            const int idx = tid + i * CI_THREADS, r = idx >> 4, q = idx & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base + r < n) {
+                v = __ldg(reinterpret_cast<const float4 *>(h + (base + r) * CI_W) + q);
+                *reinterpret_cast<float4 *>(tin + (base + r) * ld + 4 * q) = v;
+            }
+            *reinterpret_cast<float4 *>(&hs[r * CI_HS + 4 * q]) = v;
+        }
+        for (int idx = tid; idx < CI_T * n_x; idx += CI_THREADS) {
+            const int r = idx / n_x, c = idx - r * n_x;
+            if (base + r < n) tin[(base + r) * ld + CI_W + c] = extra_value(c, base + r, pts01, enc, n_enc, normal);
+        }
+        __syncthreads();
+        float acc = bias;
+#pragma unroll 16
+        for (int k = 0; k < CI_W; ++k) acc = fmaf(hs[r_dot * CI_HS + k], w4s[o_dot * 65 + k], acc);
+        const int64_t row = base + r_dot;
+        if (row < n) {
+            if (o_dot == 0) sdf[row] = acc;
+            else rgb_raw[row * 3 + (o_dot - 1)] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CI_THREADS)
+colour_in_bwd_kernel(const float *__restrict__ h, int64_t n, const float *__restrict__ W4, const float *__restrict__ dtin, int ld,
+                     int n_enc, const float *__restrict__ dsdf, const float *__restrict__ drgb, float *__restrict__ dh,
+                     float *__restrict__ dW4, float *__restrict__ db4, float *__restrict__ dpts01, float *__restrict__ denc,
+                     float *__restrict__ dnormal)
+{
+    __shared__ __align__(16) float hs[CI_T * CI_HS];
+    __shared__ __align__(16) float w4s[4 * CI_W];
+    __shared__ float d4s[CI_T * 4];
+    const int tid = threadIdx.x;
+    w4s[tid] = __ldg(W4 + tid);
+    const int o_w = tid >> 6, k_w = tid & 63;      // this thread's dW4 entry
+    float gw = 0.f, gb = 0.f;
+    const int n_extra = 3 + n_enc + 3;
+    const int64_t n_tiles = (n + CI_T - 1) / CI_T;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * CI_T;
+        __syncthreads();                 // previous tile's accumulation has read hs / d4s
+        {
+            const int r = tid >> 2, o = tid & 3;
+            const int64_t row = base + r;
+            float v = 0.f;
+            if (row < n) v = o == 0 ? (dsdf ? __ldg(dsdf + row) : 0.f) : (drgb ? __ldg(drgb + row * 3 + (o - 1)) : 0.f);
+            d4s[r * 4 + o] = v;
+        }
+        if (dW4) {
+#pragma unroll
+            for (int i = 0; i < CI_T * 16 / CI_THREADS; ++i) {
+                const int idx = tid + i * CI_THREADS, r = idx >> 4, q = idx & 15;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + r < n) v = __ldg(reinterpret_cast<const float4 *>(h + (base + r) * CI_W) + q);
+                *reinterpret_cast<float4 *>(&hs[r * CI_HS + 4 * q]) = v;
+            }
+        }
+        __syncthreads();
+        if (dh) {
+#pragma unroll
+            for (int i = 0; i < CI_T * 16 / CI_THREADS; ++i) {
+                const int idx = tid + i * CI_THREADS, r = idx >> 4, q = idx & 15;
+                if (base + r < n) {
+                    float4 g = __ldg(reinterpret_cast<const float4 *>(dtin + (base + r) * ld) + q);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const float d = d4s[r * 4 + o];
+                        const float4 w = *reinterpret_cast<const float4 *>(&w4s[o * CI_W + 4 * q]);
+                        g.x = fmaf(d, w.x, g.x); g.y = fmaf(d, w.y, g.y); g.z = fmaf(d, w.z, g.z); g.w = fmaf(d, w.w, g.w);
+                    }
+                    *reinterpret_cast<float4 *>(dh + (base + r) * CI_W + 4 * q) = g;
+                }
+            }
+        }
+        for (int idx = tid; idx < CI_T * n_extra; idx += CI_THREADS) {
+            const int r = idx / n_extra, c = idx - r * n_extra;
+            const int64_t row = base + r;
+            if (row < n) {
+                const float v = __ldg(dtin + row * ld + CI_W + c);
+                if (c < 3) { if (dpts01) dpts01[row * 3 + c] = 2.f * v; }
+                else if (c < 3 + n_enc) { if (denc) denc[row * n_enc + (c - 3)] = v; }
+                else if (dnormal) dnormal[row * 3 + (c - 3 - n_enc)] = v;
+            }
+        }
+        if (dW4) {
+#pragma unroll 16
+            for (int r = 0; r < CI_T; ++r) {
+                const float d = d4s[r * 4 + o_w];
+                gw = fmaf(d, hs[r * CI_HS + k_w], gw);
+                gb += d;
+            }
+        }
+    }
+    if (dW4) {
+        atomicAdd(dW4 + o_w * CI_W + k_w, gw);
+        if (db4 && k_w == 0) atomicAdd(db4 + o_w, gb);
+    }
+}
+
+int check_args(int64_t n, int32_t n_enc, int64_t ld)
+{
+    IA_REQUIRE(n >= 0, "ia_colour_in: n < 0");
+    IA_REQUIRE(n_enc >= 0 && n_enc <= 64, "ia_colour_in: n_enc %d out of range", n_enc);
+    IA_REQUIRE(ld >= CI_W + 3 + n_enc + 3 && (ld & 3) == 0, "ia_colour_in: row stride %lld must be a multiple of 4 and >= 64 + 3 + n_enc + 3",
+               (long long)ld);
+    return IA_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t ia_colour_in_fwd(const float *h, int64_t n, const float *W4, const float *b4, const float *pts01,
+                                    const float *enc, int32_t n_enc, const float *normal, float *tin, int64_t ld, float *sdf,
+                                    float *rgb_raw, void *stream)
+{
+    const int rc = check_args(n, n_enc, ld);
+    if (rc != IA_OK) return rc;
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(h && W4 && b4 && pts01 && normal && tin && sdf && rgb_raw && (enc || n_enc == 0), "ia_colour_in_fwd: NULL pointer");
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, CI_T), (int64_t)ia_sm_count() * 6);
+    colour_in_fwd_kernel<<<blocks, CI_THREADS, 0, (cudaStream_t)stream>>>(h, n, W4, b4, pts01, enc, n_enc, normal, tin, (int)ld, sdf, rgb_raw);
+    IA_LAUNCH_OK("colour_in_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_colour_in_bwd(const float *h, int64_t n, const float *W4, const float *dtin, int64_t ld, int32_t n_enc,
+                                    const float *dsdf, const float *drgb, float *dh, float *dW4, float *db4, float *dpts01,
+                                    float *denc, float *dnormal, void *stream)
+{
+    const int rc = check_args(n, n_enc, ld);
+    if (rc != IA_OK) return rc;
+    if (n == 0) return IA_OK;
+    IA_REQUIRE(h && W4 && dtin, "ia_colour_in_bwd: NULL pointer");
+    const unsigned blocks = (unsigned)std::min<int64_t>(ia_ceil_div(n, CI_T), (int64_t)ia_sm_count() * 6);
+    colour_in_bwd_kernel<<<blocks, CI_THREADS, 0, (cudaStream_t)stream>>>(h, n, W4, dtin, (int)ld, n_enc, dsdf, drgb, dh, dW4, db4, dpts01,
+                                                                         denc, dnormal);
+    IA_LAUNCH_OK("colour_in_bwd_kernel");
+    return IA_OK;
+}

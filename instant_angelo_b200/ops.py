@@ -18,7 +18,8 @@ _LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_fwd_grouped": 1, "ia_hashgrid_bw
              "ia_sh_bwd": 1, "ia_mlp_fwd": 1, "ia_mlp_bwd": 1, "ia_linear64_fwd": 1, "ia_linear64_bwd": 2, "ia_aabb": 1, "ia_march_count": 1, "ia_march_scan": 1,
              "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
              "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0,
-             "ia_sdf_taps_fused_fwd": 1, "ia_sdf_taps_fused_bwd": 2}
+             "ia_sdf_taps_fused_fwd": 1, "ia_sdf_taps_fused_bwd": 2, "ia_mlp_fwd_grad": 1, "ia_mlp_fwd_grad_bwd": 4,
+             "ia_colour_in_fwd": 1, "ia_colour_in_bwd": 1}
 
 
 class Profiler:
@@ -559,6 +560,52 @@ class _SdfHeadFn(torch.autograd.Function):
 def sdf_head(h, W, b, pts01, enc, normal):
     """-> (tin [N, n_feat+3+n_enc+3], sdf [N], rgb_raw [N,3]); see _SdfHeadFn."""
     return _SdfHeadFn.apply(h, W, b, pts01, enc, normal)
+
+
+class _ColourInFn(torch.autograd.Function):
+    """Input row of the colour head with the SDF network's output layer folded into the colour network's first layer
+    (ia_colour_in_fwd / _bwd): tin = [h | pts01*2-1 | enc | normal | 0-pad], sdf = h.W4[0] + b4[0], rgb_raw = h W4[1:4]^T + b4[1:4]."""
+
+    @staticmethod
+    def forward(ctx, h, W4, b4, pts01, enc, normal, ld):
+        L.require_cuda(h, W4, b4, pts01, enc, normal)
+        h, W4, b4, pts01, enc, normal = L.f32c(h), L.f32c(W4), L.f32c(b4), L.f32c(pts01), L.f32c(enc), L.f32c(normal)
+        n, n_enc = h.shape[0], enc.shape[1]
+        tin = torch.empty(n, ld, device=h.device, dtype=torch.float32)
+        sdf = torch.empty(n, device=h.device, dtype=torch.float32)
+        rgb_raw = torch.empty(n, 3, device=h.device, dtype=torch.float32)
+        _run("ia_colour_in_fwd", L.ptr(h), n, L.ptr(W4), L.ptr(b4), L.ptr(pts01), L.ptr(enc), n_enc, L.ptr(normal), L.ptr(tin), ld,
+             L.ptr(sdf), L.ptr(rgb_raw), L.stream(), work=2.0 * n * 4 * 64)
+        ctx.save_for_backward(h, W4)
+        ctx.dims = (n_enc, ld)
+        return tin, sdf, rgb_raw
+
+    @staticmethod
+    def backward(ctx, dtin, dsdf, drgb):
+        h, W4 = ctx.saved_tensors
+        n_enc, ld = ctx.dims
+        n = h.shape[0]
+        dtin = L.f32c(dtin)
+        dsdf = L.f32c(dsdf) if dsdf is not None else None
+        drgb = L.f32c(drgb) if drgb is not None else None
+        need = ctx.needs_input_grad
+        dh = torch.empty_like(h) if need[0] else None
+        dW = torch.zeros_like(W4) if (need[1] or need[2]) else None
+        db = torch.zeros(4, device=h.device) if need[2] else None
+        dpts = torch.empty(n, 3, device=h.device) if need[3] else None
+        denc = torch.empty(n, n_enc, device=h.device) if need[4] else None
+        dnrm = torch.empty(n, 3, device=h.device) if need[5] else None
+        if n > 0:
+            _run("ia_colour_in_bwd", L.ptr(h), n, L.ptr(W4), L.ptr(dtin), ld, n_enc, L.ptr(dsdf), L.ptr(drgb), L.ptr(dh), L.ptr(dW), L.ptr(db),
+                 L.ptr(dpts), L.ptr(denc), L.ptr(dnrm), L.stream(), work=4.0 * n * 4 * 64)
+        elif dh is not None:
+            dh.zero_()
+        return dh, (dW if need[1] else None), db, dpts, denc, dnrm, None
+
+
+def colour_in(h, W4, b4, pts01, enc, normal, ld: int):
+    """-> (tin [N, ld], sdf [N], rgb_raw [N,3]); see _ColourInFn."""
+    return _ColourInFn.apply(h, W4, b4, pts01, enc, normal, int(ld))
 
 
 def mlp_apply(in0: Optional[torch.Tensor], in1: Optional[torch.Tensor], params: torch.Tensor, desc: L.MlpDesc,

@@ -8,10 +8,17 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+import os
+
+from . import _lib as _L
 from . import ops
 from . import registry as models
 from .network_utils import get_encoding, get_mlp, update_module_step
 from .utils import get_activation
+
+
+# IA_FOLD_HEAD=0: keep the geometry output layer as its own (fp32 FFMA) projection in front of the colour network (A/B runs)
+_FOLD_HEAD = os.environ.get("IA_FOLD_HEAD", "1") not in ("0", "")
 
 
 @models.register("volume-radiance")
@@ -51,8 +58,33 @@ class VolumeRadiance(nn.Module):
         """forward(cat[geometry_out, pts01*2-1], dirs, normals) with geometry_out = h @ w_last.T + b_last applied inside
         the assembly.  Returns (color [S,3], sdf [S])."""
         dirs_embd = self.encoding(((dirs + 1.0) / 2.0).view(-1, self.n_dir_dims))
-        tin, sdf, rgb_raw = ops.sdf_head(h, w_last, b_last, pts01.reshape(-1, 3), dirs_embd, normals.reshape(-1, 3))
-        color = self.network(tin).view(*dirs.shape[:-1], self.n_output_dims).float()
+        net = self.network
+        n_feat = w_last.shape[0]
+        if _FOLD_HEAD and n_feat >= 4 and net.n_hidden_layers == 2 and net.precision == _L.IA_MLP_TC_F16 and h.shape[0] > 0:
+            # Fold the geometry output layer into the colour network's first layer: with out = Wl h + bl,
+            #   Wc0 [out | rest] + bc0 = (Wc0[:, :n_feat] Wl) h + Wc0[:, n_feat:] rest + (bc0 + Wc0[:, :n_feat] bl),
+            # so the colour network reads h (64 columns) instead of the n_feat-wide geometry output and the 64 -> n_feat
+            # projection of every sample (forward and backward) disappears; the compositions are 64 x n_feat x 64 products of
+            # parameters, done once per step as element-wise kernels.
+            flat = net.flat_params()
+            n_in, wd = net.n_input_dims, net.n_neurons
+            wc0 = flat[:wd * n_in].view(wd, n_in)
+            bc0 = flat[wd * n_in:wd * n_in + wd]
+            rest = flat[wd * n_in + wd:]
+            head = wc0[:, :n_feat]
+            m = (head[:, :, None] * w_last[None, :, :]).sum(1)                        # [wd, 64]
+            b_eff = bc0 + (head * b_last[None, :]).sum(1)
+            n_tail = n_in - n_feat                                                   # pts (3) | dirs_embd | normal (3)
+            ld = (wd + n_tail + 3) // 4 * 4                                          # 16-byte aligned rows
+            pad = wc0.new_zeros(wd, ld - wd - n_tail)
+            w_eff = torch.cat([m, wc0[:, n_feat:], pad], dim=1)
+            flat_eff = torch.cat([w_eff.reshape(-1), b_eff, rest])
+            tin, sdf, rgb_raw = ops.colour_in(h, w_last[:4], b_last[:4], pts01.reshape(-1, 3), dirs_embd, normals.reshape(-1, 3), ld)
+            desc = ops.make_mlp_desc(0, ld, net.n_hidden_layers, net.n_output_dims, net.hidden_act, 1.0, 0.0, net.precision)
+            color = net._post(ops.mlp_apply(None, tin, flat_eff, desc)).view(*dirs.shape[:-1], self.n_output_dims).float()
+        else:
+            tin, sdf, rgb_raw = ops.sdf_head(h, w_last, b_last, pts01.reshape(-1, 3), dirs_embd, normals.reshape(-1, 3))
+            color = net(tin).view(*dirs.shape[:-1], self.n_output_dims).float()
         if "color_activation" in self.config:
             act = get_activation(self.config["color_activation"])
             color = act(color) + act(rgb_raw.view(*dirs.shape[:-1], 3)) if self.dual else act(color)

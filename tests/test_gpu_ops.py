@@ -1009,6 +1009,38 @@ def test_sdf_head_matches_torch(cuda_lib, n, n_feat, n_enc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,n_enc", [(1, 16), (1003, 16), (70_001, 9)])
+def test_colour_in_matches_torch(cuda_lib, n, n_enc):
+    """ia_colour_in_fwd/bwd (geometry output layer folded into the colour network's first layer): the assembled row, the four
+    geometry outputs that are used outside the colour network, and every gradient against plain torch."""
+    from instant_angelo_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n)
+    h = torch.randn(n, 64, device="cuda", generator=g).requires_grad_(True)
+    W4 = (torch.randn(4, 64, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    b4 = torch.randn(4, device="cuda", generator=g).requires_grad_(True)
+    pts = torch.rand(n, 3, device="cuda", generator=g).requires_grad_(True)
+    enc = torch.randn(n, n_enc, device="cuda", generator=g).requires_grad_(True)
+    nrm = torch.randn(n, 3, device="cuda", generator=g).requires_grad_(True)
+    ld = (64 + 3 + n_enc + 3 + 3) // 4 * 4
+    tin, sdf, rgb = ops.colour_in(h, W4, b4, pts, enc, nrm, ld)
+    ct, cs, cr = (torch.randn(n, ld, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g),
+                  torch.randn(n, 3, device="cuda", generator=g))
+    ((tin * ct).sum() + (sdf * cs).sum() + (rgb * cr).sum()).backward()
+    got = [t.grad.clone() for t in (h, W4, b4, pts, enc, nrm)]
+    for t in (h, W4, b4, pts, enc, nrm):
+        t.grad = None
+    out4 = h.double() @ W4.double().t() + b4.double()
+    tin_ref = torch.cat([h.double(), pts.double() * 2 - 1, enc.double(), nrm.double(),
+                         torch.zeros(n, ld - 64 - 6 - n_enc, device="cuda", dtype=torch.float64)], 1)
+    ((tin_ref * ct.double()).sum() + (out4[:, 0] * cs.double()).sum() + (out4[:, 1:4] * cr.double()).sum()).backward()
+    assert_close(tin, tin_ref, rtol=1e-6, atol=1e-6, name="tin")
+    assert_close(sdf, out4[:, 0], rtol=1e-5, atol=1e-5, name="sdf")
+    assert_close(rgb, out4[:, 1:4], rtol=1e-5, atol=1e-5, name="rgb_raw")
+    for name, a, t in zip(("dh", "dW4", "db4", "dpts", "denc", "dnormal"), got, (h, W4, b4, pts, enc, nrm)):
+        rt, at = grad_tol(t.grad, 2e-5)
+        assert_close(a, t.grad, rtol=rt, atol=at, name=name)
+
+
 def test_empty_inputs_are_accepted_everywhere(cuda_lib):
     """Zero rows / zero rays (a batch whose rays all miss): every operator returns an empty result of the right shape and
     a zero / empty gradient, as the nerfacc and tcnn bindings do (the C ABI sees NULL data pointers with n = 0)."""

@@ -1445,6 +1445,8 @@ extern "C" int32_t ia_debug_tc_timing(int32_t enable, unsigned long long *out8_h
     return 0;
 }
 
+int ia_tc_launch_bwd_duo96(int pW0, int pb0, int pW1, int pb1, int pWl, int pbl, const float *in1, int64_t n, const float *params,
+                           const float *dout, int64_t ld_dout, float *din1, float *dparams, const float *gmax, cudaStream_t stream);
 int ia_mlp_fwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, const float *, int32_t, float *, int64_t, void *);
 int ia_mlp_bwd_fp32(const ia_mlp_desc *, const float *, const float *, int64_t, const float *, const float *, int32_t, int64_t,
                     float *, float *, float *, void *);
@@ -1586,6 +1588,13 @@ int launch_bwd_tc(const TcDims &D, const float *in0, const float *in1, int64_t n
     // the tap evaluations of the SDF network (one output column): two tiles in flight per CTA (mlp_tc_bwd_duo_kernel);
     // IA_TC_DUO=0 selects the single-tile software pipeline (A/B runs)
     static const bool duo_env = getenv("IA_TC_DUO") == nullptr || atoi(getenv("IA_TC_DUO")) != 0;
+    // the colour head after the output-layer fold (88 input columns, ReLU, 3 outputs): its own two-tile kernel (mlp_tc3.cu)
+    if (G == nullptr && !sp && D.n_in0 == 0 && D.n_in1 == 88 && D.nh == 2 && D.nou == 3 && D.n_out == 3 && duo_env) {
+        int rc = absmax_slot(dout, n, 3, ld_dout, (cudaStream_t)stream, &gmax);
+        if (rc) return rc;
+        return ia_tc_launch_bwd_duo96(D.pW0, D.pb0, D.pW1, D.pb1, D.pWl, D.pbl, in1, n, params, dout, ld_dout, din1, dparams, gmax,
+                                      (cudaStream_t)stream);
+    }
     if (G == nullptr && geo && (D.nou == 0 || D.nou == 1) && duo_env) {
         const DuoPlan DP = make_duo_plan();
         const unsigned dblocks = (unsigned)std::min<int64_t>(ia_ceil_div(n_tiles, 2), (int64_t)ia_sm_count());

@@ -334,6 +334,7 @@ MLP_CASES = {
     "geometry_full": (3, 32, 2, 65, True, True, 65),
     "geometry_sdf": (3, 32, 2, 65, True, True, 1),
     "texture": (0, 87, 2, 3, False, False, 3),
+    "texture_fold": (0, 88, 2, 3, False, False, 3),      # colour head after the output-layer fold: mlp_tc_bwd_duo96_kernel
     "v3_weight": (0, 71, 2, 1, False, False, 1),
     "bg_geometry": (3, 32, 1, 8, False, False, 8),
     "bg_texture": (0, 24, 2, 3, False, False, 3),

@@ -10,6 +10,8 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 20
 torch.manual_seed(0)
 if case == "geo":
     n0, n1, nh, nout, act, nou = 3, 32, 2, 65, L.IA_ACT_SOFTPLUS100, 1
+elif case == "tex88":       # colour head after the output-layer fold (mlp_tc_bwd_duo96_kernel)
+    n0, n1, nh, nout, act, nou = 0, 88, 2, 3, L.IA_ACT_RELU, 3
 else:
     n0, n1, nh, nout, act, nou = 0, 87, 2, 3, L.IA_ACT_RELU, 3
 desc = ops.make_mlp_desc(n0, n1, nh, nout, act, 2.0, -1.0, prec)

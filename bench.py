@@ -542,15 +542,20 @@ def run_b200(args):
                 "avg_launch_ms": ms / max(calls, 1), "algorithmic_flop_per_launch": work / max(calls, 1),
                 "note": "algorithmic FLOP = 2*MAC of the unpadded fp32 network (x2 for backward).  The kernel issues 3 f16 MMAs "
                         "per product (fp32-equivalent hi/lo split), pads K to 16 and recomputes the forward inside backward: for "
-                        "35->64->64->1 that is 5.2x the algorithmic FLOP on the tensor pipe (ncu: tensor pipe active 22.8 %). It "
-                        "is bound by its per-row activation epilogues and the serial MMA issue, not by the tensor pipe: see "
-                        "DESIGN.md section 4.2 and profiles/r01_ncu_mlp_tc.md"}
+                        "35->64->64->1 that is 5.2x the algorithmic FLOP on the tensor pipe (ncu of the two-tile kernel: tensor pipe "
+                        "active 29.7 %, every MMA at the pipe's full rate). It is bound by the dependent phase chain of a tile "
+                        "(store -> barrier -> MMA -> wait -> Softplus epilogue, six MUFU per element) of which two are in flight per "
+                        "SM, not by the tensor pipe: see DESIGN.md section 4.2 and profiles/r02_ncu_mlp_duo.md"}
     else:
         achieved = work / (ms / 1e3) / 1e9
         peak = peaks["hbm_gbs"]
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peaks["source"], "launches": calls, "avg_launch_ms": ms / max(calls, 1),
-                "algorithmic_bytes_per_launch": work / max(calls, 1)}
+                "algorithmic_bytes_per_launch": work / max(calls, 1),
+                "note": "algorithmic bytes = BASELINE.md section 3 per point-evaluation (every corner counted as an HBM access) against "
+                        "the HBM copy peak; rows that share cells (the six taps of a sample, neighbouring samples of a ray) are served "
+                        "by L1 / L2, so this fraction can exceed 1 -- the hard bounds for resident tables are the measured sector-gather "
+                        "peaks in hashgrid_microbench.sector_gather_peaks (DESIGN.md section 4.1)"}
 
     try:        # reporting only: never lose the bench line over it
         step_roof = step_roofline(fg_total / total_rays, (full_total - fg_total) / total_rays, value / world, peaks, args.grad_type,

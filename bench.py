@@ -40,6 +40,7 @@ import torch  # noqa: E402
 GLOBAL_STEP0 = 19000          # all 16 levels active (start_level 4 + (19000-5000)//1000 >= 16), curvature weight 0.5
 RAYS_PER_GPU = 8192           # max_train_num_rays of the config
 OCC_WARMUP_UPDATES = 16
+L2_WINDOW = None              # what ParamArena.pin_tables_in_l2 was granted (--l2-persist), for the bench line
 AR_EVENTS = None              # list of (start, end) CUDA events around the gradient all-reduce while the timed region runs
 
 
@@ -191,6 +192,8 @@ def build_b200(args, rank, world, device):
         var_arena.broadcast_params(0)
     opt = FusedAdamW(arena, lr=0.01)
     opt_var = FusedAdamW(var_arena, lr=0.001)
+    global L2_WINDOW
+    L2_WINDOW = arena.pin_tables_in_l2(args.l2_persist << 20) if args.l2_persist > 0 else None
     return cfg, model, arena, var_arena, opt, opt_var
 
 
@@ -587,7 +590,8 @@ def run_b200(args):
                     "centre evaluation returns the last hidden layer from the same kernel and applies the output layer with "
                     "the streaming fp32 linear64 kernels") if args.mlp == "tc" else "fp32 FFMA kernels",
             "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
-            "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)"},
+            "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)",
+            "l2_window": L2_WINDOW},
         "step_ms": step_stats,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
@@ -790,6 +794,8 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=0,
                     help="rays per step of the bounded CPU-oracle sample (0: ~15 s of CPU work for cpu_baseline, 512 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-persist", dest="l2_persist", type=int, default=int(os.environ.get("IA_L2_PERSIST_MB", "0")),
+                    help="MB of hash table to keep in a persisting L2 window (ia_l2_persist); 0 = off")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

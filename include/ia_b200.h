@@ -362,6 +362,17 @@ int32_t ia_adamw_step(float *param, const float *grad, float *exp_avg, float *ex
                       float grad_scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * L2 residency of the hash tables      (no reference counterpart: tcnn leaves the tables to the L2's LRU;
+ *                                      the tables gathered at models/network_utils.py:56-59 are re-fetched
+ *                                      from HBM after every [N, L*F] activation pass on a 126 MB L2)
+ * ------------------------------------------------------------------------------------------------ */
+/* Marks [base, base + bytes) as a persisting access-policy window of `stream` (every kernel enqueued on it
+ * afterwards) and reserves the matching L2 set-aside; bytes is clipped to the device's limits, hit_ratio is
+ * the fraction of the window that keeps the persisting property.  bytes == 0 removes the window and resets
+ * the persisting lines.  info_host (NULL or 3 int64): L2 size, set-aside granted, window bytes granted. */
+int32_t ia_l2_persist(const void *base, int64_t bytes, float hit_ratio, int64_t *info_host, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement aids (not part of the drop-in surface; used by bench.py and tools/)
  * ------------------------------------------------------------------------------------------------ */
 /* Random 32-byte-sector gather micro-benchmark (the L2 peak "must be measured on the box"): n_threads

@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libia_b200.so")
+LIB_PATH = os.environ.get("IA_LIB_PATH") or os.path.join(_HERE, "_build", "libia_b200.so")   # IA_LIB_PATH: A/B builds (build.py)
 IA_MAX_LEVELS = 32
 
 IA_ACT_NONE, IA_ACT_RELU, IA_ACT_SOFTPLUS100, IA_ACT_SIGMOID = 0, 1, 2, 3
@@ -119,6 +119,7 @@ SIGNATURES = {
     "ia_composite_fwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_composite_bwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_adamw_step": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _P]),
+    "ia_l2_persist": (_I32, [_P, _I64, _F, C.POINTER(C.c_int64 * 3), _P]),
     "ia_debug_sector_gather": (_I32, [_P, _I64, _I64, _I32, _P, _P]),
     "ia_debug_hashgrid_fwd_generic": (_I32, [_I32]),
     "ia_debug_tc_timing": (_I32, [_I32, C.POINTER(C.c_ulonglong)]),

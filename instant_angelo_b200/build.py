@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "_build")
+BUILD = os.environ.get("IA_BUILD_DIR") or os.path.join(HERE, "_build")     # A/B builds: IA_BUILD_DIR + IA_NVCC_EXTRA, loaded with IA_LIB_PATH
 LIB = os.path.join(BUILD, "libia_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
@@ -24,7 +24,8 @@ SOURCES = ["capi.cu", "hashgrid.cu", "sh.cu", "march.cu", "composite.cu", "mlp.c
 EXTRA = {"march.cu": ["-fmad=false"]}
 if os.environ.get("IA_TC_TIMING"):     # cycle accounting of the tensor-core MLP kernels (tools/prof_mlp.py --timing); off in product builds
     EXTRA["mlp_tc.cu"] = ["-DIA_TC_TIMING=1"]
-COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"] + \
+    os.environ.get("IA_NVCC_EXTRA", "").split()
 
 
 def _deps():

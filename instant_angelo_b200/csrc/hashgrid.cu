@@ -79,7 +79,7 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
         const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;     // 16 levels: shift, no integer division
-        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+        if (base + r < n) IA_ST_STREAM(&out2[(base + r) * row2 + c2], *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]));
     }
 }
 
@@ -170,7 +170,7 @@ hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const float2 *
     float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
         const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;     // 16 levels: shift, no integer division
-        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+        if (base + r < n) IA_ST_STREAM(&out2[(base + r) * row2 + c2], *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]));
     }
 }
 
@@ -247,7 +247,7 @@ hashgrid_fwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
     float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
     for (int i = tid; i < TP * row2; i += HG_THREADS) {
         const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;
-        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+        if (base + r < n) IA_ST_STREAM(&out2[(base + r) * row2 + c2], *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]));
     }
 }
 
@@ -269,7 +269,7 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
         const int r = i / row2, c2 = i - r * row2;
         float2 g = make_float2(0.f, 0.f);
-        if (base + r < n) g = __ldg(dy2 + (base + r) * row2 + c2);
+        if (base + r < n) g = IA_LD_STREAM(dy2 + (base + r) * row2 + c2);
         *reinterpret_cast<float2 *>(&tile[r * HG_ROW + 2 * c2]) = g;
     }
     float px = 0.f, py = 0.f, pz = 0.f;
@@ -396,7 +396,7 @@ hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
     float2 *__restrict__ out2 = reinterpret_cast<float2 *>(out);
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
         const int r = row2 == 16 ? (i >> 4) : i / row2, c2 = i - r * row2;     // 16 levels: shift, no integer division
-        if (base + r < n) out2[(base + r) * row2 + c2] = *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]);
+        if (base + r < n) IA_ST_STREAM(&out2[(base + r) * row2 + c2], *reinterpret_cast<const float2 *>(&tile[r * HG_ROW + 2 * c2]));
     }
 }
 
@@ -416,7 +416,7 @@ hashgrid_bwd_input_bwd_table_kernel(const float *__restrict__ x, int64_t n, cons
     for (int i = tid; i < HG_TILE * row2; i += HG_THREADS) {
         const int r = i / row2, c2 = i - r * row2;
         float2 g = make_float2(0.f, 0.f);
-        if (base + r < n) g = __ldg(dy2 + (base + r) * row2 + c2);
+        if (base + r < n) g = IA_LD_STREAM(dy2 + (base + r) * row2 + c2);
         *reinterpret_cast<float2 *>(&tile[r * HG_ROW + 2 * c2]) = g;
     }
     float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
@@ -549,7 +549,7 @@ hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
     for (int i = tid; i < TP * row2; i += HG_THREADS) {
         const int r = i / row2, c2 = i - r * row2;
         float2 g = make_float2(0.f, 0.f);
-        if (base + r < n) g = __ldg(dy2 + (base + r) * row2 + c2);
+        if (base + r < n) g = IA_LD_STREAM(dy2 + (base + r) * row2 + c2);
         *reinterpret_cast<float2 *>(&tile[r * HG_ROW + 2 * c2]) = g;
     }
     for (int i = tid; i < TP * 3; i += HG_THREADS) xs[i] = (base * 3 + i < n * 3) ? __ldg(x + base * 3 + i) : 0.f;

@@ -41,6 +41,16 @@ static inline int64_t ia_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b
 int ia_sm_count();
 
 #ifdef __CUDACC__
+// [N, L*F]-sized activation streams are written once and read once, a whole L2 later: evict-first hints keep them from
+// pushing the hash tables out of the L2 (IA_NO_STREAM_HINTS: plain accesses, for A/B builds)
+#ifndef IA_NO_STREAM_HINTS
+#define IA_LD_STREAM(p) __ldcs(p)
+#define IA_ST_STREAM(p, v) __stcs((p), (v))
+#else
+#define IA_LD_STREAM(p) __ldg(p)
+#define IA_ST_STREAM(p, v) (*(p) = (v))
+#endif
+
 __device__ __forceinline__ float ia_warp_sum(float v)
 {
 #pragma unroll

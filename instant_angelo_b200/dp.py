@@ -47,6 +47,31 @@ class ParamArena:
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 p.grad = g
 
+    def pin_tables_in_l2(self, max_bytes: int = 96 << 20) -> dict:
+        """Persisting L2 window over the leading run of large parameters (the hash tables come first in the arena): the
+        gathers of a step then hit the L2 set-aside instead of re-fetching table lines that the [N, L*F] activation
+        streams evicted.  The window is clipped to `max_bytes` and to what the device grants; the persisting fraction is
+        scaled so that the set-aside is not over-subscribed."""
+        from . import ops
+        if not self.data.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        tables = [(off, p.numel()) for p, off in zip(self.params, self.offsets) if p.numel() >= (1 << 20)]
+        if not tables:
+            return {}
+        lo = tables[0][0]
+        hi = lo
+        for off, n in tables:                 # contiguous prefix of tables that fits the budget
+            if (off + n - lo) * 4 > max_bytes and hi > lo:
+                break
+            hi = off + n
+        window = self.data[lo:hi]
+        probe = ops.l2_persist(window, 1.0)
+        ratio = min(1.0, probe["set_aside_bytes"] / max(probe["window_bytes"], 1))
+        if ratio < 1.0:
+            probe = ops.l2_persist(window, ratio)
+        probe["hit_ratio"] = ratio
+        return probe
+
     def all_reduce(self, group=None) -> None:
         """Sum over ranks (the mean's 1/G is applied by the optimizer)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -906,3 +906,18 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
     _run("ia_adamw_step", L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
                                    C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                    C.c_float(weight_decay), int(step), C.c_float(grad_scale), L.stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# L2 residency of the hash tables
+# ---------------------------------------------------------------------------------------------
+
+def l2_persist(t: Optional[torch.Tensor], hit_ratio: float = 1.0) -> dict:
+    """Persisting access-policy window over `t` on the current stream (None removes it): the hash tables stay in the L2's
+    set-aside across the [N, L*F] activation passes that would otherwise evict them (ia_l2_persist)."""
+    info = (C.c_int64 * 3)()
+    if t is None:
+        _run("ia_l2_persist", None, 0, C.c_float(0.0), C.byref(info), L.stream())
+    else:
+        _run("ia_l2_persist", L.ptr(t), t.numel() * t.element_size(), C.c_float(hit_ratio), C.byref(info), L.stream())
+    return {"l2_bytes": int(info[0]), "set_aside_bytes": int(info[1]), "window_bytes": int(info[2])}

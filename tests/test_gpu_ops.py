@@ -242,6 +242,30 @@ def test_hashgrid_scatters_into_the_gradient_arena(cuda_lib):
     assert float(gt.abs().max()) > 0.0
 
 
+def test_l2_persist_window_grant_and_reset(cuda_lib):
+    """ia_l2_persist: the window is clipped to the device limits, results do not change, bytes == 0 resets, bad args fail."""
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS["small_mixed"]
+    plan = ops.make_grid_plan(**cfg)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1000, 3, generator=g).cuda()
+    table = (torch.randn(plan.n_params, generator=g) * 0.1).cuda()
+    before = ops.hashgrid_encode(x, table, plan, plan.n_levels).clone()
+    info = ops.l2_persist(table, 1.0)
+    assert info["l2_bytes"] > 0 and 0 < info["window_bytes"] <= table.numel() * 4
+    assert 0 < info["set_aside_bytes"] <= info["window_bytes"]
+    assert torch.equal(ops.hashgrid_encode(x, table, plan, plan.n_levels), before)
+    info = ops.l2_persist(None)
+    assert info["window_bytes"] == 0 and info["set_aside_bytes"] == 0
+    assert torch.equal(ops.hashgrid_encode(x, table, plan, plan.n_levels), before)
+    lib = L.load()
+    assert lib.ia_l2_persist(L.ptr(table), 1024, C.c_float(1.5), None, L.stream()) == -1      # IA_ERR_INVALID_ARG
+    assert lib.ia_l2_persist(None, 1024, C.c_float(1.0), None, L.stream()) == -1
+    assert b"l2_persist" in lib.ia_last_error_string()
+
+
 def test_hashgrid_abi_entry_points_and_errors(cuda_lib):
     """ia_hashgrid_bwd_table / ia_hashgrid_bwd_input agree with the fused ia_hashgrid_bwd; bad args fail loudly."""
     import ctypes as C

@@ -193,7 +193,7 @@ def build_b200(args, rank, world, device):
     opt = FusedAdamW(arena, lr=0.01)
     opt_var = FusedAdamW(var_arena, lr=0.001)
     global L2_WINDOW
-    L2_WINDOW = arena.pin_tables_in_l2(args.l2_persist << 20) if args.l2_persist > 0 else None
+    L2_WINDOW = arena.pin_tables_in_l2(args.l2_persist << 20) if getattr(args, "l2_persist", 0) > 0 else None
     return cfg, model, arena, var_arena, opt, opt_var
 
 
@@ -335,14 +335,20 @@ def hashgrid_microbench(device, peaks):
     for log2_t in (19, 21):
         plan_t = ops.make_grid_plan(16, 2, log2_t, 32, 1.3195079107728942)
         table_t = torch.randn(plan_t.n_params, device=device, generator=g) * 0.1
+        table_h = ops.table_to_half(table_t)
         for active in (4, 16):
             for label, pts, dst in (("incoherent 2^22 uniform points", x, out), ("ray-coherent 8192 rays x 512 steps", x_coh, out_c)):
                 npts = pts.shape[0]
                 ms = timed(lambda: lib.ia_hashgrid_fwd(pts.data_ptr(), npts, table_t.data_ptr(), C.byref(plan_t), active, dst.data_ptr(), s))
                 bpp = ops.hashgrid_bytes_per_point(plan_t, active, "fwd")
-                grid.append({"log2_T": log2_t, "active_levels": active, "points": label, "ms": ms, "gevals_per_s": npts / ms / 1e6,
+                grid.append({"log2_T": log2_t, "active_levels": active, "points": label, "table": "fp32", "ms": ms, "gevals_per_s": npts / ms / 1e6,
                              "algorithmic_GBps": npts * bpp / ms / 1e6, "frac_of_hbm": npts * bpp / ms / 1e6 / peaks["hbm_gbs"]})
-        del table_t
+                # the same gathers from the fp16 shadow table (opt-in `table_precision: fp16`), against ITS algorithmic bytes
+                ms = timed(lambda: lib.ia_hashgrid_fwd_h(pts.data_ptr(), npts, table_h.data_ptr(), C.byref(plan_t), active, dst.data_ptr(), s))
+                bpp = ops.hashgrid_bytes_per_point(plan_t, active, "fwd", param_bytes=2)
+                grid.append({"log2_T": log2_t, "active_levels": active, "points": label, "table": "fp16", "ms": ms, "gevals_per_s": npts / ms / 1e6,
+                             "algorithmic_GBps": npts * bpp / ms / 1e6, "frac_of_hbm": npts * bpp / ms / 1e6 / peaks["hbm_gbs"]})
+        del table_t, table_h
     res["fwd_grid"] = grid
     # L2 / HBM random 32-byte-sector gather peaks: table resident in the 126 MB L2 vs. larger than it
     big = torch.randn((1 << 30) // 4, device=device, generator=g)            # 1 GiB
@@ -472,6 +478,7 @@ def run_b200(args):
     per_step_max = all_steps.max(dim=0).values
     step_stats = {"min_ms": float(per_step_max.min()), "median_ms": float(per_step_max.median()), "max_ms": float(per_step_max.max()),
                   "per_rank_mean_ms": [float(v) for v in all_steps.mean(dim=1)],
+                  "slowest_steps": [[int(i), round(float(per_step_max[i]), 2)] for i in torch.argsort(per_step_max, descending=True)[:3]],
                   "note": "device time between consecutive step boundaries (CUDA events); min/median/max over the K timed steps "
                           "of the per-step maximum over ranks"}
     if world > 1 and all_ar.numel():
@@ -591,7 +598,8 @@ def run_b200(args):
                     "the streaming fp32 linear64 kernels") if args.mlp == "tc" else "fp32 FFMA kernels",
             "optimizer": "fused AdamW inside the timed region", "occupancy_refresh": "every 16th step inside the timed region",
             "parallelism": f"dp{world} (ray-sharded, one NCCL all-reduce of the gradient arena per step)",
-            "l2_window": L2_WINDOW},
+            "l2_window": L2_WINDOW,
+            "hash_tables": "fp16 shadow (IA_TABLE_FP16=1)" if os.environ.get("IA_TABLE_FP16", "0") not in ("0", "") else "fp32"},
         "step_ms": step_stats,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},

@@ -107,6 +107,21 @@ int32_t ia_hashgrid_jvp(const float *x, int64_t n, const float *table, const flo
 int32_t ia_hashgrid_bwd_input_bwd_table(const float *x, int64_t n, const float *v, const float *dy,
                                         const ia_grid_plan *plan, int32_t active_levels, float *dtable, void *stream);
 
+/* fp16 shadow tables (opt-in, `table_precision: fp16` in the encoding config): the arena the optimizer owns stays fp32,
+ * the gathers read a __half2-per-entry copy refreshed by ia_table_to_half once per optimizer step -- tcnn's own arrangement
+ * (fp32 master parameters, fp16 copy for compute; the reference runs tcnn in fp16, models/network_utils.py:57).  Same
+ * indices and interpolation as the fp32 entry points; table_h has plan->offset[n_levels] entries of 4 bytes; interpolation
+ * and every gradient stay fp32.  group == 6 selects the grouped scatter as in ia_hashgrid_bwd_grouped, any other value the
+ * plain kernel; dtable / dx may be NULL. */
+int32_t ia_table_to_half(const float *table, int64_t n_floats, void *table_h, void *stream);
+int32_t ia_hashgrid_fwd_h(const float *x, int64_t n, const void *table_h, const ia_grid_plan *plan_host,
+                          int32_t active_levels, float *out, void *stream);
+int32_t ia_hashgrid_bwd_h(const float *x, int64_t n, const void *table_h, const float *dy,
+                          const ia_grid_plan *plan_host, int32_t active_levels, int32_t group, float *dtable, float *dx,
+                          void *stream);
+int32_t ia_hashgrid_jvp_h(const float *x, int64_t n, const void *table_h, const float *v, const ia_grid_plan *plan,
+                          int32_t active_levels, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Spherical harmonics                  replaces tcnn.Encoding(otype=SphericalHarmonics) built at
  *                                      models/network_utils.py:90-91, called at models/texture.py:25,52,129,134

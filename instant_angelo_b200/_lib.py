@@ -80,6 +80,10 @@ SIGNATURES = {
     "ia_hashgrid_bwd_grouped": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _I32, _P, _P, _P]),
     "ia_hashgrid_jvp": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _P, _P]),
     "ia_hashgrid_bwd_input_bwd_table": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _P, _P]),
+    "ia_table_to_half": (_I32, [_P, _I64, _P, _P]),
+    "ia_hashgrid_fwd_h": (_I32, [_P, _I64, _P, C.POINTER(GridPlan), _I32, _P, _P]),
+    "ia_hashgrid_bwd_h": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _I32, _P, _P, _P]),
+    "ia_hashgrid_jvp_h": (_I32, [_P, _I64, _P, _P, C.POINTER(GridPlan), _I32, _P, _P]),
     "ia_sh_fwd": (_I32, [_P, _I64, _I32, _P, _P]),
     "ia_sh_bwd": (_I32, [_P, _I64, _I32, _P, _P, _P]),
     "ia_mlp_param_count": (_I64, [C.POINTER(MlpDesc)]),

@@ -13,17 +13,26 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "ia_common.cuh"
 #include "hashgrid_device.cuh"
 
 namespace {
 
+// One table entry (F = 2 features) as float2.  Tables are fp32 (float2 entries: the arena the optimizer owns) or an fp16
+// shadow copy of it (__half2 entries, ia_table_to_half): 4-byte gathers, eight entries per 32-byte sector, half the L2 / HBM
+// footprint -- tcnn's own storage precision for the gathered copy (reference models/network_utils.py:57 runs tcnn in fp16).
+__device__ __forceinline__ float2 ld_entry(const float2 *__restrict__ t, uint32_t i) { return __ldg(t + i); }
+__device__ __forceinline__ float2 ld_entry(const __half2 *__restrict__ t, uint32_t i) { return __half22float2(__ldg(t + i)); }
+
 constexpr int HG_TILE = 128;     // points per CTA
 constexpr int HG_THREADS = 256;  // 2 lanes per point
 constexpr int HG_ROW = 34;       // padded floats per tile row (32 + 2): conflict-free float2 stores
 
+template <typename TT>
 __global__ void __launch_bounds__(HG_THREADS)
-hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const GridParams P,
+hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const TT *__restrict__ table, const GridParams P,
                     float *__restrict__ out)
 {
     __shared__ float tile[HG_TILE * HG_ROW];
@@ -51,7 +60,7 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         const float scale = P.scale[l];
         const uint32_t res = P.res[l], size = P.size[l];
         const bool hashed = P.hashed[l] != 0;
-        const float2 *__restrict__ tl = table + P.offset[l];
+        const TT *__restrict__ tl = table + P.offset[l];
         const CellCoords c = locate(px, py, pz, scale);
         const uint32_t cx = c.ix + xc;
         const float wx = xc ? c.wx : 1.f - c.wx;
@@ -60,10 +69,10 @@ hashgrid_fwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
             uint32_t i00, i10, i01, i11;
             if (!oob) corner4<false>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
             else corner4<true>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
-            v00 = __ldg(tl + i00);
-            v10 = __ldg(tl + i10);
-            v01 = __ldg(tl + i01);
-            v11 = __ldg(tl + i11);
+            v00 = ld_entry(tl, i00);
+            v10 = ld_entry(tl, i10);
+            v01 = ld_entry(tl, i01);
+            v11 = ld_entry(tl, i11);
         }
         const float w00 = wx * (1.f - c.wy) * (1.f - c.wz), w10 = wx * c.wy * (1.f - c.wz);
         const float w01 = wx * (1.f - c.wy) * c.wz, w11 = wx * c.wy * c.wz;
@@ -113,8 +122,8 @@ __device__ __forceinline__ void corner_indices(uint32_t cx, uint32_t iy, uint32_
     }
 }
 
-template <bool HASHED>
-__device__ __forceinline__ void fwd_level(int l, const GridParams &P, const float2 *__restrict__ table, float px, float py,
+template <bool HASHED, typename TT>
+__device__ __forceinline__ void fwd_level(int l, const GridParams &P, const TT *__restrict__ table, float px, float py,
                                           float pz, uint32_t xc, float *tile_row, bool oob)
 {
     const float scale = P.scale[l];
@@ -125,10 +134,10 @@ __device__ __forceinline__ void fwd_level(int l, const GridParams &P, const floa
     if (HASHED || !oob) corner_indices<HASHED>(c.ix + xc, c.iy, c.iz, P.res[l], P.size[l], i00, i10, i01, i11);
     else corner4<true>(c.ix + xc, c.iy, c.iz, P.res[l], P.size[l], false, i00, i10, i01, i11);
     // one 32-bit add per corner (level offset + entry), widened once by the address computation
-    const float2 v00 = __ldg(table + (off + i00));
-    const float2 v10 = __ldg(table + (off + i10));
-    const float2 v01 = __ldg(table + (off + i01));
-    const float2 v11 = __ldg(table + (off + i11));
+    const float2 v00 = ld_entry(table, off + i00);
+    const float2 v10 = ld_entry(table, off + i10);
+    const float2 v01 = ld_entry(table, off + i01);
+    const float2 v11 = ld_entry(table, off + i11);
     const float w00 = wx * (1.f - c.wy) * (1.f - c.wz), w10 = wx * c.wy * (1.f - c.wz);
     const float w01 = wx * (1.f - c.wy) * c.wz, w11 = wx * c.wy * c.wz;
     float a0 = w00 * v00.x + w10 * v10.x + w01 * v01.x + w11 * v11.x;
@@ -142,8 +151,9 @@ __device__ __forceinline__ void fwd_level(int l, const GridParams &P, const floa
 // of a training step (ncu: issue slots 91 % busy, profiles/r01_ncu_hashgrid_step.md): dense and hashed levels in separate
 // loops (P.n_dense), 32-bit entry offsets, and rows past n computed on a copy of the last point instead of predicating
 // every load (they are not written out).  Same indices and the same interpolation expression as hashgrid_fwd_kernel.
+template <typename TT>
 __global__ void __launch_bounds__(HG_THREADS)
-hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const GridParams P,
+hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const TT *__restrict__ table, const GridParams P,
                           float *__restrict__ out)
 {
     __shared__ float tile[HG_TILE * HG_ROW];
@@ -161,9 +171,9 @@ hashgrid_fwd_split_kernel(const float *__restrict__ x, int64_t n, const float2 *
     const int nd = P.n_dense < P.active ? P.n_dense : P.active;
     const bool oob = point_outside(px, py, pz);
 #pragma unroll 2
-    for (int l = 0; l < nd; ++l) fwd_level<false>(l, P, table, px, py, pz, xc, tile_row, oob);
+    for (int l = 0; l < nd; ++l) fwd_level<false, TT>(l, P, table, px, py, pz, xc, tile_row, oob);
 #pragma unroll 4
-    for (int l = nd; l < P.active; ++l) fwd_level<true>(l, P, table, px, py, pz, xc, tile_row, false);
+    for (int l = nd; l < P.active; ++l) fwd_level<true, TT>(l, P, table, px, py, pz, xc, tile_row, false);
     __syncthreads();
 
     const int row2 = P.n_levels;  // float2 per output row (F = 2)
@@ -251,9 +261,9 @@ hashgrid_fwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
     }
 }
 
-template <bool WITH_TABLE, bool WITH_INPUT>
+template <bool WITH_TABLE, bool WITH_INPUT, typename TT>
 __global__ void __launch_bounds__(HG_THREADS)
-hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table,
+hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const TT *__restrict__ table,
                     const float *__restrict__ dy, const GridParams P, float2 *__restrict__ dtable,
                     float *__restrict__ dx)
 {
@@ -308,8 +318,8 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         if (WITH_INPUT) {
             float d00 = 0.f, d10 = 0.f, d01 = 0.f, d11 = 0.f;
             if (valid) {
-                const float2 *__restrict__ tl = table + P.offset[l];
-                const float2 v00 = __ldg(tl + i00), v10 = __ldg(tl + i10), v01 = __ldg(tl + i01), v11 = __ldg(tl + i11);
+                const TT *__restrict__ tl = table + P.offset[l];
+                const float2 v00 = ld_entry(tl, i00), v10 = ld_entry(tl, i10), v01 = ld_entry(tl, i01), v11 = ld_entry(tl, i11);
                 d00 = v00.x * g.x + v00.y * g.y;
                 d10 = v10.x * g.x + v10.y * g.y;
                 d01 = v01.x * g.x + v01.y * g.y;
@@ -340,8 +350,9 @@ hashgrid_bwd_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
 //   d(dy)[l,f]            = scale_l * sum_axis v_axis * d interp_{l,f} / d axis          (hashgrid_jvp_kernel, gather)
 //   d(table)[corner c, f] += scale_l * dy[l,f] * sum_axis v_axis * d w_c / d axis       (hashgrid_bwd_input_bwd_table_kernel)
 // Same (point, x-corner) lane-pair mapping and tile staging as the first-order kernels.
+template <typename TT>
 __global__ void __launch_bounds__(HG_THREADS)
-hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table, const float *__restrict__ v,
+hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const TT *__restrict__ table, const float *__restrict__ v,
                     const GridParams P, float *__restrict__ out)
 {
     __shared__ float tile[HG_TILE * HG_ROW];
@@ -364,7 +375,7 @@ hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
         const float scale = P.scale[l];
         const uint32_t res = P.res[l], size = P.size[l];
         const bool hashed = P.hashed[l] != 0;
-        const float2 *__restrict__ tl = table + P.offset[l];
+        const TT *__restrict__ tl = table + P.offset[l];
         const CellCoords c = locate(px, py, pz, scale);
         const uint32_t cx = c.ix + xc;
         const float wx = xc ? c.wx : 1.f - c.wx;
@@ -373,10 +384,10 @@ hashgrid_jvp_kernel(const float *__restrict__ x, int64_t n, const float2 *__rest
             uint32_t i00, i10, i01, i11;
             if (!oob) corner4<false>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
             else corner4<true>(cx, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
-            v00 = __ldg(tl + i00);
-            v10 = __ldg(tl + i10);
-            v01 = __ldg(tl + i01);
-            v11 = __ldg(tl + i11);
+            v00 = ld_entry(tl, i00);
+            v10 = ld_entry(tl, i10);
+            v01 = ld_entry(tl, i01);
+            v11 = ld_entry(tl, i11);
         }
         const float uy = 1.f - c.wy, uz = 1.f - c.wz;
         // coefficients of the four corners of this x side in sum_axis v_axis * d w / d axis
@@ -465,9 +476,9 @@ constexpr int HGG_GROUPS = 32;   // groups per CTA (256 threads = 32 groups x 2 
 
 // The level walk of one thread of hashgrid_bwd_grouped_kernel: (group grp, x side xc, levels ls, ls+4, ...).  TOTAL: some tap
 // of the group lies outside the unit cube, cells may lie outside the grid (cold instance, see point_outside()).
-template <int G, bool WITH_TABLE, bool WITH_INPUT, bool TOTAL>
+template <int G, bool WITH_TABLE, bool WITH_INPUT, bool TOTAL, typename TT>
 __device__ __forceinline__ void grouped_walk(const GridParams &P, const float *tile, const float *xs, int grp, int ls, uint32_t xc,
-                                             int n_valid, const float2 *__restrict__ table, float2 *__restrict__ dtable,
+                                             int n_valid, const TT *__restrict__ table, float2 *__restrict__ dtable,
                                              float (&gx)[G], float (&gy)[G], float (&gz)[G])
 {
     for (int l = ls; l < P.active; l += 4) {
@@ -475,7 +486,7 @@ __device__ __forceinline__ void grouped_walk(const GridParams &P, const float *t
         const uint32_t res = P.res[l], size = P.size[l];
         const bool hashed = P.hashed[l] != 0;
         float2 *__restrict__ dl = WITH_TABLE ? dtable + P.offset[l] : nullptr;
-        const float2 *__restrict__ tl = WITH_INPUT ? table + P.offset[l] : nullptr;
+        const TT *__restrict__ tl = WITH_INPUT ? table + P.offset[l] : nullptr;
         uint32_t px = 0, py = 0, pz = 0;               // pending cell (any uint32 is a legal coordinate: points outside the
         bool pending = false;                           // unit cube have negative cells, so no in-band sentinel)
         float2 a00 = make_float2(0.f, 0.f), a10 = a00, a01 = a00, a11 = a00;
@@ -504,10 +515,10 @@ __device__ __forceinline__ void grouped_walk(const GridParams &P, const float *t
                 if (WITH_INPUT) {
                     uint32_t i00, i10, i01, i11;
                     corner4<TOTAL>(c.ix + xc, c.iy, c.iz, res, size, hashed, i00, i10, i01, i11);
-                    v00 = __ldg(tl + i00);
-                    v10 = __ldg(tl + i10);
-                    v01 = __ldg(tl + i01);
-                    v11 = __ldg(tl + i11);
+                    v00 = ld_entry(tl, i00);
+                    v10 = ld_entry(tl, i10);
+                    v01 = ld_entry(tl, i01);
+                    v11 = ld_entry(tl, i11);
                 }
             }
             const float2 g = *reinterpret_cast<const float2 *>(&tile[p * HG_ROW + 2 * l]);
@@ -533,9 +544,9 @@ __device__ __forceinline__ void grouped_walk(const GridParams &P, const float *t
     }
 }
 
-template <int G, bool WITH_TABLE, bool WITH_INPUT>
+template <int G, bool WITH_TABLE, bool WITH_INPUT, typename TT>
 __global__ void __launch_bounds__(HG_THREADS, HGG_MINB)
-hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2 *__restrict__ table,
+hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const TT *__restrict__ table,
                             const float *__restrict__ dy, const GridParams P, float2 *__restrict__ dtable,
                             float *__restrict__ dx)
 {
@@ -567,8 +578,8 @@ hashgrid_bwd_grouped_kernel(const float *__restrict__ x, int64_t n, const float2
         const int p = grp * G + k;
         oob = oob || (p < n_valid && point_outside(xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]));
     }
-    if (!oob) grouped_walk<G, WITH_TABLE, WITH_INPUT, false>(P, tile, xs, grp, ls, xc, n_valid, table, dtable, gx, gy, gz);
-    else grouped_walk<G, WITH_TABLE, WITH_INPUT, true>(P, tile, xs, grp, ls, xc, n_valid, table, dtable, gx, gy, gz);
+    if (!oob) grouped_walk<G, WITH_TABLE, WITH_INPUT, false, TT>(P, tile, xs, grp, ls, xc, n_valid, table, dtable, gx, gy, gz);
+    else grouped_walk<G, WITH_TABLE, WITH_INPUT, true, TT>(P, tile, xs, grp, ls, xc, n_valid, table, dtable, gx, gy, gz);
     if (WITH_INPUT) {
         // the 8 lanes (4 level slots x 2 x-corners) of a group hold partial sums: butterfly over the low 3 lane bits
 #pragma unroll
@@ -648,8 +659,9 @@ extern "C" int32_t ia_debug_hashgrid_fwd_generic(int32_t on)
     return IA_OK;
 }
 
-extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table, const ia_grid_plan *plan,
-                                   int32_t active_levels, float *out, void *stream)
+template <typename TT>
+static int32_t hg_fwd(const float *x, int64_t n, const TT *table, const ia_grid_plan *plan, int32_t active_levels, float *out,
+                      void *stream)
 {
     GridParams P;
     int rc = fill_params(plan, active_levels, &P);
@@ -661,13 +673,23 @@ extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table
     static const bool generic_env = getenv("IA_HASHGRID_FWD_GENERIC") != nullptr;
     const bool generic = g_fwd_generic < 0 ? generic_env : g_fwd_generic != 0;
     if (P.n_dense >= 0 && !generic)
-        hashgrid_fwd_split_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
-            x, n, reinterpret_cast<const float2 *>(table), P, out);
+        hashgrid_fwd_split_kernel<TT><<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(x, n, table, P, out);
     else
-        hashgrid_fwd_kernel<<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(
-            x, n, reinterpret_cast<const float2 *>(table), P, out);
+        hashgrid_fwd_kernel<TT><<<(unsigned)blocks, HG_THREADS, 0, (cudaStream_t)stream>>>(x, n, table, P, out);
     IA_LAUNCH_OK("hashgrid_fwd_kernel");
     return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_fwd(const float *x, int64_t n, const float *table, const ia_grid_plan *plan,
+                                   int32_t active_levels, float *out, void *stream)
+{
+    return hg_fwd(x, n, reinterpret_cast<const float2 *>(table), plan, active_levels, out, stream);
+}
+
+extern "C" int32_t ia_hashgrid_fwd_h(const float *x, int64_t n, const void *table_h, const ia_grid_plan *plan,
+                                     int32_t active_levels, float *out, void *stream)
+{
+    return hg_fwd(x, n, reinterpret_cast<const __half2 *>(table_h), plan, active_levels, out, stream);
 }
 
 extern "C" int32_t ia_hashgrid_fwd_grouped(const float *x, int64_t n, const float *table, const ia_grid_plan *plan,
@@ -685,9 +707,9 @@ extern "C" int32_t ia_hashgrid_fwd_grouped(const float *x, int64_t n, const floa
     return IA_OK;
 }
 
-extern "C" int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table, const float *dy,
-                                   const ia_grid_plan *plan, int32_t active_levels, float *dtable, float *dx,
-                                   void *stream)
+template <typename TT>
+static int32_t hg_bwd(const float *x, int64_t n, const TT *table, const float *dy, const ia_grid_plan *plan, int32_t active_levels,
+                      float *dtable, float *dx, void *stream)
 {
     GridParams P;
     int rc = fill_params(plan, active_levels, &P);
@@ -697,23 +719,22 @@ extern "C" int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table
     if (n == 0 || (!dtable && !dx)) return IA_OK;
     const unsigned blocks = (unsigned)ia_ceil_div(n, HG_TILE);
     cudaStream_t s = (cudaStream_t)stream;
-    const float2 *t2 = reinterpret_cast<const float2 *>(table);
     float2 *d2 = reinterpret_cast<float2 *>(dtable);
     if (dtable && dx)
-        hashgrid_bwd_kernel<true, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+        hashgrid_bwd_kernel<true, true, TT><<<blocks, HG_THREADS, 0, s>>>(x, n, table, dy, P, d2, dx);
     else if (dtable)
-        hashgrid_bwd_kernel<true, false><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+        hashgrid_bwd_kernel<true, false, TT><<<blocks, HG_THREADS, 0, s>>>(x, n, table, dy, P, d2, dx);
     else
-        hashgrid_bwd_kernel<false, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+        hashgrid_bwd_kernel<false, true, TT><<<blocks, HG_THREADS, 0, s>>>(x, n, table, dy, P, d2, dx);
     IA_LAUNCH_OK("hashgrid_bwd_kernel");
     return IA_OK;
 }
 
-extern "C" int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const float *table, const float *dy,
-                                           const ia_grid_plan *plan, int32_t active_levels, int32_t group, float *dtable,
-                                           float *dx, void *stream)
+template <typename TT>
+static int32_t hg_bwd_grouped(const float *x, int64_t n, const TT *table, const float *dy, const ia_grid_plan *plan,
+                              int32_t active_levels, int32_t group, float *dtable, float *dx, void *stream)
 {
-    if (group != 6) return ia_hashgrid_bwd(x, n, table, dy, plan, active_levels, dtable, dx, stream);
+    if (group != 6) return hg_bwd(x, n, table, dy, plan, active_levels, dtable, dx, stream);
     GridParams P;
     int rc = fill_params(plan, active_levels, &P);
     if (rc) return rc;
@@ -722,16 +743,37 @@ extern "C" int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const floa
     if (n == 0 || (!dtable && !dx)) return IA_OK;
     const unsigned blocks = (unsigned)ia_ceil_div(n, HGG_GROUPS * 6);
     cudaStream_t s = (cudaStream_t)stream;
-    const float2 *t2 = reinterpret_cast<const float2 *>(table);
     float2 *d2 = reinterpret_cast<float2 *>(dtable);
     if (dtable && dx)
-        hashgrid_bwd_grouped_kernel<6, true, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+        hashgrid_bwd_grouped_kernel<6, true, true, TT><<<blocks, HG_THREADS, 0, s>>>(x, n, table, dy, P, d2, dx);
     else if (dtable)
-        hashgrid_bwd_grouped_kernel<6, true, false><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+        hashgrid_bwd_grouped_kernel<6, true, false, TT><<<blocks, HG_THREADS, 0, s>>>(x, n, table, dy, P, d2, dx);
     else
-        hashgrid_bwd_grouped_kernel<6, false, true><<<blocks, HG_THREADS, 0, s>>>(x, n, t2, dy, P, d2, dx);
+        hashgrid_bwd_grouped_kernel<6, false, true, TT><<<blocks, HG_THREADS, 0, s>>>(x, n, table, dy, P, d2, dx);
     IA_LAUNCH_OK("hashgrid_bwd_grouped_kernel");
     return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_bwd(const float *x, int64_t n, const float *table, const float *dy,
+                                   const ia_grid_plan *plan, int32_t active_levels, float *dtable, float *dx,
+                                   void *stream)
+{
+    return hg_bwd(x, n, reinterpret_cast<const float2 *>(table), dy, plan, active_levels, dtable, dx, stream);
+}
+
+extern "C" int32_t ia_hashgrid_bwd_grouped(const float *x, int64_t n, const float *table, const float *dy,
+                                           const ia_grid_plan *plan, int32_t active_levels, int32_t group, float *dtable,
+                                           float *dx, void *stream)
+{
+    return hg_bwd_grouped(x, n, reinterpret_cast<const float2 *>(table), dy, plan, active_levels, group, dtable, dx, stream);
+}
+
+// fp16 shadow tables: the gathers of the input gradient read `table_h`; the table gradient stays fp32 (it never reads the table)
+extern "C" int32_t ia_hashgrid_bwd_h(const float *x, int64_t n, const void *table_h, const float *dy,
+                                     const ia_grid_plan *plan, int32_t active_levels, int32_t group, float *dtable, float *dx,
+                                     void *stream)
+{
+    return hg_bwd_grouped(x, n, reinterpret_cast<const __half2 *>(table_h), dy, plan, active_levels, group, dtable, dx, stream);
 }
 
 extern "C" int32_t ia_hashgrid_bwd_table(const float *x, int64_t n, const float *dy, const ia_grid_plan *plan,
@@ -748,17 +790,51 @@ extern "C" int32_t ia_hashgrid_bwd_input(const float *x, int64_t n, const float 
     return ia_hashgrid_bwd(x, n, table, dy, plan, active_levels, nullptr, dx, stream);
 }
 
-extern "C" int32_t ia_hashgrid_jvp(const float *x, int64_t n, const float *table, const float *v, const ia_grid_plan *plan,
-                                   int32_t active_levels, float *out, void *stream)
+template <typename TT>
+static int32_t hg_jvp(const float *x, int64_t n, const TT *table, const float *v, const ia_grid_plan *plan, int32_t active_levels,
+                      float *out, void *stream)
 {
     GridParams P;
     int rc = fill_params(plan, active_levels, &P);
     if (rc) return rc;
     IA_REQUIRE(n >= 0 && (n == 0 || (x && table && v && out)), "hashgrid_jvp: NULL pointer with n=%lld", (long long)n);
     if (n == 0) return IA_OK;
-    hashgrid_jvp_kernel<<<(unsigned)ia_ceil_div(n, HG_TILE), HG_THREADS, 0, (cudaStream_t)stream>>>(
-        x, n, reinterpret_cast<const float2 *>(table), v, P, out);
+    hashgrid_jvp_kernel<TT><<<(unsigned)ia_ceil_div(n, HG_TILE), HG_THREADS, 0, (cudaStream_t)stream>>>(x, n, table, v, P, out);
     IA_LAUNCH_OK("hashgrid_jvp_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_hashgrid_jvp(const float *x, int64_t n, const float *table, const float *v, const ia_grid_plan *plan,
+                                   int32_t active_levels, float *out, void *stream)
+{
+    return hg_jvp(x, n, reinterpret_cast<const float2 *>(table), v, plan, active_levels, out, stream);
+}
+
+extern "C" int32_t ia_hashgrid_jvp_h(const float *x, int64_t n, const void *table_h, const float *v, const ia_grid_plan *plan,
+                                     int32_t active_levels, float *out, void *stream)
+{
+    return hg_jvp(x, n, reinterpret_cast<const __half2 *>(table_h), v, plan, active_levels, out, stream);
+}
+
+// fp32 table -> its fp16 shadow (round to nearest even); n = number of floats (2 per entry), a multiple of 2
+namespace {
+__global__ void table_to_half_kernel(const float2 *__restrict__ src, int64_t n2, __half2 *__restrict__ dst)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += step) dst[i] = __float22half2_rn(__ldg(src + i));
+}
+}  // namespace
+
+extern "C" int32_t ia_table_to_half(const float *table, int64_t n, void *table_h, void *stream)
+{
+    IA_REQUIRE(n >= 0 && (n & 1) == 0 && (n == 0 || (table && table_h)), "table_to_half: bad arguments (n=%lld)", (long long)n);
+    if (n == 0) return IA_OK;
+    const int64_t n2 = n / 2;
+    const int64_t want = ia_ceil_div(n2, 256);
+    const int64_t cap = (int64_t)ia_sm_count() * 16;
+    table_to_half_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(table), n2, reinterpret_cast<__half2 *>(table_h));
+    IA_LAUNCH_OK("table_to_half_kernel");
     return IA_OK;
 }
 

@@ -148,9 +148,9 @@ class VolumeSDF(BaseImplicitGeometry):
             return None
         x = pts01.reshape(-1, 3)
         flat = net.flat_params() if flat is None else flat
-        enc = ops.hashgrid_encode(x, grid.params, grid.plan, active)
+        enc = ops.hashgrid_encode(x, grid.params, grid.plan, active, table_h=grid.shadow())
         h, g0, g1 = ops.mlp_fwd_grad(x, enc, flat, desc)
-        g01 = ops.hashgrid_input_grad(x, grid.params, g1, grid.plan, active) + g0
+        g01 = ops.hashgrid_input_grad(x, grid.params, g1, grid.plan, active, grid.shadow()) + g0
         # points01 = (points + r) / (2 r)   (AABB contraction, models/geometry.py:24)
         grad = (g01 / (2.0 * self.radius)).view(*pts01.shape[:-1], 3)
         return h, grad, flat
@@ -182,7 +182,7 @@ class VolumeSDF(BaseImplicitGeometry):
             n_hidden = flat.numel() - (n_out * width + n_out)
             out = ops.linear64(h, flat[n_hidden:n_hidden + n_out * width].view(n_out, width), flat[n_hidden + n_out * width:])
             return out, grad
-        enc = ops.hashgrid_encode(x, grid.params, grid.plan, active)
+        enc = ops.hashgrid_encode(x, grid.params, grid.plan, active, table_h=grid.shadow())
         parts = ([x * enc_mod.xyz_scale + enc_mod.xyz_offset] if enc_mod.include_xyz else []) + [enc]
         e = torch.cat(parts, dim=-1)
         if not e.requires_grad:
@@ -194,7 +194,7 @@ class VolumeSDF(BaseImplicitGeometry):
         keep = self.training
         (g_e,) = torch.autograd.grad(sdf, e, grad_outputs=torch.ones_like(sdf), create_graph=keep, retain_graph=True)
         n_xyz = 3 if enc_mod.include_xyz else 0
-        g01 = ops.hashgrid_input_grad(x, grid.params, g_e[:, n_xyz:].contiguous(), grid.plan, active)
+        g01 = ops.hashgrid_input_grad(x, grid.params, g_e[:, n_xyz:].contiguous(), grid.plan, active, grid.shadow())
         if enc_mod.include_xyz:
             g01 = g01 + g_e[:, :3] * enc_mod.xyz_scale
         # points01 = (points + r) / (2 r)   (AABB contraction, models/geometry.py:24)

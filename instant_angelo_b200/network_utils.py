@@ -11,6 +11,7 @@ concatenated input).
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -43,6 +44,14 @@ class Encoding(nn.Module):
             g = torch.Generator().manual_seed(seed)
             self.params = nn.Parameter((torch.rand(self.plan.n_params, generator=g) * 2 - 1) * 1e-4)
             self.n_output_dims = self.plan.n_levels * self.plan.n_features
+            # `table_precision: fp16` (not a tcnn key; IA_TABLE_FP16=1 sets it for every grid): the gathers read an fp16
+            # shadow of .params -- tcnn's own arrangement of fp32 master parameters + fp16 compute copy.  Off by default:
+            # results then differ from the fp32-table oracle by the rounding of the table entries (2^-11 relative).
+            prec = str(cfg.get("table_precision", "fp16" if os.environ.get("IA_TABLE_FP16", "0") not in ("0", "") else "fp32"))
+            if prec not in ("fp32", "fp16"):
+                raise ValueError(f"table_precision must be fp32 or fp16 (got {prec})")
+            self.table_precision = prec
+            self._shadow, self._shadow_stale, self._shadow_version = None, True, -1
         elif self.otype == "SphericalHarmonics":
             assert n_input_dims == 3
             self.degree = int(cfg["degree"])
@@ -51,11 +60,30 @@ class Encoding(nn.Module):
         else:
             raise NotImplementedError(f"encoding otype {self.otype}")
 
+    def shadow(self) -> Optional[torch.Tensor]:
+        """The fp16 copy of .params the gathers read (None under table_precision fp32).  Re-derived when the parameters may
+        have changed: after update_step() (the reference's per-step hook runs right after the optimizer step; the fused AdamW
+        writes through raw pointers, which torch's version counter does not see) and after any in-place torch operation on
+        .params (load_state_dict, a torch optimizer)."""
+        if self.otype != "HashGrid" or self.table_precision != "fp16":
+            return None
+        p = self.params
+        if self._shadow is None or self._shadow.device != p.device or self._shadow_stale or self._shadow_version != p._version:
+            if self._shadow is not None and self._shadow.device != p.device:
+                self._shadow = None
+            self._shadow = ops.table_to_half(p, self._shadow)
+            self._shadow_stale, self._shadow_version = False, p._version
+        return self._shadow
+
+    def update_step(self, epoch, global_step):
+        if self.otype == "HashGrid":
+            self._shadow_stale = True
+
     def forward(self, x: torch.Tensor, active_levels: Optional[int] = None, group: int = 1) -> torch.Tensor:
         if not x.is_cuda:
             raise NotImplementedError("Only support cuda inputs.")
         if self.otype == "HashGrid":
-            return ops.hashgrid_encode(x, self.params, self.plan, active_levels, group)
+            return ops.hashgrid_encode(x, self.params, self.plan, active_levels, group, self.shadow())
         return ops.sh_encode(x, self.degree)
 
 
@@ -91,6 +119,7 @@ class ProgressiveBandHashGrid(nn.Module):
         self.current_level = min(self.start_level + max(global_step - self.start_step, 0) // self.update_steps, self.n_level)
         self._mask_level = max(self._mask_level, self.current_level)
         self.mask[: self.current_level * self.n_features_per_level] = 1.0
+        self.encoding.update_step(epoch, global_step)
 
 
 class CompositeEncoding(nn.Module):
@@ -301,7 +330,7 @@ def fused_encode_mlp(encoding: CompositeEncoding, network: VanillaMLP, x: torch.
     elif isinstance(inner, Encoding) and inner.otype == "HashGrid":
         grid, active = inner, inner.plan.n_levels
     if grid is not None and ops.sdf_fused_enabled() and encoding.include_xyz and x.is_cuda and \
-            network.output_activation_name in (None, "none", "None"):
+            grid.table_precision == "fp32" and network.output_activation_name in (None, "none", "None"):
         desc = ops.make_mlp_desc(3, grid.n_output_dims, network.n_hidden_layers, network.n_output_dims, network.hidden_act,
                                  encoding.xyz_scale, encoding.xyz_offset, network.precision)
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or grid.params.requires_grad)

@@ -84,12 +84,17 @@ def make_grid_plan(n_levels: int, n_features: int, log2_hashmap_size: int, base_
 
 class _HashGridFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, table, plan, active_levels, group=1):
+    def forward(ctx, x, table, plan, active_levels, group=1, table_h=None):
         L.require_cuda(x, table)
         x = L.f32c(x)
         n = x.shape[0]
         out = torch.empty(n, plan.n_levels * plan.n_features, device=x.device, dtype=torch.float32)
-        if group == 6 and _FWD_GROUPED:
+        ctx.table_h = table_h
+        if table_h is not None:
+            _check_shadow(table, table_h)
+            _run("ia_hashgrid_fwd_h", L.ptr(x), n, L.ptr(table_h), C.byref(plan), active_levels, L.ptr(out), L.stream(),
+                 tag="f16 table", work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd", param_bytes=2))
+        elif group == 6 and _FWD_GROUPED:
             _run("ia_hashgrid_fwd_grouped", L.ptr(x), n, L.ptr(table), C.byref(plan), active_levels, group, L.ptr(out), L.stream(),
                  tag="g6", work=n * hashgrid_bytes_per_point(plan, active_levels, "fwd"))
         else:
@@ -115,7 +120,10 @@ class _HashGridFn(torch.autograd.Function):
             work = (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_table") if need_t else 0) + \
                    (hashgrid_bytes_per_point(ctx.plan, ctx.active, "bwd_input") if need_x else 0)
             tag = ("table+input" if need_t and need_x else "table" if need_t else "input") + (f",g{ctx.group}" if ctx.group > 1 else "")
-            if ctx.group > 1:
+            if ctx.table_h is not None:
+                _run("ia_hashgrid_bwd_h", L.ptr(x), n, L.ptr(ctx.table_h), L.ptr(dy), C.byref(ctx.plan), ctx.active, ctx.group,
+                     L.ptr(dtable), L.ptr(dx), L.stream(), tag=tag + ",f16 table", work=n * work)
+            elif ctx.group > 1:
                 _run("ia_hashgrid_bwd_grouped", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(ctx.plan), ctx.active, ctx.group,
                      L.ptr(dtable), L.ptr(dx), L.stream(), tag=tag, work=n * work)
             else:
@@ -123,7 +131,23 @@ class _HashGridFn(torch.autograd.Function):
                      L.ptr(dtable), L.ptr(dx), L.stream(), tag=tag, work=n * work)
         elif need_x:
             dx.zero_()
-        return dx, (None if sink is not None else dtable), None, None, None
+        return dx, (None if sink is not None else dtable), None, None, None, None
+
+
+def _check_shadow(table: torch.Tensor, table_h: torch.Tensor) -> None:
+    if table_h.dtype != torch.float16 or table_h.numel() != table.numel() or not table_h.is_contiguous() or table_h.device != table.device:
+        raise ValueError("fp16 shadow table must be a contiguous float16 tensor with the table's element count on its device")
+
+
+def table_to_half(table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp16 shadow of a hash table (round to nearest even): what the gathers read under `table_precision: fp16`."""
+    L.require_cuda(table)
+    table = table.detach()
+    if out is None:
+        out = torch.empty(table.numel(), device=table.device, dtype=torch.float16)
+    _check_shadow(table, out)
+    _run("ia_table_to_half", L.ptr(table), table.numel(), L.ptr(out), L.stream())
+    return out
 
 
 # ia_hashgrid_fwd_grouped (one thread walks the six taps of a (group, level) and re-fetches corners only on a cell change) was
@@ -165,12 +189,13 @@ def mlp_flops_per_row(desc: L.MlpDesc, n_out_used: int) -> int:
 
 
 def hashgrid_encode(x: torch.Tensor, table: torch.Tensor, plan: L.GridPlan, active_levels: Optional[int] = None,
-                    group: int = 1) -> torch.Tensor:
+                    group: int = 1, table_h: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [N,3] in [0,1] -> [N, L*F]; levels >= active_levels are exact zeros (the progressive mask).
-    group=6: rows come in groups of 6 spatially close points (finite-difference taps) -- a hint for the backward scatter."""
+    group=6: rows come in groups of 6 spatially close points (finite-difference taps) -- a hint for the backward scatter.
+    table_h: fp16 shadow of `table` (table_to_half) that the gathers read instead; gradients still go to `table`."""
     if active_levels is None:
         active_levels = plan.n_levels
-    return _HashGridFn.apply(x, table, plan, int(active_levels), int(group))
+    return _HashGridFn.apply(x, table, plan, int(active_levels), int(group), table_h)
 
 
 class _HashGridInputGradFn(torch.autograd.Function):
@@ -179,13 +204,19 @@ class _HashGridInputGradFn(torch.autograd.Function):
     d(table) (ia_hashgrid_bwd_input_bwd_table); no gradient w.r.t. x (sample positions are not trainable)."""
 
     @staticmethod
-    def forward(ctx, x, table, dy, plan, active_levels):
+    def forward(ctx, x, table, dy, plan, active_levels, table_h=None):
         L.require_cuda(x, table, dy)
         x, dy = L.f32c(x), L.f32c(dy)
         n = x.shape[0]
         dx = torch.empty(n, 3, device=x.device, dtype=torch.float32)
-        _run("ia_hashgrid_bwd_input", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(plan), active_levels, L.ptr(dx), L.stream(),
-             tag="analytic normal", work=n * hashgrid_bytes_per_point(plan, active_levels, "bwd_input"))
+        ctx.table_h = table_h
+        if table_h is not None:
+            _check_shadow(table, table_h)
+            _run("ia_hashgrid_bwd_h", L.ptr(x), n, L.ptr(table_h), L.ptr(dy), C.byref(plan), active_levels, 1, None, L.ptr(dx),
+                 L.stream(), tag="analytic normal,f16 table", work=n * hashgrid_bytes_per_point(plan, active_levels, "bwd_input", 2))
+        else:
+            _run("ia_hashgrid_bwd_input", L.ptr(x), n, L.ptr(table), L.ptr(dy), C.byref(plan), active_levels, L.ptr(dx), L.stream(),
+                 tag="analytic normal", work=n * hashgrid_bytes_per_point(plan, active_levels, "bwd_input"))
         ctx.save_for_backward(x, table, dy)
         ctx.plan, ctx.active = plan, active_levels
         ctx.sink_param = table if getattr(table, "_ia_grad_inplace", False) else None
@@ -208,17 +239,21 @@ class _HashGridInputGradFn(torch.autograd.Function):
                 dtable = None
         if ctx.needs_input_grad[2]:
             ddy = torch.empty_like(dy)
-            _run("ia_hashgrid_jvp", L.ptr(x), n, L.ptr(table), L.ptr(v), C.byref(ctx.plan), ctx.active, L.ptr(ddy), L.stream(),
-                 work=n * hashgrid_bytes_per_point(ctx.plan, ctx.active, "fwd"))
-        return None, dtable, ddy, None, None
+            if ctx.table_h is not None:
+                _run("ia_hashgrid_jvp_h", L.ptr(x), n, L.ptr(ctx.table_h), L.ptr(v), C.byref(ctx.plan), ctx.active, L.ptr(ddy),
+                     L.stream(), work=n * hashgrid_bytes_per_point(ctx.plan, ctx.active, "fwd", 2))
+            else:
+                _run("ia_hashgrid_jvp", L.ptr(x), n, L.ptr(table), L.ptr(v), C.byref(ctx.plan), ctx.active, L.ptr(ddy), L.stream(),
+                     work=n * hashgrid_bytes_per_point(ctx.plan, ctx.active, "fwd"))
+        return None, dtable, ddy, None, None, None
 
 
 def hashgrid_input_grad(x: torch.Tensor, table: torch.Tensor, dy: torch.Tensor, plan: L.GridPlan,
-                        active_levels: Optional[int] = None) -> torch.Tensor:
+                        active_levels: Optional[int] = None, table_h: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[N,3] = J(x; table)^T dy, differentiable w.r.t. table and dy (see _HashGridInputGradFn)."""
     if active_levels is None:
         active_levels = plan.n_levels
-    return _HashGridInputGradFn.apply(x, table, dy, plan, int(active_levels))
+    return _HashGridInputGradFn.apply(x, table, dy, plan, int(active_levels), table_h)
 
 
 # ---------------------------------------------------------------------------------------------

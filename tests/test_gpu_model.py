@@ -457,6 +457,48 @@ def test_baseline_configs_full_size_match_oracle(cuda_lib, which, gs, mlp_otype)
     assert active == min(16, 4 + (gs - 5000) // 1000)
 
 
+def test_fp16_shadow_tables_equal_fp32_path_on_rounded_tables(cuda_lib, golden_dir, monkeypatch):
+    """IA_TABLE_FP16=1 / `table_precision: fp16` (opt-in): a whole training step -- finite-difference taps, curvature, background
+    model, losses, backward -- with the gathers reading fp16 shadow tables equals the default fp32-table step on a state dict
+    whose tables were rounded to fp16: the shadow changes what a gather returns and nothing else.  Against the fp32 oracle on
+    the un-rounded tables the mode deviates by that rounding, which is why it is off by default."""
+    from instant_angelo_b200.losses import training_loss
+    fx = load_golden(golden_dir, "neus_dualcolor_bg")
+    cfg = golden_model_config(**GOLDEN_CASES["neus_dualcolor_bg"])
+    gs = int(fx["global_step"])
+    batch = golden_batch(fx, "cuda")
+    c = lambda k: torch.from_numpy(fx[k]).cuda()
+    state = golden_state_dict(fx)
+    tables = [k for k in state if k.endswith("encoding.encoding.params") or k.endswith("encoding.params")]
+    assert tables
+    results = []
+    for shadow in (True, False):
+        sd = {k: v.clone() for k, v in state.items()}
+        if shadow:
+            monkeypatch.setenv("IA_TABLE_FP16", "1")
+        else:
+            monkeypatch.delenv("IA_TABLE_FP16", raising=False)
+            for k in tables:
+                sd[k] = sd[k].half().float()
+        model = build_product(cfg, sd, gs, torch.from_numpy(fx["background_color"]), "FullyFusedMLP")
+        grid = model.geometry.encoding.encoding.encoding
+        assert grid.table_precision == ("fp16" if shadow else "fp32")
+        out = model(batch["rays"], stratified_u=c("u_fg"), rand_directions=c("rand_directions"), stratified_u_bg=c("u_bg"))
+        terms = training_loss(model, out, batch, golden_loss_config(), gs)
+        terms["loss"].backward()
+        torch.cuda.synchronize()
+        results.append((out, terms, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (o0, t0, g0), (o1, t1, g1) = results
+    assert torch.equal(o0["ray_indices"], o1["ray_indices"]) and torch.equal(o0["ray_indices_bg"], o1["ray_indices_bg"])
+    for k in ("comp_rgb_full", "opacity", "depth", "sdf_samples", "sdf_grad_samples", "sdf_laplace_samples", "weights", "comp_rgb_bg"):
+        assert torch.equal(o0[k], o1[k]), k
+    assert_close(t0["loss"], t1["loss"], rtol=1e-6, atol=1e-8, name="loss")
+    assert set(g0) == set(g1)
+    for n in g0:                                   # atomic-add order of the scatters is the only difference
+        rt, at = grad_tol(g1[n], 1e-5)
+        assert_close(g0[n], g1[n], rtol=rt, atol=at, name="grad " + n)
+
+
 def test_fused_head_matches_generic_path(cuda_lib, golden_dir, monkeypatch):
     """NeuSModel.forward_ takes the fused SDF-head / colour-input assembly (ops.sdf_head) when geometry and texture
     support it; with IA_NO_FUSED_HEAD it goes through VolumeSDF.forward -> feature -> texture.forward like the

@@ -129,6 +129,100 @@ def test_hashgrid_grouped_backward(cuda_lib, cfg_name, active):
 
 
 @pytest.mark.parametrize("cfg_name", ["sparse_2p19", "small_mixed"])
+@pytest.mark.parametrize("group", [1, 6])
+def test_hashgrid_fp16_shadow_table(cuda_lib, cfg_name, group):
+    """`table_precision: fp16`: the kernels that read an fp16 shadow (ia_hashgrid_fwd_h / _bwd_h / _jvp_h) compute, bit for bit,
+    what the fp32 kernels compute on the table rounded to fp16 (the shadow only changes what a gather returns), the table
+    gradient lands on the fp32 table, and against the CPU oracle on the ROUNDED table the usual tolerances hold -- the
+    deviation from the un-rounded oracle is the rounding of the entries (2^-11 relative), which is why the mode is opt-in."""
+    from instant_angelo_b200 import ops
+    cfg = GRID_CFGS[cfg_name]
+    plan_ref, plan = tc.grid_plan(**cfg), ops.make_grid_plan(**cfg)
+    g = torch.Generator().manual_seed(23)
+    S = 211
+    centre = torch.rand(S, 1, 3, generator=g) * 0.98 + 0.01
+    signs = torch.tensor([[1.0, 0, 0], [-1.0, 0, 0], [0, 1.0, 0], [0, -1.0, 0], [0, 0, 1.0], [0, 0, -1.0]])
+    x = (centre + signs * 2e-3).clamp(0, 1).reshape(-1, 3).contiguous()
+    n = x.shape[0]
+    table = torch.randn(plan_ref.n_params, generator=g) * 0.1
+    dy = torch.randn(n, plan_ref.n_output_dims, generator=g)
+    v = torch.randn(n, 3, generator=g)
+    act = min(11, cfg["n_levels"])
+
+    tg = table.cuda().requires_grad_(True)
+    th = ops.table_to_half(tg)
+    assert th.dtype == torch.float16 and torch.equal(th, table.cuda().half())             # round to nearest even, as torch
+    rounded = th.float().requires_grad_(True)                                              # fp32 kernels on the rounded table
+    xg, xr = x.cuda().requires_grad_(True), x.cuda().requires_grad_(True)
+    y_h = ops.hashgrid_encode(xg, tg, plan, act, group, table_h=th)
+    y_r = ops.hashgrid_encode(xr, rounded, plan, act, group)
+    assert torch.equal(y_h, y_r)
+    y_h.backward(dy.cuda())
+    y_r.backward(dy.cuda())
+    assert torch.equal(xg.grad, xr.grad)
+    rt, at = grad_tol(rounded.grad, 1e-6)               # same kernel, same addends: only the order of the atomic adds differs
+    assert_close(tg.grad, rounded.grad, rtol=rt, atol=at, name="dtable (atomic order only)")
+    # second-order pair of the analytic normal
+    tg2, rounded2 = table.cuda().requires_grad_(True), th.float().requires_grad_(True)
+    dyg, dyr = dy.cuda().requires_grad_(True), dy.cuda().requires_grad_(True)
+    dx_h = ops.hashgrid_input_grad(x.cuda(), tg2, dyg, plan, act, th)
+    dx_r = ops.hashgrid_input_grad(x.cuda(), rounded2, dyr, plan, act)
+    assert torch.equal(dx_h, dx_r)
+    (dx_h * v.cuda()).sum().backward()
+    (dx_r * v.cuda()).sum().backward()
+    assert torch.equal(dyg.grad, dyr.grad)
+    rt, at = grad_tol(rounded2.grad, 1e-6)
+    assert_close(tg2.grad, rounded2.grad, rtol=rt, atol=at, name="dtable 2nd order (atomic order only)")
+    # oracle on the rounded table
+    xo, to = x.clone().requires_grad_(True), th.float().cpu().requires_grad_(True)
+    y_ref = tc.hashgrid_forward(xo, to, plan_ref, act)
+    y_ref.backward(dy)
+    assert_close(y_h, y_ref, rtol=1e-5, atol=1e-6, name="enc vs oracle(rounded table)")
+    assert_close(tg.grad, to.grad, rtol=1e-4, atol=1e-5, name="dtable vs oracle")
+    # ... and the distance to the un-rounded oracle is the rounding of the entries
+    y_full = tc.hashgrid_forward(x, table, plan_ref, act)
+    assert float((y_h.cpu() - y_full).abs().max()) <= 2.0 ** -11 * float(table.abs().max()) * 1.01
+    # argument checks
+    with pytest.raises(ValueError):
+        ops.hashgrid_encode(xg, tg, plan, act, group, table_h=th[:-2])
+    with pytest.raises(ValueError):
+        ops.hashgrid_encode(xg, tg, plan, act, group, table_h=th.float())
+
+
+def test_encoding_fp16_shadow_follows_the_parameters(cuda_lib):
+    """Encoding(table_precision='fp16'): the shadow is re-derived after update_step() (the hook that follows the fused
+    optimizer's raw-pointer writes) and after in-place torch writes; state-dict keys are those of the fp32 module."""
+    from instant_angelo_b200 import ops
+    from instant_angelo_b200.network_utils import get_encoding
+    cfg = {"otype": "ProgressiveBandHashGrid", "n_levels": 8, "n_features_per_level": 2, "log2_hashmap_size": 12, "base_resolution": 8,
+           "per_level_scale": 1.5, "start_level": 4, "start_step": 0, "update_steps": 1, "include_xyz": True}
+    enc_h = get_encoding(3, {**cfg, "table_precision": "fp16"}).cuda()
+    enc_f = get_encoding(3, cfg).cuda()
+    assert list(enc_h.state_dict().keys()) == list(enc_f.state_dict().keys())
+    grid = enc_h.encoding.encoding
+    with torch.no_grad():
+        grid.params.mul_(1e3)
+    enc_h.update_step(0, 10)
+    enc_f.update_step(0, 10)
+    x = torch.rand(500, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    enc_f.load_state_dict({k: v.half().float() for k, v in enc_h.state_dict().items()})
+    assert torch.equal(enc_h(x), enc_f(x))
+    # raw-pointer update (what ia_adamw_step does): invisible to torch's version counter, picked up at the next update_step
+    ops.adamw_step(grid.params.data, torch.ones_like(grid.params), torch.zeros_like(grid.params), torch.zeros_like(grid.params),
+                   0.05, 0.9, 0.99, 1e-15, 0.0, 1)
+    stale = enc_h(x)
+    enc_h.update_step(0, 11)
+    fresh = enc_h(x)
+    enc_f.load_state_dict({k: v.half().float() for k, v in enc_h.state_dict().items()})
+    assert torch.equal(fresh, enc_f(x)) and not torch.equal(stale, fresh)
+    # in-place torch write: seen through the version counter without update_step
+    with torch.no_grad():
+        grid.params.add_(0.01)
+    enc_f.load_state_dict({k: v.half().float() for k, v in enc_h.state_dict().items()})
+    assert torch.equal(enc_h(x), enc_f(x))
+
+
+@pytest.mark.parametrize("cfg_name", ["sparse_2p19", "small_mixed"])
 def test_hashgrid_points_outside_unit_cube(cuda_lib, cfg_name):
     """tcnn's index is total: for x outside [0,1] the cell coordinates are negative / beyond the grid, the uint32 stride
     sum wraps and `% size` (dense levels) / the hash mask (hashed levels) keep it inside the level.  The sparse-point

@@ -218,6 +218,8 @@ typedef struct ia_wn_desc {
 } ia_wn_desc;
 int32_t ia_weightnorm_flat_fwd(const ia_wn_desc *desc_host, float *flat, void *stream);
 int32_t ia_weightnorm_flat_bwd(const ia_wn_desc *desc_host, const float *dflat, void *stream);
+/* Same adjoint, ADDED to dg / dv / db (the parameters' slices of a gradient arena that is zeroed once per step). */
+int32_t ia_weightnorm_flat_bwd_acc(const ia_wn_desc *desc_host, const float *dflat, void *stream);
 
 /* Wide output layer for the feature mode above: out[n, n_out] = h[n, 64] W[n_out, 64]^T + b (n_out <= 128), fp32.
  * Backward: dh[n,64] = dout W (may be NULL); dW[n_out,64] += dout^T h and db[n_out] += sum dout (ACCUMULATED; may be NULL). */
@@ -367,6 +369,35 @@ int32_t ia_composite_bwd(const ia_composite_args *args_host, const float *alpha,
                          const float *g_comp_rgb, const float *g_comp_normal,
                          float *d_alpha_in, float *d_sdf, float *d_normal, float *d_inv_s, float *d_sigma,
                          float *d_rgb, float *d_nrm, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss terms of the training step      replaces the tensor expressions of systems/neus.py:132-160 and
+ *                                      systems/criterions.py:155-159 (binary_cross_entropy)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ia_loss_args {
+    int64_t n_rays, n_samples;
+    float lambda_rgb_mse, lambda_rgb_l1, lambda_eikonal, lambda_mask, lambda_opaque, lambda_sparsity, lambda_curvature;
+    float sparsity_scale;
+} ia_loss_args;
+/* Forward: terms[8] = (rgb_mse, rgb_l1, eikonal, mask, opaque, sparsity, curvature, n_valid) and
+ * loss[1] = sum lambda_k terms_k in the reference's order of additions.
+ *   rgb_*   : mean over the channels of the rays with valid[r] != 0 of (comp_rgb - rgb_gt)^2 / |.|      (:134-138)
+ *   eikonal : mean_s (|sdf_grad_s| - 1)^2                                                                (:140-141)
+ *   opaque  : BCE(o, o), mask: BCE(o, fg_mask) on o = clamp(opacity, 1e-3, 1 - 1e-3); fg_mask NULL = no mask term (:143-150)
+ *   sparsity: mean_s exp(-sparsity_scale |sdf_s|)                                                        (:152-153)
+ *   curvature: mean_s |laplace_s|, only when laplace != NULL and lambda_curvature > 0                    (:155-159)
+ * Means over empty sets are nan, as in the reference.  valid is one byte per ray.  workspace: device memory of
+ * ia_neus_losses_workspace_bytes() (zeroed by the call). */
+int64_t ia_neus_losses_workspace_bytes(void);
+int32_t ia_neus_losses_fwd(const ia_loss_args *args_host, const float *comp_rgb, const float *rgb_gt, const uint8_t *valid,
+                           const float *opacity, const float *fg_mask, const float *sdf_grad, const float *sdf,
+                           const float *laplace, void *workspace, float *terms, float *loss, void *stream);
+/* Backward of loss[0]: dloss is a DEVICE scalar (the upstream gradient); each d_* may be NULL (not wanted) and is
+ * overwritten.  The gradient of BCE(o, o) flows through both of its arguments, as autograd's does in the reference. */
+int32_t ia_neus_losses_bwd(const ia_loss_args *args_host, const float *comp_rgb, const float *rgb_gt, const uint8_t *valid,
+                           const float *opacity, const float *fg_mask, const float *sdf_grad, const float *sdf,
+                           const float *laplace, const float *terms, const float *dloss, float *d_comp_rgb,
+                           float *d_opacity, float *d_sdf_grad, float *d_sdf, float *d_laplace, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused AdamW over a flat arena        replaces torch.optim.AdamW as configured at

@@ -63,6 +63,12 @@ class WnDesc(C.Structure):
                 ("dg", C.c_void_p * IA_WN_MAX_LAYERS), ("dv", C.c_void_p * IA_WN_MAX_LAYERS), ("db", C.c_void_p * IA_WN_MAX_LAYERS)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int64), ("lambda_rgb_mse", C.c_float), ("lambda_rgb_l1", C.c_float),
+                ("lambda_eikonal", C.c_float), ("lambda_mask", C.c_float), ("lambda_opaque", C.c_float),
+                ("lambda_sparsity", C.c_float), ("lambda_curvature", C.c_float), ("sparsity_scale", C.c_float)]
+
+
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 
@@ -96,6 +102,7 @@ SIGNATURES = {
                                      _P, _P, _P]),
     "ia_weightnorm_flat_fwd": (_I32, [C.POINTER(WnDesc), _P, _P]),
     "ia_weightnorm_flat_bwd": (_I32, [C.POINTER(WnDesc), _P, _P]),
+    "ia_weightnorm_flat_bwd_acc": (_I32, [C.POINTER(WnDesc), _P, _P]),
     "ia_linear64_fwd": (_I32, [_P, _I64, _P, _P, _I32, _P, _I64, _P]),
     "ia_linear64_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _P, _I32, _P, _P, _P, _P]),
     "ia_sdf_head_fwd": (_I32, [_P, _I64, _P, _P, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
@@ -122,6 +129,9 @@ SIGNATURES = {
     "ia_visibility": (_I32, [_P, _P, _I64, _F, _F, _P, _P]),
     "ia_composite_fwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_composite_bwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ia_neus_losses_workspace_bytes": (_I64, []),
+    "ia_neus_losses_fwd": (_I32, [C.POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ia_neus_losses_bwd": (_I32, [C.POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_adamw_step": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _P]),
     "ia_l2_persist": (_I32, [_P, _I64, _F, C.POINTER(C.c_int64 * 3), _P]),
     "ia_debug_sector_gather": (_I32, [_P, _I64, _I64, _I32, _P, _P]),

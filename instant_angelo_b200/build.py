@@ -20,7 +20,7 @@ BUILD = os.environ.get("IA_BUILD_DIR") or os.path.join(HERE, "_build")     # A/B
 LIB = os.path.join(BUILD, "libia_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["capi.cu", "hashgrid.cu", "sh.cu", "march.cu", "composite.cu", "mlp.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc3.cu", "adam.cu", "sdf_taps.cu", "linear64.cu", "weightnorm.cu", "colour_in.cu"]
+SOURCES = ["capi.cu", "hashgrid.cu", "sh.cu", "march.cu", "composite.cu", "mlp.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc3.cu", "adam.cu", "sdf_taps.cu", "linear64.cu", "weightnorm.cu", "colour_in.cu", "losses.cu"]
 EXTRA = {"march.cu": ["-fmad=false"]}
 if os.environ.get("IA_TC_TIMING"):     # cycle accounting of the tensor-core MLP kernels (tools/prof_mlp.py --timing); off in product builds
     EXTRA["mlp_tc.cu"] = ["-DIA_TC_TIMING=1"]

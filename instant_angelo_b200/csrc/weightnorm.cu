@@ -24,7 +24,9 @@ __device__ __forceinline__ float warp_sum(float x)
     return x;
 }
 
-template <bool BWD>
+// ACC (backward only): add to dg / dv / db instead of overwriting them -- the destinations are the parameters' slices of the
+// gradient arena (zeroed once per step), so no autograd accumulation pass follows.  Each element is owned by one warp.
+template <bool BWD, bool ACC>
 __global__ void weightnorm_kernel(const WnParams P, float *__restrict__ flat, const float *__restrict__ dflat)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -57,11 +59,14 @@ __global__ void weightnorm_kernel(const WnParams P, float *__restrict__ flat, co
         }
         if (P.dv[L] != nullptr) {
             float *__restrict__ dv = P.dv[L] + (long long)o * n_in;
-            for (int k = lane; k < n_in; k += 32) dv[k] = wn ? s * (dw[k] - dot * v[k] / nrm) : dw[k];
+            for (int k = lane; k < n_in; k += 32) {
+                const float t = wn ? s * (dw[k] - dot * v[k] / nrm) : dw[k];
+                dv[k] = ACC ? dv[k] + t : t;
+            }
         }
         if (lane == 0) {
-            if (wn && P.dg[L] != nullptr) P.dg[L][o] = dot;
-            if (P.db[L] != nullptr) P.db[L][o] = dflat[bofs];
+            if (wn && P.dg[L] != nullptr) P.dg[L][o] = ACC ? P.dg[L][o] + dot : dot;
+            if (P.db[L] != nullptr) P.db[L][o] = ACC ? P.db[L][o] + dflat[bofs] : dflat[bofs];
         }
     }
 }
@@ -105,7 +110,7 @@ extern "C" int32_t ia_weightnorm_flat_fwd(const ia_wn_desc *desc, float *flat, v
     if (rc) return rc;
     IA_REQUIRE(flat != nullptr, "weightnorm_flat_fwd: flat is NULL");
     const int rows = P.row0[IA_WN_MAX_LAYERS];
-    weightnorm_kernel<false><<<(unsigned)ia_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(P, flat, nullptr);
+    weightnorm_kernel<false, false><<<(unsigned)ia_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(P, flat, nullptr);
     IA_LAUNCH_OK("weightnorm_kernel<fwd>");
     return IA_OK;
 }
@@ -117,7 +122,19 @@ extern "C" int32_t ia_weightnorm_flat_bwd(const ia_wn_desc *desc, const float *d
     if (rc) return rc;
     IA_REQUIRE(dflat != nullptr, "weightnorm_flat_bwd: dflat is NULL");
     const int rows = P.row0[IA_WN_MAX_LAYERS];
-    weightnorm_kernel<true><<<(unsigned)ia_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(P, nullptr, dflat);
+    weightnorm_kernel<true, false><<<(unsigned)ia_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(P, nullptr, dflat);
     IA_LAUNCH_OK("weightnorm_kernel<bwd>");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_weightnorm_flat_bwd_acc(const ia_wn_desc *desc, const float *dflat, void *stream)
+{
+    WnParams P;
+    int rc = fill(desc, &P, true);
+    if (rc) return rc;
+    IA_REQUIRE(dflat != nullptr, "weightnorm_flat_bwd_acc: dflat is NULL");
+    const int rows = P.row0[IA_WN_MAX_LAYERS];
+    weightnorm_kernel<true, true><<<(unsigned)ia_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(P, nullptr, dflat);
+    IA_LAUNCH_OK("weightnorm_kernel<bwd, acc>");
     return IA_OK;
 }

@@ -1,10 +1,13 @@
 """Loss terms of reference systems/neus.py:130-194 and the scalar schedules C() of systems/base.py:28-45."""
 from __future__ import annotations
 
+import os
 from typing import Dict
 
 import torch
 import torch.nn.functional as F
+
+from . import ops
 
 
 def C(value, global_step: int, current_epoch: int = 0) -> float:
@@ -57,30 +60,46 @@ def training_loss(model, out: Dict[str, torch.Tensor], batch: Dict[str, torch.Te
     """reference systems/neus.py:130-194.  Returns every term plus 'loss'."""
     c = lambda v: C(v, global_step, current_epoch)
     terms = {}
-    # mean over the valid rays' channels, as F.mse_loss / F.l1_loss on comp_rgb_full[valid] (systems/neus.py:134-138),
-    # written as a masked sum so that no boolean compaction (a host read-back per use) sits inside the step;
-    # with no valid ray both forms give 0/0 = nan
     valid = out["rays_valid_full"][..., 0]
-    diff = torch.where(valid[:, None], out["comp_rgb_full"] - batch["rgb"], 0.0)
-    n_valid = valid.sum().to(diff.dtype) * diff.shape[-1]
-    terms["rgb_mse"] = (diff * diff).sum() / n_valid
-    loss = terms["rgb_mse"] * c(loss_cfg["lambda_rgb_mse"])
-    terms["rgb_l1"] = diff.abs().sum() / n_valid
-    loss = loss + terms["rgb_l1"] * c(loss_cfg["lambda_rgb_l1"])
-    terms["eikonal"] = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
-    loss = loss + terms["eikonal"] * c(loss_cfg["lambda_eikonal"])
-    opacity = torch.clamp(out["opacity"].squeeze(-1), 1.0e-3, 1.0 - 1.0e-3)
-    if has_mask and "fg_mask" in batch:
-        terms["mask"] = binary_cross_entropy(opacity, batch["fg_mask"].float())
-        loss = loss + terms["mask"] * c(loss_cfg["lambda_mask"])
-    terms["opaque"] = binary_cross_entropy(opacity, opacity)
-    loss = loss + terms["opaque"] * c(loss_cfg["lambda_opaque"])
-    terms["sparsity"] = torch.exp(-loss_cfg["sparsity_scale"] * out["sdf_samples"].abs()).mean()
-    loss = loss + terms["sparsity"] * c(loss_cfg["lambda_sparsity"])
-    if c(loss_cfg["lambda_curvature"]) > 0:
-        assert "sdf_laplace_samples" in out, "Need geometry.grad_type='finite_difference' to get SDF Laplace samples"
-        terms["curvature"] = out["sdf_laplace_samples"].abs().mean()
-        loss = loss + terms["curvature"] * c(loss_cfg["lambda_curvature"])
+    use_mask = has_mask and "fg_mask" in batch
+    if out["comp_rgb_full"].is_cuda and os.environ.get("IA_NO_FUSED_LOSSES") is None:
+        # the per-ray / per-sample terms and their weighted sum as one kernel forward and one backward (ops.neus_losses):
+        # as tensor expressions they are ~120 launches per step
+        want_curv = c(loss_cfg["lambda_curvature"]) > 0
+        if want_curv:
+            assert "sdf_laplace_samples" in out, "Need geometry.grad_type='finite_difference' to get SDF Laplace samples"
+        lambdas = {"rgb_mse": c(loss_cfg["lambda_rgb_mse"]), "rgb_l1": c(loss_cfg["lambda_rgb_l1"]),
+                   "eikonal": c(loss_cfg["lambda_eikonal"]), "mask": c(loss_cfg["lambda_mask"]) if use_mask else 0.0,
+                   "opaque": c(loss_cfg["lambda_opaque"]), "sparsity": c(loss_cfg["lambda_sparsity"]),
+                   "curvature": c(loss_cfg["lambda_curvature"])}
+        loss, named = ops.neus_losses(out["comp_rgb_full"], batch["rgb"], valid, out["opacity"],
+                                      batch["fg_mask"].float() if use_mask else None, out["sdf_grad_samples"], out["sdf_samples"],
+                                      out["sdf_laplace_samples"] if want_curv else None, lambdas, float(loss_cfg["sparsity_scale"]))
+        terms.update(named)
+    else:
+        # mean over the valid rays' channels, as F.mse_loss / F.l1_loss on comp_rgb_full[valid] (systems/neus.py:134-138),
+        # written as a masked sum so that no boolean compaction (a host read-back per use) sits inside the step;
+        # with no valid ray both forms give 0/0 = nan
+        diff = torch.where(valid[:, None], out["comp_rgb_full"] - batch["rgb"], 0.0)
+        n_valid = valid.sum().to(diff.dtype) * diff.shape[-1]
+        terms["rgb_mse"] = (diff * diff).sum() / n_valid
+        loss = terms["rgb_mse"] * c(loss_cfg["lambda_rgb_mse"])
+        terms["rgb_l1"] = diff.abs().sum() / n_valid
+        loss = loss + terms["rgb_l1"] * c(loss_cfg["lambda_rgb_l1"])
+        terms["eikonal"] = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
+        loss = loss + terms["eikonal"] * c(loss_cfg["lambda_eikonal"])
+        opacity = torch.clamp(out["opacity"].squeeze(-1), 1.0e-3, 1.0 - 1.0e-3)
+        if use_mask:
+            terms["mask"] = binary_cross_entropy(opacity, batch["fg_mask"].float())
+            loss = loss + terms["mask"] * c(loss_cfg["lambda_mask"])
+        terms["opaque"] = binary_cross_entropy(opacity, opacity)
+        loss = loss + terms["opaque"] * c(loss_cfg["lambda_opaque"])
+        terms["sparsity"] = torch.exp(-loss_cfg["sparsity_scale"] * out["sdf_samples"].abs()).mean()
+        loss = loss + terms["sparsity"] * c(loss_cfg["lambda_sparsity"])
+        if c(loss_cfg["lambda_curvature"]) > 0:
+            assert "sdf_laplace_samples" in out, "Need geometry.grad_type='finite_difference' to get SDF Laplace samples"
+            terms["curvature"] = out["sdf_laplace_samples"].abs().mean()
+            loss = loss + terms["curvature"] * c(loss_cfg["lambda_curvature"])
     # systems/neus.py:161-171 (inactive in every shipped config: lambda_distortion = lambda_distortion_bg = 0)
     if c(loss_cfg.get("lambda_distortion", 0.0)) > 0:
         terms["distortion"] = flatten_eff_distloss(out["weights"], out["points"], out["intervals"], out["ray_indices"])

@@ -311,6 +311,7 @@ class _MLPFn(torch.autograd.Function):
              tag=f"{desc.n_in0 + desc.n_in1}>{n_out_used}/{desc.n_out}")
         ctx.save_for_backward(in0, in1, params)
         ctx.desc, ctx.nou = desc, n_out_used
+        ctx.acc = getattr(params, "_ia_acc", None)
         return out
 
     @staticmethod
@@ -323,12 +324,13 @@ class _MLPFn(torch.autograd.Function):
         needp = ctx.needs_input_grad[2]
         d0 = torch.empty_like(in0) if need0 else None
         d1 = torch.empty_like(in1) if need1 else None
-        dp = torch.zeros_like(params) if needp else None
+        sink = _flat_sink(ctx.acc) if needp else None
+        dp = (sink if sink is not None else torch.zeros_like(params)) if needp else None
         if n > 0:
             _run("ia_mlp_bwd", C.byref(ctx.desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dout), ctx.nou,
                  dout.shape[1], L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=2 * n * mlp_flops_per_row(ctx.desc, ctx.nou),
                  tag=f"{ctx.desc.n_in0 + ctx.desc.n_in1}>{ctx.nou}/{ctx.desc.n_out}")
-        return d0, d1, dp, None, None
+        return d0, d1, (None if sink is not None else dp), None, None
 
 
 class _MLPGradFn(torch.autograd.Function):
@@ -350,6 +352,7 @@ class _MLPGradFn(torch.autograd.Function):
              work=flops, tag=f"{desc.n_in0 + desc.n_in1}>h+g")
         ctx.save_for_backward(in0, in1, params)
         ctx.desc = desc
+        ctx.acc = getattr(params, "_ia_acc", None)
         return h, g0, g1
 
     @staticmethod
@@ -363,12 +366,13 @@ class _MLPGradFn(torch.autograd.Function):
         need0, need1, needp = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d0 = torch.empty_like(in0) if need0 else None
         d1 = torch.empty_like(in1) if need1 else None
-        dp = torch.zeros_like(params) if needp else None
+        sink = _flat_sink(ctx.acc) if needp else None
+        dp = (sink if sink is not None else torch.zeros_like(params)) if needp else None
         if n > 0:
             flops = 2 * n * (7 * desc.width * desc.width + 4 * desc.width * (desc.n_in0 + desc.n_in1))     # 4 + 2 W0-shaped, 4 + 3 W1-shaped GEMMs... per row
             _run("ia_mlp_fwd_grad_bwd", C.byref(desc), L.ptr(in0), L.ptr(in1), n, L.ptr(params), L.ptr(dh), L.ptr(dg0), L.ptr(dg1),
                  L.ptr(d0), L.ptr(d1), L.ptr(dp), L.stream(), work=flops, tag=f"{desc.n_in0 + desc.n_in1}>h+g")
-        return d0, d1, dp, None
+        return d0, d1, (None if sink is not None else dp), None
 
 
 def mlp_fwd_grad_supported(desc: L.MlpDesc) -> bool:
@@ -462,10 +466,17 @@ def sdf_fused_supported(desc: L.MlpDesc, plan: L.GridPlan, needs_grad: bool) -> 
 
 class _WeightNormFlatFn(torch.autograd.Function):
     """Flat effective parameters [W0 b0 W1 b1 ...] of a VanillaMLP from its per-layer (weight_g | None, weight_v | weight,
-    bias) tensors in one launch, with the weight-norm adjoint in backward (reference models/network_utils.py:115-134)."""
+    bias) tensors in one launch, with the weight-norm adjoint in backward (reference models/network_utils.py:115-134).
+
+    Gradient plumbing without autograd accumulation passes: `acc` is a zeroed buffer of the flat vector's shape that the
+    consumers of `flat` (the MLP backward kernels, which flush their weight gradients with atomic adds anyway) add into
+    directly, returning None to autograd (_flat_sink); this backward then runs once every consumer is done -- autograd
+    calls it with None, or with the sum of what arrived through ordinary operators (slices of `flat`) -- and adds the
+    weight-norm adjoint straight into the parameters' slices of the gradient arena when they have one (_grad_sink).
+    A step with 13 network evaluations and 30 small parameter tensors otherwise spends ~60 add / fill launches here."""
 
     @staticmethod
-    def forward(ctx, has_g, *tensors):
+    def forward(ctx, has_g, acc, *tensors):
         n_layers = len(has_g)
         assert n_layers <= L.IA_WN_MAX_LAYERS
         d = L.WnDesc()
@@ -484,34 +495,69 @@ class _WeightNormFlatFn(torch.autograd.Function):
         _run("ia_weightnorm_flat_fwd", C.byref(d), L.ptr(flat), L.stream())
         ctx.save_for_backward(*keep)
         ctx.has_g = has_g
+        ctx.acc = acc
+        ctx.leaves = tensors                       # the parameter objects themselves (their .grad may be an arena slice)
+        ctx.set_materialize_grads(False)
         return flat
 
     @staticmethod
     def backward(ctx, dflat):
+        acc = ctx.acc
+        if acc is not None and getattr(acc, "_ia_used", False):
+            dflat = acc if dflat is None else dflat + acc
+        if dflat is None:
+            return (None, None) + (None,) * len(ctx.leaves)
         dflat = L.f32c(dflat)
         saved = list(ctx.saved_tensors)
+        sinks = [_grad_sink(t if getattr(t, "_ia_grad_inplace", False) else None) for t in ctx.leaves]
+        in_place = all(s is not None for s in sinks)
         d = L.WnDesc()
         d.n_layers = len(ctx.has_g)
         grads, k = [], 0
         for i, hg in enumerate(ctx.has_g):
             g = saved[k] if hg else None
             v, b = saved[k + hg], saved[k + hg + 1]
+            if in_place:
+                dg = sinks[k] if hg else None
+                dv, db = sinks[k + hg], sinks[k + hg + 1]
+            else:
+                dg = torch.empty_like(g) if hg else None
+                dv, db = torch.empty_like(v), torch.empty_like(b)
             k += 2 + hg
             d.n_out[i], d.n_in[i] = v.shape[0], v.shape[1]
             d.g[i], d.v[i], d.b[i] = L.ptr(g), L.ptr(v), L.ptr(b)
-            dg = torch.empty_like(g) if hg else None
-            dv, db = torch.empty_like(v), torch.empty_like(b)
             d.dg[i], d.dv[i], d.db[i] = L.ptr(dg), L.ptr(dv), L.ptr(db)
             grads += ([dg] if hg else []) + [dv, db]
-        _run("ia_weightnorm_flat_bwd", C.byref(d), L.ptr(dflat), L.stream())
-        return (None, *grads)
+        _run("ia_weightnorm_flat_bwd_acc" if in_place else "ia_weightnorm_flat_bwd", C.byref(d), L.ptr(dflat), L.stream())
+        if acc is not None and getattr(acc, "_ia_used", False):
+            acc.zero_()                            # a second backward through a retained graph starts from zero again
+            acc._ia_used = False
+        if in_place:
+            return (None, None) + (None,) * len(ctx.leaves)
+        return (None, None, *grads)
 
 
 def weightnorm_flat(layers) -> torch.Tensor:
     """layers: [(weight_g or None, weight_v / weight [out, in], bias [out]), ...] -> flat [sum(out*in + out)]."""
     has_g = tuple(int(g is not None) for g, _, _ in layers)
     tensors = [t for g, v, b in layers for t in ((g, v, b) if g is not None else (v, b))]
-    return _WeightNormFlatFn.apply(has_g, *tensors)
+    acc = None
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors) and not _NO_GRAD_SINK:
+        total = sum(v.numel() + b.numel() for _, v, b in layers)
+        acc = torch.zeros(total, device=tensors[0].device, dtype=torch.float32)
+    flat = _WeightNormFlatFn.apply(has_g, acc, *tensors)
+    if acc is not None:
+        flat._ia_acc = acc
+    return flat
+
+
+def _flat_sink(acc) -> Optional[torch.Tensor]:
+    """Called inside a backward: the accumulator of a flat parameter vector made by weightnorm_flat() that this backward
+    may add its parameter gradient into (it then returns None for that input).  Not under create_graph."""
+    if acc is None or torch.is_grad_enabled() or _NO_GRAD_SINK:
+        return None
+    acc._ia_used = True
+    return acc
 
 
 class _Linear64Fn(torch.autograd.Function):
@@ -956,3 +1002,68 @@ def l2_persist(t: Optional[torch.Tensor], hit_ratio: float = 1.0) -> dict:
     else:
         _run("ia_l2_persist", L.ptr(t), t.numel() * t.element_size(), C.c_float(hit_ratio), C.byref(info), L.stream())
     return {"l2_bytes": int(info[0]), "set_aside_bytes": int(info[1]), "window_bytes": int(info[2])}
+
+
+# ---------------------------------------------------------------------------------------------
+# loss terms of the training step  (reference systems/neus.py:132-160)
+# ---------------------------------------------------------------------------------------------
+
+LOSS_TERMS = ("rgb_mse", "rgb_l1", "eikonal", "mask", "opaque", "sparsity", "curvature")
+
+
+class _NeusLossesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, args, comp_rgb, rgb_gt, valid, opacity, fg_mask, sdf_grad, sdf, laplace):
+        L.require_cuda(comp_rgb, rgb_gt, valid, opacity, sdf_grad, sdf)
+        comp_rgb, rgb_gt, opacity = L.f32c(comp_rgb), L.f32c(rgb_gt), L.f32c(opacity)
+        sdf_grad, sdf = L.f32c(sdf_grad), L.f32c(sdf)
+        fg_mask = L.f32c(fg_mask) if fg_mask is not None else None
+        laplace = L.f32c(laplace) if laplace is not None else None
+        valid = valid.contiguous()
+        if valid.dtype not in (torch.bool, torch.uint8):
+            raise ValueError("valid must be a bool / uint8 tensor")
+        dev = comp_rgb.device
+        ws = torch.empty(int(L.load().ia_neus_losses_workspace_bytes()), device=dev, dtype=torch.uint8)
+        out = torch.empty(9, device=dev, dtype=torch.float32)            # terms[8] | loss
+        _run("ia_neus_losses_fwd", C.byref(args), L.ptr(comp_rgb), L.ptr(rgb_gt), L.ptr(valid), L.ptr(opacity), L.ptr(fg_mask),
+             L.ptr(sdf_grad), L.ptr(sdf), L.ptr(laplace), L.ptr(ws), L.ptr(out), out.data_ptr() + 32, L.stream())
+        ctx.save_for_backward(comp_rgb, rgb_gt, valid, opacity, fg_mask, sdf_grad, sdf, laplace, out)
+        ctx.args = args
+        loss, terms = out[8], out[:8]
+        ctx.mark_non_differentiable(terms)
+        return loss, terms
+
+    @staticmethod
+    def backward(ctx, dloss, _dterms):
+        comp_rgb, rgb_gt, valid, opacity, fg_mask, sdf_grad, sdf, laplace, out = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dloss = L.f32c(dloss).reshape(1)
+        d_rgb = torch.empty_like(comp_rgb) if need[1] else None
+        d_op = torch.empty_like(opacity) if need[4] else None
+        d_g = torch.empty_like(sdf_grad) if need[6] else None
+        d_s = torch.empty_like(sdf) if need[7] else None
+        d_l = torch.empty_like(laplace) if (laplace is not None and need[8]) else None
+        _run("ia_neus_losses_bwd", C.byref(ctx.args), L.ptr(comp_rgb), L.ptr(rgb_gt), L.ptr(valid), L.ptr(opacity), L.ptr(fg_mask),
+             L.ptr(sdf_grad), L.ptr(sdf), L.ptr(laplace), L.ptr(out), L.ptr(dloss), L.ptr(d_rgb), L.ptr(d_op), L.ptr(d_g), L.ptr(d_s),
+             L.ptr(d_l), L.stream())
+        return None, d_rgb, None, None, d_op, None, d_g, d_s, d_l
+
+
+def neus_losses(comp_rgb, rgb_gt, valid, opacity, fg_mask, sdf_grad, sdf, laplace, lambdas: dict, sparsity_scale: float):
+    """The per-ray / per-sample loss terms of reference systems/neus.py:132-160 and their weighted sum in one launch (one more
+    in backward).  comp_rgb [R,3], rgb_gt [R,3], valid [R] bool, opacity [R], fg_mask [R] or None, sdf_grad [S,3], sdf [S],
+    laplace [S] or None; lambdas: {'rgb_mse', 'rgb_l1', 'eikonal', 'mask', 'opaque', 'sparsity', 'curvature'} -> float.
+    Returns (loss scalar, {term: 0-d tensor}); the terms are values for logging (not differentiable), the scalar is."""
+    n_rays, n_samples = comp_rgb.shape[0], sdf.reshape(-1).shape[0]
+    args = L.LossArgs(n_rays, n_samples, float(lambdas["rgb_mse"]), float(lambdas["rgb_l1"]), float(lambdas["eikonal"]),
+                      float(lambdas.get("mask", 0.0)), float(lambdas["opaque"]), float(lambdas["sparsity"]),
+                      float(lambdas.get("curvature", 0.0)), float(sparsity_scale))
+    loss, terms = _NeusLossesFn.apply(args, comp_rgb.reshape(-1, 3), rgb_gt.reshape(-1, 3), valid.reshape(-1), opacity.reshape(-1),
+                                      None if fg_mask is None else fg_mask.reshape(-1), sdf_grad.reshape(-1, 3), sdf.reshape(-1),
+                                      None if laplace is None else laplace.reshape(-1))
+    named = {k: terms[i] for i, k in enumerate(LOSS_TERMS)}
+    if fg_mask is None:
+        named.pop("mask")
+    if laplace is None or float(lambdas.get("curvature", 0.0)) <= 0:
+        named.pop("curvature")
+    return loss, named

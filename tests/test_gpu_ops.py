@@ -1275,3 +1275,71 @@ def test_weightnorm_flat_matches_torch(cuda_lib):
             for a, r, nm in ((gg, gr, "dg"), (v, vr, "dv"), (b, br, "db")):
                 if a is not None:
                     assert_close(a.grad, r.grad.float(), rtol=1e-5, atol=1e-6, name=nm)
+
+
+@pytest.mark.parametrize("with_mask,with_curv,n_rays,n_samples", [(False, True, 777, 50021), (True, False, 64, 300), (True, True, 1, 1),
+                                                                   (False, True, 3000, 0)])
+def test_neus_losses_match_tensor_expressions(cuda_lib, with_mask, with_curv, n_rays, n_samples):
+    """ops.neus_losses (ia_neus_losses_fwd / _bwd: every per-ray and per-sample loss term of reference systems/neus.py:132-160
+    and their weighted sum, one launch each way) against the same expressions as float64 tensor operators with autograd:
+    values to 1e-5, gradients to 1e-4 of each tensor's scale; clamp edges of the opacity, invalid rays, exact zeros of
+    sdf / laplace (sign(0) = 0) and a vanishing sdf gradient included."""
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(n_rays + n_samples)
+    comp = torch.rand(n_rays, 3, generator=g) * 1.2
+    gt = torch.rand(n_rays, 3, generator=g)
+    valid = torch.rand(n_rays, generator=g) > 0.2
+    if n_rays > 4:
+        valid[0], valid[1] = True, False
+    opacity = torch.rand(n_rays, 1, generator=g)
+    if n_rays > 8:
+        opacity[:6, 0] = torch.tensor([0.0, 1.0, 1e-3, 1.0 - 1e-3, 5e-4, 0.99999])
+    mask = (torch.rand(n_rays, generator=g) > 0.5) if with_mask else None
+    sgrad = torch.randn(n_samples, 3, generator=g) * 1.5
+    sdf = torch.randn(n_samples, generator=g) * 0.01
+    lap = torch.rand(n_samples, 1, generator=g) - 0.3
+    if n_samples > 8:
+        sgrad[0] = 0.0
+        sdf[1] = 0.0
+        lap[2] = 0.0
+    lambdas = {"rgb_mse": 10.0, "rgb_l1": 0.5, "eikonal": 0.1, "mask": 0.7 if with_mask else 0.0, "opaque": 0.3, "sparsity": 0.2,
+               "curvature": 5e-4 if with_curv else 0.0}
+    scale = 1.0
+
+    def expr(comp, opacity, sgrad, sdf, lap, dt):
+        diff = torch.where(valid[:, None], comp - gt.to(dt), torch.zeros((), dtype=dt))
+        n_valid = valid.sum().to(dt) * 3
+        t = {"rgb_mse": (diff * diff).sum() / n_valid, "rgb_l1": diff.abs().sum() / n_valid,
+             "eikonal": ((torch.linalg.norm(sgrad, ord=2, dim=-1) - 1.0) ** 2).mean()}
+        o = torch.clamp(opacity.squeeze(-1), 1.0e-3, 1.0 - 1.0e-3)
+        bce = lambda a, b: -(b * torch.log(a) + (1 - b) * torch.log(1 - a)).mean()
+        if with_mask:
+            t["mask"] = bce(o, mask.to(dt))
+        t["opaque"] = bce(o, o)
+        t["sparsity"] = torch.exp(-scale * sdf.abs()).mean()
+        if with_curv:
+            t["curvature"] = lap.abs().mean()
+        return sum(t[k] * lambdas[k] for k in t), t
+
+    leaves64 = [v.double().requires_grad_(True) for v in (comp, opacity, sgrad, sdf, lap)]
+    loss64, terms64 = expr(*leaves64, torch.float64)
+    leaves = [v.cuda().requires_grad_(True) for v in (comp, opacity, sgrad, sdf, lap)]
+    loss, terms = ops.neus_losses(leaves[0], gt.cuda(), valid.cuda(), leaves[1], mask.cuda().float() if with_mask else None, leaves[2],
+                                  leaves[3], leaves[4] if with_curv else None, lambdas, scale)
+    assert set(terms) == set(terms64)
+    if n_samples == 0:
+        assert torch.isnan(loss) and torch.isnan(loss64)           # means over zero samples, as in the reference
+        return
+    for k in terms64:
+        assert not terms[k].requires_grad
+        assert_close(terms[k], terms64[k], rtol=1e-5, atol=1e-7, name=k)
+    assert_close(loss, loss64, rtol=1e-5, atol=1e-7, name="loss")
+    up = 0.37
+    (loss * up).backward()
+    (loss64 * up).backward()
+    for name, a, b in zip(("comp_rgb", "opacity", "sdf_grad", "sdf", "laplace"), leaves, leaves64):
+        if name == "laplace" and not with_curv:
+            assert a.grad is None
+            continue
+        rt, at = grad_tol(b.grad, 1e-4, floor=1e-9)
+        assert_close(a.grad, b.grad, rtol=rt, atol=at, name="d " + name)

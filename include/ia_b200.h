@@ -281,6 +281,17 @@ int32_t ia_curv_angle_fwd(const float *normals, const float *gshift, int64_t n, 
 int32_t ia_curv_angle_bwd(const float *normals, const float *gshift, int64_t n, const float *dlaplace, float *dnormals,
                           float *dgshift, void *stream);
 
+/* Sample points of the marched intervals (models/neus.py:153-157 background, :218-223 foreground):
+ *   midpoints = (t_starts + t_ends) / 2, positions = rays_o[ri] + rays_d[ri] * midpoints, t_dirs = rays_d[ri],
+ *   dists = t_ends - t_starts; each operation rounded as the tensor expression (no fused multiply-add): the background
+ * marcher prunes on a density evaluated at these positions.  t_dirs / midpoints / dists may be NULL. */
+int32_t ia_ray_samples(const float *rays_o, const float *rays_d, const int32_t *ray_indices, const float *t_starts,
+                       const float *t_ends, int64_t n, float *positions, float *t_dirs, float *midpoints, float *dists,
+                       void *stream);
+/* F.normalize(x, p=2, dim=-1, eps) for x[n,3] (models/neus.py:229, 247; systems/neus.py:182-183) and its adjoint. */
+int32_t ia_normalize3_fwd(const float *x, int64_t n, float eps, float *out, void *stream);
+int32_t ia_normalize3_bwd(const float *x, const float *dout, int64_t n, float eps, float *dx, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Occupancy grid + ray marching        replaces nerfacc.OccupancyGrid / ray_aabb_intersect /
  *                                      ray_marching as called at models/neus.py:64-74, 108-111, 153,

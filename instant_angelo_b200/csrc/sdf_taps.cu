@@ -242,3 +242,100 @@ extern "C" int32_t ia_curv_angle_bwd(const float *normals, const float *gshift, 
     IA_LAUNCH_OK("curv_angle_bwd_kernel");
     return IA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sample points of the marched intervals and the normalisation of the SDF gradient: the tensor expressions between the
+// marcher and the networks (reference models/neus.py:153-157, 218-223: t_origins / t_dirs gathers, midpoints, positions,
+// dists; :229 F.normalize), one launch each instead of ~9 / ~12 (forward + backward) element-wise launches per call.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// positions = rays_o[ri] + rays_d[ri] * ((t0 + t1) / 2), rounded operation by operation as the tensor expression is (no
+// fused multiply-add): the background marcher prunes samples on a density evaluated at these positions, and the sample
+// set is a bit-exact contract
+__global__ void ray_samples_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int32_t *__restrict__ ri,
+                                   const float *__restrict__ t0, const float *__restrict__ t1, int64_t n, float *__restrict__ pos,
+                                   float *__restrict__ dirs, float *__restrict__ mid, float *__restrict__ dist)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = ri[i];
+    const float a = t0[i], b = t1[i];
+    const float m = __fmul_rn(__fadd_rn(a, b), 0.5f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float d = __ldg(rays_d + 3 * r + c);
+        pos[3 * i + c] = __fadd_rn(__ldg(rays_o + 3 * r + c), __fmul_rn(d, m));
+        if (dirs) dirs[3 * i + c] = d;
+    }
+    if (mid) mid[i] = m;
+    if (dist) dist[i] = __fsub_rn(b, a);
+}
+
+__global__ void normalize3_fwd_kernel(const float *__restrict__ x, int64_t n, float eps, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+    const float den = fmaxf(sqrtf(a * a + b * b + c * c), eps);      // F.normalize: x / max(|x|, eps)
+    out[3 * i] = a / den;
+    out[3 * i + 1] = b / den;
+    out[3 * i + 2] = c / den;
+}
+
+// y = x / max(|x|, eps):  |x| > eps: dx = (g - y (y . g)) / |x| ;  otherwise (the clamp passes no gradient to the norm) dx = g / eps
+__global__ void normalize3_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t n, float eps,
+                                      float *__restrict__ dx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+    const float ga = g[3 * i], gb = g[3 * i + 1], gc = g[3 * i + 2];
+    const float nrm = sqrtf(a * a + b * b + c * c);
+    if (nrm > eps) {
+        const float inv = 1.f / nrm;
+        const float ya = a * inv, yb = b * inv, yc = c * inv;
+        const float dot = ya * ga + yb * gb + yc * gc;
+        dx[3 * i] = (ga - ya * dot) * inv;
+        dx[3 * i + 1] = (gb - yb * dot) * inv;
+        dx[3 * i + 2] = (gc - yc * dot) * inv;
+    } else {
+        const float inv = 1.f / eps;
+        dx[3 * i] = ga * inv;
+        dx[3 * i + 1] = gb * inv;
+        dx[3 * i + 2] = gc * inv;
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t ia_ray_samples(const float *rays_o, const float *rays_d, const int32_t *ray_indices, const float *t_starts,
+                                  const float *t_ends, int64_t n, float *positions, float *t_dirs, float *midpoints, float *dists,
+                                  void *stream)
+{
+    IA_REQUIRE(n >= 0 && (n == 0 || (rays_o && rays_d && ray_indices && t_starts && t_ends && positions)),
+               "ray_samples: NULL pointer with n=%lld", (long long)n);
+    if (n == 0) return IA_OK;
+    ray_samples_kernel<<<(unsigned)ia_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, ray_indices, t_starts, t_ends, n,
+                                                                                        positions, t_dirs, midpoints, dists);
+    IA_LAUNCH_OK("ray_samples_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_normalize3_fwd(const float *x, int64_t n, float eps, float *out, void *stream)
+{
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && out)) && eps > 0.f, "normalize3_fwd: bad arguments (n=%lld)", (long long)n);
+    if (n == 0) return IA_OK;
+    normalize3_fwd_kernel<<<(unsigned)ia_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, eps, out);
+    IA_LAUNCH_OK("normalize3_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_normalize3_bwd(const float *x, const float *dout, int64_t n, float eps, float *dx, void *stream)
+{
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && dout && dx)) && eps > 0.f, "normalize3_bwd: bad arguments (n=%lld)", (long long)n);
+    if (n == 0) return IA_OK;
+    normalize3_bwd_kernel<<<(unsigned)ia_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dout, n, eps, dx);
+    IA_LAUNCH_OK("normalize3_bwd_kernel");
+    return IA_OK;
+}

@@ -110,8 +110,10 @@ def training_loss(model, out: Dict[str, torch.Tensor], batch: Dict[str, torch.Te
     if c(loss_cfg["lambda_sdf_l1"]) > 0 and batch.get("pts") is not None:
         sdf_p, grad_p = model.geometry(batch["pts"], with_grad=True, with_feature=False)
         terms["sdf_l1"] = (F.l1_loss(sdf_p, torch.zeros_like(sdf_p)) * batch["pts_weights"]).mean(dim=0)   # Appendix C-11
-        n_gt = F.normalize(batch["pts_normal"], p=2, dim=-1)
-        n_pr = F.normalize(grad_p, p=2, dim=-1)
+        if grad_p.is_cuda:
+            n_gt, n_pr = ops.normalize3(batch["pts_normal"]), ops.normalize3(grad_p)
+        else:
+            n_gt, n_pr = F.normalize(batch["pts_normal"], p=2, dim=-1), F.normalize(grad_p, p=2, dim=-1)
         terms["normal_cos"] = (1.0 - torch.sum(n_pr * n_gt, dim=-1)).mean()
         loss = loss + terms["sdf_l1"] * c(loss_cfg["lambda_sdf_l1"])
         loss = loss + terms["normal_cos"] * c(loss_cfg.get("lambda_normal", loss_cfg["lambda_sdf_l1"]))

@@ -166,8 +166,8 @@ class NeuSModel(nn.Module):
         of sample counts then sit at the start of the step instead of draining the GPU queue in the middle of it."""
 
         def sigma_fn(t_starts, t_ends, ray_indices):
-            ri = ray_indices.long()
-            positions = rays_o[ri] + rays_d[ri] * (t_starts + t_ends) / 2.0
+            # rays_o[ri] + rays_d[ri] * (t_starts + t_ends) / 2.0 : the same roundings (a product halved == the product of the half)
+            positions = ops.ray_samples(rays_o, rays_d, ray_indices, t_starts, t_ends, False, False, False)[0]
             return self.geometry_bg.density(positions)[..., None]
 
         _, t_max = ray_aabb_intersect(rays_o, rays_d, self._aabb_host)
@@ -186,10 +186,7 @@ class NeuSModel(nn.Module):
             marched = self.march_bg_(rays_o, rays_d, stratified_u)
         ray_indices, t_starts, t_ends, packed_info = marched
         ri = ray_indices.long()
-        t_dirs = rays_d[ri]
-        midpoints = (t_starts + t_ends) / 2.0
-        positions = rays_o[ri] + t_dirs * midpoints
-        intervals = t_ends - t_starts
+        positions, t_dirs, midpoints, intervals = ops.ray_samples(rays_o, rays_d, ray_indices, t_starts, t_ends)
         density, feature = self.geometry_bg(positions)
         rgb = self.texture_bg(feature, t_dirs)
         weights, opacity, depth, comp_rgb, _, _ = ops.composite_density(
@@ -218,25 +215,21 @@ class NeuSModel(nn.Module):
         # read-back does not drain the GPU queue in the middle of the step
         marched_bg = self.march_bg_(rays_o, rays_d, stratified_u_bg) if self.learned_background else None
         ri = ray_indices.long()
-        t_origins = rays_o[ri]
-        t_dirs = rays_d[ri]
-        midpoints = (t_starts + t_ends) / 2.0
-        positions = t_origins + t_dirs * midpoints
-        dists = t_ends - t_starts
+        positions, t_dirs, midpoints, dists = ops.ray_samples(rays_o, rays_d, ray_indices, t_starts, t_ends)
         fused_head = getattr(self.geometry, "supports_fused_head", lambda: False)() and \
             getattr(self.texture, "supports_fused_head", lambda g: False)(self.geometry)
         if fused_head:
             # same arithmetic as the generic branch below; the 65-wide `feature` and the colour head's 87-wide input row
             # are assembled in one buffer (ops.sdf_head) instead of out -> cat -> cat
             h, pts01, sdf_grad, sdf_laplace, w_last, b_last = self.geometry.forward_hidden(positions, rand_directions)
-            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            normal = ops.normalize3(sdf_grad)
             rgb, sdf = self.texture.forward_fused_head(h, w_last, b_last, pts01, t_dirs, normal)
             if not self.training:
                 sdf, sdf_grad, sdf_laplace, rgb, normal = (v.detach() for v in (sdf, sdf_grad, sdf_laplace, rgb, normal))
         else:
             sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True, with_laplace=True,
                                                                 rand_directions=rand_directions)
-            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            normal = ops.normalize3(sdf_grad)
             rgb = self.texture(feature, t_dirs, normal)
         inv_s = self.variance.inv_s.reshape(1).clip(1e-6, 1e6)
         weights, opacity, depth, comp_rgb, comp_normal, alpha = ops.composite_neus(
@@ -244,7 +237,7 @@ class NeuSModel(nn.Module):
             t_mid=midpoints.reshape(-1), rgb=rgb, nrm=normal)
         opacity, depth = opacity[:, None], depth[:, None]
         rays_fg = opacity > 0.1
-        comp_normal = F.normalize(comp_normal, p=2, dim=-1)
+        comp_normal = ops.normalize3(comp_normal)
         comp_normal = comp_normal * rays_fg.float()      # Appendix C-9
         out = {"comp_rgb": comp_rgb, "comp_normal": comp_normal, "opacity": opacity, "depth": depth,
                "rays_valid": opacity > 0,

@@ -1067,3 +1067,52 @@ def neus_losses(comp_rgb, rgb_gt, valid, opacity, fg_mask, sdf_grad, sdf, laplac
     if laplace is None or float(lambdas.get("curvature", 0.0)) <= 0:
         named.pop("curvature")
     return loss, named
+
+
+# ---------------------------------------------------------------------------------------------
+# glue between the marcher and the networks  (reference models/neus.py:153-157, 218-223, 229)
+# ---------------------------------------------------------------------------------------------
+
+@torch.no_grad()
+def ray_samples(rays_o, rays_d, ray_indices, t_starts, t_ends, want_dirs=True, want_mid=True, want_dists=True):
+    """(positions [S,3], t_dirs [S,3], midpoints [S,1], dists [S,1]) of marched samples in one launch; rays carry no gradient
+    on the training path (callers with differentiable rays keep the tensor expression)."""
+    L.require_cuda(rays_o, rays_d, ray_indices, t_starts, t_ends)
+    rays_o, rays_d, t_starts, t_ends = L.f32c(rays_o), L.f32c(rays_d), L.f32c(t_starts), L.f32c(t_ends)
+    ri = ray_indices.contiguous()
+    if ri.dtype != torch.int32:
+        ri = ri.int()
+    n = ri.shape[0]
+    dev = rays_o.device
+    pos = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    dirs = torch.empty(n, 3, device=dev, dtype=torch.float32) if want_dirs else None
+    mid = torch.empty(n, 1, device=dev, dtype=torch.float32) if want_mid else None
+    dist = torch.empty(n, 1, device=dev, dtype=torch.float32) if want_dists else None
+    _run("ia_ray_samples", L.ptr(rays_o), L.ptr(rays_d), L.ptr(ri), L.ptr(t_starts), L.ptr(t_ends), n, L.ptr(pos), L.ptr(dirs),
+         L.ptr(mid), L.ptr(dist), L.stream())
+    return pos, dirs, mid, dist
+
+
+class _Normalize3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        L.require_cuda(x)
+        x = L.f32c(x)
+        out = torch.empty_like(x)
+        _run("ia_normalize3_fwd", L.ptr(x), x.shape[0], C.c_float(eps), L.ptr(out), L.stream())
+        ctx.save_for_backward(x)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = L.f32c(g)
+        dx = torch.empty_like(x)
+        _run("ia_normalize3_bwd", L.ptr(x), L.ptr(g), x.shape[0], C.c_float(ctx.eps), L.ptr(dx), L.stream())
+        return dx, None
+
+
+def normalize3(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=-1, eps) for [..., 3] CUDA tensors: one launch forward, one backward."""
+    return _Normalize3Fn.apply(x.reshape(-1, 3), float(eps)).view(x.shape)

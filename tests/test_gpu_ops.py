@@ -1293,7 +1293,7 @@ def test_neus_losses_match_tensor_expressions(cuda_lib, with_mask, with_curv, n_
         valid[0], valid[1] = True, False
     opacity = torch.rand(n_rays, 1, generator=g)
     if n_rays > 8:
-        opacity[:6, 0] = torch.tensor([0.0, 1.0, 1e-3, 1.0 - 1e-3, 5e-4, 0.99999])
+        opacity[:6, 0] = torch.tensor([0.0, 1.0, 1.001e-3, 1.0 - 1.001e-3, 5e-4, 0.99999])    # both sides of the clamp edges
     mask = (torch.rand(n_rays, generator=g) > 0.5) if with_mask else None
     sgrad = torch.randn(n_samples, 3, generator=g) * 1.5
     sdf = torch.randn(n_samples, generator=g) * 0.01
@@ -1343,3 +1343,43 @@ def test_neus_losses_match_tensor_expressions(cuda_lib, with_mask, with_curv, n_
             continue
         rt, at = grad_tol(b.grad, 1e-4, floor=1e-9)
         assert_close(a.grad, b.grad, rtol=rt, atol=at, name="d " + name)
+
+
+def test_ray_samples_bit_exact_and_normalize3(cuda_lib):
+    """ops.ray_samples == the tensor expressions of reference models/neus.py:153-157 / 218-223 bit for bit (the background
+    marcher prunes on a density evaluated at these positions); ops.normalize3 == F.normalize (values to 1 ulp, adjoint to
+    1e-6), including rows at and below eps."""
+    from instant_angelo_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    R, S = 300, 20011
+    rays_o = (torch.randn(R, 3, generator=g) * 2).cuda()
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda()
+    ri = torch.sort(torch.randint(0, R, (S,), generator=g)).values.int().cuda()
+    t0 = (torch.rand(S, 1, generator=g) * 5).cuda()
+    t1 = t0 + (torch.rand(S, 1, generator=g) * 0.02).cuda()
+    pos, dirs, mid, dist = ops.ray_samples(rays_o, rays_d, ri, t0, t1)
+    l = ri.long()
+    assert torch.equal(mid, (t0 + t1) / 2.0) and torch.equal(dist, t1 - t0) and torch.equal(dirs, rays_d[l])
+    assert torch.equal(pos, rays_o[l] + rays_d[l] * ((t0 + t1) / 2.0))
+    assert torch.equal(pos, rays_o[l] + rays_d[l] * (t0 + t1) / 2.0)          # the marcher's sigma_fn spelling
+    only = ops.ray_samples(rays_o, rays_d, ri, t0, t1, False, False, False)
+    assert torch.equal(only[0], pos) and only[1] is None and only[2] is None and only[3] is None
+    empty = ops.ray_samples(rays_o, rays_d, ri[:0], t0[:0], t1[:0])
+    assert empty[0].shape == (0, 3) and empty[2].shape == (0, 1)
+
+    x = torch.randn(5003, 3, generator=g)
+    x[0] = 0.0
+    x[1] = torch.tensor([1e-13, 0.0, 0.0])
+    x[2] = torch.tensor([3e-7, -4e-7, 0.0])
+    up = torch.randn(5003, 3, generator=g)
+    xa, xb = x.cuda().requires_grad_(True), x.double().requires_grad_(True)
+    ya, yb = ops.normalize3(xa), torch.nn.functional.normalize(xb, p=2, dim=-1)
+    assert_close(ya, yb, rtol=3e-7, atol=1e-12, name="normalize3")
+    ya.backward(up.cuda())
+    yb.backward(up.double())
+    assert_close(xa.grad[3:], xb.grad[3:], rtol=1e-5, atol=1e-6, name="normalize3 adjoint")
+    assert_close(xa.grad[:2], xb.grad[:2], rtol=1e-6, atol=0.0, name="normalize3 adjoint below eps")     # g / eps
+    rt, at = grad_tol(xb.grad[2:3], 1e-5)
+    assert_close(xa.grad[2:3], xb.grad[2:3], rtol=rt, atol=at, name="normalize3 adjoint, tiny row")
+    y3 = ops.normalize3(x.cuda().view(5003, 1, 3))
+    assert y3.shape == (5003, 1, 3)

@@ -22,6 +22,12 @@ from .nerfacc_api import ContractionType
 from .network_utils import fused_encode_mlp, get_encoding, get_encoding_with_network, get_mlp, update_module_step
 from .utils import get_activation, scale_anything
 
+# Rows of a centre evaluation are the packed samples of the marched rays: consecutive rows are neighbours along a ray (one
+# render step apart), so at the coarse levels runs of them share a cell exactly as the six finite-difference taps of a sample
+# do -- the grouped scatter (ia_hashgrid_bwd_grouped: same-cell contributions merged in registers before the atomic adds)
+# applies to them too.  IA_CENTER_GROUP=1 restores the plain scatter (A/B).
+_CENTER_GROUP = int(os.environ.get("IA_CENTER_GROUP", "6"))
+
 
 def contract_to_unisphere(x, radius, contraction_type):
     """reference models/geometry.py:19-31."""
@@ -80,7 +86,7 @@ class VolumeDensity(BaseImplicitGeometry):
 
     def forward(self, points):
         points = contract_to_unisphere(points, self.radius, self.contraction_type)
-        out = self.encoding_with_network(points.view(-1, self.n_input_dims)).view(*points.shape[:-1], self.n_output_dims).float()
+        out = self.encoding_with_network(points.view(-1, self.n_input_dims), group=_CENTER_GROUP).view(*points.shape[:-1], self.n_output_dims).float()
         density, feature = out[..., 0], out
         if "density_activation" in self.config:
             density = get_activation(self.config["density_activation"])(density + float(self.config["density_bias"]))
@@ -222,7 +228,7 @@ class VolumeSDF(BaseImplicitGeometry):
             if analytic:
                 out, grad = self._analytic_eval(pts01, flat)
             else:
-                out = self._net(pts01, self.n_output_dims if need_full else 1, flat)
+                out = self._net(pts01, self.n_output_dims if need_full else 1, flat, group=_CENTER_GROUP)
             out = out.view(*pts01.shape[:-1], out.shape[-1])
             sdf = out[..., 0]
             feature = None
@@ -287,7 +293,7 @@ class VolumeSDF(BaseImplicitGeometry):
             if self.grad_type == "analytic":
                 h, grad, flat = self._analytic_hidden(pts01, flat)
             else:
-                h = self._net(pts01, 0, flat)
+                h = self._net(pts01, 0, flat, group=_CENTER_GROUP)
                 grad = self._fd_gradient(points, eps, flat)
             if rand_directions is None:
                 rand_directions = torch.randn_like(pts01)

@@ -309,8 +309,8 @@ class EncodingWithNetwork(nn.Module):
         super().__init__()
         self.encoding, self.network = encoding, network
 
-    def forward(self, x: torch.Tensor, n_out_used: Optional[int] = None, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return fused_encode_mlp(self.encoding, self.network, x, n_out_used, flat)
+    def forward(self, x: torch.Tensor, n_out_used: Optional[int] = None, flat: Optional[torch.Tensor] = None, group: int = 1) -> torch.Tensor:
+        return fused_encode_mlp(self.encoding, self.network, x, n_out_used, flat, group)
 
     def update_step(self, epoch, global_step):
         update_module_step(self.encoding, epoch, global_step)

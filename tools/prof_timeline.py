@@ -34,7 +34,7 @@ prev_end = None
 agg = collections.OrderedDict()
 for k in kern:
     name = k.name
-    short = name.split("(")[0].replace("void ", "").replace("at::native::", "").replace("(anonymous namespace)::", "")[:70]
+    short = name.replace("void ", "").replace("at::native::", "").replace("(anonymous namespace)::", "").split("(")[0][:70]
     gap = 0 if prev_end is None else k.time_range.start - prev_end
     prev_end = k.time_range.end
     dur = k.time_range.end - k.time_range.start

@@ -499,6 +499,61 @@ def test_fp16_shadow_tables_equal_fp32_path_on_rounded_tables(cuda_lib, golden_d
         assert_close(g0[n], g1[n], rtol=rt, atol=at, name="grad " + n)
 
 
+def test_fused_glue_and_gradient_sinks_match_the_autograd_path(cuda_lib, golden_dir, monkeypatch):
+    """The step as the bench runs it -- parameters re-homed in a ParamArena (hash-table scatters and the weight-norm adjoint
+    add straight into the gradient arena), MLP weight gradients accumulated behind weightnorm_flat, fused loss kernels,
+    ia_ray_samples / ia_normalize3, grouped scatter for the centre rows -- against the same step with every one of those
+    switched off (tensor expressions + autograd accumulation): same loss, same gradient for every parameter; and a second
+    step through the same arena after zero_grad() starts from clean accumulators."""
+    from instant_angelo_b200 import geometry as geo_mod
+    from instant_angelo_b200 import ops
+    from instant_angelo_b200.dp import ParamArena
+    from instant_angelo_b200.losses import training_loss
+    fx = load_golden(golden_dir, "neus_dualcolor_bg")
+    cfg = golden_model_config(**GOLDEN_CASES["neus_dualcolor_bg"])
+    gs = int(fx["global_step"])
+    batch = golden_batch(fx, "cuda")
+    c = lambda k: torch.from_numpy(fx[k]).cuda()
+
+    def step(model):
+        out = model(batch["rays"], stratified_u=c("u_fg"), rand_directions=c("rand_directions"), stratified_u_bg=c("u_bg"))
+        terms = training_loss(model, out, batch, golden_loss_config(), gs)
+        terms["loss"].backward()
+        torch.cuda.synchronize()
+        return terms
+
+    fast = build_product(cfg, golden_state_dict(fx), gs, torch.from_numpy(fx["background_color"]), "FullyFusedMLP")
+    arena = ParamArena(list(fast.parameters()))
+    arena.zero_grad()
+    t_fast = step(fast)
+    named = [(n, p) for n, p in fast.named_parameters() if p.numel() > 0]      # (the SH encodings hold an empty .params)
+    g_fast = {n: p.grad.clone() for n, p in named}
+    for n, p in named:                                                      # everything landed IN the arena
+        off = arena.offsets[[id(q) for q in arena.params].index(id(p))]
+        assert p.grad.data_ptr() == arena.grad[off:off + p.numel()].data_ptr(), n
+    arena.zero_grad()
+    t_again = step(fast)                                                     # accumulators were left clean
+    assert float(t_again["loss"]) == float(t_fast["loss"])
+    for n, p in named:
+        rt, at = grad_tol(g_fast[n], 1e-5)
+        assert_close(p.grad, g_fast[n], rtol=rt, atol=at, name="second step grad " + n)
+
+    monkeypatch.setenv("IA_NO_FUSED_LOSSES", "1")
+    monkeypatch.setattr(ops, "_NO_GRAD_SINK", True)
+    monkeypatch.setattr(geo_mod, "_CENTER_GROUP", 1)
+    plain = build_product(cfg, golden_state_dict(fx), gs, torch.from_numpy(fx["background_color"]), "FullyFusedMLP")
+    t_plain = step(plain)
+    assert set(t_plain) == set(t_fast)
+    for k in t_plain:
+        assert_close(t_fast[k], t_plain[k], rtol=1e-5, atol=1e-7, name="term " + k)
+    g_plain = {n: p.grad for n, p in plain.named_parameters() if p.numel() > 0}
+    assert set(g_plain) == set(g_fast)
+    for n in g_plain:
+        assert g_plain[n] is not None, n
+        rt, at = grad_tol(g_plain[n], 1e-4)
+        assert_close(g_fast[n], g_plain[n], rtol=rt, atol=at, name="grad " + n)
+
+
 def test_fused_head_matches_generic_path(cuda_lib, golden_dir, monkeypatch):
     """NeuSModel.forward_ takes the fused SDF-head / colour-input assembly (ops.sdf_head) when geometry and texture
     support it; with IA_NO_FUSED_HEAD it goes through VolumeSDF.forward -> feature -> texture.forward like the

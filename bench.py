@@ -34,7 +34,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # sample counts change every step: no cudaMalloc stalls
+# Marched sample counts change every step, so every activation tensor has a new size every step: with exact-size blocks a
+# record-high count finds no cached block and the pool grows inside the timed region -- cudaMalloc / cuMemMap stalls of
+# 30-600 ms on this (virtualised) box, at deterministic step indices (tools/diag_stalls.py).  Sizes rounded to eighths of a
+# power of two land in the same bucket step after step (measured: 0 stalls in 6 runs, against 3 in 6 with expandable segments).
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8")
 import torch  # noqa: E402
 
 GLOBAL_STEP0 = 19000          # all 16 levels active (start_level 4 + (19000-5000)//1000 >= 16), curvature weight 0.5
@@ -59,7 +63,7 @@ class ClockSampler:
     background thread (the nvidia-smi CLI in loop mode re-enumerates every GPU on each tick and measurably stalls
     kernel launches of the process being measured)."""
 
-    def __init__(self, gpu_index: int, period_s: float = 0.2):
+    def __init__(self, gpu_index: int, period_s: float = float(os.environ.get("IA_CLOCK_PERIOD_S", "0.2"))):
         self.idx, self.period = gpu_index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = None
@@ -418,12 +422,14 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     gs = GLOBAL_STEP0
-    # allocator head-room: one untimed step on a 25 % larger ray batch, so that a timed step whose marched sample count
-    # exceeds everything seen during warm-up does not grow the CUDA memory pool (a cuMemMap stall of tens of ms)
-    big, big_bg = make_batches(1, n_rays + n_rays // 4, rank + 7919, pin=False)[0]
-    batch, bg = unpack_batch(big.to(device), big_bg.to(device))
-    train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs - 1, world)
-    del big, big_bg, batch, bg
+    # allocator head-room: untimed steps on 25 % and 12.5 % larger ray batches (the next two size buckets of the caching
+    # allocator, see PYTORCH_CUDA_ALLOC_CONF above), so that a timed step whose marched sample count exceeds everything seen
+    # during warm-up does not grow the CUDA memory pool
+    for extra in (n_rays // 4, n_rays // 8):
+        big, big_bg = make_batches(1, n_rays + extra, rank + 7919, pin=False)[0]
+        batch, bg = unpack_batch(big.to(device), big_bg.to(device))
+        train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs - 1, world)
+        del big, big_bg, batch, bg
     for i in range(W):
         batch, bg = unpack_batch(*dev_batches[i])
         train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)

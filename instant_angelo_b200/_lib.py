@@ -179,7 +179,9 @@ def ptr(t) -> int | None:
 
 
 def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device.  (torch.cuda.current_stream() builds a Stream object
+    through three Python layers, ~18 us a call, 80 calls a step: 1.5 ms of a launch-bound 7 ms step at 256-1024 rays.)"""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def require_cuda(*tensors) -> None:

@@ -4,10 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, argparse
 import bench
 
-args = argparse.Namespace(mlp="tc", rays=8192, steps=3, warmup=3)
+RAYS = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+args = argparse.Namespace(mlp="tc", rays=RAYS, steps=3, warmup=3)
 dev = torch.device("cuda", 0)
 cfg, model, arena, var_arena, opt, opt_var = bench.build_b200(args, 0, 1, dev)
-batches = [(b.to(dev), g.to(dev)) for b, g in bench.make_batches(12, 8192, 0, pin=False)]
+batches = [(b.to(dev), g.to(dev)) for b, g in bench.make_batches(12, RAYS, 0, pin=False)]
 gs = bench.GLOBAL_STEP0 + 1
 for i in range(4):
     b, bg = bench.unpack_batch(*batches[i]); bench.train_step(cfg, model, arena, var_arena, opt, opt_var, b, bg, gs, 1); gs += 1
@@ -23,10 +24,11 @@ print(f"4 steps: host loop {1e3*(t1-t0)/4:.1f} ms/step, + final sync {1e3*(t2-t1
 # (2) host-only cost: sync first so no call ever waits on the GPU queue... the marching sync still waits for the GPU
 pr = cProfile.Profile()
 pr.enable()
-for i in range(8, 10):
+for i in range(8, 12):
     b, bg = bench.unpack_batch(*batches[i]); bench.train_step(cfg, model, arena, var_arena, opt, opt_var, b, bg, gs, 1); gs += 1
 pr.disable()
 torch.cuda.synchronize()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28)
-print(s.getvalue()[:6000])
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(40)
+pstats.Stats(pr, stream=s).sort_stats("cumtime").print_stats(60)
+print(s.getvalue()[:30000])

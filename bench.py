@@ -425,15 +425,22 @@ def run_b200(args):
     # allocator head-room: untimed steps on 25 % and 12.5 % larger ray batches (the next two size buckets of the caching
     # allocator, see PYTORCH_CUDA_ALLOC_CONF above), so that a timed step whose marched sample count exceeds everything seen
     # during warm-up does not grow the CUDA memory pool
-    for extra in (n_rays // 4, n_rays // 8):
-        big, big_bg = make_batches(1, n_rays + extra, rank + 7919, pin=False)[0]
-        batch, bg = unpack_batch(big.to(device), big_bg.to(device))
-        train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs - 1, world)
-        del big, big_bg, batch, bg
+    def headroom(step):
+        for extra in (n_rays // 4, n_rays // 8):
+            big, big_bg = make_batches(1, n_rays + extra, rank + 7919, pin=False)[0]
+            batch, bg = unpack_batch(big.to(device), big_bg.to(device))
+            train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, step, world)
+            del big, big_bg, batch, bg
+
+    headroom(gs - 1)
     for i in range(W):
         batch, bg = unpack_batch(*dev_batches[i])
         train_step(cfg, model, arena, var_arena, opt, opt_var, batch, bg, gs, world)
         gs += 1
+    # ... and spare 2 MB blocks for the allocator's small pool (per-step scalars, event-sized tensors): its growth inside the
+    # timed region is a cudaMalloc too (tools/diag_stalls.py: +2 MB at the second timed step, a 30-80 ms stall on this box)
+    spare = [torch.empty(1 << 20, dtype=torch.uint8, device=device) for _ in range(32)]
+    del spare
     prof = ops.PROFILER
     prof.reset()
     prof.enabled, prof.timing = True, rank == 0          # launch counting everywhere, CUDA-event timing on rank 0 only
@@ -509,6 +516,7 @@ def run_b200(args):
     full_total = sum_over_ranks(n_samples_full)
 
     # ---- end-to-end measurement (`e2e`): host pinned rays -> H2D -> step -> loss D2H, every step -------
+    headroom(gs - 1)            # the model has trained K steps since the first head-room steps: its sample counts have drifted
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()

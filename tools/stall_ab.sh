@@ -1,6 +1,6 @@
 run() { # label, args...
   label=$1; shift
-  for i in 1 2 3 4 5; do python bench.py --no-cpu-baseline --steps 50 "$@" > gpurun_out/s3_ab.json 2>/dev/null; python - <<PY
+  for i in 1 2 3 4 5 6; do python bench.py --no-cpu-baseline --steps 50 "$@" > gpurun_out/s3_ab.json 2>/dev/null; python - <<PY
 import json
 d=json.loads(open("gpurun_out/s3_ab.json").read().strip().splitlines()[-1])
 s=d["step_ms"]
@@ -10,5 +10,3 @@ PY
 }
 run sparse --config sparse
 run dense21 --config dense21
-run analytic --grad-type analytic
-run wrefl --config wreflection

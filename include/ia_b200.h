@@ -288,6 +288,9 @@ int32_t ia_curv_angle_bwd(const float *normals, const float *gshift, int64_t n, 
 int32_t ia_ray_samples(const float *rays_o, const float *rays_d, const int32_t *ray_indices, const float *t_starts,
                        const float *t_ends, int64_t n, float *positions, float *t_dirs, float *midpoints, float *dists,
                        void *stream);
+/* contract_to_unisphere (models/geometry.py:19-31) of positions that carry no gradient: IA_AABB -> (x + r) / 2r;
+ * IA_UN_BOUNDED_SPHERE -> that, then y = 2x - 1, y <- (2 - 1/|y|) y/|y| where |y| > 1, y/4 + 0.5. */
+int32_t ia_contract(const float *x, int64_t n, float radius, int32_t contraction_type, float *out, void *stream);
 /* F.normalize(x, p=2, dim=-1, eps) for x[n,3] (models/neus.py:229, 247; systems/neus.py:182-183) and its adjoint. */
 int32_t ia_normalize3_fwd(const float *x, int64_t n, float eps, float *out, void *stream);
 int32_t ia_normalize3_bwd(const float *x, const float *dout, int64_t n, float eps, float *dx, void *stream);

@@ -118,6 +118,7 @@ SIGNATURES = {
     "ia_curv_angle_fwd": (_I32, [_P, _P, _I64, _P, _P]),
     "ia_curv_angle_bwd": (_I32, [_P, _P, _I64, _P, _P, _P, _P]),
     "ia_ray_samples": (_I32, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "ia_contract": (_I32, [_P, _I64, _F, _I32, _P, _P]),
     "ia_normalize3_fwd": (_I32, [_P, _I64, _F, _P, _P]),
     "ia_normalize3_bwd": (_I32, [_P, _P, _I64, _F, _P, _P]),
     "ia_occ_workspace_bytes": (_I64, [_I64]),

@@ -339,3 +339,46 @@ extern "C" int32_t ia_normalize3_bwd(const float *x, const float *dout, int64_t 
     IA_LAUNCH_OK("normalize3_bwd_kernel");
     return IA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// contract_to_unisphere (reference models/geometry.py:19-31) for sample positions that carry no gradient: the AABB
+// normalisation (x + r) / 2r, or the un-bounded-sphere contraction of the background model -- as tensor expressions 3 and
+// 11 element-wise launches per call, on up to 8 M rows when the background occupancy grid refreshes.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void contract_kernel(const float *__restrict__ x, int64_t n, float r, int type, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float two_r = r - (-r);
+    float v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v[d] = (x[3 * i + d] - (-r)) / two_r;             // scale_anything(x, (-r, r), (0, 1))
+    if (type == IA_UN_BOUNDED_SPHERE) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = v[d] * 2.f - 1.f;
+        const float mag = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (mag > 1.f) {
+            const float k = 2.f - 1.f / mag;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) v[d] = k * (v[d] / mag);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = v[d] / 4.f + 0.5f;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) out[3 * i + d] = v[d];
+}
+}  // namespace
+
+extern "C" int32_t ia_contract(const float *x, int64_t n, float radius, int32_t contraction_type, float *out, void *stream)
+{
+    IA_REQUIRE(n >= 0 && (n == 0 || (x && out)), "contract: NULL pointer with n=%lld", (long long)n);
+    IA_REQUIRE(radius > 0.f, "contract: radius must be > 0");
+    IA_REQUIRE(contraction_type == IA_AABB || contraction_type == IA_UN_BOUNDED_SPHERE, "contract: unsupported contraction type %d",
+               contraction_type);
+    if (n == 0) return IA_OK;
+    contract_kernel<<<(unsigned)ia_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, radius, contraction_type, out);
+    IA_LAUNCH_OK("contract_kernel");
+    return IA_OK;
+}

@@ -31,6 +31,9 @@ _CENTER_GROUP = int(os.environ.get("IA_CENTER_GROUP", "6"))
 
 def contract_to_unisphere(x, radius, contraction_type):
     """reference models/geometry.py:19-31."""
+    if x.is_cuda and not x.requires_grad and x.shape[-1] == 3 and x.dtype == torch.float32 and \
+            contraction_type in (ContractionType.AABB, ContractionType.UN_BOUNDED_SPHERE):
+        return ops.contract(x, float(radius), int(contraction_type))           # one launch instead of 3 / 11
     if contraction_type == ContractionType.AABB:
         return scale_anything(x, (-radius, radius), (0, 1))
     if contraction_type == ContractionType.UN_BOUNDED_SPHERE:

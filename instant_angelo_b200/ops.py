@@ -1116,3 +1116,13 @@ class _Normalize3Fn(torch.autograd.Function):
 def normalize3(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     """F.normalize(x, p=2, dim=-1, eps) for [..., 3] CUDA tensors: one launch forward, one backward."""
     return _Normalize3Fn.apply(x.reshape(-1, 3), float(eps)).view(x.shape)
+
+
+@torch.no_grad()
+def contract(x: torch.Tensor, radius: float, contraction_type: int) -> torch.Tensor:
+    """contract_to_unisphere (reference models/geometry.py:19-31) in one launch, for positions without gradient."""
+    L.require_cuda(x)
+    x = L.f32c(x)
+    out = torch.empty_like(x)
+    _run("ia_contract", L.ptr(x), x.numel() // 3, C.c_float(radius), int(contraction_type), L.ptr(out), L.stream())
+    return out

@@ -1383,3 +1383,25 @@ def test_ray_samples_bit_exact_and_normalize3(cuda_lib):
     assert_close(xa.grad[2:3], xb.grad[2:3], rtol=rt, atol=at, name="normalize3 adjoint, tiny row")
     y3 = ops.normalize3(x.cuda().view(5003, 1, 3))
     assert y3.shape == (5003, 1, 3)
+
+
+def test_contract_matches_tensor_expressions(cuda_lib):
+    """ops.contract (ia_contract) == contract_to_unisphere's tensor expressions (reference models/geometry.py:19-31) for
+    both contractions, inside and far outside the box; inputs that require grad keep the differentiable expressions."""
+    from instant_angelo_b200 import geometry as geo
+    from instant_angelo_b200.nerfacc_api import ContractionType
+    g = torch.Generator().manual_seed(4)
+    x = torch.cat([torch.randn(4001, 3, generator=g), torch.randn(500, 3, generator=g) * 40.0,
+                   torch.tensor([[0.0, 0.0, 0.0], [1.5, -1.5, 1.5], [3.0, 0.0, 0.0]])]).cuda()
+    for ct in (ContractionType.AABB, ContractionType.UN_BOUNDED_SPHERE):
+        fast = geo.contract_to_unisphere(x, 1.5, ct)
+        xr = x.clone().requires_grad_(True)
+        slow = geo.contract_to_unisphere(xr, 1.5, ct)                    # tensor expressions (differentiable)
+        assert slow.requires_grad and not fast.requires_grad and fast.shape == slow.shape
+        assert_close(fast, slow, rtol=2e-6, atol=2e-7, name=f"contract {ct.name}")
+        if ct == ContractionType.UN_BOUNDED_SPHERE:
+            assert float(fast.min()) >= 0.0 and float(fast.max()) <= 1.0
+    assert geo.contract_to_unisphere(x.view(-1, 1, 3), 1.5, ContractionType.AABB).shape == (x.shape[0], 1, 3)
+    with pytest.raises(RuntimeError):
+        from instant_angelo_b200 import ops
+        ops.contract(x, 1.5, 1)                                           # UN_BOUNDED_TANH is not on the path

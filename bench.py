@@ -439,7 +439,8 @@ def run_b200(args):
         gs += 1
     # ... and spare 2 MB blocks for the allocator's small pool (per-step scalars, event-sized tensors): its growth inside the
     # timed region is a cudaMalloc too (tools/diag_stalls.py: +2 MB at the second timed step, a 30-80 ms stall on this box)
-    spare = [torch.empty(1 << 20, dtype=torch.uint8, device=device) for _ in range(32)]
+    spare = [torch.empty(1 << 20, dtype=torch.uint8, device=device) for _ in range(32)] + \
+            [torch.empty(8 << 20, dtype=torch.uint8, device=device) for _ in range(16)]      # 1-10 MB requests: 20 MB blocks
     del spare
     prof = ops.PROFILER
     prof.reset()

@@ -259,6 +259,15 @@ int32_t ia_colour_in_fwd(const float *h, int64_t n, const float *W4, const float
 int32_t ia_colour_in_bwd(const float *h, int64_t n, const float *W4, const float *dtin, int64_t ld, int32_t n_enc,
                          const float *dsdf, const float *drgb, float *dh, float *dW4, float *db4, float *dpts01, float *denc,
                          float *dnormal, void *stream);
+/* The fold in parameter space (once per step): flat = colour network [Wc0[64, n_in] | bc0[64] | rest[n_rest]], the geometry
+ * output layer w_last[n_feat, 64], b_last[n_feat] ->
+ *   flat_eff = [W_eff[64, ld] | b_eff[64] | rest],  W_eff[o] = [Wc0[o, :n_feat] w_last | Wc0[o, n_feat:] | 0], b_eff = bc0 + Wc0[:, :n_feat] b_last
+ * (Wc0 [feature | rest] = (Wc0[:, :n_feat] Wl) h + ...: models/texture.py:26-29 applied to models/geometry.py:206-207).
+ * Backward: dflat is ADDED to (NULL = not wanted), dw_last / db_last are written (NULL = not wanted). */
+int32_t ia_fold_head_fwd(const float *flat, const float *w_last, const float *b_last, int32_t n_in, int32_t n_feat, int32_t ld,
+                         int64_t n_rest, float *flat_eff, void *stream);
+int32_t ia_fold_head_bwd(const float *dflat_eff, const float *flat, const float *w_last, const float *b_last, int32_t n_in,
+                         int32_t n_feat, int32_t ld, int64_t n_rest, float *dflat, float *dw_last, float *db_last, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Finite-difference / curvature stages  fused elementwise stages of VolumeSDF.forward
@@ -383,6 +392,17 @@ int32_t ia_composite_bwd(const ia_composite_args *args_host, const float *alpha,
                          const float *g_comp_rgb, const float *g_comp_normal,
                          float *d_alpha_in, float *d_sdf, float *d_normal, float *d_inv_s, float *d_sigma,
                          float *d_rgb, float *d_nrm, void *stream);
+
+/* Per-ray mix of the foreground and background renders (models/neus.py:186, 272-276):
+ *   comp_rgb_bg = comp_rgb_bg_raw + background_color (1 - opacity_bg), comp_rgb_full = comp_rgb + comp_rgb_bg (1 - opacity),
+ *   rays_valid = opacity > 0, rays_valid_bg = opacity_bg > 0, rays_valid_full = rays_valid | rays_valid_bg  (one byte per ray).
+ * Backward: g_* may be NULL (zero), d_* may be NULL (not wanted); background_color [3] is a device array without gradient. */
+int32_t ia_ray_mix_fwd(const float *comp_rgb, const float *opacity, const float *comp_rgb_bg_raw, const float *opacity_bg,
+                       const float *background_color, int64_t n_rays, float *comp_rgb_bg, float *comp_rgb_full,
+                       uint8_t *rays_valid, uint8_t *rays_valid_bg, uint8_t *rays_valid_full, void *stream);
+int32_t ia_ray_mix_bwd(const float *opacity, const float *opacity_bg, const float *background_color, const float *comp_rgb_bg,
+                       const float *g_comp_rgb_bg, const float *g_comp_rgb_full, int64_t n_rays, float *d_comp_rgb,
+                       float *d_opacity, float *d_comp_rgb_bg_raw, float *d_opacity_bg, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss terms of the training step      replaces the tensor expressions of systems/neus.py:132-160 and

@@ -109,6 +109,8 @@ SIGNATURES = {
     "ia_sdf_head_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "ia_colour_in_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _P, _P]),
     "ia_colour_in_bwd": (_I32, [_P, _I64, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ia_fold_head_fwd": (_I32, [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P]),
+    "ia_fold_head_bwd": (_I32, [_P, _P, _P, _P, _I32, _I32, _I32, _I64, _P, _P, _P, _P]),
     "ia_fd_taps_fwd": (_I32, [_P, _I64, _F, _F, _P, _P]),
     "ia_fd_taps_bwd": (_I32, [_P, _I64, _F, _F, _P, _P, _P]),
     "ia_fd_grad_fwd": (_I32, [_P, _I64, _F, _P, _P]),
@@ -133,6 +135,8 @@ SIGNATURES = {
     "ia_visibility": (_I32, [_P, _P, _I64, _F, _F, _P, _P]),
     "ia_composite_fwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_composite_bwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ia_ray_mix_fwd": (_I32, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "ia_ray_mix_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "ia_neus_losses_workspace_bytes": (_I64, []),
     "ia_neus_losses_fwd": (_I32, [C.POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_neus_losses_bwd": (_I32, [C.POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

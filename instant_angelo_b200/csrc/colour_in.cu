@@ -188,3 +188,111 @@ extern "C" int32_t ia_colour_in_bwd(const float *h, int64_t n, const float *W4, 
     IA_LAUNCH_OK("colour_in_bwd_kernel");
     return IA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The fold itself, in parameter space: the colour network's flat parameter vector with the geometry output layer composed
+// into its first layer (texture.forward_fused_head):
+//   W_eff[o, :] = [ sum_k Wc0[o,k] Wl[k,:]  (64 columns) | Wc0[o, n_feat:] | 0-pad ],  b_eff[o] = bc0[o] + sum_k Wc0[o,k] bl[k],
+// followed by the untouched rest of the colour network.  As tensor expressions (broadcast product + sum + cat, and their
+// autograd) this is 8 launches forward and 28 in backward for a 64 x 65 x 64 product of parameters.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int FH_W = 64;
+
+__global__ void fold_head_fwd_kernel(const float *__restrict__ flat, const float *__restrict__ wl, const float *__restrict__ bl,
+                                     int n_in, int n_feat, int ld, int n_rest, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_w = FH_W * ld;
+    if (i < n_w) {
+        const int o = i / ld, c = i - o * ld;
+        const float *w = flat + o * n_in;
+        float v = 0.f;
+        if (c < FH_W) {
+            for (int k = 0; k < n_feat; ++k) v = fmaf(w[k], wl[k * FH_W + c], v);
+        } else if (c - FH_W < n_in - n_feat) {
+            v = w[n_feat + (c - FH_W)];
+        }
+        out[i] = v;
+    } else if (i < n_w + FH_W) {
+        const int o = i - n_w;
+        const float *w = flat + o * n_in;
+        float v = flat[FH_W * n_in + o];
+        for (int k = 0; k < n_feat; ++k) v = fmaf(w[k], bl[k], v);
+        out[i] = v;
+    } else if (i < n_w + FH_W + n_rest) {
+        out[i] = flat[FH_W * n_in + FH_W + (i - n_w - FH_W)];
+    }
+}
+
+// g = d(out).  dflat is ADDED to (it may be the accumulator behind the colour network's flat vector), dwl / dbl are written.
+__global__ void fold_head_bwd_kernel(const float *__restrict__ g, const float *__restrict__ flat, const float *__restrict__ wl,
+                                     const float *__restrict__ bl, int n_in, int n_feat, int ld, int n_rest,
+                                     float *__restrict__ dflat, float *__restrict__ dwl, float *__restrict__ dbl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_w0 = FH_W * n_in, n_w = FH_W * ld;
+    const float *gb = g + n_w;
+    if (i < n_w0) {                                          // d Wc0[o, k]
+        const int o = i / n_in, k = i - o * n_in;
+        float v;
+        if (k < n_feat) {
+            v = gb[o] * bl[k];
+            const float *gm = g + o * ld, *w = wl + k * FH_W;
+            for (int c = 0; c < FH_W; ++c) v = fmaf(gm[c], w[c], v);
+        } else {
+            v = g[o * ld + FH_W + (k - n_feat)];
+        }
+        if (dflat) dflat[i] += v;
+    } else if (i < n_w0 + FH_W) {                            // d bc0
+        if (dflat) dflat[i] += gb[i - n_w0];
+    } else if (i < n_w0 + FH_W + n_rest) {                   // rest of the colour network
+        if (dflat) dflat[i] += g[n_w + FH_W + (i - n_w0 - FH_W)];
+    } else if (i < n_w0 + FH_W + n_rest + n_feat * FH_W) {   // d Wl[k, c]
+        const int j = i - (n_w0 + FH_W + n_rest), k = j / FH_W, c = j - k * FH_W;
+        float v = 0.f;
+        for (int o = 0; o < FH_W; ++o) v = fmaf(g[o * ld + c], flat[o * n_in + k], v);
+        if (dwl) dwl[j] = v;
+    } else if (i < n_w0 + FH_W + n_rest + n_feat * FH_W + n_feat) {   // d bl[k]
+        const int k = i - (n_w0 + FH_W + n_rest + n_feat * FH_W);
+        float v = 0.f;
+        for (int o = 0; o < FH_W; ++o) v = fmaf(gb[o], flat[o * n_in + k], v);
+        if (dbl) dbl[k] = v;
+    }
+}
+
+int fold_check(const float *flat, const float *wl, const float *bl, int n_in, int n_feat, int ld, int64_t n_rest, const char *who)
+{
+    IA_REQUIRE(flat && wl && bl, "%s: NULL pointer", who);
+    IA_REQUIRE(n_feat >= 1 && n_feat <= n_in && ld >= FH_W + (n_in - n_feat) && n_rest >= 0 && n_rest < (1 << 24) && ld < 4096,
+               "%s: bad shape (n_in %d, n_feat %d, ld %d)", who, n_in, n_feat, ld);
+    return IA_OK;
+}
+}  // namespace
+
+extern "C" int32_t ia_fold_head_fwd(const float *flat, const float *w_last, const float *b_last, int32_t n_in, int32_t n_feat,
+                                    int32_t ld, int64_t n_rest, float *flat_eff, void *stream)
+{
+    int rc = fold_check(flat, w_last, b_last, n_in, n_feat, ld, n_rest, "fold_head_fwd");
+    if (rc) return rc;
+    IA_REQUIRE(flat_eff != nullptr, "fold_head_fwd: flat_eff is NULL");
+    const int total = FH_W * ld + FH_W + (int)n_rest;
+    fold_head_fwd_kernel<<<(unsigned)ia_ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(flat, w_last, b_last, n_in, n_feat, ld,
+                                                                                               (int)n_rest, flat_eff);
+    IA_LAUNCH_OK("fold_head_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_fold_head_bwd(const float *dflat_eff, const float *flat, const float *w_last, const float *b_last, int32_t n_in,
+                                    int32_t n_feat, int32_t ld, int64_t n_rest, float *dflat, float *dw_last, float *db_last,
+                                    void *stream)
+{
+    int rc = fold_check(flat, w_last, b_last, n_in, n_feat, ld, n_rest, "fold_head_bwd");
+    if (rc) return rc;
+    IA_REQUIRE(dflat_eff != nullptr, "fold_head_bwd: dflat_eff is NULL");
+    const int total = FH_W * n_in + FH_W + (int)n_rest + n_feat * FH_W + n_feat;
+    fold_head_bwd_kernel<<<(unsigned)ia_ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(dflat_eff, flat, w_last, b_last, n_in, n_feat,
+                                                                                               ld, (int)n_rest, dflat, dw_last, db_last);
+    IA_LAUNCH_OK("fold_head_bwd_kernel");
+    return IA_OK;
+}

@@ -278,3 +278,83 @@ extern "C" int32_t ia_composite_bwd(const ia_composite_args *args, const float *
     IA_LAUNCH_OK("composite_bwd_kernel");
     return IA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-ray mix of the foreground and background renders (reference models/neus.py:186 and :272-276):
+//   comp_rgb_bg = comp_rgb_bg_raw + background_color (1 - opacity_bg),  comp_rgb_full = comp_rgb + comp_rgb_bg (1 - opacity),
+//   rays_valid = opacity > 0, rays_valid_bg = opacity_bg > 0, rays_valid_full = their OR
+// -- ten element-wise launches on [R, 3] tensors and a dozen in backward, one each here.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void ray_mix_fwd_kernel(const float *__restrict__ rgb, const float *__restrict__ op, const float *__restrict__ rgb_bg_raw,
+                                   const float *__restrict__ op_bg, const float *__restrict__ bg_color, int64_t n,
+                                   float *__restrict__ rgb_bg, float *__restrict__ rgb_full, uint8_t *__restrict__ valid,
+                                   uint8_t *__restrict__ valid_bg, uint8_t *__restrict__ valid_full)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float o = op[i], ob = op_bg[i];
+    const float t = 1.0f - o, tb = 1.0f - ob;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float b = __fadd_rn(rgb_bg_raw[3 * i + c], __fmul_rn(bg_color[c], tb));        // rounded as the tensor expression
+        rgb_bg[3 * i + c] = b;
+        rgb_full[3 * i + c] = __fadd_rn(rgb[3 * i + c], __fmul_rn(b, t));
+    }
+    const bool v = o > 0.f, vb = ob > 0.f;
+    valid[i] = v;
+    valid_bg[i] = vb;
+    valid_full[i] = v || vb;
+}
+
+__global__ void ray_mix_bwd_kernel(const float *__restrict__ op, const float *__restrict__ op_bg, const float *__restrict__ bg_color,
+                                   const float *__restrict__ rgb_bg, const float *__restrict__ g_bg, const float *__restrict__ g_full,
+                                   int64_t n, float *__restrict__ d_rgb, float *__restrict__ d_op, float *__restrict__ d_rgb_bg_raw,
+                                   float *__restrict__ d_op_bg)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float t = 1.0f - op[i];
+    float dop = 0.f, dopb = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float gf = g_full ? g_full[3 * i + c] : 0.f;
+        const float gb = (g_bg ? g_bg[3 * i + c] : 0.f) + gf * t;        // total gradient of comp_rgb_bg
+        if (d_rgb) d_rgb[3 * i + c] = gf;
+        if (d_rgb_bg_raw) d_rgb_bg_raw[3 * i + c] = gb;
+        dop -= gf * rgb_bg[3 * i + c];
+        dopb -= gb * bg_color[c];
+    }
+    if (d_op) d_op[i] = dop;
+    if (d_op_bg) d_op_bg[i] = dopb;
+}
+}  // namespace
+
+extern "C" int32_t ia_ray_mix_fwd(const float *comp_rgb, const float *opacity, const float *comp_rgb_bg_raw, const float *opacity_bg,
+                                  const float *background_color, int64_t n_rays, float *comp_rgb_bg, float *comp_rgb_full,
+                                  uint8_t *rays_valid, uint8_t *rays_valid_bg, uint8_t *rays_valid_full, void *stream)
+{
+    IA_REQUIRE(n_rays >= 0 && (n_rays == 0 || (comp_rgb && opacity && comp_rgb_bg_raw && opacity_bg && background_color && comp_rgb_bg &&
+                                               comp_rgb_full && rays_valid && rays_valid_bg && rays_valid_full)),
+               "ray_mix_fwd: NULL pointer with n_rays=%lld", (long long)n_rays);
+    if (n_rays == 0) return IA_OK;
+    ray_mix_fwd_kernel<<<(unsigned)ia_ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        comp_rgb, opacity, comp_rgb_bg_raw, opacity_bg, background_color, n_rays, comp_rgb_bg, comp_rgb_full, rays_valid, rays_valid_bg,
+        rays_valid_full);
+    IA_LAUNCH_OK("ray_mix_fwd_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_ray_mix_bwd(const float *opacity, const float *opacity_bg, const float *background_color, const float *comp_rgb_bg,
+                                  const float *g_comp_rgb_bg, const float *g_comp_rgb_full, int64_t n_rays, float *d_comp_rgb,
+                                  float *d_opacity, float *d_comp_rgb_bg_raw, float *d_opacity_bg, void *stream)
+{
+    IA_REQUIRE(n_rays >= 0 && (n_rays == 0 || (opacity && opacity_bg && background_color && comp_rgb_bg)),
+               "ray_mix_bwd: NULL pointer with n_rays=%lld", (long long)n_rays);
+    if (n_rays == 0) return IA_OK;
+    ray_mix_bwd_kernel<<<(unsigned)ia_ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        opacity, opacity_bg, background_color, comp_rgb_bg, g_comp_rgb_bg, g_comp_rgb_full, n_rays, d_comp_rgb, d_opacity,
+        d_comp_rgb_bg_raw, d_opacity_bg);
+    IA_LAUNCH_OK("ray_mix_bwd_kernel");
+    return IA_OK;
+}

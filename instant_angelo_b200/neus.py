@@ -9,6 +9,7 @@ background density compositing another (ops.composite_density).  Random draws ma
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -179,7 +180,9 @@ class NeuSModel(nn.Module):
                 render_step_size=self.render_step_size_bg, stratified=self.randomized, cone_angle=self.cone_angle_bg,
                 alpha_thre=0.0, stratified_u=stratified_u, return_packed=True)
 
-    def forward_bg_(self, rays, stratified_u: Optional[torch.Tensor] = None, marched=None):
+    def forward_bg_(self, rays, stratified_u: Optional[torch.Tensor] = None, marched=None, mix_later: bool = False):
+        """mix_later (forward_ only): leave `comp_rgb` without the background colour and `rays_valid` unset -- forward_ applies
+        both together with the foreground / background mix in one kernel (ops.ray_mix)."""
         n_rays = rays.shape[0]
         rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
         if marched is None:
@@ -192,8 +195,9 @@ class NeuSModel(nn.Module):
         weights, opacity, depth, comp_rgb, _, _ = ops.composite_density(
             density, t_starts.reshape(-1), t_ends.reshape(-1), packed_info, t_mid=midpoints.reshape(-1), rgb=rgb)
         opacity, depth = opacity[:, None], depth[:, None]
-        comp_rgb = comp_rgb + self.background_color * (1.0 - opacity)
-        out = {"comp_rgb": comp_rgb, "opacity": opacity, "depth": depth, "rays_valid": opacity > 0,
+        if not mix_later:
+            comp_rgb = comp_rgb + self.background_color * (1.0 - opacity)
+        out = {"comp_rgb": comp_rgb, "opacity": opacity, "depth": depth, "rays_valid": None if mix_later else opacity > 0,
                "num_samples": torch.full((1,), len(t_starts), dtype=torch.int32, device=rays.device)}
         if self.training:
             out.update({"weights": weights.view(-1), "points": midpoints.view(-1), "intervals": intervals.view(-1),
@@ -236,17 +240,24 @@ class NeuSModel(nn.Module):
             sdf, normal, t_dirs, dists.reshape(-1), inv_s, self.cos_anneal_ratio, packed_info,
             t_mid=midpoints.reshape(-1), rgb=rgb, nrm=normal)
         opacity, depth = opacity[:, None], depth[:, None]
+        fused_mix = self.learned_background and rays.is_cuda and os.environ.get("IA_NO_RAY_MIX") is None
         rays_fg = opacity > 0.1
         comp_normal = ops.normalize3(comp_normal)
         comp_normal = comp_normal * rays_fg.float()      # Appendix C-9
         out = {"comp_rgb": comp_rgb, "comp_normal": comp_normal, "opacity": opacity, "depth": depth,
-               "rays_valid": opacity > 0,
+               "rays_valid": None if fused_mix else opacity > 0,
                "num_samples": torch.full((1,), len(t_starts), dtype=torch.int32, device=rays.device)}
         if self.training:
             out.update({"sdf_samples": sdf, "sdf_grad_samples": sdf_grad, "weights": weights.view(-1),
                         "points": midpoints.view(-1), "intervals": dists.view(-1), "ray_indices": ri.view(-1),
                         "sdf_laplace_samples": sdf_laplace})
-        if self.learned_background:
+        if fused_mix:
+            # comp_rgb_bg + background colour, the foreground / background mix and the three validity masks in one kernel
+            out_bg = self.forward_bg_(rays, stratified_u=stratified_u_bg, marched=marched_bg, mix_later=True)
+            bgc = self.background_color.to(device=rays.device, dtype=torch.float32).reshape(3)
+            rgb_bg, rgb_full, valid, valid_bg, valid_full = ops.ray_mix(comp_rgb, opacity, out_bg["comp_rgb"], out_bg["opacity"], bgc)
+            out["rays_valid"], out_bg["comp_rgb"], out_bg["rays_valid"] = valid, rgb_bg, valid_bg
+        elif self.learned_background:
             out_bg = self.forward_bg_(rays, stratified_u=stratified_u_bg, marched=marched_bg)
         else:
             out_bg = {"comp_rgb": self.background_color[None, :].expand(*comp_rgb.shape),
@@ -256,9 +267,12 @@ class NeuSModel(nn.Module):
         # dynamic ray sampling (reference systems/neus.py:125-128) uses them instead of num_samples_full.item()
         self.last_num_samples = len(t_starts)
         self.last_num_samples_full = len(t_starts) + (len(marched_bg[1]) if marched_bg is not None else 0)
-        out_full = {"comp_rgb": out["comp_rgb"] + out_bg["comp_rgb"] * (1.0 - out["opacity"]),
-                    "num_samples": out["num_samples"] + out_bg["num_samples"],
-                    "rays_valid": out["rays_valid"] | out_bg["rays_valid"]}
+        if fused_mix:
+            out_full = {"comp_rgb": rgb_full, "num_samples": out["num_samples"] + out_bg["num_samples"], "rays_valid": valid_full}
+        else:
+            out_full = {"comp_rgb": out["comp_rgb"] + out_bg["comp_rgb"] * (1.0 - out["opacity"]),
+                        "num_samples": out["num_samples"] + out_bg["num_samples"],
+                        "rays_valid": out["rays_valid"] | out_bg["rays_valid"]}
         return {**out, **{k + "_bg": v for k, v in out_bg.items()}, **{k + "_full": v for k, v in out_full.items()}}
 
     def forward(self, rays, **rng):

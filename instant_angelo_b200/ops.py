@@ -684,6 +684,43 @@ class _ColourInFn(torch.autograd.Function):
         return dh, (dW if need[1] else None), db, dpts, denc, dnrm, None
 
 
+class _FoldHeadFn(torch.autograd.Function):
+    """flat_eff of texture.forward_fused_head (ia_fold_head_fwd / _bwd): the geometry output layer composed into the colour
+    network's first layer, in parameter space, one launch each way.  The gradient w.r.t. the colour network's flat vector goes
+    into the accumulator behind it when there is one (_flat_sink)."""
+
+    @staticmethod
+    def forward(ctx, flat, w_last, b_last, n_in, n_feat, ld):
+        L.require_cuda(flat, w_last, b_last)
+        acc = getattr(flat, "_ia_acc", None)
+        flat, w_last, b_last = L.f32c(flat), L.f32c(w_last), L.f32c(b_last)
+        n_rest = flat.numel() - 64 * n_in - 64
+        out = torch.empty(64 * ld + 64 + n_rest, device=flat.device, dtype=torch.float32)
+        _run("ia_fold_head_fwd", L.ptr(flat), L.ptr(w_last), L.ptr(b_last), n_in, n_feat, ld, n_rest, L.ptr(out), L.stream())
+        ctx.save_for_backward(flat, w_last, b_last)
+        ctx.dims, ctx.acc = (n_in, n_feat, ld, n_rest), acc
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        flat, w_last, b_last = ctx.saved_tensors
+        n_in, n_feat, ld, n_rest = ctx.dims
+        need = ctx.needs_input_grad
+        g = L.f32c(g)
+        sink = _flat_sink(ctx.acc) if need[0] else None
+        dflat = (sink if sink is not None else torch.zeros_like(flat)) if need[0] else None
+        dwl = torch.empty_like(w_last) if need[1] else None
+        dbl = torch.empty_like(b_last) if need[2] else None
+        _run("ia_fold_head_bwd", L.ptr(g), L.ptr(flat), L.ptr(w_last), L.ptr(b_last), n_in, n_feat, ld, n_rest, L.ptr(dflat),
+             L.ptr(dwl), L.ptr(dbl), L.stream())
+        return (None if sink is not None else dflat), dwl, dbl, None, None, None
+
+
+def fold_head(flat, w_last, b_last, n_in: int, n_feat: int, ld: int) -> torch.Tensor:
+    """-> flat_eff [64*ld + 64 + rest]; see _FoldHeadFn."""
+    return _FoldHeadFn.apply(flat, w_last, b_last, int(n_in), int(n_feat), int(ld))
+
+
 def colour_in(h, W4, b4, pts01, enc, normal, ld: int):
     """-> (tin [N, ld], sdf [N], rgb_raw [N,3]); see _ColourInFn."""
     return _ColourInFn.apply(h, W4, b4, pts01, enc, normal, int(ld))
@@ -1126,3 +1163,42 @@ def contract(x: torch.Tensor, radius: float, contraction_type: int) -> torch.Ten
     out = torch.empty_like(x)
     _run("ia_contract", L.ptr(x), x.numel() // 3, C.c_float(radius), int(contraction_type), L.ptr(out), L.stream())
     return out
+
+
+class _RayMixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, op, rgb_bg_raw, op_bg, bg_color):
+        L.require_cuda(rgb, op, rgb_bg_raw, op_bg, bg_color)
+        rgb, op, rgb_bg_raw, op_bg, bg_color = L.f32c(rgb), L.f32c(op), L.f32c(rgb_bg_raw), L.f32c(op_bg), L.f32c(bg_color)
+        n = rgb.shape[0]
+        dev = rgb.device
+        rgb_bg, rgb_full = torch.empty_like(rgb), torch.empty_like(rgb)
+        valid = torch.empty(3, n, 1, device=dev, dtype=torch.bool)
+        _run("ia_ray_mix_fwd", L.ptr(rgb), L.ptr(op), L.ptr(rgb_bg_raw), L.ptr(op_bg), L.ptr(bg_color), n, L.ptr(rgb_bg), L.ptr(rgb_full),
+             valid.data_ptr(), valid.data_ptr() + n, valid.data_ptr() + 2 * n, L.stream())
+        ctx.save_for_backward(op, op_bg, bg_color, rgb_bg)
+        v0, v1, v2 = valid[0], valid[1], valid[2]
+        ctx.mark_non_differentiable(v0, v1, v2)
+        return rgb_bg, rgb_full, v0, v1, v2
+
+    @staticmethod
+    def backward(ctx, g_bg, g_full, _a, _b, _c):
+        op, op_bg, bg_color, rgb_bg = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        n = op.shape[0]
+        g_bg = L.f32c(g_bg) if g_bg is not None else None
+        g_full = L.f32c(g_full) if g_full is not None else None
+        d_rgb = torch.empty(n, 3, device=op.device) if need[0] else None
+        d_op = torch.empty_like(op) if need[1] else None
+        d_raw = torch.empty(n, 3, device=op.device) if need[2] else None
+        d_opb = torch.empty_like(op_bg) if need[3] else None
+        _run("ia_ray_mix_bwd", L.ptr(op), L.ptr(op_bg), L.ptr(bg_color), L.ptr(rgb_bg), L.ptr(g_bg), L.ptr(g_full), n, L.ptr(d_rgb),
+             L.ptr(d_op), L.ptr(d_raw), L.ptr(d_opb), L.stream())
+        return d_rgb, d_op, d_raw, d_opb, None
+
+
+def ray_mix(comp_rgb, opacity, comp_rgb_bg_raw, opacity_bg, background_color):
+    """Foreground / background mix of reference models/neus.py:186, 272-276 in one launch each way.
+    comp_rgb [R,3], opacity [R,1], comp_rgb_bg_raw [R,3], opacity_bg [R,1], background_color [3] ->
+    (comp_rgb_bg [R,3], comp_rgb_full [R,3], rays_valid [R,1], rays_valid_bg [R,1], rays_valid_full [R,1])."""
+    return _RayMixFn.apply(comp_rgb, opacity, comp_rgb_bg_raw, opacity_bg, background_color)

@@ -68,17 +68,20 @@ class VolumeRadiance(nn.Module):
             # parameters, done once per step as element-wise kernels.
             flat = net.flat_params()
             n_in, wd = net.n_input_dims, net.n_neurons
-            wc0 = flat[:wd * n_in].view(wd, n_in)
-            bc0 = flat[wd * n_in:wd * n_in + wd]
-            rest = flat[wd * n_in + wd:]
-            head = wc0[:, :n_feat]
-            m = (head[:, :, None] * w_last[None, :, :]).sum(1)                        # [wd, 64]
-            b_eff = bc0 + (head * b_last[None, :]).sum(1)
             n_tail = n_in - n_feat                                                   # pts (3) | dirs_embd | normal (3)
             ld = (wd + n_tail + 3) // 4 * 4                                          # 16-byte aligned rows
-            pad = wc0.new_zeros(wd, ld - wd - n_tail)
-            w_eff = torch.cat([m, wc0[:, n_feat:], pad], dim=1)
-            flat_eff = torch.cat([w_eff.reshape(-1), b_eff, rest])
+            if wd == 64 and os.environ.get("IA_NO_FOLD_KERNEL") is None:
+                flat_eff = ops.fold_head(flat, w_last, b_last, n_in, n_feat, ld)     # one launch (and one in backward)
+            else:
+                wc0 = flat[:wd * n_in].view(wd, n_in)
+                bc0 = flat[wd * n_in:wd * n_in + wd]
+                rest = flat[wd * n_in + wd:]
+                head = wc0[:, :n_feat]
+                m = (head[:, :, None] * w_last[None, :, :]).sum(1)                    # [wd, 64]
+                b_eff = bc0 + (head * b_last[None, :]).sum(1)
+                pad = wc0.new_zeros(wd, ld - wd - n_tail)
+                w_eff = torch.cat([m, wc0[:, n_feat:], pad], dim=1)
+                flat_eff = torch.cat([w_eff.reshape(-1), b_eff, rest])
             tin, sdf, rgb_raw = ops.colour_in(h, w_last[:4], b_last[:4], pts01.reshape(-1, 3), dirs_embd, normals.reshape(-1, 3), ld)
             desc = ops.make_mlp_desc(0, ld, net.n_hidden_layers, net.n_output_dims, net.hidden_act, 1.0, 0.0, net.precision)
             color = net._post(ops.mlp_apply(None, tin, flat_eff, desc)).view(*dirs.shape[:-1], self.n_output_dims).float()

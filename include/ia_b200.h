@@ -351,6 +351,15 @@ int32_t ia_march_write(const float *rays_o, const float *rays_d, const float *t_
 /* nerfacc render_visibility on packed samples (sequential per-ray transmittance). */
 int32_t ia_visibility(const float *alphas, const int32_t *packed_info, int64_t n_rays, float early_stop_eps,
                       float alpha_thre, uint8_t *visible, void *stream);
+/* The visibility pruning of nerfacc.ray_marching with a sigma_fn (models/neus.py:144-149, 159-169) together with the
+ * compaction it is followed by: alpha = 1 - exp(-sigma (t_end - t_start)) per sample, the transmittance test of
+ * ia_visibility, and -- count -> ia_march_scan -> ia_march_total -> write, the marcher's structure -- the kept samples'
+ * ray_indices / t_starts / t_ends with their packed_info.  visible [S] and num_kept [n_rays] are scratch between the calls. */
+int32_t ia_prune_count(const float *sigmas, const float *t_starts, const float *t_ends, const int32_t *packed_info,
+                       int64_t n_rays, float early_stop_eps, float alpha_thre, uint8_t *visible, int32_t *num_kept, void *stream);
+int32_t ia_prune_write(const uint8_t *visible, const int32_t *packed_info, const int32_t *packed_info_kept,
+                       const float *t_starts, const float *t_ends, int64_t n_rays, int32_t *ray_indices_kept,
+                       float *t_starts_kept, float *t_ends_kept, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-ray segmented compositing        replaces NeuSModel.get_alpha (models/neus.py:117-139) +

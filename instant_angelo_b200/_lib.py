@@ -133,6 +133,8 @@ SIGNATURES = {
     "ia_march_total": (_I32, [_P, C.POINTER(C.c_int64), _P]),
     "ia_march_write": (_I32, [_P, _P, _P, _P, _I64, C.POINTER(GridDesc), _P, _F, _F, _P, _P, _P, _P, _P]),
     "ia_visibility": (_I32, [_P, _P, _I64, _F, _F, _P, _P]),
+    "ia_prune_count": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _P, _P, _P]),
+    "ia_prune_write": (_I32, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "ia_composite_fwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_composite_bwd": (_I32, [C.POINTER(CompositeArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_ray_mix_fwd": (_I32, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),

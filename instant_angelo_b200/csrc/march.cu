@@ -234,6 +234,52 @@ visibility_kernel(const float *__restrict__ alphas, const int32_t *__restrict__ 
     }
 }
 
+// ---- visibility pruning of marched samples with their compaction (nerfacc.ray_marching with sigma_fn: alphas from the
+// densities, render_visibility, boolean indexing of the three sample arrays and a new packed_info) as count -> scan -> write,
+// the marcher's own structure, instead of ~22 tensor-operator launches.  alpha = 1 - exp(-sigma (t1 - t0)) is rounded
+// operation by operation like the tensor expression; T and the test are those of visibility_kernel.
+__global__ void __launch_bounds__(128)
+prune_count_kernel(const float *__restrict__ sigmas, const float *__restrict__ t0, const float *__restrict__ t1,
+                   const int32_t *__restrict__ packed_info, int64_t n_rays, float early_stop_eps, float alpha_thre,
+                   uint8_t *__restrict__ vis, int32_t *__restrict__ num_kept)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const int64_t base = packed_info[2 * i];
+    const int cnt = packed_info[2 * i + 1];
+    float T = 1.0f;
+    int kept = 0;
+    for (int j = 0; j < cnt; ++j) {
+        const float a = __fsub_rn(1.0f, expf(__fmul_rn(-sigmas[base + j], __fsub_rn(t1[base + j], t0[base + j]))));
+        bool v = T >= early_stop_eps;
+        if (alpha_thre > 0.0f) v = v && (a >= alpha_thre);
+        vis[base + j] = v ? 1 : 0;
+        kept += v ? 1 : 0;
+        T = T * (1.0f - a);
+    }
+    num_kept[i] = kept;
+}
+
+__global__ void __launch_bounds__(128)
+prune_write_kernel(const uint8_t *__restrict__ vis, const int32_t *__restrict__ packed_old, const int32_t *__restrict__ packed_new,
+                   const float *__restrict__ t0, const float *__restrict__ t1, int64_t n_rays, int32_t *__restrict__ out_ri,
+                   float *__restrict__ out_t0, float *__restrict__ out_t1)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const int64_t base = packed_old[2 * i];
+    const int cnt = packed_old[2 * i + 1];
+    int64_t dst = packed_new[2 * i];
+    for (int j = 0; j < cnt; ++j) {
+        if (vis[base + j]) {
+            out_ri[dst] = (int32_t)i;
+            out_t0[dst] = t0[base + j];
+            out_t1[dst] = t1[base + j];
+            ++dst;
+        }
+    }
+}
+
 // ---- occupancy grid ---------------------------------------------------------------------------------
 
 __global__ void fill_kernel(float *p, int64_t n, float v)
@@ -398,6 +444,31 @@ extern "C" int32_t ia_visibility(const float *alphas, const int32_t *packed_info
     visibility_kernel<<<(unsigned)ia_ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
         alphas, packed_info, n_rays, early_stop_eps, alpha_thre, visible);
     IA_LAUNCH_OK("visibility_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_prune_count(const float *sigmas, const float *t_starts, const float *t_ends, const int32_t *packed_info,
+                                  int64_t n_rays, float early_stop_eps, float alpha_thre, uint8_t *visible, int32_t *num_kept,
+                                  void *stream)
+{
+    // visible / sigmas / t_* are NULL when no ray has a sample (empty tensors): every count in packed_info is then zero
+    IA_REQUIRE(n_rays >= 0 && (n_rays == 0 || (packed_info && num_kept)), "prune_count: NULL pointer");
+    if (n_rays == 0) return IA_OK;
+    prune_count_kernel<<<(unsigned)ia_ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+        sigmas, t_starts, t_ends, packed_info, n_rays, early_stop_eps, alpha_thre, visible, num_kept);
+    IA_LAUNCH_OK("prune_count_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_prune_write(const uint8_t *visible, const int32_t *packed_info, const int32_t *packed_info_kept,
+                                  const float *t_starts, const float *t_ends, int64_t n_rays, int32_t *ray_indices_kept,
+                                  float *t_starts_kept, float *t_ends_kept, void *stream)
+{
+    IA_REQUIRE(n_rays >= 0 && (n_rays == 0 || (visible && packed_info && packed_info_kept)), "prune_write: NULL pointer");
+    if (n_rays == 0) return IA_OK;
+    prune_write_kernel<<<(unsigned)ia_ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+        visible, packed_info, packed_info_kept, t_starts, t_ends, n_rays, ray_indices_kept, t_starts_kept, t_ends_kept);
+    IA_LAUNCH_OK("prune_write_kernel");
     return IA_OK;
 }
 

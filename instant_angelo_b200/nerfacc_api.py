@@ -8,6 +8,8 @@ the random draws that nerfacc makes internally.
 """
 from __future__ import annotations
 
+import os
+
 from enum import IntEnum
 from typing import Callable, Optional, Tuple, Union
 
@@ -217,6 +219,13 @@ def ray_marching(rays_o: torch.Tensor, rays_d: torch.Tensor, t_min: Optional[tor
                                                             float(render_step_size), float(cone_angle))
     t_starts, t_ends = t_starts[:, None], t_ends[:, None]
     if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
+        if sigma_fn is not None and os.environ.get("IA_NO_FUSED_PRUNE") is None:
+            # alphas, visibility, compaction and the new packed_info as count -> scan -> write (ops.prune_samples)
+            sigmas = sigma_fn(t_starts, t_ends, ray_indices)
+            ray_indices, t_starts, t_ends, packed_kept = ops.prune_samples(sigmas, t_starts, t_ends, packed_info, early_stop_eps, alpha_thre)
+            if return_packed:
+                return ray_indices, t_starts, t_ends, packed_kept
+            return ray_indices, t_starts, t_ends
         if sigma_fn is not None:
             sigmas = sigma_fn(t_starts, t_ends, ray_indices)
             alphas = 1.0 - torch.exp(-sigmas * (t_ends - t_starts))

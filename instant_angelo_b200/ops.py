@@ -909,6 +909,34 @@ def march(rays_o, rays_d, t_min, t_max, grid: L.GridDesc, bitfield: Optional[tor
 
 
 @torch.no_grad()
+def prune_samples(sigmas, t_starts, t_ends, packed_info, early_stop_eps: float, alpha_thre: float):
+    """nerfacc.ray_marching's sigma_fn pruning and the compaction after it (reference models/neus.py:144-149, 159-169) as
+    count -> scan -> write: (ray_indices [S'] i32, t_starts [S',1], t_ends [S',1], packed_info [R,2] i32) of the kept samples."""
+    L.require_cuda(sigmas, t_starts, t_ends, packed_info)
+    sigmas, t0, t1 = L.f32c(sigmas.reshape(-1)), L.f32c(t_starts.reshape(-1)), L.f32c(t_ends.reshape(-1))
+    packed_info = packed_info.contiguous()
+    n, S = packed_info.shape[0], sigmas.shape[0]
+    dev = sigmas.device
+    vis = torch.empty(S, device=dev, dtype=torch.uint8)
+    num = torch.empty(n, device=dev, dtype=torch.int32)
+    packed = torch.empty(n, 2, device=dev, dtype=torch.int32)
+    total_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+    s = L.stream()
+    _run("ia_prune_count", L.ptr(sigmas), L.ptr(t0), L.ptr(t1), L.ptr(packed_info), n, C.c_float(early_stop_eps), C.c_float(alpha_thre),
+         L.ptr(vis), L.ptr(num), s)
+    _run("ia_march_scan", L.ptr(num), n, L.ptr(packed), L.ptr(total_dev), None, s)
+    total = C.c_int64(0)
+    _run("ia_march_total", L.ptr(total_dev), C.byref(total), s)
+    K = int(total.value)
+    ri = torch.empty(K, device=dev, dtype=torch.int32)
+    k0 = torch.empty(K, 1, device=dev, dtype=torch.float32)
+    k1 = torch.empty(K, 1, device=dev, dtype=torch.float32)
+    if K > 0:
+        _run("ia_prune_write", L.ptr(vis), L.ptr(packed_info), L.ptr(packed), L.ptr(t0), L.ptr(t1), n, L.ptr(ri), L.ptr(k0), L.ptr(k1), s)
+    return ri, k0, k1, packed
+
+
+@torch.no_grad()
 def visibility(alphas: torch.Tensor, packed_info: torch.Tensor, early_stop_eps: float, alpha_thre: float) -> torch.Tensor:
     L.require_cuda(alphas, packed_info)
     alphas = L.f32c(alphas.reshape(-1))

@@ -1405,3 +1405,37 @@ def test_contract_matches_tensor_expressions(cuda_lib):
     with pytest.raises(RuntimeError):
         from instant_angelo_b200 import ops
         ops.contract(x, 1.5, 1)                                           # UN_BOUNDED_TANH is not on the path
+
+
+@pytest.mark.parametrize("alpha_thre", [0.0, 0.02])
+def test_ray_marching_fused_prune_is_bit_exact(cuda_lib, monkeypatch, alpha_thre):
+    """nerfacc.ray_marching with a sigma_fn (the background marcher, reference models/neus.py:144-169): the fused pruning
+    (ia_prune_count -> ia_march_scan -> ia_prune_write) returns exactly what the tensor-operator chain returns -- alphas from
+    the densities, render_visibility, boolean compaction, pack_info --, including rays that keep a single sample."""
+    from instant_angelo_b200.nerfacc_api import ContractionType, OccupancyGrid, ray_marching
+    g = torch.Generator().manual_seed(31)
+    R = 700
+    rays_o = (torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * 0.8).cuda()
+    rays_d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda()
+    grid = OccupancyGrid(roi_aabb=torch.tensor([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]), resolution=64,
+                         contraction_type=ContractionType.UN_BOUNDED_SPHERE).cuda()
+    grid.set_binary(torch.rand(64, 64, 64, generator=g) > 0.4)
+
+    def sigma_fn(t_starts, t_ends, ray_indices):
+        ri = ray_indices.long()
+        x = rays_o[ri] + rays_d[ri] * (t_starts + t_ends) / 2.0
+        s = 40.0 * torch.sin(7.0 * x).prod(dim=-1, keepdim=True).abs() * (x.norm(dim=-1, keepdim=True) < 3.0)
+        return torch.where(ri[:, None] % 11 == 0, torch.full_like(s, 1e4), s)      # some rays go opaque at once
+
+    def run():
+        return ray_marching(rays_o, rays_d, grid=grid, sigma_fn=sigma_fn, near_plane=0.1, far_plane=1e3, render_step_size=0.01,
+                            stratified=False, cone_angle=0.01, alpha_thre=alpha_thre, return_packed=True)
+
+    fused = run()
+    monkeypatch.setenv("IA_NO_FUSED_PRUNE", "1")
+    plain = run()
+    assert fused[0].numel() > 1000 and fused[0].numel() == plain[0].numel()
+    for a, b, name in zip(fused, plain, ("ray_indices", "t_starts", "t_ends", "packed_info")):
+        assert a.dtype == b.dtype and a.shape == b.shape, name
+        assert torch.equal(a, b), name
+    assert int((fused[3][:, 1] <= 1).sum()) > 0            # rays that went opaque at their first sample keep only that one

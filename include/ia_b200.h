@@ -442,6 +442,16 @@ int32_t ia_neus_losses_bwd(const ia_loss_args *args_host, const float *comp_rgb,
                            const float *laplace, const float *terms, const float *dloss, float *d_comp_rgb,
                            float *d_opacity, float *d_sdf_grad, float *d_sdf, float *d_laplace, void *stream);
 
+/* The sparse-point terms (systems/neus.py:173-186) from the SDF and its gradient at the n SfM points:
+ *   out4 = (sdf_l1, normal_cos, lambda_sdf_l1 sdf_l1 + lambda_normal normal_cos, mean(weights)),
+ *   sdf_l1 = mean|sdf| * mean(weights) (the reference multiplies the SCALAR l1 loss by the weights: Appendix C-11),
+ *   normal_cos = mean(1 - normalize(grad) . normalize(normal_gt)).  Backward of out4[2] w.r.t. sdf and grad (dloss: device
+ * scalar; weights and normal_gt carry no gradient).  workspace: ia_neus_losses_workspace_bytes(). */
+int32_t ia_point_losses_fwd(const float *sdf, const float *grad, const float *normal_gt, const float *weights, int64_t n,
+                            float lambda_sdf_l1, float lambda_normal, void *workspace, float *out4, void *stream);
+int32_t ia_point_losses_bwd(const float *sdf, const float *grad, const float *normal_gt, int64_t n, float lambda_sdf_l1,
+                            float lambda_normal, const float *out4, const float *dloss, float *d_sdf, float *d_grad, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused AdamW over a flat arena        replaces torch.optim.AdamW as configured at
  *                                      configs/neuralangelo-colmap_sparse.yaml:134-139 (systems/utils.py:314-325)

@@ -142,6 +142,8 @@ SIGNATURES = {
     "ia_neus_losses_workspace_bytes": (_I64, []),
     "ia_neus_losses_fwd": (_I32, [C.POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ia_neus_losses_bwd": (_I32, [C.POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ia_point_losses_fwd": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _P, _P, _P]),
+    "ia_point_losses_bwd": (_I32, [_P, _P, _P, _I64, _F, _F, _P, _P, _P, _P, _P]),
     "ia_adamw_step": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _P]),
     "ia_l2_persist": (_I32, [_P, _I64, _F, C.POINTER(C.c_int64 * 3), _P]),
     "ia_debug_sector_gather": (_I32, [_P, _I64, _I64, _I32, _P, _P]),

@@ -109,6 +109,12 @@ def training_loss(model, out: Dict[str, torch.Tensor], batch: Dict[str, torch.Te
         loss = loss + terms["distortion_bg"] * c(loss_cfg["lambda_distortion_bg"])
     if c(loss_cfg["lambda_sdf_l1"]) > 0 and batch.get("pts") is not None:
         sdf_p, grad_p = model.geometry(batch["pts"], with_grad=True, with_feature=False)
+        if grad_p.is_cuda and os.environ.get("IA_NO_FUSED_LOSSES") is None and sdf_p.numel() > 0:
+            part, named = ops.point_losses(sdf_p, grad_p, batch["pts_normal"], batch["pts_weights"], c(loss_cfg["lambda_sdf_l1"]),
+                                           c(loss_cfg.get("lambda_normal", loss_cfg["lambda_sdf_l1"])))
+            terms.update(named)
+            terms["loss"] = loss + part
+            return terms
         terms["sdf_l1"] = (F.l1_loss(sdf_p, torch.zeros_like(sdf_p)) * batch["pts_weights"]).mean(dim=0)   # Appendix C-11
         if grad_p.is_cuda:
             n_gt, n_pr = ops.normalize3(batch["pts_normal"]), ops.normalize3(grad_p)

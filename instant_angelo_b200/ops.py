@@ -1230,3 +1230,39 @@ def ray_mix(comp_rgb, opacity, comp_rgb_bg_raw, opacity_bg, background_color):
     comp_rgb [R,3], opacity [R,1], comp_rgb_bg_raw [R,3], opacity_bg [R,1], background_color [3] ->
     (comp_rgb_bg [R,3], comp_rgb_full [R,3], rays_valid [R,1], rays_valid_bg [R,1], rays_valid_full [R,1])."""
     return _RayMixFn.apply(comp_rgb, opacity, comp_rgb_bg_raw, opacity_bg, background_color)
+
+
+class _PointLossesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdf, grad, normal_gt, weights, lam_sdf, lam_normal):
+        L.require_cuda(sdf, grad, normal_gt, weights)
+        sdf, grad, normal_gt, weights = L.f32c(sdf), L.f32c(grad), L.f32c(normal_gt), L.f32c(weights)
+        n = sdf.shape[0]
+        ws = torch.empty(int(L.load().ia_neus_losses_workspace_bytes()), device=sdf.device, dtype=torch.uint8)
+        out = torch.empty(4, device=sdf.device, dtype=torch.float32)
+        _run("ia_point_losses_fwd", L.ptr(sdf), L.ptr(grad), L.ptr(normal_gt), L.ptr(weights), n, C.c_float(lam_sdf), C.c_float(lam_normal),
+             L.ptr(ws), L.ptr(out), L.stream())
+        ctx.save_for_backward(sdf, grad, normal_gt, out)
+        ctx.lams = (lam_sdf, lam_normal)
+        terms = out[:2]
+        ctx.mark_non_differentiable(terms)
+        return out[2], terms
+
+    @staticmethod
+    def backward(ctx, dloss, _dterms):
+        sdf, grad, normal_gt, out = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dloss = L.f32c(dloss).reshape(1)
+        d_sdf = torch.empty_like(sdf) if need[0] else None
+        d_grad = torch.empty_like(grad) if need[1] else None
+        _run("ia_point_losses_bwd", L.ptr(sdf), L.ptr(grad), L.ptr(normal_gt), sdf.shape[0], C.c_float(ctx.lams[0]), C.c_float(ctx.lams[1]),
+             L.ptr(out), L.ptr(dloss), L.ptr(d_sdf), L.ptr(d_grad), L.stream())
+        return d_sdf, d_grad, None, None, None, None
+
+
+def point_losses(sdf, grad, normal_gt, weights, lambda_sdf_l1: float, lambda_normal: float):
+    """Sparse-point terms of reference systems/neus.py:173-186 and their weighted sum in one launch each way.
+    -> (weighted sum, {'sdf_l1', 'normal_cos'}); the terms are values for logging (not differentiable)."""
+    total, terms = _PointLossesFn.apply(sdf.reshape(-1), grad.reshape(-1, 3), normal_gt.reshape(-1, 3), weights.reshape(-1),
+                                        float(lambda_sdf_l1), float(lambda_normal))
+    return total, {"sdf_l1": terms[0], "normal_cos": terms[1]}

@@ -1439,3 +1439,36 @@ def test_ray_marching_fused_prune_is_bit_exact(cuda_lib, monkeypatch, alpha_thre
         assert a.dtype == b.dtype and a.shape == b.shape, name
         assert torch.equal(a, b), name
     assert int((fused[3][:, 1] <= 1).sum()) > 0            # rays that went opaque at their first sample keep only that one
+
+
+def test_point_losses_match_tensor_expressions(cuda_lib):
+    """ops.point_losses (ia_point_losses_fwd / _bwd) against reference systems/neus.py:173-186 as float64 tensor operators:
+    sdf_l1 = (F.l1_loss(sdf, 0) * weights).mean() -- a scalar times the weights, Appendix C-11 --, normal_cos, their weighted sum
+    and its gradients w.r.t. the SDF values and the SDF gradients (zero SDF value and vanishing gradient rows included)."""
+    from instant_angelo_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(12)
+    n = 8192
+    sdf = torch.randn(n, generator=g) * 0.02
+    grad = torch.randn(n, 3, generator=g)
+    ngt = torch.randn(n, 3, generator=g) * 3.0
+    w = torch.rand(n, generator=g)
+    sdf[0] = 0.0
+    grad[1] = 0.0
+    lam1, lam2 = 0.37, 0.11
+    s64, g64 = sdf.double().requires_grad_(True), grad.double().requires_grad_(True)
+    t1 = (F.l1_loss(s64, torch.zeros_like(s64)) * w.double()).mean(dim=0)
+    t2 = (1.0 - torch.sum(F.normalize(g64, p=2, dim=-1) * F.normalize(ngt.double(), p=2, dim=-1), dim=-1)).mean()
+    tot64 = t1 * lam1 + t2 * lam2
+    sc, gc = sdf.cuda().requires_grad_(True), grad.cuda().requires_grad_(True)
+    tot, terms = ops.point_losses(sc, gc, ngt.cuda(), w.cuda(), lam1, lam2)
+    assert_close(terms["sdf_l1"], t1, rtol=1e-5, atol=1e-9, name="sdf_l1")
+    assert_close(terms["normal_cos"], t2, rtol=1e-5, atol=1e-8, name="normal_cos")
+    assert_close(tot, tot64, rtol=1e-5, atol=1e-8, name="total")
+    (tot * 1.7).backward()
+    (tot64 * 1.7).backward()
+    rt, at = grad_tol(s64.grad, 1e-5, floor=1e-12)
+    assert_close(sc.grad, s64.grad, rtol=rt, atol=at, name="d sdf")
+    rt, at = grad_tol(g64.grad[2:], 1e-4, floor=1e-12)
+    assert_close(gc.grad[2:], g64.grad[2:], rtol=rt, atol=at, name="d grad")
+    assert float(sc.grad[0]) == 0.0 and torch.isfinite(gc.grad).all()

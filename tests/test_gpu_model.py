@@ -40,7 +40,7 @@ def build_product(cfg_dict, state_dict, global_step, background_color, mlp_otype
     return model
 
 
-def compare_step(model, out, terms, want_out, want_terms, want_grads, rtol=1e-3):
+def compare_step(model, out, terms, want_out, want_terms, want_grads, rtol=1e-3, l2_tol=2e-4):
     """want_* are dicts of numpy arrays / tensors from the golden fixture or the oracle."""
     for k in ["ray_indices", "ray_indices_bg"]:
         if k in want_out:
@@ -64,6 +64,14 @@ def compare_step(model, out, terms, want_out, want_terms, want_grads, rtol=1e-3)
         assert p.grad is not None, f"{name} received no gradient"
         rt, at = grad_tol(want_grads[name], rtol)
         assert_close(p.grad, want_grads[name], rtol=rt, atol=at, name="grad " + name)
+        # the entry-wise bound above is relative to the tensor's scale (small entries are loosely held); the aggregate bound
+        # holds the whole tensor: relative L2 error 2e-4 (measured against the reference-generated fixtures: <= 3.4e-5 for
+        # every tensor, median 1e-6, both arithmetic modes -- profiles/r02_parity_l2.txt)
+        e = torch.as_tensor(np.asarray(want_grads[name])).double().reshape(-1)
+        a = p.grad.detach().cpu().double().reshape(-1)
+        if float(e.norm()) > 0:
+            rel = float((a - e).norm() / e.norm())
+            assert rel < l2_tol, f"grad {name}: relative L2 error {rel:.2e} >= {l2_tol}"
         checked += 1
     assert checked >= 10
 

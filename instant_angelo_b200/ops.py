@@ -1062,6 +1062,7 @@ def l2_persist(t: Optional[torch.Tensor], hit_ratio: float = 1.0) -> dict:
     """Persisting access-policy window over `t` on the current stream (None removes it): the hash tables stay in the L2's
     set-aside across the [N, L*F] activation passes that would otherwise evict them (ia_l2_persist)."""
     info = (C.c_int64 * 3)()
+    L.require_cuda(t)
     if t is None:
         _run("ia_l2_persist", None, 0, C.c_float(0.0), C.byref(info), L.stream())
     else:

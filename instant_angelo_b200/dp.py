@@ -8,7 +8,7 @@ its own shard of the ray batch, and ONE NCCL all-reduce(sum) over the gradient a
 because every rank refreshes them with the same seed -- no broadcast."""
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import Iterable, List
 
 import torch
 import torch.distributed as dist

@@ -8,13 +8,11 @@ hash-grid launches + three fused-MLP launches; the 12 tap evaluations compute th
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from . import registry as models

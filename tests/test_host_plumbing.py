@@ -1,7 +1,6 @@
 """CPU: host-side logic around the round-2 kernels that needs no GPU -- the fp16-shadow option of the hash-grid module, the
 loss assembly's tensor-expression form (what the fused kernels are held against on the GPU), the refusal of CPU tensors by
 every new operator (there is no CPU fallback), and the environment switches."""
-import numpy as np
 import pytest
 import torch
 

@@ -349,6 +349,23 @@ int32_t ia_march_write(const float *rays_o, const float *rays_d, const float *t_
                        float step_size, float cone_angle, const int32_t *packed_info, int32_t *ray_indices,
                        float *t_starts, float *t_ends, void *stream);
 /* nerfacc render_visibility on packed samples (sequential per-ray transmittance). */
+/* Two marches of the same rays in one launch pair (the foreground march through the AABB grid and the background march through
+ * the contracted grid, models/neus.py:209-220 and :159-169): ia_march_pair(write = 0) counts both, two ia_march_scan calls and
+ * ONE ia_march_totals read-back follow, ia_march_pair(write = 1) emits both.  Same per-ray function as ia_march_count / _write. */
+typedef struct ia_march_set {
+    const float *t_min, *t_max;
+    const ia_grid_desc *grid;       /* host */
+    const uint32_t *bitfield;
+    float step_size, cone_angle;
+    const int32_t *packed_info;     /* write pass */
+    int32_t *num_steps;             /* count pass */
+    int32_t *ray_indices;           /* write pass */
+    float *t_starts, *t_ends;       /* write pass */
+} ia_march_set;
+int32_t ia_march_pair(const float *rays_o, const float *rays_d, int64_t n_rays, const ia_march_set *a_host, const ia_march_set *b_host,
+                      int32_t write, void *stream);
+/* totals_host[count] <- totals_dev[count]; synchronises the stream (like ia_march_total, for several totals at once). */
+int32_t ia_march_totals(const int64_t *totals_dev, int32_t count, int64_t *totals_host, void *stream);
 int32_t ia_visibility(const float *alphas, const int32_t *packed_info, int64_t n_rays, float early_stop_eps,
                       float alpha_thre, uint8_t *visible, void *stream);
 /* The visibility pruning of nerfacc.ray_marching with a sigma_fn (models/neus.py:144-149, 159-169) together with the

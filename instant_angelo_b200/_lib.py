@@ -46,6 +46,12 @@ class GridDesc(C.Structure):
     _fields_ = [("roi", C.c_float * 6), ("res", C.c_int32 * 3), ("contraction", C.c_int32)]
 
 
+class MarchSet(C.Structure):
+    _fields_ = [("t_min", C.c_void_p), ("t_max", C.c_void_p), ("grid", C.POINTER(GridDesc)), ("bitfield", C.c_void_p),
+                ("step_size", C.c_float), ("cone_angle", C.c_float), ("packed_info", C.c_void_p), ("num_steps", C.c_void_p),
+                ("ray_indices", C.c_void_p), ("t_starts", C.c_void_p), ("t_ends", C.c_void_p)]
+
+
 class CompositeArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n_rays", C.c_int64), ("n_samples", C.c_int64), ("packed_info", C.c_void_p),
                 ("alpha_in", C.c_void_p), ("sdf", C.c_void_p), ("normal", C.c_void_p), ("dirs", C.c_void_p),
@@ -132,6 +138,8 @@ SIGNATURES = {
     "ia_march_scan": (_I32, [_P, _I64, _P, _P, _P, _P]),
     "ia_march_total": (_I32, [_P, C.POINTER(C.c_int64), _P]),
     "ia_march_write": (_I32, [_P, _P, _P, _P, _I64, C.POINTER(GridDesc), _P, _F, _F, _P, _P, _P, _P, _P]),
+    "ia_march_pair": (_I32, [_P, _P, _I64, C.POINTER(MarchSet), C.POINTER(MarchSet), _I32, _P]),
+    "ia_march_totals": (_I32, [_P, _I32, C.POINTER(C.c_int64 * 2), _P]),
     "ia_visibility": (_I32, [_P, _P, _I64, _F, _F, _P, _P]),
     "ia_prune_count": (_I32, [_P, _P, _P, _P, _I64, _F, _F, _P, _P, _P]),
     "ia_prune_write": (_I32, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),

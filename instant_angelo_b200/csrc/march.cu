@@ -78,15 +78,12 @@ __device__ __forceinline__ float distance_to_next_voxel(const float xyz[3], cons
 
 // One thread per ray.  WRITE=false: count pass.  WRITE=true: emit samples at packed_info[r].offset.
 template <bool WRITE>
-__global__ void __launch_bounds__(64)
-march_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ t_min,
-             const float *__restrict__ t_max, int64_t n_rays, const GridDev G, const uint32_t *__restrict__ bits,
-             float step_size, float cone_angle, const int32_t *__restrict__ packed_info,
-             int32_t *__restrict__ num_steps, int32_t *__restrict__ ray_indices, float *__restrict__ t_starts,
-             float *__restrict__ t_ends)
+__device__ __forceinline__ void march_ray(int64_t i, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                          const float *__restrict__ t_min, const float *__restrict__ t_max, const GridDev &G,
+                                          const uint32_t *__restrict__ bits, float step_size, float cone_angle,
+                                          const int32_t *__restrict__ packed_info, int32_t *__restrict__ num_steps,
+                                          int32_t *__restrict__ ray_indices, float *__restrict__ t_starts, float *__restrict__ t_ends)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rays) return;
     const float o[3] = {rays_o[3 * i], rays_o[3 * i + 1], rays_o[3 * i + 2]};
     const float d[3] = {rays_d[3 * i], rays_d[3 * i + 1], rays_d[3 * i + 2]};
     const float inv_d[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
@@ -130,6 +127,46 @@ march_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
         }
     }
     if (!WRITE) num_steps[i] = j;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(64)
+march_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ t_min,
+             const float *__restrict__ t_max, int64_t n_rays, const GridDev G, const uint32_t *__restrict__ bits,
+             float step_size, float cone_angle, const int32_t *__restrict__ packed_info,
+             int32_t *__restrict__ num_steps, int32_t *__restrict__ ray_indices, float *__restrict__ t_starts,
+             float *__restrict__ t_ends)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    march_ray<WRITE>(i, rays_o, rays_d, t_min, t_max, G, bits, step_size, cone_angle, packed_info, num_steps, ray_indices, t_starts, t_ends);
+}
+
+// Two marches of the same rays in one launch (blockIdx.y selects the set): the foreground march through the AABB grid and the
+// background march through the contracted grid (reference models/neus.py:209-220 and :159-169) are independent, and one
+// thread per ray leaves either of them with 128 CTAs of 64 threads on 148 SMs -- latency bound, half the machine idle.
+struct MarchSet {
+    const float *t_min, *t_max;
+    GridDev G;
+    const uint32_t *bits;
+    float step_size, cone_angle;
+    const int32_t *packed_info;
+    int32_t *num_steps, *ray_indices;
+    float *t_starts, *t_ends;
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(64)
+march_pair_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, int64_t n_rays, const MarchSet A, const MarchSet B)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    if (blockIdx.y == 0)
+        march_ray<WRITE>(i, rays_o, rays_d, A.t_min, A.t_max, A.G, A.bits, A.step_size, A.cone_angle, A.packed_info, A.num_steps,
+                         A.ray_indices, A.t_starts, A.t_ends);
+    else
+        march_ray<WRITE>(i, rays_o, rays_d, B.t_min, B.t_max, B.G, B.bits, B.step_size, B.cone_angle, B.packed_info, B.num_steps,
+                         B.ray_indices, B.t_starts, B.t_ends);
 }
 
 __global__ void __launch_bounds__(256)
@@ -433,6 +470,49 @@ extern "C" int32_t ia_march_write(const float *rays_o, const float *rays_d, cons
         rays_o, rays_d, t_min, t_max, n_rays, G, bitfield, step_size, cone_angle, packed_info, nullptr, ray_indices,
         t_starts, t_ends);
     IA_LAUNCH_OK("march_kernel<write>");
+    return IA_OK;
+}
+
+namespace {
+int to_set(const ia_march_set *h, bool write, MarchSet *S, const char *which)
+{
+    IA_REQUIRE(h != nullptr, "march_pair: set %s is NULL", which);
+    int rc = to_grid(h->grid, &S->G);
+    if (rc) return rc;
+    IA_REQUIRE(h->step_size > 0.f, "march_pair: render_step_size of set %s must be > 0", which);
+    IA_REQUIRE(h->t_min && h->t_max, "march_pair: t_min / t_max of set %s is NULL", which);
+    IA_REQUIRE(write ? (h->packed_info != nullptr) : (h->num_steps != nullptr), "march_pair: set %s lacks the %s-pass buffers", which,
+               write ? "write" : "count");
+    S->t_min = h->t_min; S->t_max = h->t_max; S->bits = h->bitfield;
+    S->step_size = h->step_size; S->cone_angle = h->cone_angle;
+    S->packed_info = h->packed_info; S->num_steps = h->num_steps;
+    S->ray_indices = h->ray_indices; S->t_starts = h->t_starts; S->t_ends = h->t_ends;
+    return IA_OK;
+}
+}  // namespace
+
+extern "C" int32_t ia_march_pair(const float *rays_o, const float *rays_d, int64_t n_rays, const ia_march_set *a, const ia_march_set *b,
+                                 int32_t write, void *stream)
+{
+    MarchSet A, B;
+    int rc = to_set(a, write != 0, &A, "a");
+    if (rc) return rc;
+    rc = to_set(b, write != 0, &B, "b");
+    if (rc) return rc;
+    IA_REQUIRE(n_rays >= 0 && (n_rays == 0 || (rays_o && rays_d)), "march_pair: NULL rays");
+    if (n_rays == 0) return IA_OK;
+    const dim3 grid((unsigned)ia_ceil_div(n_rays, 64), 2);
+    if (write) march_pair_kernel<true><<<grid, 64, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, A, B);
+    else march_pair_kernel<false><<<grid, 64, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, A, B);
+    IA_LAUNCH_OK("march_pair_kernel");
+    return IA_OK;
+}
+
+extern "C" int32_t ia_march_totals(const int64_t *totals_dev, int32_t count, int64_t *totals_host, void *stream)
+{
+    IA_REQUIRE(totals_dev && totals_host && count >= 1 && count <= 16, "march_totals: bad arguments");
+    IA_CUDA_OK(cudaMemcpyAsync(totals_host, totals_dev, sizeof(int64_t) * (size_t)count, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    IA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     return IA_OK;
 }
 

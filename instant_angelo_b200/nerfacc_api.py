@@ -196,6 +196,18 @@ def ray_marching(rays_o: torch.Tensor, rays_d: torch.Tensor, t_min: Optional[tor
         raise NotImplementedError("Only support cuda inputs.")
     if alpha_fn is not None and sigma_fn is not None:
         raise ValueError("Only one of `alpha_fn` and `sigma_fn` should be provided.")
+    t_min, t_max, gdesc, bitfield = march_inputs(rays_o, rays_d, t_min, t_max, scene_aabb, grid, near_plane, far_plane, render_step_size,
+                                                 stratified, stratified_u, scene_aabb_host)
+    packed_info, ray_indices, t_starts, t_ends = ops.march(rays_o, rays_d, t_min, t_max, gdesc, bitfield,
+                                                            float(render_step_size), float(cone_angle))
+    return march_finish(rays_o.shape[0], packed_info, ray_indices, t_starts, t_ends, sigma_fn, alpha_fn, early_stop_eps, alpha_thre,
+                        return_packed)
+
+
+def march_inputs(rays_o, rays_d, t_min, t_max, scene_aabb, grid, near_plane, far_plane, render_step_size, stratified, stratified_u,
+                 scene_aabb_host=None):
+    """The part of nerfacc.ray_marching in front of the marching kernel: ray / AABB test, near / far clamps, stratified
+    offset, grid descriptor.  -> (t_min, t_max, grid desc, bitfield)."""
     n_rays = rays_o.shape[0]
     if t_min is None or t_max is None:
         if scene_aabb is not None:
@@ -215,8 +227,11 @@ def ray_marching(rays_o: torch.Tensor, rays_d: torch.Tensor, t_min: Optional[tor
         gdesc, bitfield = grid.grid_desc, grid.bitfield
     else:
         gdesc, bitfield = ops.make_grid_desc([-1e10] * 3 + [1e10] * 3, [1, 1, 1], int(ContractionType.AABB)), None
-    packed_info, ray_indices, t_starts, t_ends = ops.march(rays_o, rays_d, t_min, t_max, gdesc, bitfield,
-                                                            float(render_step_size), float(cone_angle))
+    return t_min, t_max, gdesc, bitfield
+
+
+def march_finish(n_rays, packed_info, ray_indices, t_starts, t_ends, sigma_fn, alpha_fn, early_stop_eps, alpha_thre, return_packed):
+    """The part of nerfacc.ray_marching behind the marching kernel: visibility pruning through sigma_fn / alpha_fn."""
     t_starts, t_ends = t_starts[:, None], t_ends[:, None]
     if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
         if sigma_fn is not None and os.environ.get("IA_NO_FUSED_PRUNE") is None:

@@ -180,6 +180,29 @@ class NeuSModel(nn.Module):
                 render_step_size=self.render_step_size_bg, stratified=self.randomized, cone_angle=self.cone_angle_bg,
                 alpha_thre=0.0, stratified_u=stratified_u, return_packed=True)
 
+    @torch.no_grad()
+    def march_both_(self, rays_o, rays_d, stratified_u=None, stratified_u_bg=None):
+        """The foreground march of forward_ (models/neus.py:209-220) and the background march of forward_bg_ (:153-169,
+        march_bg_) with the marching kernels of the two launched as a pair: same inputs, same per-ray function, same
+        outputs as ray_marching(...) twice."""
+        from .nerfacc_api import march_finish, march_inputs
+        fg = march_inputs(rays_o, rays_d, None, None, self.scene_aabb, self.occupancy_grid if self.grid_prune else None, None, None,
+                          self.render_step_size, self.randomized, stratified_u, self._aabb_host)
+        _, t_max = ray_aabb_intersect(rays_o, rays_d, self._aabb_host)
+        near_plane = torch.where(t_max > 1e9, self.near_plane_bg, t_max)
+        bg = march_inputs(rays_o, rays_d, None, None, None, self.occupancy_grid_bg if self.grid_prune else None, near_plane,
+                          self.far_plane_bg, self.render_step_size_bg, self.randomized, stratified_u_bg)
+        out_fg, out_bg = ops.march_pair(rays_o, rays_d, (*fg, self.render_step_size, 0.0), (*bg, self.render_step_size_bg, self.cone_angle_bg))
+
+        def sigma_fn(t_starts, t_ends, ray_indices):
+            positions = ops.ray_samples(rays_o, rays_d, ray_indices, t_starts, t_ends, False, False, False)[0]
+            return self.geometry_bg.density(positions)[..., None]
+
+        n = rays_o.shape[0]
+        marched_fg = march_finish(n, *out_fg, None, None, 1e-4, 0.0, True)
+        marched_bg = march_finish(n, *out_bg, sigma_fn, None, 1e-4, 0.0, True)
+        return marched_fg, marched_bg
+
     def forward_bg_(self, rays, stratified_u: Optional[torch.Tensor] = None, marched=None, mix_later: bool = False):
         """mix_later (forward_ only): leave `comp_rgb` without the background colour and `rays_valid` unset -- forward_ applies
         both together with the foreground / background mix in one kernel (ops.ray_mix)."""
@@ -209,15 +232,20 @@ class NeuSModel(nn.Module):
                  stratified_u_bg: Optional[torch.Tensor] = None):
         n_rays = rays.shape[0]
         rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
-        with torch.no_grad():
-            ray_indices, t_starts, t_ends, packed_info = ray_marching(
-                rays_o, rays_d, scene_aabb=self.scene_aabb, scene_aabb_host=self._aabb_host,
-                grid=self.occupancy_grid if self.grid_prune else None, alpha_fn=None, near_plane=None, far_plane=None,
-                render_step_size=self.render_step_size, stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0,
-                stratified_u=stratified_u, return_packed=True)
-        # background marching is independent of the foreground networks: issue it now so that its sample-count
-        # read-back does not drain the GPU queue in the middle of the step
-        marched_bg = self.march_bg_(rays_o, rays_d, stratified_u_bg) if self.learned_background else None
+        if self.learned_background and rays.is_cuda and os.environ.get("IA_NO_MARCH_PAIR") is None:
+            # both marches in one count launch, one read-back of both totals and one write launch (ops.march_pair): each of
+            # them alone is one thread per ray -- 128 small CTAs on 148 SMs, latency bound
+            (ray_indices, t_starts, t_ends, packed_info), marched_bg = self.march_both_(rays_o, rays_d, stratified_u, stratified_u_bg)
+        else:
+            with torch.no_grad():
+                ray_indices, t_starts, t_ends, packed_info = ray_marching(
+                    rays_o, rays_d, scene_aabb=self.scene_aabb, scene_aabb_host=self._aabb_host,
+                    grid=self.occupancy_grid if self.grid_prune else None, alpha_fn=None, near_plane=None, far_plane=None,
+                    render_step_size=self.render_step_size, stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0,
+                    stratified_u=stratified_u, return_packed=True)
+            # background marching is independent of the foreground networks: issue it now so that its sample-count
+            # read-back does not drain the GPU queue in the middle of the step
+            marched_bg = self.march_bg_(rays_o, rays_d, stratified_u_bg) if self.learned_background else None
         ri = ray_indices.long()
         positions, t_dirs, midpoints, dists = ops.ray_samples(rays_o, rays_d, ray_indices, t_starts, t_ends)
         fused_head = getattr(self.geometry, "supports_fused_head", lambda: False)() and \

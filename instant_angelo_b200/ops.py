@@ -19,7 +19,7 @@ _LAUNCHES = {"ia_hashgrid_fwd": 1, "ia_hashgrid_fwd_grouped": 1, "ia_hashgrid_bw
              "ia_march_total": 0, "ia_march_write": 1, "ia_visibility": 1, "ia_occ_update": 4, "ia_occ_pack": 1,
              "ia_composite_fwd": 1, "ia_composite_bwd": 1, "ia_adamw_step": 1, "ia_hashgrid_plan": 0,
              "ia_sdf_taps_fused_fwd": 1, "ia_sdf_taps_fused_bwd": 2, "ia_mlp_fwd_grad": 1, "ia_mlp_fwd_grad_bwd": 4,
-             "ia_colour_in_fwd": 1, "ia_colour_in_bwd": 1}
+             "ia_colour_in_fwd": 1, "ia_colour_in_bwd": 1, "ia_march_totals": 0, "ia_l2_persist": 0}
 
 
 class Profiler:
@@ -906,6 +906,42 @@ def march(rays_o, rays_d, t_min, t_max, grid: L.GridDesc, bitfield: Optional[tor
                                    L.ptr(bitfield), C.c_float(step_size), C.c_float(cone_angle), L.ptr(packed),
                                    L.ptr(ray_indices), L.ptr(t_starts), L.ptr(t_ends), s)
     return packed, ray_indices, t_starts, t_ends
+
+
+@torch.no_grad()
+def march_pair(rays_o, rays_d, set_a, set_b):
+    """Two marches of the same rays (set = (t_min, t_max, grid desc, bitfield, step_size, cone_angle)) with one count launch,
+    one read-back of both totals and one write launch.  Returns ((packed_info, ray_indices, t_starts, t_ends), (...)) exactly
+    as two march() calls would."""
+    L.require_cuda(rays_o, rays_d, set_a[0], set_a[1], set_b[0], set_b[1])
+    rays_o, rays_d = L.f32c(rays_o), L.f32c(rays_d)
+    n, dev, s = rays_o.shape[0], rays_o.device, L.stream()
+    totals_dev = torch.zeros(2, device=dev, dtype=torch.int64)
+    sets, keep = [], []
+    for k, (t_min, t_max, grid, bitfield, step, cone) in enumerate((set_a, set_b)):
+        t_min, t_max = L.f32c(t_min), L.f32c(t_max)
+        num = torch.empty(n, device=dev, dtype=torch.int32)
+        packed = torch.empty(n, 2, device=dev, dtype=torch.int32)
+        ms = L.MarchSet(L.ptr(t_min), L.ptr(t_max), C.pointer(grid), L.ptr(bitfield), float(step), float(cone), L.ptr(packed), L.ptr(num),
+                        None, None, None)
+        sets.append(ms)
+        keep.append((t_min, t_max, num, packed, grid, bitfield))
+    _run("ia_march_pair", L.ptr(rays_o), L.ptr(rays_d), n, C.byref(sets[0]), C.byref(sets[1]), 0, s)
+    for k in range(2):
+        _run("ia_march_scan", L.ptr(keep[k][2]), n, L.ptr(keep[k][3]), totals_dev.data_ptr() + 8 * k, None, s)
+    totals = (C.c_int64 * 2)()
+    _run("ia_march_totals", L.ptr(totals_dev), 2, C.byref(totals), s)
+    outs = []
+    for k in range(2):
+        S = int(totals[k])
+        ri = torch.empty(S, device=dev, dtype=torch.int32)
+        t0 = torch.empty(S, device=dev, dtype=torch.float32)
+        t1 = torch.empty(S, device=dev, dtype=torch.float32)
+        sets[k].ray_indices, sets[k].t_starts, sets[k].t_ends = L.ptr(ri), L.ptr(t0), L.ptr(t1)
+        outs.append((keep[k][3], ri, t0, t1))
+    if int(totals[0]) + int(totals[1]) > 0:
+        _run("ia_march_pair", L.ptr(rays_o), L.ptr(rays_d), n, C.byref(sets[0]), C.byref(sets[1]), 1, s)
+    return outs[0], outs[1]
 
 
 @torch.no_grad()

@@ -510,7 +510,7 @@ def test_fp16_shadow_tables_equal_fp32_path_on_rounded_tables(cuda_lib, golden_d
 def test_fused_glue_and_gradient_sinks_match_the_autograd_path(cuda_lib, golden_dir, monkeypatch):
     """The step as the bench runs it -- parameters re-homed in a ParamArena (hash-table scatters and the weight-norm adjoint
     add straight into the gradient arena), MLP weight gradients accumulated behind weightnorm_flat, fused loss kernels,
-    ia_ray_samples / ia_normalize3 / ia_ray_mix / ia_fold_head, grouped scatter for the centre rows -- against the same step with every one of those
+    ia_ray_samples / ia_normalize3 / ia_ray_mix / ia_fold_head / ia_march_pair, grouped scatter for the centre rows -- against the same step with every one of those
     switched off (tensor expressions + autograd accumulation): same loss, same gradient for every parameter; and a second
     step through the same arena after zero_grad() starts from clean accumulators."""
     from instant_angelo_b200 import geometry as geo_mod
@@ -548,6 +548,7 @@ def test_fused_glue_and_gradient_sinks_match_the_autograd_path(cuda_lib, golden_
 
     monkeypatch.setenv("IA_NO_FUSED_LOSSES", "1")
     monkeypatch.setenv("IA_NO_RAY_MIX", "1")
+    monkeypatch.setenv("IA_NO_MARCH_PAIR", "1")
     monkeypatch.setenv("IA_NO_FOLD_KERNEL", "1")
     monkeypatch.setattr(ops, "_NO_GRAD_SINK", True)
     monkeypatch.setattr(geo_mod, "_CENTER_GROUP", 1)
@@ -557,6 +558,8 @@ def test_fused_glue_and_gradient_sinks_match_the_autograd_path(cuda_lib, golden_
     out_plain = plain(batch["rays"], stratified_u=c("u_fg"), rand_directions=c("rand_directions"), stratified_u_bg=c("u_bg"))
     for k in ("comp_rgb_full", "comp_rgb_bg", "comp_rgb", "opacity"):
         assert_close(out_fast[k], out_plain[k], rtol=1e-6, atol=1e-7, name=k)
+    for k in ("ray_indices", "ray_indices_bg", "points", "intervals", "points_bg", "intervals_bg"):     # paired vs separate marches
+        assert torch.equal(out_fast[k], out_plain[k]), k
     for k in ("rays_valid", "rays_valid_bg", "rays_valid_full"):
         assert out_fast[k].dtype == torch.bool and out_fast[k].shape == out_plain[k].shape and torch.equal(out_fast[k], out_plain[k]), k
     assert set(t_plain) == set(t_fast)

@@ -51,7 +51,7 @@ class Encoding(nn.Module):
             if prec not in ("fp32", "fp16"):
                 raise ValueError(f"table_precision must be fp32 or fp16 (got {prec})")
             self.table_precision = prec
-            self._shadow, self._shadow_stale, self._shadow_version = None, True, -1
+            self._shadow, self._shadow_stale, self._shadow_version, self._shadow_epoch = None, True, -1, -1
         elif self.otype == "SphericalHarmonics":
             assert n_input_dims == 3
             self.degree = int(cfg["degree"])
@@ -62,17 +62,18 @@ class Encoding(nn.Module):
 
     def shadow(self) -> Optional[torch.Tensor]:
         """The fp16 copy of .params the gathers read (None under table_precision fp32).  Re-derived when the parameters may
-        have changed: after update_step() (the reference's per-step hook runs right after the optimizer step; the fused AdamW
-        writes through raw pointers, which torch's version counter does not see) and after any in-place torch operation on
-        .params (load_state_dict, a torch optimizer)."""
+        have changed: after any fused optimizer step of this process (ops.param_epoch(): ia_adamw_step writes through raw
+        pointers, which torch's version counter does not see), after update_step() (the reference's per-step hook) and after
+        any in-place torch operation on .params (load_state_dict, a torch optimizer)."""
         if self.otype != "HashGrid" or self.table_precision != "fp16":
             return None
         p = self.params
-        if self._shadow is None or self._shadow.device != p.device or self._shadow_stale or self._shadow_version != p._version:
+        if self._shadow is None or self._shadow.device != p.device or self._shadow_stale or self._shadow_version != p._version \
+                or self._shadow_epoch != ops.param_epoch():
             if self._shadow is not None and self._shadow.device != p.device:
                 self._shadow = None
             self._shadow = ops.table_to_half(p, self._shadow)
-            self._shadow_stale, self._shadow_version = False, p._version
+            self._shadow_stale, self._shadow_version, self._shadow_epoch = False, p._version, ops.param_epoch()
         return self._shadow
 
     def update_step(self, epoch, global_step):

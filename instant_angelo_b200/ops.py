@@ -1083,8 +1083,18 @@ def composite_alpha(alpha, packed_info, t_mid=None, rgb=None, nrm=None):
 # optimizer
 # ---------------------------------------------------------------------------------------------
 
+_PARAM_EPOCH = 0      # bumped by every ia_adamw_step: raw-pointer parameter writes that torch's version counters do not see
+
+
+def param_epoch() -> int:
+    """Number of fused optimizer steps issued by this process (Encoding.shadow() re-derives its fp16 copy when it moves)."""
+    return _PARAM_EPOCH
+
+
 @torch.no_grad()
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
     _run("ia_adamw_step", L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(),
                                    C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                    C.c_float(weight_decay), int(step), C.c_float(grad_scale), L.stream())

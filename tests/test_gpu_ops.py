@@ -207,13 +207,22 @@ def test_encoding_fp16_shadow_follows_the_parameters(cuda_lib):
     x = torch.rand(500, 3, generator=torch.Generator().manual_seed(1)).cuda()
     enc_f.load_state_dict({k: v.half().float() for k, v in enc_h.state_dict().items()})
     assert torch.equal(enc_h(x), enc_f(x))
-    # raw-pointer update (what ia_adamw_step does): invisible to torch's version counter, picked up at the next update_step
+    # fused optimizer step (raw-pointer writes, invisible to torch's version counter): ops.param_epoch() moves
     ops.adamw_step(grid.params.data, torch.ones_like(grid.params), torch.zeros_like(grid.params), torch.zeros_like(grid.params),
                    0.05, 0.9, 0.99, 1e-15, 0.0, 1)
+    fresh = enc_h(x)                                # no update_step in between: the optimizer step itself marked the copy stale
+    enc_f.load_state_dict({k: v.half().float() for k, v in enc_h.state_dict().items()})
+    assert torch.equal(fresh, enc_f(x))
+    # a raw write that bypasses ops.adamw_step (the bare ABI call) is invisible to both counters: picked up at the next update_step
+    import ctypes as C
+    from instant_angelo_b200 import _lib as L
+    m, v, g1 = torch.zeros_like(grid.params), torch.zeros_like(grid.params), torch.ones_like(grid.params)
+    L.check(L.load().ia_adamw_step(L.ptr(grid.params), L.ptr(g1), L.ptr(m), L.ptr(v), grid.params.numel(), C.c_float(0.05), C.c_float(0.9),
+                                   C.c_float(0.99), C.c_float(1e-15), C.c_float(0.0), 1, C.c_float(1.0), L.stream()))
     stale = enc_h(x)
     enc_h.update_step(0, 11)
     fresh = enc_h(x)
-    enc_f.load_state_dict({k: v.half().float() for k, v in enc_h.state_dict().items()})
+    enc_f.load_state_dict({k: v_.half().float() for k, v_ in enc_h.state_dict().items()})
     assert torch.equal(fresh, enc_f(x)) and not torch.equal(stale, fresh)
     # in-place torch write: seen through the version counter without update_step
     with torch.no_grad():
